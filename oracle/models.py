@@ -1,0 +1,170 @@
+"""Functional CPU restatement of the three reference forwards (test infrastructure).
+
+Each function takes the reference `state_dict` (keys of SURVEY.md App. C) and an input
+`[B,1,T]`, and follows the reference op order so that fp32 results agree with the reference
+modules to rounding (pinned by tests/golden/*.npz, generated from /root/reference).
+Eval-mode semantics only (BatchNorm uses running stats; inference.py:55,70,89 call .eval()).
+
+`dtype=torch.float64` gives the high-precision tie-breaker used when judging which of two
+fp32 results is closer to the true value.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+_SLOPE = 0.2  # every LeakyReLU in the reference uses 0.2 (App. B.8)
+_EPS = 1e-5   # nn.BatchNorm1d default
+
+
+def _p(sd, key, dtype):
+    return sd[key].to(dtype)
+
+
+def _conv(sd, prefix, x, padding=0, dilation=1):
+    dt = x.dtype
+    return F.conv1d(x, _p(sd, prefix + ".weight", dt), _p(sd, prefix + ".bias", dt),
+                    padding=padding, dilation=dilation)
+
+
+def _bn(sd, prefix, x):
+    dt = x.dtype
+    return F.batch_norm(x, _p(sd, prefix + ".running_mean", dt), _p(sd, prefix + ".running_var", dt),
+                        _p(sd, prefix + ".weight", dt), _p(sd, prefix + ".bias", dt),
+                        training=False, eps=_EPS)
+
+
+def _lrelu(x):
+    return F.leaky_relu(x, _SLOPE)
+
+
+# --------------------------------------------------------------------------- denoiser
+def _unet_block(sd, prefix, x):
+    """conv3-BN-LReLU x2  (denoiser.py:51-60)."""
+    x = _lrelu(_bn(sd, prefix + ".1", _conv(sd, prefix + ".0", x, padding=1)))
+    x = _lrelu(_bn(sd, prefix + ".4", _conv(sd, prefix + ".3", x, padding=1)))
+    return x
+
+
+def detect_impulses(x):
+    """Analytic impulse mask (denoiser.py:62-86; closed form SURVEY.md App. B.6)."""
+    d1 = F.pad((x[:, :, 1:] - x[:, :, :-1]).abs(), (0, 1))
+    d2 = F.pad((d1[:, :, 1:] - d1[:, :, :-1]).abs(), (0, 1))
+    score = (d2 * 2.0 + d1 + x.abs() * 0.5) / 3.5
+    box = torch.ones(1, 1, 5, dtype=x.dtype) / 5
+    return F.conv1d(score, box, padding=2).clamp(0, 1)
+
+
+def denoiser_forward(sd, x, dtype=torch.float32, return_features=False):
+    """AudioDenoiser.forward (denoiser.py:88-144): [B,1,T] -> [B,1,T], T >= 8."""
+    x = x.to(dtype)
+    audio_in = x
+    skips = []
+    for i in range(3):
+        x = _unet_block(sd, f"encoder.{i}", x)
+        skips.append(x)
+        x = F.max_pool1d(x, 2, 2)                      # floor pooling (:18,:107)
+    x = _unet_block(sd, "bottleneck", x)
+    for i in range(3):
+        w = _p(sd, f"decoder.{2 * i}.weight", dtype)
+        b = _p(sd, f"decoder.{2 * i}.bias", dtype)
+        x = F.conv_transpose1d(x, w, b, stride=2)      # k2 s2 (:31-33)
+        skip = skips[2 - i]
+        if x.shape[2] != skip.shape[2]:
+            x = F.pad(x, [0, skip.shape[2] - x.shape[2]])  # right zero-pad (:121-122)
+        x = _unet_block(sd, f"decoder.{2 * i + 1}", torch.cat((skip, x), dim=1))  # skip first (:124)
+    feats = x
+    m = _lrelu(_conv(sd, "transient_detector.0", feats, padding=1))
+    m = _lrelu(_conv(sd, "transient_detector.2", m, padding=1))
+    m = torch.sigmoid(_conv(sd, "transient_detector.4", m, padding=1))
+    mask = torch.maximum(m, detect_impulses(audio_in))                        # (:134)
+    y = _conv(sd, "final_conv", feats) * (1.0 - mask * 0.9)                  # (:137-142)
+    return (y, feats) if return_features else y
+
+
+# --------------------------------------------------------------------------- super-resolution
+def super_resolution_forward(sd, x, dtype=torch.float32):
+    """AudioSuperResolution(upscale_factor=2).forward (super_resolution.py:66-101): [B,1,T] -> [B,1,2T]."""
+    x = x.to(dtype)
+    f0 = _lrelu(_conv(sd, "initial.0", x, padding=3))
+    r = f0
+    for i in range(4):                                  # ResidualBlockEfficient (:115-122)
+        p = f"residual_blocks.{i}"
+        o = _lrelu(_bn(sd, p + ".bn1", _conv(sd, p + ".conv1", r, padding=1)))
+        o = _bn(sd, p + ".bn2", _conv(sd, p + ".conv2", o, padding=1))
+        r = o + r
+    r = _bn(sd, "middle.1", _conv(sd, "middle.0", r, padding=1))
+    f = f0 + r
+    w = _p(sd, "upsample_blocks.0.0.weight", dtype)
+    b = _p(sd, "upsample_blocks.0.0.bias", dtype)
+    f = _lrelu(F.conv_transpose1d(f, w, b, stride=2, padding=1))             # k4 s2 p1 (:47-51)
+    f = _lrelu(_conv(sd, "hf_emphasis.0", f, padding=2))
+    y = _conv(sd, "reconstruction", f, padding=3)
+    up = F.interpolate(x, scale_factor=2, mode="linear", align_corners=False)  # (:96-98)
+    return y + up
+
+
+# --------------------------------------------------------------------------- stereo separator
+def lstm_explicit(x_btc, w_ih, w_hh, b_ih, b_hh):
+    """Step-by-step LSTM (gate order i,f,g,o; h0=c0=0; App. B.5).  Slow: small T only."""
+    B, T, _ = x_btc.shape
+    H = w_hh.shape[1]
+    h = x_btc.new_zeros(B, H)
+    c = x_btc.new_zeros(B, H)
+    out = []
+    xp = x_btc @ w_ih.t() + b_ih
+    for t in range(T):
+        g = xp[:, t] + h @ w_hh.t() + b_hh
+        i, f, gg, o = g.split(H, dim=1)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        out.append(h)
+    return torch.stack(out, dim=1)
+
+
+def _lstm_fast(sd, x_btc, h0c0=None):
+    """Same recurrence through ATen's fused CPU LSTM (what nn.LSTM dispatches to)."""
+    dt = x_btc.dtype
+    B = x_btc.shape[0]
+    H = sd["lstm.weight_hh_l0"].shape[1]
+    if h0c0 is None:
+        h0c0 = (x_btc.new_zeros(1, B, H), x_btc.new_zeros(1, B, H))
+    flat = [_p(sd, "lstm.weight_ih_l0", dt), _p(sd, "lstm.weight_hh_l0", dt),
+            _p(sd, "lstm.bias_ih_l0", dt), _p(sd, "lstm.bias_hh_l0", dt)]
+    out, hn, cn = torch.lstm(x_btc, h0c0, flat, True, 1, 0.0, False, False, True)
+    return out, (hn, cn)
+
+
+def stereo_encoder(sd, x):
+    f = _lrelu(_bn(sd, "encoder.0.1", _conv(sd, "encoder.0.0", x, padding=3)))
+    for i, d in zip(range(1, 5), (1, 2, 4, 8)):          # (:49-64), no residual add in the code
+        f = _lrelu(_bn(sd, f"encoder.{i}.1", _conv(sd, f"encoder.{i}.0", f, padding=d, dilation=d)))
+        f = _lrelu(_bn(sd, f"encoder.{i}.4", _conv(sd, f"encoder.{i}.3", f)))
+    return f
+
+
+def stereo_decoder(sd, side, z):
+    z = _lrelu(_bn(sd, f"{side}.1", _conv(sd, f"{side}.0", z, padding=3)))
+    z = _lrelu(_bn(sd, f"{side}.4", _conv(sd, f"{side}.3", z, padding=3)))
+    z = _lrelu(_bn(sd, f"{side}.7", _conv(sd, f"{side}.6", z, padding=3)))
+    return _conv(sd, f"{side}.9", z, padding=3)
+
+
+def stereo_forward(sd, x, dtype=torch.float32, explicit_lstm=False, state=None, return_state=False):
+    """StereoSeparator.forward (stereo_separator.py:85-122): [B,1,T] -> [B,2,T].
+
+    `state=(h,c)` / `return_state` expose the LSTM carry for the whole-file-exact mode
+    (SURVEY.md section 8 n2); the reference itself always starts from zeros (:107).
+    """
+    x = x.to(dtype).contiguous()
+    e = stereo_encoder(sd, x).permute(0, 2, 1).contiguous()      # [B,T,128] (:104)
+    if explicit_lstm:
+        assert state is None
+        z = lstm_explicit(e, _p(sd, "lstm.weight_ih_l0", dtype), _p(sd, "lstm.weight_hh_l0", dtype),
+                          _p(sd, "lstm.bias_ih_l0", dtype), _p(sd, "lstm.bias_hh_l0", dtype))
+        new_state = None
+    else:
+        z, new_state = _lstm_fast(sd, e, state)
+    z = z.permute(0, 2, 1).contiguous()                          # [B,64,T] (:113)
+    y = torch.cat([stereo_decoder(sd, "left_decoder", z), stereo_decoder(sd, "right_decoder", z)], dim=1)
+    return (y, new_state) if return_state else y
