@@ -1,0 +1,135 @@
+/*
+ * audiorestore.h -- C-ABI of libaudiorestore_sm100.so (B200 / sm_100a).
+ *
+ * The reference (JonathanBedrava/ml-audio-restoration) is pure Python/PyTorch and has no FFI
+ * of its own; these entry points are what a binding for its inference hot path would bind.
+ * Each one names the reference interface it replaces (file:line under the reference root).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a non-zero AR_ERR_* code otherwise;
+ *     ar_last_error() returns a thread-local human-readable message (the Python shim turns
+ *     it into RuntimeError/ValueError, preserving the reference's exception convention).
+ *   - all pointers named x/y/audio/chunks/out/workspace are DEVICE pointers unless the
+ *     function name ends in _host; the caller owns them.  Handles own the packed weights.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no entry point
+ *     synchronises the device except ar_restore_host (which must, to hand back host data)
+ *     and the *_create functions (weight upload).
+ *   - tensors are fp32, contiguous, in the reference's layout: audio batches are
+ *     [B,1,T], stereo outputs [B,2,T] (denoiser.py:93, super_resolution.py:69,
+ *     stereo_separator.py:88).
+ *   - there is no CPU fallback: on a machine without an sm_100 device *_create fails.
+ */
+#ifndef AUDIORESTORE_H_
+#define AUDIORESTORE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AR_OK 0
+#define AR_ERR_INVALID 1   /* bad argument / shape (reference: RuntimeError from ATen)      */
+#define AR_ERR_WEIGHTS 2   /* missing / mis-shaped state_dict entry (load_state_dict strict) */
+#define AR_ERR_CUDA 3      /* CUDA runtime failure                                           */
+#define AR_ERR_WORKSPACE 4 /* workspace too small                                            */
+
+#define AR_MODEL_DENOISER 0  /* AudioDenoiser()                       denoiser.py:6          */
+#define AR_MODEL_SUPER_RES 1 /* AudioSuperResolution(upscale_factor=2) super_resolution.py:6 */
+#define AR_MODEL_STEREO 2    /* StereoSeparator(32, 64, 1)            stereo_separator.py:5  */
+
+#define AR_ENGINE_UMMA 0 /* tcgen05 implicit-GEMM conv engine (product path)                 */
+#define AR_ENGINE_SIMT 1 /* CUDA-core fp32 conv engine (debug cross-check only)              */
+
+typedef struct ar_model_s* ar_model_t;
+typedef struct ar_chain_s* ar_chain_t;
+
+/* One state_dict entry: HOST pointer to contiguous fp32 data (int64 num_batches_tracked
+ * entries are not passed; eval-mode BatchNorm ignores them). */
+typedef struct {
+  const char* name;  /* exact reference key, e.g. "encoder.0.0.weight" (App. C)            */
+  const float* data; /* host fp32                                                           */
+  int ndim;
+  int64_t shape[4];
+} ar_tensor_t;
+
+const char* ar_last_error(void);
+int ar_version(void);
+
+/* Select the conv engine used by subsequently created models (default AR_ENGINE_UMMA). */
+int ar_set_conv_engine(int engine);
+
+/* Replaces: model construction + torch.load + load_state_dict(strict) + .to(device) + .eval()
+ * (inference.py:51-55, 66-70, 85-89).  Folds eval-mode BatchNorm into the conv weights,
+ * rounds tensor-core operands to TF32, packs into the kernels' layouts, uploads.  */
+int ar_model_create(int kind, const ar_tensor_t* tensors, int n_tensors, int device, ar_model_t* out);
+void ar_model_destroy(ar_model_t m);
+int ar_model_kind(ar_model_t m);
+
+/* Bytes of device scratch ar_model_forward needs for a [B,1,T] batch. */
+int ar_model_workspace_bytes(ar_model_t m, int B, int T, size_t* bytes);
+
+/* Replaces nn.Module.forward under eval()/no_grad():
+ *   denoiser  : x[B,1,T] -> y[B,1,T]    (denoiser.py:88-144; T >= 8 else AR_ERR_INVALID)
+ *   super-res : x[B,1,T] -> y[B,1,2T]   (super_resolution.py:66-101)
+ *   stereo    : x[B,1,T] -> y[B,2,T]    (stereo_separator.py:85-122; LSTM state starts at 0) */
+int ar_model_forward(ar_model_t m, const float* x, float* y, int B, int T,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stereo forward with explicit LSTM carry (whole-file-exact mode):
+ * state_in/state_out are [B,2,64] (h then c) device buffers; either may be NULL. */
+int ar_stereo_forward_state(ar_model_t m, const float* x, float* y, int B, int T,
+                            const float* state_in, float* state_out,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* denoise -> (super-res) -> stereo on a batch of equal-length chunks
+ * (the three model applications of inference.py:59-61,73-75,93-95).  sr may be NULL
+ * (enable_super_resolution=False): y is [B,2,T] instead of [B,2,2T]. */
+int ar_chain_create(ar_model_t denoiser, ar_model_t sr, ar_model_t stereo, ar_chain_t* out);
+void ar_chain_destroy(ar_chain_t c);
+int ar_chain_workspace_bytes(ar_chain_t c, int B, int T, size_t* bytes);
+int ar_chain_forward(ar_chain_t c, const float* x, float* y, int B, int T,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces normalize_audio (audio_processing.py:58-87) without its two host syncs:
+ * in-place RMS -> target_db over all n elements, then peak-limit to 1.0; rms==0 leaves the
+ * data untouched.  scratch: >= AR_NORMALIZE_SCRATCH_BYTES of device memory. */
+#define AR_NORMALIZE_SCRATCH_BYTES 16384
+int ar_normalize(float* audio, int64_t n, float target_db, void* scratch, void* stream);
+
+/* Chunk / stitch (vocabulary of chunk_audio, audio_processing.py:229-253; tail zero-pad of
+ * trainer.py:656-665).  hop = chunk_size - overlap, overlap <= chunk_size/2.
+ *   ar_num_chunks     : chunks needed for n samples
+ *   ar_split_chunks   : audio[n] -> chunks[n_chunks,1,chunk_size] for chunk indices
+ *                       [first, first+count)
+ *   ar_overlap_add    : y[n_chunks,C,rate*chunk_size] -> out[C, rate*n] with linear
+ *                       cross-fades over rate*overlap samples (gather form, deterministic) */
+int ar_num_chunks(int64_t n, int chunk_size, int overlap, int* n_chunks);
+int ar_split_chunks(const float* audio, int64_t n, float* chunks, int first, int count,
+                    int chunk_size, int overlap, void* stream);
+int ar_overlap_add(const float* y, float* out, int64_t n, int n_chunks, int channels,
+                   int chunk_size, int overlap, int rate, void* stream);
+
+/* Measurement hooks (bench.py): kernels launched so far by this library, and -- while enabled --
+ * CUDA-event timing of every launch on its own stream, summed per category
+ * (0 conv engine, 1 LSTM recurrence, 2 stems, 3 tails, 4 normalize, 5 split/overlap-add).
+ * ar_profile_read synchronises on the recorded events, returns the sums since the last read
+ * (ms, algorithmic FLOPs, launch counts; arrays of n <= AR_PROFILE_CATEGORIES) and clears them. */
+#define AR_PROFILE_CATEGORIES 6
+int ar_profile_enable(int on);
+int ar_profile_read(double* ms, double* flops, long long* launches, int n);
+long long ar_launch_count(void);
+
+/* Debug / test hook: one conv layer on channel-blocked activations through the selected
+ * engine; lets tests compare the tcgen05 engine with the SIMT one layer by layer.
+ * x: [B,Cin,T] plain fp32, w: [Cout,Cin,k] host fp32, bias: [Cout] host fp32,
+ * y: [B,Cout,T] plain fp32 (device).  */
+int ar_debug_conv1d(const float* x, const float* w_host, const float* bias_host, float* y,
+                    int B, int Cin, int Cout, int T, int k, int dilation, int lrelu,
+                    int engine, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUDIORESTORE_H_ */

@@ -1,0 +1,167 @@
+// extern "C" surface of libaudiorestore_sm100.so (see include/audiorestore.h).
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ar_common.cuh"
+#include "pointwise.cuh"
+#include "prof.cuh"
+
+namespace ar {
+struct Model;
+const char* last_error();
+int set_engine(int e);
+int model_create(int kind, const ar_tensor_t* tensors, int n, int device, Model** out);
+int model_workspace_bytes(const Model* m, int B, int T, size_t* bytes);
+int model_forward(const Model* m, const float* x, float* y, int B, int T, const float* st_in, float* st_out, void* ws,
+                  size_t ws_bytes, cudaStream_t stream);
+void model_destroy(Model* m);
+int model_kind(const Model* m);
+struct ConvLayerPublic;
+int debug_conv(const float* x, const float* w_host, const float* bias_host, float* y, int B, int Cin, int Cout, int T, int k,
+               int dil, int lrelu, int engine, cudaStream_t stream);
+}  // namespace ar
+
+struct ar_model_s;  // == ar::Model
+struct ar_chain_s {
+  ar::Model* den;
+  ar::Model* sr;
+  ar::Model* st;
+};
+
+static inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+extern "C" {
+
+const char* ar_last_error(void) { return ar::last_error(); }
+int ar_version(void) { return 100; }
+int ar_set_conv_engine(int engine) { return ar::set_engine(engine); }
+
+int ar_model_create(int kind, const ar_tensor_t* tensors, int n_tensors, int device, ar_model_t* out) {
+  ar::Model* m = nullptr;
+  int r = ar::model_create(kind, tensors, n_tensors, device, &m);
+  if (r == AR_OK) *out = reinterpret_cast<ar_model_t>(m);
+  return r;
+}
+void ar_model_destroy(ar_model_t m) { ar::model_destroy(reinterpret_cast<ar::Model*>(m)); }
+int ar_model_kind(ar_model_t m) { return m ? ar::model_kind(reinterpret_cast<ar::Model*>(m)) : -1; }
+
+int ar_model_workspace_bytes(ar_model_t m, int B, int T, size_t* bytes) {
+  return ar::model_workspace_bytes(reinterpret_cast<ar::Model*>(m), B, T, bytes);
+}
+
+int ar_model_forward(ar_model_t m, const float* x, float* y, int B, int T, void* workspace, size_t workspace_bytes, void* stream) {
+  return ar::model_forward(reinterpret_cast<ar::Model*>(m), x, y, B, T, nullptr, nullptr, workspace, workspace_bytes,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ar_stereo_forward_state(ar_model_t m, const float* x, float* y, int B, int T, const float* state_in, float* state_out,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  AR_CHECK(m && ar::model_kind(reinterpret_cast<ar::Model*>(m)) == AR_MODEL_STEREO, AR_ERR_INVALID,
+           "ar_stereo_forward_state: not a stereo model");
+  return ar::model_forward(reinterpret_cast<ar::Model*>(m), x, y, B, T, state_in, state_out, workspace, workspace_bytes,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ar_chain_create(ar_model_t denoiser, ar_model_t sr, ar_model_t stereo, ar_chain_t* out) {
+  AR_CHECK(out && denoiser && stereo, AR_ERR_INVALID, "ar_chain_create: denoiser and stereo models are required");
+  AR_CHECK(ar_model_kind(denoiser) == AR_MODEL_DENOISER && ar_model_kind(stereo) == AR_MODEL_STEREO &&
+               (sr == nullptr || ar_model_kind(sr) == AR_MODEL_SUPER_RES),
+           AR_ERR_INVALID, "ar_chain_create: model kinds do not match their slots");
+  ar_chain_s* c = new ar_chain_s;
+  c->den = reinterpret_cast<ar::Model*>(denoiser);
+  c->sr = reinterpret_cast<ar::Model*>(sr);
+  c->st = reinterpret_cast<ar::Model*>(stereo);
+  *out = c;
+  return AR_OK;
+}
+void ar_chain_destroy(ar_chain_t c) { delete c; }
+
+static int chain_layout(ar_chain_t c, int B, int T, size_t* y1, size_t* y2, size_t* ws, size_t* total) {
+  AR_CHECK(c && B >= 1 && T >= 1, AR_ERR_INVALID, "chain: bad argument");
+  const int rate = c->sr ? 2 : 1;
+  size_t w_den = 0, w_sr = 0, w_st = 0;
+  AR_TRY(ar::model_workspace_bytes(c->den, B, T, &w_den));
+  if (c->sr) AR_TRY(ar::model_workspace_bytes(c->sr, B, T, &w_sr));
+  AR_TRY(ar::model_workspace_bytes(c->st, B, rate * T, &w_st));
+  *y1 = align256((size_t)B * T * sizeof(float));
+  *y2 = c->sr ? align256((size_t)B * 2 * T * sizeof(float)) : 0;
+  *ws = std::max(w_den, std::max(w_sr, w_st));
+  *total = *y1 + *y2 + *ws + 256;
+  return AR_OK;
+}
+
+int ar_chain_workspace_bytes(ar_chain_t c, int B, int T, size_t* bytes) {
+  size_t y1, y2, ws;
+  AR_CHECK(bytes != nullptr, AR_ERR_INVALID, "chain: null bytes");
+  return chain_layout(c, B, T, &y1, &y2, &ws, bytes);
+}
+
+int ar_chain_forward(ar_chain_t c, const float* x, float* y, int B, int T, void* workspace, size_t workspace_bytes, void* stream) {
+  size_t y1b, y2b, wsb, total;
+  AR_TRY(chain_layout(c, B, T, &y1b, &y2b, &wsb, &total));
+  AR_CHECK(workspace && workspace_bytes >= total, AR_ERR_WORKSPACE, "chain: workspace too small (need " + std::to_string(total) + " bytes)");
+  char* base = reinterpret_cast<char*>(align256(reinterpret_cast<uintptr_t>(workspace)));
+  float* y1 = reinterpret_cast<float*>(base);
+  float* y2 = reinterpret_cast<float*>(base + y1b);
+  void* ws = base + y1b + y2b;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  AR_TRY(ar::model_forward(c->den, x, y1, B, T, nullptr, nullptr, ws, wsb, s));
+  const float* st_in = y1;
+  int Ts = T;
+  if (c->sr) {
+    AR_TRY(ar::model_forward(c->sr, y1, y2, B, T, nullptr, nullptr, ws, wsb, s));
+    st_in = y2;
+    Ts = 2 * T;
+  }
+  return ar::model_forward(c->st, st_in, y, B, Ts, nullptr, nullptr, ws, wsb, s);
+}
+
+int ar_normalize(float* audio, int64_t n, float target_db, void* scratch, void* stream) {
+  AR_CHECK(audio && scratch, AR_ERR_INVALID, "ar_normalize: null pointer");
+  ar::ProfScope ps(ar::CAT_NORM, reinterpret_cast<cudaStream_t>(stream), 0.0, 2);
+  return ar::launch_normalize(audio, n, target_db, reinterpret_cast<float*>(scratch), reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ar_num_chunks(int64_t n, int chunk_size, int overlap, int* n_chunks) {
+  AR_CHECK(n_chunks != nullptr, AR_ERR_INVALID, "ar_num_chunks: null output");
+  AR_CHECK(chunk_size > 0 && overlap >= 0 && overlap <= chunk_size / 2, AR_ERR_INVALID, "overlap must be in [0, chunk_size // 2]");
+  AR_CHECK(n > 0, AR_ERR_INVALID, "empty audio");
+  const int64_t hop = chunk_size - overlap;
+  const int64_t k = n <= chunk_size ? 1 : (n - overlap + hop - 1) / hop;
+  AR_CHECK(k < (1LL << 31), AR_ERR_INVALID, "too many chunks");
+  *n_chunks = (int)k;
+  return AR_OK;
+}
+
+int ar_split_chunks(const float* audio, int64_t n, float* chunks, int first, int count, int chunk_size, int overlap, void* stream) {
+  int total = 0;
+  AR_TRY(ar_num_chunks(n, chunk_size, overlap, &total));
+  AR_CHECK(audio && chunks && first >= 0 && count >= 0 && first + count <= total, AR_ERR_INVALID, "ar_split_chunks: bad chunk range");
+  ar::ProfScope ps(ar::CAT_CHUNK, reinterpret_cast<cudaStream_t>(stream), 0.0);
+  return ar::launch_split(audio, n, chunks, first, count, chunk_size, overlap, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ar_overlap_add(const float* y, float* out, int64_t n, int n_chunks, int channels, int chunk_size, int overlap, int rate,
+                   void* stream) {
+  int total = 0;
+  AR_TRY(ar_num_chunks(n, chunk_size, overlap, &total));
+  AR_CHECK(y && out && n_chunks == total && channels >= 1 && rate >= 1, AR_ERR_INVALID, "ar_overlap_add: bad argument");
+  ar::ProfScope ps(ar::CAT_CHUNK, reinterpret_cast<cudaStream_t>(stream), 0.0);
+  return ar::launch_ola(y, out, n, n_chunks, channels, chunk_size, overlap, rate, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ar_profile_enable(int on) { return ar::prof_enable(on); }
+int ar_profile_read(double* ms, double* flops, long long* launches, int n) {
+  AR_CHECK(ms && flops && launches && n >= 1 && n <= AR_PROFILE_CATEGORIES, AR_ERR_INVALID, "ar_profile_read: bad argument");
+  return ar::prof_read(ms, flops, launches, n);
+}
+long long ar_launch_count(void) { return ar::prof_launch_count(); }
+
+int ar_debug_conv1d(const float* x, const float* w_host, const float* bias_host, float* y, int B, int Cin, int Cout, int T, int k,
+                    int dilation, int lrelu, int engine, void* stream) {
+  return ar::debug_conv(x, w_host, bias_host, y, B, Cin, Cout, T, k, dilation, lrelu, engine, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,301 @@
+// tcgen05 implicit-GEMM Conv1d engine for sm_100a.
+//
+//   D[128 time rows, N out channels] (fp32, TMEM) += sum over taps j, input-channel blocks kb
+//        A_j,kb[128 x 8] (tf32, smem, K-major, no swizzle)  x  B_j,kb[8 x N] (tf32, smem, K-major)
+//
+// * Activations live in HBM as C4 ([C/4][Tp][4], see ar_common.cuh), so the rows a tile needs
+//   for ALL taps of one 4-channel chunk are one contiguous run: one cp.async.bulk (TMA, UBLKCP)
+//   per chunk.  In shared memory chunk c of a stage sits at c*R*16 bytes (R = 128 + reach), which is
+//   exactly the canonical no-swizzle K-major UMMA layout ((8,m),(4,2)) with SBO = 128 B
+//   (8 rows x 16 B) and LBO = R*16 B.  Tap j (dilation d) is the same descriptor with its
+//   start address advanced by j*d*16 bytes -- no im2col, no per-tap reload.
+// * Weights are pre-packed per (channel block, tap) as [2][N][4] => LBO = N*16 B, SBO = 128 B;
+//   a stage's weights are one contiguous bulk copy.
+// * Warp roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer (also zeroes out-of-range
+//   rows of edge tiles = conv zero padding), warps 2..5 = epilogue (TMEM -> registers ->
+//   bias/LeakyReLU/residual/TF32-round -> coalesced float4 stores, + fused max-pool or
+//   2x interleave).  Accumulators are double-buffered in TMEM so the epilogue of tile i
+//   overlaps the MMAs of tile i+1.  Persistent grid: one CTA per SM, static tile striding.
+#include "ar_common.cuh"
+
+namespace ar {
+
+constexpr int UMMA_THREADS = 192;
+constexpr int SMEM_BUDGET = 227 * 1024;
+constexpr int BAR_BYTES = 256;
+
+struct UmmaCfg {
+  int kbs;          // 8-channel K blocks per pipeline stage
+  int stages;
+  int R;            // activation rows per chunk per tile
+  int a_bytes, w_bytes, stage_bytes;
+  int ncol;         // TMEM columns per accumulator buffer (pow2 >= N)
+  int tmem_cols;    // allocated columns (2 buffers)
+  int nks;          // pipeline stages per tile = Cin / (8*kbs)
+  int smem_bytes;
+};
+
+// ----------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t_start = 0;
+  for (uint32_t spins = 0;; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (spins == 64) t_start = clock64();
+    if (spins > 64 && (spins & 1023) == 0 && clock64() - t_start > 4000000000LL) {
+      // ~2 s: a wedged pipeline becomes an error, not a hung GPU
+      printf("conv_umma: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=0.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
+         ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+
+// ----------------------------------------------------------------------------- kernel
+__global__ void __launch_bounds__(UMMA_THREADS, 1)
+conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ UmmaCfg cfg, int num_tiles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_base + cfg.stages * cfg.stage_bytes;
+  // barrier slots (8 bytes each): full[stages], empty[stages], tmem_full[2], tmem_empty[2], tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (cfg.stages + s); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * cfg.stages + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * cfg.stages + 2 + i); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + cfg.stages * cfg.stage_bytes + 8 * (2 * cfg.stages + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < cfg.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar(i), 1);
+      mbar_init(tempty_bar(i), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), (uint32_t)cfg.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tpi = p.tiles_per_item;
+  const int R = cfg.R;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int b = tile / tpi;
+        const int t0 = (tile % tpi) * TILE_M;
+        for (int ks = 0; ks < cfg.nks; ++ks, ++it) {
+          const int s = it % cfg.stages;
+          const uint32_t ph = (uint32_t)(it / cfg.stages) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_expect_tx(full_bar(s), (uint32_t)cfg.stage_bytes);
+          const uint32_t a_dst = smem_base + s * cfg.stage_bytes;
+          const int chunk0 = p.in_coff4 + ks * cfg.kbs * 2;
+          for (int c = 0; c < cfg.kbs * 2; ++c)
+            bulk_g2s(a_dst + c * R * 16, p.in + act_off(p.in_bs, p.in_Tp, b, chunk0 + c, t0 - p.pad_left),
+                     (uint32_t)(R * 16), full_bar(s));
+          bulk_g2s(a_dst + cfg.a_bytes, p.w + (size_t)ks * (cfg.w_bytes / 4), (uint32_t)cfg.w_bytes, full_bar(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    // instruction descriptor: D=F32, A=B=TF32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+    int it = 0, tl = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+      const int t0 = (tile % tpi) * TILE_M;
+      const int buf = tl & 1;
+      const uint32_t aph = (uint32_t)(tl >> 1) & 1u;
+      mbar_wait(tempty_bar(buf), aph ^ 1u);
+      tc_fence_after();
+      const int tfirst = t0 - p.pad_left;                 // time of local row 0
+      const bool edge = (tfirst < 0) || (tfirst + R > p.Tin);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * cfg.ncol);
+      for (int ks = 0; ks < cfg.nks; ++ks, ++it) {
+        const int s = it % cfg.stages;
+        const uint32_t ph = (uint32_t)(it / cfg.stages) & 1u;
+        mbar_wait(full_bar(s), ph);
+        uint8_t* a_ptr = smem + s * cfg.stage_bytes;
+        if (edge) {  // conv zero padding: rows outside [0, Tin) become zeros
+          for (int r = lane; r < R; r += 32) {
+            const int t = tfirst + r;
+            if (t < 0 || t >= p.Tin)
+              for (int c = 0; c < cfg.kbs * 2; ++c)
+                *reinterpret_cast<float4*>(a_ptr + (c * R + r) * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          fence_async_smem();
+          __syncwarp();
+        }
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_s = smem_base + s * cfg.stage_bytes;
+          const uint32_t w_s = a_s + cfg.a_bytes;
+          for (int kb = 0; kb < cfg.kbs; ++kb) {
+            for (int j = 0; j < p.taps; ++j) {
+              const uint64_t adesc = make_desc(a_s + (kb * 2 * R + j * p.dil) * 16, (uint32_t)(R * 16), 128u);
+              const uint64_t bdesc = make_desc(w_s + (kb * p.taps + j) * p.N * 32, (uint32_t)(p.N * 16), 128u);
+              umma_tf32(d_tmem, adesc, bdesc, idesc, (ks | kb | j) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(empty_bar(s));                       // frees the smem stage when the MMAs retire
+          if (ks == cfg.nks - 1) umma_commit(tfull_bar(buf));  // accumulator ready for the epilogue
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int tl = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+      const int b = tile / tpi;
+      const int t = (tile % tpi) * TILE_M + q * 32 + lane;
+      const int buf = tl & 1;
+      const uint32_t aph = (uint32_t)(tl >> 1) & 1u;
+      mbar_wait(tfull_bar(buf), aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * cfg.ncol);
+      for (int col0 = 0; col0 < p.N; col0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + col0, r);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          epilogue_chunk(p, b, t, col0 + 4 * c,
+                         make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]),
+                                     __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3])));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)cfg.tmem_cols);
+}
+
+// ----------------------------------------------------------------------------- host side
+static bool pick_cfg(const ConvParams& p, UmmaCfg& c) {
+  c.R = TILE_M + (p.taps - 1) * p.dil;
+  int ncol = 32;
+  while (ncol < p.N) ncol <<= 1;
+  c.ncol = ncol;
+  c.tmem_cols = 2 * ncol;
+  for (int kbs = 4; kbs >= 1; kbs >>= 1) {
+    if (p.Cin % (8 * kbs)) continue;
+    c.kbs = kbs;
+    c.a_bytes = kbs * 2 * c.R * 16;
+    c.w_bytes = kbs * p.taps * p.N * 32;
+    c.stage_bytes = c.a_bytes + c.w_bytes;
+    int stages = (SMEM_BUDGET - BAR_BYTES) / c.stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages >= 3 || (kbs == 1 && stages >= 2)) {
+      c.stages = stages;
+      c.nks = p.Cin / (8 * kbs);
+      c.smem_bytes = stages * c.stage_bytes + BAR_BYTES;
+      return true;
+    }
+  }
+  return false;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+int launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
+  AR_CHECK(p.Cin % 8 == 0 && p.N % 16 == 0 && p.N >= 16 && p.N <= 256, AR_ERR_INVALID, "conv_umma: unsupported channel counts");
+  AR_CHECK(p.pad_left <= HALO && (p.taps - 1) * p.dil - p.pad_left <= HALO, AR_ERR_INVALID, "conv_umma: conv reach exceeds HALO");
+  UmmaCfg cfg;
+  AR_CHECK(pick_cfg(p, cfg), AR_ERR_INVALID, "conv_umma: no pipeline configuration fits shared memory");
+  static int max_smem_set = 0;
+  if (max_smem_set < cfg.smem_bytes) {
+    AR_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    max_smem_set = SMEM_BUDGET;
+  }
+  const int num_tiles = p.B * p.tiles_per_item;
+  const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
+  conv_umma_kernel<<<grid, UMMA_THREADS, cfg.smem_bytes, stream>>>(p, cfg, num_tiles);
+  AR_CUDA_OK(cudaGetLastError());
+  return AR_OK;
+}
+
+}  // namespace ar

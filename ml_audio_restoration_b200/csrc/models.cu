@@ -1,0 +1,671 @@
+// Host side of libaudiorestore_sm100: state_dict -> folded / packed device weights, the
+// workspace planner, and the three model forwards + the chain expressed as kernel sequences.
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "ar_common.cuh"
+#include "pointwise.cuh"
+#include "prof.cuh"
+
+namespace ar {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+const char* last_error() { return g_err.c_str(); }
+static int g_engine = AR_ENGINE_UMMA;
+int set_engine(int e) {
+  if (e != AR_ENGINE_UMMA && e != AR_ENGINE_SIMT) { set_error("unknown conv engine"); return AR_ERR_INVALID; }
+  g_engine = e;
+  return AR_OK;
+}
+
+// ============================================================================ weight folding / packing
+static float tf32_round_host(float x) {  // round-to-nearest (ties away), like cvt.rna.tf32.f32
+  uint32_t u;
+  std::memcpy(&u, &x, 4);
+  if ((u & 0x7F800000u) != 0x7F800000u) u = (u + 0x1000u) & 0xFFFFE000u;
+  std::memcpy(&x, &u, 4);
+  return x;
+}
+
+struct Table {
+  std::map<std::string, const ar_tensor_t*> m;
+  const float* get(const std::string& name, std::initializer_list<int64_t> shape) const {
+    auto it = m.find(name);
+    if (it == m.end()) { set_error("Missing key(s) in state_dict: \"" + name + "\""); return nullptr; }
+    const ar_tensor_t* t = it->second;
+    bool ok = t->ndim == (int)shape.size() && t->data != nullptr;
+    int i = 0;
+    for (int64_t s : shape) { if (ok && t->shape[i] != s) ok = false; ++i; }
+    if (!ok) { set_error("size mismatch for " + name); return nullptr; }
+    return t->data;
+  }
+};
+
+// A conv expressed as the GEMM the engines run: G[tap][cin][n] (+ bias[n]).
+struct Gemm {
+  int Cin = 0, N = 0, taps = 1, dil = 1, pad_left = 0;
+  std::vector<float> G, bias;
+  void init(int cin, int n, int t, int d, int pl) {
+    Cin = cin; N = n; taps = t; dil = d; pad_left = pl;
+    G.assign((size_t)t * cin * n, 0.f);
+    bias.assign(n, 0.f);
+  }
+  float& at(int tap, int cin, int n) { return G[((size_t)tap * Cin + cin) * N + n]; }
+};
+
+struct ConvLayer {  // device-resident packed layer
+  int Cin, N, taps, dil, pad_left;
+  size_t w_off, b_off;  // float offsets into the model blob
+  double macs_per_row;  // algorithmic MACs of the reference op per input time step (structural zeros excluded)
+};
+
+struct Blob {
+  std::vector<float> host;
+  size_t push(const float* p, size_t n) {
+    size_t off = (host.size() + 63) / 64 * 64;  // 256-byte aligned
+    host.resize(off + n);
+    std::memcpy(host.data() + off, p, n * sizeof(float));
+    return off;
+  }
+  size_t push(const std::vector<float>& v) { return push(v.data(), v.size()); }
+  ConvLayer push_gemm(Gemm& g) {  // [Cin/8][taps][2][N][4], tf32-rounded
+    std::vector<float> w((size_t)g.Cin * g.taps * g.N);
+    for (int kb = 0; kb < g.Cin / 8; ++kb)
+      for (int t = 0; t < g.taps; ++t)
+        for (int h = 0; h < 2; ++h)
+          for (int n = 0; n < g.N; ++n)
+            for (int j = 0; j < 4; ++j)
+              w[((((size_t)kb * g.taps + t) * 2 + h) * g.N + n) * 4 + j] = tf32_round_host(g.at(t, kb * 8 + h * 4 + j, n));
+    ConvLayer L{g.Cin, g.N, g.taps, g.dil, g.pad_left, 0, 0, 0.0};
+    for (float v : g.G) L.macs_per_row += (v != 0.f) ? 1.0 : 0.0;  // == Cin*N*taps except the 2-phase ConvT
+    L.w_off = push(w);
+    L.b_off = push(g.bias);
+    return L;
+  }
+};
+
+// BN(eval) fold: s = gamma / sqrt(var + eps); W' = W*s; b' = (b - mean)*s + beta  (App. B.4)
+struct Fold { std::vector<float> s, b; };
+static bool fold_bn(const Table& t, const std::string& conv, const std::string& bn, int cout, Fold& f) {
+  const float* b = t.get(conv + ".bias", {cout});
+  if (!b) return false;
+  f.s.assign(cout, 1.f);
+  f.b.assign(b, b + cout);
+  if (bn.empty()) return true;
+  const float* g = t.get(bn + ".weight", {cout});
+  const float* be = t.get(bn + ".bias", {cout});
+  const float* mu = t.get(bn + ".running_mean", {cout});
+  const float* var = t.get(bn + ".running_var", {cout});
+  if (!g || !be || !mu || !var) return false;
+  for (int o = 0; o < cout; ++o) {
+    const float s = g[o] / std::sqrt(var[o] + 1e-5f);
+    f.s[o] = s;
+    f.b[o] = (b[o] - mu[o]) * s + be[o];
+  }
+  return true;
+}
+
+// nn.Conv1d(cin, cout, k, padding=dil*(k-1)/2, dilation=dil) [+ BN] into columns [n_off, n_off+cout) of g.
+static bool add_conv(const Table& t, const std::string& conv, const std::string& bn, int cin, int cout, int k, Gemm& g, int n_off = 0) {
+  const float* W = t.get(conv + ".weight", {cout, cin, k});
+  Fold f;
+  if (!W || !fold_bn(t, conv, bn, cout, f)) return false;
+  for (int o = 0; o < cout; ++o) {
+    for (int c = 0; c < cin; ++c)
+      for (int j = 0; j < k; ++j) g.at(j, c, n_off + o) = W[((size_t)o * cin + c) * k + j] * f.s[o];
+    g.bias[n_off + o] = f.b[o];
+  }
+  return true;
+}
+
+static bool make_conv(const Table& t, Blob& blob, const std::string& conv, const std::string& bn, int cin, int cout, int k, int dil,
+                      ConvLayer& out) {
+  Gemm g;
+  g.init(cin, cout, k, dil, dil * (k - 1) / 2);
+  if (!add_conv(t, conv, bn, cin, cout, k, g)) return false;
+  out = blob.push_gemm(g);
+  return true;
+}
+
+// ============================================================================ model objects
+struct StemW { size_t w_off, b_off; int taps; };
+
+struct Model {
+  int kind = -1, device = 0, engine = AR_ENGINE_UMMA;
+  float* blob = nullptr;
+  std::map<std::string, ConvLayer> conv;
+  StemW stem{};
+  // denoiser tail
+  size_t td_w0 = 0, td_b0 = 0, td_w1 = 0, td_b1 = 0, td_w2 = 0, td_wf = 0;
+  float td_b2 = 0.f, td_bf = 0.f;
+  // final k7 convs (sr: 1, stereo: 2)
+  size_t fin_w[2] = {0, 0};
+  float fin_b[2] = {0.f, 0.f};
+  size_t whh_off = 0;
+  ~Model() { if (blob) cudaFree(blob); }
+};
+
+static bool stem_pack(const Table& t, Blob& blob, const std::string& conv, const std::string& bn, int k, StemW& s) {
+  const float* W = t.get(conv + ".weight", {32, 1, k});
+  Fold f;
+  if (!W || !fold_bn(t, conv, bn, 32, f)) return false;
+  std::vector<float> w(32 * k);
+  for (int o = 0; o < 32; ++o)
+    for (int j = 0; j < k; ++j) w[o * k + j] = W[o * k + j] * f.s[o];
+  s.w_off = blob.push(w);
+  s.b_off = blob.push(f.b);
+  s.taps = k;
+  return true;
+}
+
+static bool build_denoiser(const Table& t, Blob& blob, Model& m) {
+  const int F[3] = {32, 64, 128};
+  if (!stem_pack(t, blob, "encoder.0.0", "encoder.0.1", 3, m.stem)) return false;
+  if (!make_conv(t, blob, "encoder.0.3", "encoder.0.4", 32, 32, 3, 1, m.conv["enc0b"])) return false;
+  if (!make_conv(t, blob, "encoder.1.0", "encoder.1.1", 32, 64, 3, 1, m.conv["enc1a"])) return false;
+  if (!make_conv(t, blob, "encoder.1.3", "encoder.1.4", 64, 64, 3, 1, m.conv["enc1b"])) return false;
+  if (!make_conv(t, blob, "encoder.2.0", "encoder.2.1", 64, 128, 3, 1, m.conv["enc2a"])) return false;
+  if (!make_conv(t, blob, "encoder.2.3", "encoder.2.4", 128, 128, 3, 1, m.conv["enc2b"])) return false;
+  if (!make_conv(t, blob, "bottleneck.0", "bottleneck.1", 128, 256, 3, 1, m.conv["bot_a"])) return false;
+  if (!make_conv(t, blob, "bottleneck.3", "bottleneck.4", 256, 256, 3, 1, m.conv["bot_b"])) return false;
+  for (int i = 0; i < 3; ++i) {
+    const int f = F[2 - i];
+    const std::string up = "decoder." + std::to_string(2 * i), blk = "decoder." + std::to_string(2 * i + 1);
+    // ConvTranspose1d(2f, f, k=2, s=2): y[2t+j] = W[:,:,j]^T x[t] + b  (App. B.1) -> N = 2f, columns [j*f + o]
+    const float* W = t.get(up + ".weight", {2 * f, f, 2});
+    const float* b = t.get(up + ".bias", {f});
+    if (!W || !b) return false;
+    Gemm g;
+    g.init(2 * f, 2 * f, 1, 1, 0);
+    for (int c = 0; c < 2 * f; ++c)
+      for (int o = 0; o < f; ++o)
+        for (int j = 0; j < 2; ++j) g.at(0, c, j * f + o) = W[((size_t)c * f + o) * 2 + j];
+    for (int o = 0; o < f; ++o) g.bias[o] = g.bias[f + o] = b[o];
+    m.conv["up" + std::to_string(i)] = blob.push_gemm(g);
+    if (!make_conv(t, blob, blk + ".0", blk + ".1", 2 * f, f, 3, 1, m.conv["dec" + std::to_string(i) + "a"])) return false;
+    if (!make_conv(t, blob, blk + ".3", blk + ".4", f, f, 3, 1, m.conv["dec" + std::to_string(i) + "b"])) return false;
+  }
+  // transient detector + final conv (CUDA-core tail kernel)
+  const float* W0 = t.get("transient_detector.0.weight", {16, 32, 3});
+  const float* B0 = t.get("transient_detector.0.bias", {16});
+  const float* W1 = t.get("transient_detector.2.weight", {8, 16, 3});
+  const float* B1 = t.get("transient_detector.2.bias", {8});
+  const float* W2 = t.get("transient_detector.4.weight", {1, 8, 3});
+  const float* B2 = t.get("transient_detector.4.bias", {1});
+  const float* WF = t.get("final_conv.weight", {1, 32, 1});
+  const float* BF = t.get("final_conv.bias", {1});
+  if (!W0 || !B0 || !W1 || !B1 || !W2 || !B2 || !WF || !BF) return false;
+  std::vector<float> w0(3 * 8 * 16 * 4), w1(3 * 4 * 8 * 4), w2(24);
+  for (int j = 0; j < 3; ++j)
+    for (int c = 0; c < 8; ++c)
+      for (int o = 0; o < 16; ++o)
+        for (int i = 0; i < 4; ++i) w0[((j * 8 + c) * 16 + o) * 4 + i] = W0[(o * 32 + 4 * c + i) * 3 + j];
+  for (int j = 0; j < 3; ++j)
+    for (int c = 0; c < 4; ++c)
+      for (int o = 0; o < 8; ++o)
+        for (int i = 0; i < 4; ++i) w1[((j * 4 + c) * 8 + o) * 4 + i] = W1[(o * 16 + 4 * c + i) * 3 + j];
+  for (int j = 0; j < 3; ++j)
+    for (int c = 0; c < 8; ++c) w2[j * 8 + c] = W2[c * 3 + j];
+  m.td_w0 = blob.push(w0); m.td_b0 = blob.push(B0, 16);
+  m.td_w1 = blob.push(w1); m.td_b1 = blob.push(B1, 8);
+  m.td_w2 = blob.push(w2); m.td_wf = blob.push(WF, 32);
+  m.td_b2 = B2[0]; m.td_bf = BF[0];
+  return true;
+}
+
+static bool build_sr(const Table& t, Blob& blob, Model& m) {
+  if (!stem_pack(t, blob, "initial.0", "", 7, m.stem)) return false;
+  for (int i = 0; i < 4; ++i) {
+    const std::string p = "residual_blocks." + std::to_string(i);
+    if (!make_conv(t, blob, p + ".conv1", p + ".bn1", 32, 32, 3, 1, m.conv["rb" + std::to_string(i) + "a"])) return false;
+    if (!make_conv(t, blob, p + ".conv2", p + ".bn2", 32, 32, 3, 1, m.conv["rb" + std::to_string(i) + "b"])) return false;
+  }
+  if (!make_conv(t, blob, "middle.0", "middle.1", 32, 32, 3, 1, m.conv["middle"])) return false;
+  // ConvTranspose1d(32,32,k=4,s=2,p=1) as a 3-tap, 2-phase conv (App. B.2):
+  //   y[2t]   = W[..,1]^T x[t] + W[..,3]^T x[t-1]      -> columns [0,32)
+  //   y[2t+1] = W[..,2]^T x[t] + W[..,0]^T x[t+1]      -> columns [32,64)
+  const float* W = t.get("upsample_blocks.0.0.weight", {32, 32, 4});
+  const float* b = t.get("upsample_blocks.0.0.bias", {32});
+  if (!W || !b) return false;
+  Gemm g;
+  g.init(32, 64, 3, 1, 1);
+  for (int c = 0; c < 32; ++c)
+    for (int o = 0; o < 32; ++o) {
+      const float* w4 = W + ((size_t)c * 32 + o) * 4;
+      g.at(0, c, o) = w4[3];
+      g.at(1, c, o) = w4[1];
+      g.at(1, c, 32 + o) = w4[2];
+      g.at(2, c, 32 + o) = w4[0];
+    }
+  for (int o = 0; o < 32; ++o) g.bias[o] = g.bias[32 + o] = b[o];
+  m.conv["up"] = blob.push_gemm(g);
+  if (!make_conv(t, blob, "hf_emphasis.0", "", 32, 32, 5, 1, m.conv["hf"])) return false;
+  const float* WR = t.get("reconstruction.weight", {1, 32, 7});
+  const float* BR = t.get("reconstruction.bias", {1});
+  if (!WR || !BR) return false;
+  m.fin_w[0] = blob.push(WR, 224);
+  m.fin_b[0] = BR[0];
+  return true;
+}
+
+static bool build_stereo(const Table& t, Blob& blob, Model& m) {
+  if (!stem_pack(t, blob, "encoder.0.0", "encoder.0.1", 7, m.stem)) return false;
+  const int dims[4][2] = {{32, 64}, {64, 128}, {128, 128}, {128, 128}};
+  for (int i = 0; i < 4; ++i) {
+    const std::string p = "encoder." + std::to_string(i + 1);
+    if (!make_conv(t, blob, p + ".0", p + ".1", dims[i][0], dims[i][1], 3, 1 << i, m.conv["enc" + std::to_string(i + 1) + "a"])) return false;
+    if (!make_conv(t, blob, p + ".3", p + ".4", dims[i][1], dims[i][1], 1, 1, m.conv["enc" + std::to_string(i + 1) + "b"])) return false;
+  }
+  // LSTM input projection as a k=1 conv 128 -> 256 with bias b_ih + b_hh (App. B.5)
+  const float* Wih = t.get("lstm.weight_ih_l0", {256, 128});
+  const float* Whh = t.get("lstm.weight_hh_l0", {256, 64});
+  const float* bih = t.get("lstm.bias_ih_l0", {256});
+  const float* bhh = t.get("lstm.bias_hh_l0", {256});
+  if (!Wih || !Whh || !bih || !bhh) return false;
+  Gemm g;
+  g.init(128, 256, 1, 1, 0);
+  for (int o = 0; o < 256; ++o) {
+    for (int c = 0; c < 128; ++c) g.at(0, c, o) = Wih[o * 128 + c];
+    g.bias[o] = bih[o] + bhh[o];
+  }
+  m.conv["xproj"] = blob.push_gemm(g);
+  m.whh_off = blob.push(Whh, 256 * 64);
+  // decoders: first layers of L and R share their input -> one GEMM with N = 256
+  Gemm d0;
+  d0.init(64, 256, 7, 1, 3);
+  if (!add_conv(t, "left_decoder.0", "left_decoder.1", 64, 128, 7, d0, 0)) return false;
+  if (!add_conv(t, "right_decoder.0", "right_decoder.1", 64, 128, 7, d0, 128)) return false;
+  m.conv["dec0"] = blob.push_gemm(d0);
+  const char* sides[2] = {"left_decoder", "right_decoder"};
+  for (int s = 0; s < 2; ++s) {
+    const std::string p = sides[s], tag = s ? "R" : "L";
+    if (!make_conv(t, blob, p + ".3", p + ".4", 128, 64, 7, 1, m.conv["dec1" + tag])) return false;
+    if (!make_conv(t, blob, p + ".6", p + ".7", 64, 32, 7, 1, m.conv["dec2" + tag])) return false;
+    const float* WF = t.get(p + ".9.weight", {1, 32, 7});
+    const float* BF = t.get(p + ".9.bias", {1});
+    if (!WF || !BF) return false;
+    m.fin_w[s] = blob.push(WF, 224);
+    m.fin_b[s] = BF[0];
+  }
+  return true;
+}
+
+int model_create(int kind, const ar_tensor_t* tensors, int n, int device, Model** out) {
+  AR_CHECK(out != nullptr && (tensors != nullptr || n == 0), AR_ERR_INVALID, "model_create: null argument");
+  int ndev = 0;
+  AR_CUDA_OK(cudaGetDeviceCount(&ndev));
+  AR_CHECK(device >= 0 && device < ndev, AR_ERR_CUDA, "model_create: no such CUDA device (this library has no CPU fallback)");
+  cudaDeviceProp prop;
+  AR_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  AR_CHECK(prop.major == 10, AR_ERR_CUDA, std::string("model_create: device is sm_") + std::to_string(prop.major * 10 + prop.minor) + ", this library is built for sm_100a only");
+  Table t;
+  for (int i = 0; i < n; ++i) t.m[tensors[i].name] = &tensors[i];
+  std::unique_ptr<Model> m(new Model);
+  m->kind = kind;
+  m->device = device;
+  m->engine = g_engine;
+  Blob blob;
+  bool ok = false;
+  if (kind == AR_MODEL_DENOISER) ok = build_denoiser(t, blob, *m);
+  else if (kind == AR_MODEL_SUPER_RES) ok = build_sr(t, blob, *m);
+  else if (kind == AR_MODEL_STEREO) ok = build_stereo(t, blob, *m);
+  else { set_error("model_create: unknown model kind"); return AR_ERR_INVALID; }
+  if (!ok) return AR_ERR_WEIGHTS;
+  AR_CUDA_OK(cudaSetDevice(device));
+  AR_CUDA_OK(cudaMalloc(&m->blob, blob.host.size() * sizeof(float)));
+  AR_CUDA_OK(cudaMemcpy(m->blob, blob.host.data(), blob.host.size() * sizeof(float), cudaMemcpyHostToDevice));
+  *out = m.release();
+  return AR_OK;
+}
+
+// ============================================================================ workspace arena
+// First-fit arena over the caller's workspace.  The same allocation sequence runs in a dry
+// pass (sizes only) to answer *_workspace_bytes and in the real pass.
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, peak = 0;
+  bool dry = true;
+  struct Blk { size_t off, size; bool used; };
+  std::vector<Blk> blks;
+  size_t alloc(size_t bytes) {
+    bytes = (bytes + 255) / 256 * 256;
+    for (size_t i = 0; i < blks.size(); ++i)
+      if (!blks[i].used && blks[i].size >= bytes) {
+        if (blks[i].size > bytes) {
+          Blk rest{blks[i].off + bytes, blks[i].size - bytes, false};
+          blks[i].size = bytes;
+          blks.insert(blks.begin() + i + 1, rest);
+        }
+        blks[i].used = true;
+        return blks[i].off;
+      }
+    size_t off = blks.empty() ? 0 : blks.back().off + blks.back().size;
+    if (!blks.empty() && !blks.back().used) {  // grow the trailing free block
+      off = blks.back().off;
+      blks.back().size = bytes;
+      blks.back().used = true;
+    } else {
+      blks.push_back({off, bytes, true});
+    }
+    if (off + bytes > peak) peak = off + bytes;
+    return off;
+  }
+  void release(size_t off) {
+    for (size_t i = 0; i < blks.size(); ++i)
+      if (blks[i].off == off && blks[i].used) {
+        blks[i].used = false;
+        if (i + 1 < blks.size() && !blks[i + 1].used) { blks[i].size += blks[i + 1].size; blks.erase(blks.begin() + i + 1); }
+        if (i > 0 && !blks[i - 1].used) { blks[i - 1].size += blks[i].size; blks.erase(blks.begin() + i); }
+        return;
+      }
+  }
+  Act act(int B, int C, int T) {
+    Act a;
+    a.C = C; a.T = T; a.Tp = padded_rows(T);
+    a.bs = (long long)(C / 4) * a.Tp * 4;
+    const size_t off = alloc((size_t)B * a.bs * sizeof(float));
+    a.base = reinterpret_cast<float*>(base + off);
+    return a;
+  }
+  void release(const Act& a) { release((size_t)(reinterpret_cast<char*>(a.base) - base)); }
+  float* plain(size_t floats) { return reinterpret_cast<float*>(base + alloc(floats * sizeof(float))); }
+  void release_plain(float* p) { release((size_t)(reinterpret_cast<char*>(p) - base)); }
+};
+
+struct Ctx {
+  Arena ar;
+  cudaStream_t stream = nullptr;
+  int B = 0;
+  const Model* m = nullptr;
+};
+
+struct ConvOpt {
+  int in_coff4 = 0, out_coff4 = 0;
+  int mode = MODE_SAME;
+  int lrelu = 1, round_tf32 = 1;
+  const Act* pool = nullptr;
+  const Act* res = nullptr;
+  int Tout = -1;
+};
+
+static int run_conv(Ctx& c, const std::string& name, const Act& in, const Act& out, const ConvOpt& o = ConvOpt()) {
+  if (c.ar.dry) return AR_OK;
+  auto it = c.m->conv.find(name);
+  AR_CHECK(it != c.m->conv.end(), AR_ERR_INVALID, "internal: unknown conv layer " + name);
+  const ConvLayer& L = it->second;
+  ConvParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.in = in.base; p.in_bs = in.bs; p.in_Tp = in.Tp; p.in_coff4 = o.in_coff4;
+  p.Tin = in.T; p.Cin = L.Cin; p.taps = L.taps; p.dil = L.dil; p.pad_left = L.pad_left;
+  p.w = c.m->blob + L.w_off; p.bias = c.m->blob + L.b_off; p.N = L.N;
+  p.mode = o.mode;
+  p.out = out.base; p.out_bs = out.bs; p.out_Tp = out.Tp; p.out_coff4 = o.out_coff4;
+  p.Tout = o.Tout >= 0 ? o.Tout : out.T;
+  if (o.pool) { p.pool = o.pool->base; p.pool_bs = o.pool->bs; p.pool_Tp = o.pool->Tp; p.pool_coff4 = 0; }
+  if (o.res) { p.res = o.res->base; p.res_bs = o.res->bs; p.res_Tp = o.res->Tp; p.res_coff4 = 0; }
+  p.lrelu = o.lrelu; p.round_tf32 = o.round_tf32;
+  p.B = c.B;
+  p.tiles_per_item = (in.T + TILE_M - 1) / TILE_M;
+  ProfScope ps(CAT_CONV, c.stream, 2.0 * L.macs_per_row * (double)c.B * (double)in.T);
+  return c.m->engine == AR_ENGINE_SIMT ? launch_conv_simt(p, c.stream) : launch_conv_umma(p, c.stream);
+}
+
+// ---------------------------------------------------------------------------- denoiser.py:88-144
+static int denoiser_forward(Ctx& c, const float* x, float* y, int T) {
+  AR_CHECK(T >= 8, AR_ERR_INVALID, "max_pool1d(): Invalid computed output size: 0 (denoiser needs at least 8 samples)");
+  const Model& m = *c.m;
+  const int B = c.B, T1 = T / 2, T2 = T1 / 2, T3 = T2 / 2;
+  Arena& A = c.ar;
+  Act e0a = A.act(B, 32, T), cat0 = A.act(B, 64, T), p0 = A.act(B, 32, T1);
+  if (!A.dry) {
+    ProfScope ps(CAT_STEM, c.stream, 2.0 * 96 * (double)B * T);
+    AR_TRY(launch_stem(x, B, T, 3, m.blob + m.stem.w_off, m.blob + m.stem.b_off, e0a, 1, c.stream));
+  }
+  ConvOpt o; o.pool = &p0;
+  AR_TRY(run_conv(c, "enc0b", e0a, cat0, o));                 // skip s0 -> cat0[0:32], pooled -> p0
+  A.release(e0a);
+  Act e1a = A.act(B, 64, T1);
+  AR_TRY(run_conv(c, "enc1a", p0, e1a));
+  A.release(p0);
+  Act cat1 = A.act(B, 128, T1), p1 = A.act(B, 64, T2);
+  o = ConvOpt(); o.pool = &p1;
+  AR_TRY(run_conv(c, "enc1b", e1a, cat1, o));
+  A.release(e1a);
+  Act e2a = A.act(B, 128, T2);
+  AR_TRY(run_conv(c, "enc2a", p1, e2a));
+  A.release(p1);
+  Act cat2 = A.act(B, 256, T2), p2 = A.act(B, 128, T3);
+  o = ConvOpt(); o.pool = &p2;
+  AR_TRY(run_conv(c, "enc2b", e2a, cat2, o));
+  A.release(e2a);
+  Act b0 = A.act(B, 256, T3);
+  AR_TRY(run_conv(c, "bot_a", p2, b0));
+  A.release(p2);
+  Act b1 = A.act(B, 256, T3);
+  AR_TRY(run_conv(c, "bot_b", b0, b1));
+  A.release(b0);
+  // decoder level 0: up-conv writes the upper channel half of the concat buffer (skip first, :124)
+  o = ConvOpt(); o.mode = MODE_INTERLEAVE2; o.lrelu = 0; o.out_coff4 = 128 / 4; o.Tout = T2;
+  AR_TRY(run_conv(c, "up0", b1, cat2, o));
+  A.release(b1);
+  Act d0a = A.act(B, 128, T2);
+  AR_TRY(run_conv(c, "dec0a", cat2, d0a));
+  A.release(cat2);
+  Act d0b = A.act(B, 128, T2);
+  AR_TRY(run_conv(c, "dec0b", d0a, d0b));
+  A.release(d0a);
+  o = ConvOpt(); o.mode = MODE_INTERLEAVE2; o.lrelu = 0; o.out_coff4 = 64 / 4; o.Tout = T1;
+  AR_TRY(run_conv(c, "up1", d0b, cat1, o));
+  A.release(d0b);
+  Act d1a = A.act(B, 64, T1);
+  AR_TRY(run_conv(c, "dec1a", cat1, d1a));
+  A.release(cat1);
+  Act d1b = A.act(B, 64, T1);
+  AR_TRY(run_conv(c, "dec1b", d1a, d1b));
+  A.release(d1a);
+  o = ConvOpt(); o.mode = MODE_INTERLEAVE2; o.lrelu = 0; o.out_coff4 = 32 / 4; o.Tout = T;
+  AR_TRY(run_conv(c, "up2", d1b, cat0, o));
+  A.release(d1b);
+  Act d2a = A.act(B, 32, T);
+  AR_TRY(run_conv(c, "dec2a", cat0, d2a));
+  A.release(cat0);
+  Act f = A.act(B, 32, T);
+  o = ConvOpt(); o.round_tf32 = 0;  // feeds the fp32 CUDA-core tail
+  AR_TRY(run_conv(c, "dec2b", d2a, f, o));
+  A.release(d2a);
+  if (!A.dry) {
+    DenTailW w{m.blob + m.td_w0, m.blob + m.td_b0, m.blob + m.td_w1, m.blob + m.td_b1, m.blob + m.td_w2, m.blob + m.td_wf, m.td_b2, m.td_bf};
+    ProfScope ps(CAT_TAIL, c.stream, 2.0 * 1976 * (double)B * T);
+    AR_TRY(launch_den_tail(f, x, y, B, T, w, c.stream));
+  }
+  A.release(f);
+  return AR_OK;
+}
+
+// ---------------------------------------------------------------------------- super_resolution.py:66-101
+static int sr_forward(Ctx& c, const float* x, float* y, int T) {
+  AR_CHECK(T >= 1, AR_ERR_INVALID, "super-resolution: empty input");
+  const Model& m = *c.m;
+  const int B = c.B;
+  Arena& A = c.ar;
+  Act f0 = A.act(B, 32, T);
+  if (!A.dry) {
+    ProfScope ps(CAT_STEM, c.stream, 2.0 * 224 * (double)B * T);
+    AR_TRY(launch_stem(x, B, T, 7, m.blob + m.stem.w_off, m.blob + m.stem.b_off, f0, 1, c.stream));
+  }
+  Act r = f0;
+  for (int i = 0; i < 4; ++i) {
+    Act o1 = A.act(B, 32, T);
+    AR_TRY(run_conv(c, "rb" + std::to_string(i) + "a", r, o1));
+    Act r2 = A.act(B, 32, T);
+    ConvOpt o; o.lrelu = 0; o.res = &r;
+    AR_TRY(run_conv(c, "rb" + std::to_string(i) + "b", o1, r2, o));
+    A.release(o1);
+    if (i > 0) A.release(r);
+    r = r2;
+  }
+  Act mid = A.act(B, 32, T);
+  ConvOpt o; o.lrelu = 0; o.res = &f0;
+  AR_TRY(run_conv(c, "middle", r, mid, o));
+  A.release(r);
+  A.release(f0);
+  Act u = A.act(B, 32, 2 * T);
+  o = ConvOpt(); o.mode = MODE_INTERLEAVE2; o.Tout = 2 * T;
+  AR_TRY(run_conv(c, "up", mid, u, o));
+  A.release(mid);
+  Act h = A.act(B, 32, 2 * T);
+  o = ConvOpt(); o.round_tf32 = 0;
+  AR_TRY(run_conv(c, "hf", u, h, o));
+  A.release(u);
+  if (!A.dry) {
+    const int coff[1] = {0};
+    const float* w[1] = {m.blob + m.fin_w[0]};
+    ProfScope ps(CAT_TAIL, c.stream, 2.0 * 224 * (double)B * 2 * T);
+    AR_TRY(launch_final_k7(h, coff, w, m.fin_b, 1, y, B, 2 * T, x, c.stream));
+  }
+  A.release(h);
+  return AR_OK;
+}
+
+// ---------------------------------------------------------------------------- stereo_separator.py:85-122
+static int stereo_forward(Ctx& c, const float* x, float* y, int T, const float* state_in, float* state_out) {
+  AR_CHECK(T >= 1, AR_ERR_INVALID, "stereo: empty input");
+  const Model& m = *c.m;
+  const int B = c.B;
+  Arena& A = c.ar;
+  Act cur = A.act(B, 32, T);
+  if (!A.dry) {
+    ProfScope ps(CAT_STEM, c.stream, 2.0 * 224 * (double)B * T);
+    AR_TRY(launch_stem(x, B, T, 7, m.blob + m.stem.w_off, m.blob + m.stem.b_off, cur, 1, c.stream));
+  }
+  const int widths[4] = {64, 128, 128, 128};
+  for (int i = 0; i < 4; ++i) {
+    Act a = A.act(B, widths[i], T);
+    AR_TRY(run_conv(c, "enc" + std::to_string(i + 1) + "a", cur, a));
+    A.release(cur);
+    Act b = A.act(B, widths[i], T);
+    AR_TRY(run_conv(c, "enc" + std::to_string(i + 1) + "b", a, b));
+    A.release(a);
+    cur = b;
+  }
+  Act xp = A.act(B, 256, T);
+  ConvOpt o; o.lrelu = 0; o.round_tf32 = 0;  // gate pre-activations stay fp32
+  AR_TRY(run_conv(c, "xproj", cur, xp, o));
+  A.release(cur);
+  Act h = A.act(B, 64, T);
+  if (!A.dry) {
+    ProfScope ps(CAT_LSTM, c.stream, 2.0 * 16384 * (double)B * T);
+    AR_TRY(launch_lstm(xp, m.blob + m.whh_off, h, B, T, state_in, state_out, c.stream));
+  }
+  A.release(xp);
+  Act d0 = A.act(B, 256, T);
+  AR_TRY(run_conv(c, "dec0", h, d0));
+  A.release(h);
+  Act d1 = A.act(B, 128, T);
+  o = ConvOpt(); o.in_coff4 = 0; o.out_coff4 = 0;
+  AR_TRY(run_conv(c, "dec1L", d0, d1, o));
+  o.in_coff4 = 128 / 4; o.out_coff4 = 64 / 4;
+  AR_TRY(run_conv(c, "dec1R", d0, d1, o));
+  A.release(d0);
+  Act d2 = A.act(B, 64, T);
+  o = ConvOpt(); o.round_tf32 = 0;
+  AR_TRY(run_conv(c, "dec2L", d1, d2, o));
+  o.in_coff4 = 64 / 4; o.out_coff4 = 32 / 4;
+  AR_TRY(run_conv(c, "dec2R", d1, d2, o));
+  A.release(d1);
+  if (!A.dry) {
+    const int coff[2] = {0, 32 / 4};
+    const float* w[2] = {m.blob + m.fin_w[0], m.blob + m.fin_w[1]};
+    ProfScope ps(CAT_TAIL, c.stream, 2.0 * 448 * (double)B * T);
+    AR_TRY(launch_final_k7(d2, coff, w, m.fin_b, 2, y, B, T, nullptr, c.stream));
+  }
+  A.release(d2);
+  return AR_OK;
+}
+
+static int dispatch(Ctx& c, const float* x, float* y, int T, const float* st_in, float* st_out) {
+  switch (c.m->kind) {
+    case AR_MODEL_DENOISER: return denoiser_forward(c, x, y, T);
+    case AR_MODEL_SUPER_RES: return sr_forward(c, x, y, T);
+    case AR_MODEL_STEREO: return stereo_forward(c, x, y, T, st_in, st_out);
+  }
+  set_error("internal: bad model kind");
+  return AR_ERR_INVALID;
+}
+
+int model_workspace_bytes(const Model* m, int B, int T, size_t* bytes) {
+  AR_CHECK(m && bytes && B >= 1 && T >= 1, AR_ERR_INVALID, "workspace_bytes: bad argument");
+  Ctx c;
+  c.m = m; c.B = B; c.ar.dry = true;
+  AR_TRY(dispatch(c, nullptr, nullptr, T, nullptr, nullptr));
+  *bytes = c.ar.peak + 256;
+  return AR_OK;
+}
+
+int model_forward(const Model* m, const float* x, float* y, int B, int T, const float* st_in, float* st_out, void* ws,
+                  size_t ws_bytes, cudaStream_t stream) {
+  AR_CHECK(m && x && y && B >= 1 && T >= 1, AR_ERR_INVALID, "forward: bad argument");
+  size_t need = 0;
+  AR_TRY(model_workspace_bytes(m, B, T, &need));
+  AR_CHECK(ws != nullptr && ws_bytes >= need, AR_ERR_WORKSPACE, "forward: workspace too small (need " + std::to_string(need) + " bytes)");
+  Ctx c;
+  c.m = m; c.B = B; c.stream = stream;
+  c.ar.dry = false;
+  uintptr_t a = (reinterpret_cast<uintptr_t>(ws) + 255) / 256 * 256;
+  c.ar.base = reinterpret_cast<char*>(a);
+  c.ar.cap = ws_bytes;
+  return dispatch(c, x, y, T, st_in, st_out);
+}
+
+void model_destroy(Model* m) { delete m; }
+int model_kind(const Model* m) { return m->kind; }
+
+// One conv layer through a chosen engine on plain [B,C,T] tensors (test hook, ar_debug_conv1d).
+int debug_conv(const float* x, const float* w_host, const float* bias_host, float* y, int B, int Cin, int Cout, int T, int k,
+               int dil, int lrelu, int engine, cudaStream_t stream) {
+  AR_CHECK(x && w_host && bias_host && y && B >= 1 && T >= 1, AR_ERR_INVALID, "debug_conv: bad argument");
+  AR_CHECK(Cin % 8 == 0 && Cout % 16 == 0 && Cout <= 256 && (k & 1) == 1 && dil * (k - 1) / 2 <= HALO, AR_ERR_INVALID,
+           "debug_conv: unsupported shape");
+  Gemm g;
+  g.init(Cin, Cout, k, dil, dil * (k - 1) / 2);
+  for (int o = 0; o < Cout; ++o) {
+    for (int c = 0; c < Cin; ++c)
+      for (int j = 0; j < k; ++j) g.at(j, c, o) = w_host[((size_t)o * Cin + c) * k + j];
+    g.bias[o] = bias_host[o];
+  }
+  Blob blob;
+  ConvLayer L = blob.push_gemm(g);
+  Arena A;
+  A.dry = true;
+  Act in = A.act(B, Cin, T), out = A.act(B, Cout, T);
+  float* dblob = nullptr;
+  char* dws = nullptr;
+  AR_CUDA_OK(cudaMalloc(&dblob, blob.host.size() * sizeof(float)));
+  AR_CUDA_OK(cudaMalloc(&dws, A.peak));
+  AR_CUDA_OK(cudaMemcpyAsync(dblob, blob.host.data(), blob.host.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+  in.base = reinterpret_cast<float*>(dws + (reinterpret_cast<char*>(in.base) - (char*)nullptr));
+  out.base = reinterpret_cast<float*>(dws + (reinterpret_cast<char*>(out.base) - (char*)nullptr));
+  int rc = launch_plain_to_c4(x, B, Cin, T, in, stream);
+  if (rc == AR_OK) {
+    ConvParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.in = in.base; p.in_bs = in.bs; p.in_Tp = in.Tp; p.Tin = T; p.Cin = Cin; p.taps = k; p.dil = dil; p.pad_left = g.pad_left;
+    p.w = dblob + L.w_off; p.bias = dblob + L.b_off; p.N = Cout; p.mode = MODE_SAME;
+    p.out = out.base; p.out_bs = out.bs; p.out_Tp = out.Tp; p.Tout = T; p.lrelu = lrelu; p.round_tf32 = 0;
+    p.B = B; p.tiles_per_item = (T + TILE_M - 1) / TILE_M;
+    rc = engine == AR_ENGINE_SIMT ? launch_conv_simt(p, stream) : launch_conv_umma(p, stream);
+  }
+  if (rc == AR_OK) rc = launch_c4_to_plain(out, B, Cout, T, y, stream);
+  cudaError_t e = cudaStreamSynchronize(stream);
+  cudaFree(dblob);
+  cudaFree(dws);
+  if (rc == AR_OK && e != cudaSuccess) { set_error(std::string("debug_conv: ") + cudaGetErrorString(e)); rc = AR_ERR_CUDA; }
+  return rc;
+}
+
+}  // namespace ar

@@ -1,0 +1,431 @@
+// CUDA-core kernels around the tensor-core convs: Cin=1 stems, Cout=1 tails (with the fused
+// denoiser mask logic and the super-res linear-interp residual), normalize, chunk split and
+// overlap-add.  All are HBM-bound streaming passes with coalesced (float4 where the layout
+// allows) accesses.
+#include "ar_common.cuh"
+#include "pointwise.cuh"
+
+namespace ar {
+
+// ============================================================================ stem: Cin = 1
+// x[B][T] plain -> C4 out (32 channels): conv(k taps, pad k/2) + folded BN bias + LeakyReLU.
+// denoiser.py:54 (encoder.0.0), super_resolution.py:25 (initial.0), stereo_separator.py:25.
+template <int TAPS>
+__global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ x, int T, const float* __restrict__ w /*[32][TAPS]*/,
+                                                   const float* __restrict__ bias, float* __restrict__ out,
+                                                   long long out_bs, int out_Tp, int lrelu) {
+  __shared__ float sw[32 * TAPS];
+  __shared__ float sb[32];
+  for (int i = threadIdx.x; i < 32 * TAPS; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const float* xb = x + (long long)b * T;
+  float xin[TAPS];
+#pragma unroll
+  for (int j = 0; j < TAPS; ++j) {
+    const int ti = t + j - TAPS / 2;
+    xin[j] = (ti >= 0 && ti < T) ? __ldg(xb + ti) : 0.f;
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float a = sb[4 * c + i];
+#pragma unroll
+      for (int j = 0; j < TAPS; ++j) a = fmaf(sw[(4 * c + i) * TAPS + j], xin[j], a);
+      if (lrelu) a = a > 0.f ? a : LRELU_SLOPE * a;
+      v[i] = to_tf32(a);
+    }
+    *reinterpret_cast<float4*>(out + act_off(out_bs, out_Tp, b, c, t)) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+int launch_stem(const float* x, int B, int T, int taps, const float* w, const float* bias, const Act& out, int lrelu,
+                cudaStream_t stream) {
+  dim3 grid((T + 127) / 128, B);
+  if (taps == 3)
+    stem_kernel<3><<<grid, 128, 0, stream>>>(x, T, w, bias, out.base, out.bs, out.Tp, lrelu);
+  else if (taps == 7)
+    stem_kernel<7><<<grid, 128, 0, stream>>>(x, T, w, bias, out.base, out.bs, out.Tp, lrelu);
+  else {
+    set_error("stem: unsupported tap count");
+    return AR_ERR_INVALID;
+  }
+  AR_CUDA_OK(cudaGetLastError());
+  return AR_OK;
+}
+
+// ============================================================================ final k7, C(32) -> 1
+// y[b][och][t] = bias + sum_{c<32, j<7} w[c][j] * in[c][t+j-3]   (+ linear x2 interpolation of x_lr)
+// super_resolution.py:62,96-99 (reconstruction + F.interpolate residual, App. B.3);
+// stereo_separator.py:81 ({left,right}_decoder.9) with blockIdx.z selecting the side.
+struct FinalArgs {
+  const float* in;
+  long long in_bs;
+  int in_Tp;
+  int in_coff4[2];
+  const float* w[2];     // [32][7] each (c-major)
+  float bias[2];
+  float* y;              // [B][nout][T]
+  int nout;
+  int T;
+  const float* x_lr;     // optional [B][T/2] low-rate input for the interp residual
+};
+
+__global__ void __launch_bounds__(128) final_k7_kernel(const FinalArgs a) {
+  __shared__ float sw[7][32];
+  const int o = blockIdx.z;
+  for (int i = threadIdx.x; i < 224; i += blockDim.x) sw[i % 7][i / 7] = a.w[o][i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.T) return;
+  float acc = a.bias[o];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const int ti = t + j - 3;
+    if (ti < 0 || ti >= a.T) continue;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float4 v = *reinterpret_cast<const float4*>(a.in + act_off(a.in_bs, a.in_Tp, b, a.in_coff4[o] + c, ti));
+      acc = fmaf(v.x, sw[j][4 * c + 0], acc);
+      acc = fmaf(v.y, sw[j][4 * c + 1], acc);
+      acc = fmaf(v.z, sw[j][4 * c + 2], acc);
+      acc = fmaf(v.w, sw[j][4 * c + 3], acc);
+    }
+  }
+  if (a.x_lr != nullptr) {
+    const int Tl = a.T >> 1;
+    const float* xl = a.x_lr + (long long)b * Tl;
+    const int s = t >> 1;
+    const float x0 = __ldg(xl + s);
+    float up;
+    if (t & 1) {
+      const float x1 = __ldg(xl + (s + 1 < Tl ? s + 1 : Tl - 1));
+      up = 0.75f * x0 + 0.25f * x1;
+    } else {
+      const float xm = __ldg(xl + (s > 0 ? s - 1 : 0));
+      up = 0.25f * xm + 0.75f * x0;
+    }
+    acc += up;
+  }
+  a.y[((long long)b * a.nout + o) * a.T + t] = acc;
+}
+
+int launch_final_k7(const Act& in, const int* in_coff4, const float* const* w, const float* bias, int nout, float* y,
+                    int B, int T, const float* x_lr, cudaStream_t stream) {
+  FinalArgs a;
+  a.in = in.base; a.in_bs = in.bs; a.in_Tp = in.Tp;
+  for (int i = 0; i < nout; ++i) { a.in_coff4[i] = in_coff4[i]; a.w[i] = w[i]; a.bias[i] = bias[i]; }
+  a.y = y; a.nout = nout; a.T = T; a.x_lr = x_lr;
+  dim3 grid((T + 127) / 128, B, nout);
+  final_k7_kernel<<<grid, 128, 0, stream>>>(a);
+  AR_CUDA_OK(cudaGetLastError());
+  return AR_OK;
+}
+
+// ============================================================================ denoiser tail
+// f (C4, 32 ch) and the raw input x -> y:
+//   m_t = sigmoid(conv3(lrelu(conv3(lrelu(conv3(f, 32->16)), 16->8)), 8->1))   denoiser.py:39-46
+//   m_i = clamp(box5((2|d2x| + |dx| + .5|x|)/3.5), 0, 1)                        denoiser.py:62-86
+//   y   = conv1(f, 32->1) * (1 - 0.9*max(m_t, m_i))                              denoiser.py:134-142
+// Every conv zero-pads ITS OWN input at the sequence ends, so intermediate activations are
+// forced to zero outside [0,T).
+constexpr int DT = 128;  // outputs per block
+
+
+__global__ void __launch_bounds__(DT) den_tail_kernel(const float* __restrict__ fin, long long f_bs, int f_Tp,
+                                                      const float* __restrict__ x, float* __restrict__ y, int T,
+                                                      const DenTailW w) {
+  __shared__ float4 sf[8][DT + 6];
+  __shared__ float4 s0[4][DT + 4];
+  __shared__ float4 s1[2][DT + 2];
+  __shared__ float4 sw0[3 * 8 * 16];
+  __shared__ float4 sw1[3 * 4 * 8];
+  __shared__ float sb0[16], sb1[8], sw2[24], swf[32];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * DT;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 3 * 8 * 16; i += DT) sw0[i] = reinterpret_cast<const float4*>(w.w0)[i];
+  for (int i = tid; i < 3 * 4 * 8; i += DT) sw1[i] = reinterpret_cast<const float4*>(w.w1)[i];
+  if (tid < 16) sb0[tid] = w.b0[tid];
+  if (tid < 8) sb1[tid] = w.b1[tid];
+  if (tid < 24) sw2[tid] = w.w2[tid];
+  if (tid < 32) swf[tid] = w.wf[tid];
+  // f tile: rows t0-3 .. t0+DT+2
+  for (int i = tid; i < 8 * (DT + 6); i += DT) {
+    const int c = i / (DT + 6), r = i % (DT + 6);
+    const int t = t0 - 3 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t >= 0 && t < T) v = *reinterpret_cast<const float4*>(fin + act_off(f_bs, f_Tp, b, c, t));
+    sf[c][r] = v;
+  }
+  __syncthreads();
+  // td0: 32 -> 16 at rows t0-2 .. t0+DT+1 (local r in [0, DT+4)), input rows r..r+2 of sf
+  for (int r = tid; r < DT + 4; r += DT) {
+    const int t = t0 - 2 + r;
+    float acc[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) acc[o] = sb0[o];
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 v = sf[c][r + j];
+#pragma unroll
+        for (int o = 0; o < 16; ++o) {
+          const float4 k = sw0[(j * 8 + c) * 16 + o];
+          acc[o] = fmaf(v.x, k.x, fmaf(v.y, k.y, fmaf(v.z, k.z, fmaf(v.w, k.w, acc[o]))));
+        }
+      }
+    const bool ok = (t >= 0 && t < T);
+#pragma unroll
+    for (int o = 0; o < 16; ++o) acc[o] = ok ? (acc[o] > 0.f ? acc[o] : LRELU_SLOPE * acc[o]) : 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) s0[c][r] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+  }
+  __syncthreads();
+  // td1: 16 -> 8 at rows t0-1 .. t0+DT (local r in [0, DT+2))
+  for (int r = tid; r < DT + 2; r += DT) {
+    const int t = t0 - 1 + r;
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = sb1[o];
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 v = s0[c][r + j];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+          const float4 k = sw1[(j * 4 + c) * 8 + o];
+          acc[o] = fmaf(v.x, k.x, fmaf(v.y, k.y, fmaf(v.z, k.z, fmaf(v.w, k.w, acc[o]))));
+        }
+      }
+    const bool ok = (t >= 0 && t < T);
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = ok ? (acc[o] > 0.f ? acc[o] : LRELU_SLOPE * acc[o]) : 0.f;
+    s1[0][r] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    s1[1][r] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+  __syncthreads();
+  const int t = t0 + tid;
+  if (t >= T) return;
+  // td2: 8 -> 1, sigmoid
+  float m = w.b2;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const float4 a0 = s1[0][tid + j], a1 = s1[1][tid + j];
+    const float* k = sw2 + j * 8;
+    m += a0.x * k[0] + a0.y * k[1] + a0.z * k[2] + a0.w * k[3] + a1.x * k[4] + a1.y * k[5] + a1.z * k[6] + a1.w * k[7];
+  }
+  const float mt = 1.f / (1.f + expf(-m));
+  // final 1x1 conv
+  float yv = w.bf;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float4 v = sf[c][tid + 3];
+    yv += v.x * swf[4 * c] + v.y * swf[4 * c + 1] + v.z * swf[4 * c + 2] + v.w * swf[4 * c + 3];
+  }
+  // analytic impulse mask from the raw input
+  const float* xb = x + (long long)b * T;
+  float xs[8];  // x[t-2 .. t+5)
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const int ti = t - 2 + i;
+    xs[i] = (ti >= 0 && ti < T) ? __ldg(xb + ti) : 0.f;
+  }
+  float box = 0.f;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int u = t - 2 + i;
+    if (u < 0 || u >= T) continue;
+    const float d1u = (u < T - 1) ? fabsf(xs[i + 1] - xs[i]) : 0.f;
+    const float d1n = (u + 1 < T - 1) ? fabsf(xs[i + 2] - xs[i + 1]) : 0.f;
+    const float d2u = (u < T - 1) ? fabsf(d1n - d1u) : 0.f;
+    box += (d2u * 2.0f + d1u + fabsf(xs[i]) * 0.5f) / 3.5f * 0.2f;
+  }
+  const float mi = fminf(fmaxf(box, 0.f), 1.f);
+  y[(long long)b * T + t] = yv * (1.0f - fmaxf(mt, mi) * 0.9f);
+}
+
+int launch_den_tail(const Act& f, const float* x, float* y, int B, int T, const DenTailW& w, cudaStream_t stream) {
+  dim3 grid((T + DT - 1) / DT, B);
+  den_tail_kernel<<<grid, DT, 0, stream>>>(f.base, f.bs, f.Tp, x, y, T, w);
+  AR_CUDA_OK(cudaGetLastError());
+  return AR_OK;
+}
+
+// ============================================================================ normalize
+// audio_processing.py:58-87.  Pass 1: per-block sum(x^2) and max|x|; pass 2: every block
+// folds the (<= NORM_BLOCKS) partials in fp64, derives the gain on the device, scales.
+constexpr int NORM_BLOCKS = 592;  // 4 per SM
+constexpr int NORM_THREADS = 256;
+
+__global__ void __launch_bounds__(NORM_THREADS) norm_reduce_kernel(const float* __restrict__ x, long long n, float* partial) {
+  float ss = 0.f, mx = 0.f;
+  const long long n4 = n >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = x4[i];
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    ss += v * v;
+    mx = fmaxf(mx, fabsf(v));
+  }
+  __shared__ float s_ss[NORM_THREADS / 32], s_mx[NORM_THREADS / 32];
+  for (int o = 16; o > 0; o >>= 1) {
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) { s_ss[threadIdx.x >> 5] = ss; s_mx[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < NORM_THREADS / 32; ++i) { ss += s_ss[i]; mx = fmaxf(mx, s_mx[i]); }
+    partial[2 * blockIdx.x] = ss;
+    partial[2 * blockIdx.x + 1] = mx;
+  }
+}
+
+__global__ void __launch_bounds__(NORM_THREADS) norm_scale_kernel(float* __restrict__ x, long long n, const float* __restrict__ partial,
+                                                                  int nparts, float target_rms) {
+  __shared__ double s_ss[NORM_THREADS / 32];
+  __shared__ float s_mx[NORM_THREADS / 32];
+  __shared__ float s_gain, s_peak;
+  double ss = 0.0;
+  float mx = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) { ss += (double)partial[2 * i]; mx = fmaxf(mx, partial[2 * i + 1]); }
+  for (int o = 16; o > 0; o >>= 1) {
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) { s_ss[threadIdx.x >> 5] = ss; s_mx[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < NORM_THREADS / 32; ++i) { ss += s_ss[i]; mx = fmaxf(mx, s_mx[i]); }
+    const float rms = (float)sqrt(ss / (double)n);
+    float gain = 0.f, peak = 1.f;          // gain 0 => leave untouched (rms == 0 branch, :72)
+    if (rms != 0.f) {
+      gain = (1.0f / rms) * target_rms;     // torch evaluates `float / tensor` as reciprocal * float
+      const float pk = mx * gain;           // == max|x*gain| because rounding is monotonic
+      if (pk > 1.0f) peak = pk;             // :84-85
+    }
+    s_gain = gain;
+    s_peak = peak;
+  }
+  __syncthreads();
+  const float gain = s_gain, peak = s_peak;
+  if (gain == 0.f) return;
+  const bool limit = peak != 1.f;
+  const long long n4 = n >> 2;
+  float4* x4 = reinterpret_cast<float4*>(x);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = x4[i];
+    v.x *= gain; v.y *= gain; v.z *= gain; v.w *= gain;
+    if (limit) { v.x /= peak; v.y /= peak; v.z /= peak; v.w /= peak; }
+    x4[i] = v;
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = x[i] * gain;
+    if (limit) v /= peak;
+    x[i] = v;
+  }
+}
+
+int launch_normalize(float* x, long long n, float target_db, float* scratch, cudaStream_t stream) {
+  AR_CHECK(n > 0, AR_ERR_INVALID, "normalize: empty audio");
+  AR_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0, AR_ERR_INVALID, "normalize: audio must be 16-byte aligned");
+  long long want = (n / 4 + NORM_THREADS - 1) / NORM_THREADS;
+  int blocks = (int)(want < 1 ? 1 : (want > NORM_BLOCKS ? NORM_BLOCKS : want));
+  norm_reduce_kernel<<<blocks, NORM_THREADS, 0, stream>>>(x, n, scratch);
+  const float target_rms = (float)pow(10.0, (double)target_db / 20.0);
+  norm_scale_kernel<<<blocks, NORM_THREADS, 0, stream>>>(x, n, scratch, blocks, target_rms);
+  AR_CUDA_OK(cudaGetLastError());
+  return AR_OK;
+}
+
+// ============================================================================ chunk split / overlap-add
+__global__ void split_kernel(const float* __restrict__ audio, long long n, float* __restrict__ chunks, int first, int chunk_size, int hop) {
+  const int ci = blockIdx.y;
+  const long long start = (long long)(first + ci) * hop;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < chunk_size; j += gridDim.x * blockDim.x) {
+    const long long s = start + j;
+    chunks[(long long)ci * chunk_size + j] = (s < n) ? audio[s] : 0.f;  // zero-padded tail (trainer.py:660-665)
+  }
+}
+
+int launch_split(const float* audio, long long n, float* chunks, int first, int count, int chunk_size, int overlap,
+                 cudaStream_t stream) {
+  if (count <= 0) return AR_OK;
+  dim3 grid((chunk_size + 1023) / 1024 < 64 ? (chunk_size + 1023) / 1024 : 64, count);
+  split_kernel<<<grid, 256, 0, stream>>>(audio, n, chunks, first, chunk_size, chunk_size - overlap);
+  AR_CUDA_OK(cudaGetLastError());
+  return AR_OK;
+}
+
+// out[c][p] = w*y_i[c][j] + (1-w)*y_{i-1}[c][j + r*hop] inside a cross-fade, y_i[c][j] elsewhere,
+// with i = min(p / (r*hop), n_chunks-1), j = p - i*r*hop, w = (j+.5)/(r*overlap).
+__global__ void ola_kernel(const float* __restrict__ y, float* __restrict__ out, long long n_out, int n_chunks, int channels,
+                           int L /*rate*chunk*/, int H /*rate*hop*/, int V /*rate*overlap*/, float invV) {
+  const int c = blockIdx.y;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_out; p += (long long)gridDim.x * blockDim.x) {
+    long long i = p / H;
+    if (i > n_chunks - 1) i = n_chunks - 1;
+    const long long j = p - i * H;
+    float v = y[((long long)i * channels + c) * L + j];
+    if (i > 0 && j < V) {
+      const float w = ((float)j + 0.5f) * invV;
+      const float prev = y[((long long)(i - 1) * channels + c) * L + (j + H)];
+      v = v * w + prev * (1.0f - w);
+    }
+    out[(long long)c * n_out + p] = v;
+  }
+}
+
+int launch_ola(const float* y, float* out, long long n, int n_chunks, int channels, int chunk_size, int overlap, int rate,
+               cudaStream_t stream) {
+  const long long n_out = n * rate;
+  const int L = rate * chunk_size, H = rate * (chunk_size - overlap), V = rate * overlap;
+  long long want = (n_out + 255) / 256;
+  dim3 grid((unsigned)(want > 2368 ? 2368 : want), channels);
+  ola_kernel<<<grid, 256, 0, stream>>>(y, out, n_out, n_chunks, channels, L, H, V, V > 0 ? 1.0f / (float)V : 0.f);
+  AR_CUDA_OK(cudaGetLastError());
+  return AR_OK;
+}
+
+// ============================================================================ layout converters (debug conv)
+__global__ void plain_to_c4_kernel(const float* __restrict__ x, int C, int T, float* __restrict__ out, long long bs, int Tp) {
+  const int b = blockIdx.z, c4 = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  float v[4];
+  for (int i = 0; i < 4; ++i) v[i] = to_tf32(x[((long long)b * C + c4 * 4 + i) * T + t]);
+  *reinterpret_cast<float4*>(out + act_off(bs, Tp, b, c4, t)) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__global__ void c4_to_plain_kernel(const float* __restrict__ in, long long bs, int Tp, int C, int T, float* __restrict__ y) {
+  const int b = blockIdx.z, c4 = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const float4 v = *reinterpret_cast<const float4*>(in + act_off(bs, Tp, b, c4, t));
+  const float a[4] = {v.x, v.y, v.z, v.w};
+  for (int i = 0; i < 4; ++i) y[((long long)b * C + c4 * 4 + i) * T + t] = a[i];
+}
+int launch_plain_to_c4(const float* x, int B, int C, int T, const Act& out, cudaStream_t stream) {
+  dim3 grid((T + 127) / 128, C / 4, B);
+  plain_to_c4_kernel<<<grid, 128, 0, stream>>>(x, C, T, out.base, out.bs, out.Tp);
+  AR_CUDA_OK(cudaGetLastError());
+  return AR_OK;
+}
+int launch_c4_to_plain(const Act& in, int B, int C, int T, float* y, cudaStream_t stream) {
+  dim3 grid((T + 127) / 128, C / 4, B);
+  c4_to_plain_kernel<<<grid, 128, 0, stream>>>(in.base, in.bs, in.Tp, C, T, y);
+  AR_CUDA_OK(cudaGetLastError());
+  return AR_OK;
+}
+
+}  // namespace ar

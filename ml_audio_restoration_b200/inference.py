@@ -1,0 +1,295 @@
+"""Restoration pipeline: drop-in `restore_audio` / CLI (reference: src/inference.py:17-143) plus
+the batched, chunked GPU pipeline the reference does not have.
+
+Two ways through the same three native models:
+
+* whole-file (`mode="whole"`, what inference.py:59-95 does): normalise, run each model once on the
+  whole `[1,1,N]` tensor, normalise.  Exact reference semantics; the stereo LSTM is one serial
+  scan over the file, so this mode is latency-bound on long files.
+* chunked (`mode="chunked"`, default for files longer than one chunk): split into equal chunks
+  (`chunk_size`, `overlap` as in `chunk_audio`, tail zero-padded like trainer.py:660-665),
+  run denoise -> super-res -> stereo on batches of chunks with the LSTM state reset per chunk
+  (trainer.py:671), cross-fade overlap-add, normalise.  Chunks are independent, so batches
+  shard across GPUs with no collective.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from .audio_processing import load_audio, save_audio
+from .models import AudioDenoiser, AudioSuperResolution, StereoSeparator
+
+DEFAULT_CHUNK = 44100     # 2.0 s at 22.05 kHz (trainer.py:652)
+DEFAULT_OVERLAP = 2052    # hop 42048 = 0 (mod 8): chunk starts stay aligned to the U-Net's three pools
+
+
+def plan_chunks(num_samples: int, chunk_size: int = DEFAULT_CHUNK, overlap: int = DEFAULT_OVERLAP):
+    """Start offsets of the gap-free chunk plan (host mirror of `ar_num_chunks`)."""
+    if not (0 <= overlap <= chunk_size // 2):
+        raise ValueError("overlap must be in [0, chunk_size // 2]")
+    if num_samples <= 0:
+        raise ValueError("empty audio")
+    hop = chunk_size - overlap
+    n = 1 if num_samples <= chunk_size else math.ceil((num_samples - overlap) / hop)
+    return [i * hop for i in range(n)]
+
+
+def shard_range(n_items: int, rank: int, world: int):
+    """Contiguous block partition `[lo, hi)` of chunk (or file) indices for one GPU."""
+    lo = n_items * rank // world
+    hi = n_items * (rank + 1) // world
+    return lo, hi
+
+
+def _load_checkpoint(module, path, device):
+    ckpt = torch.load(path, map_location="cpu")
+    module.load_state_dict(ckpt["model_state_dict"])
+    return module.to(device).eval()
+
+
+class RestorationPipeline:
+    """denoise -> (super-res) -> stereo on one GPU, weights packed once (not per call)."""
+
+    def __init__(self, denoiser: AudioDenoiser, super_res, stereo: StereoSeparator, device="cuda"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("RestorationPipeline needs a CUDA device -- this build has no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.denoiser = denoiser.to(self.device).eval()
+        self.super_res = super_res.to(self.device).eval() if super_res is not None else None
+        self.stereo = stereo.to(self.device).eval()
+        self.rate = 2 if super_res is not None else 1
+        self._chain = None
+        self._chain_key = None
+        self._ws = None
+        self._scratch = torch.empty(_lib.NORMALIZE_SCRATCH_BYTES, dtype=torch.uint8, device=self.device)
+
+    @classmethod
+    def from_state_dicts(cls, denoiser_sd, super_res_sd, stereo_sd, device="cuda"):
+        den = AudioDenoiser()
+        den.load_state_dict(denoiser_sd)
+        sr = None
+        if super_res_sd is not None:
+            sr = AudioSuperResolution(upscale_factor=2)
+            sr.load_state_dict(super_res_sd)
+        st = StereoSeparator()
+        st.load_state_dict(stereo_sd)
+        return cls(den, sr, st, device)
+
+    # ------------------------------------------------------------------ native plumbing
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def chain(self):
+        hs = (self.denoiser.native_handle(self.device),
+              self.super_res.native_handle(self.device) if self.super_res is not None else None,
+              self.stereo.native_handle(self.device))
+        key = tuple(h.value if h is not None else None for h in hs)
+        if self._chain is None or key != self._chain_key:
+            self.close()
+            c = C.c_void_p()
+            _lib.check(_lib.lib().ar_chain_create(hs[0], hs[1], hs[2], C.byref(c)))
+            self._chain, self._chain_key = c, key
+        return self._chain
+
+    def close(self):
+        if self._chain is not None:
+            _lib.lib().ar_chain_destroy(self._chain)
+            self._chain = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(nbytes + 4096, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _normalize_(self, t: torch.Tensor, target_db: float = -20.0):
+        _lib.check(_lib.lib().ar_normalize(t.data_ptr(), t.numel(), target_db, self._scratch.data_ptr(), self._stream()))
+        return t
+
+    # ------------------------------------------------------------------ batched chain on chunks
+    def forward_chunks(self, chunks: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+        """`[B,1,T]` device chunks -> `[B,2,rate*T]` (one `ar_chain_forward`)."""
+        B, _, T = chunks.shape
+        L = _lib.lib()
+        with torch.cuda.device(self.device):
+            c = self.chain()
+            need = C.c_size_t()
+            _lib.check(L.ar_chain_workspace_bytes(c, B, T, C.byref(need)))
+            ws = self._workspace(need.value)
+            if out is None:
+                out = torch.empty((B, 2, self.rate * T), dtype=torch.float32, device=self.device)
+            _lib.check(L.ar_chain_forward(c, chunks.data_ptr(), out.data_ptr(), B, T, ws.data_ptr(), ws.numel(),
+                                          self._stream()))
+        return out
+
+    def max_batch(self, chunk_size: int, budget_bytes: int) -> int:
+        """Largest chunk batch whose chain workspace fits in `budget_bytes`."""
+        L = _lib.lib()
+        need = C.c_size_t()
+        with torch.cuda.device(self.device):
+            c = self.chain()
+            _lib.check(L.ar_chain_workspace_bytes(c, 1, chunk_size, C.byref(need)))
+        return max(1, int(budget_bytes // max(1, need.value)))
+
+    # ------------------------------------------------------------------ public entry points
+    @torch.no_grad()
+    def restore(self, audio: torch.Tensor, mode: str = "auto", chunk_size: int = DEFAULT_CHUNK,
+                overlap: int = DEFAULT_OVERLAP, batch_chunks: int = 0, normalize: bool = True,
+                chunk_range=None, return_device: bool = False) -> torch.Tensor:
+        """Mono `[1,N]` (or `[N]`) float audio, host or device -> restored stereo `[2, rate*N]`.
+
+        Host inputs are copied to the GPU (pinned memory makes the copy asynchronous) and the
+        result is copied back unless `return_device`.  `chunk_range=(lo,hi)` restricts the
+        chunked mode to a shard of the chunk plan and returns output samples
+        `[rate*lo*hop, rate*hi*hop)` (to the file end for the last shard); shards concatenate to the
+        unsharded result.  Sharded calls need `normalize=False`: `normalize_audio` is global, so the
+        caller normalises the input first and the concatenated output afterwards.
+        """
+        if audio.dim() == 1:
+            audio = audio.unsqueeze(0)
+        if audio.dim() != 2 or audio.shape[0] != 1:
+            raise RuntimeError(f"expected mono audio [1, N], got {tuple(audio.shape)}")
+        N = audio.shape[1]
+        if N == 0:
+            raise ValueError("empty audio")
+        if chunk_range is not None and normalize:
+            raise ValueError("chunk_range needs normalize=False (normalisation is global over the file)")
+        was_host = not audio.is_cuda
+        with torch.cuda.device(self.device):
+            a = audio.to(self.device, torch.float32, non_blocking=True).contiguous()
+            if a.data_ptr() == audio.data_ptr():
+                a = a.clone()
+            if normalize:
+                self._normalize_(a)
+            if mode == "auto":
+                mode = "whole" if N <= chunk_size else "chunked"
+            if mode == "whole":
+                y = self.forward_chunks(a.view(1, 1, N))[0]
+            elif mode == "chunked":
+                y = self._restore_chunked(a, N, chunk_size, overlap, batch_chunks, chunk_range)
+            else:
+                raise ValueError(f"unknown mode {mode!r}")
+            if normalize:
+                self._normalize_(y)
+            if was_host and not return_device:
+                return y.cpu()
+        return y
+
+    def _restore_chunked(self, a, N, chunk_size, overlap, batch_chunks, chunk_range):
+        L = _lib.lib()
+        n_chunks = C.c_int()
+        _lib.check(L.ar_num_chunks(N, chunk_size, overlap, C.byref(n_chunks)))
+        n_chunks = n_chunks.value
+        lo, hi = (0, n_chunks) if chunk_range is None else chunk_range
+        if not (0 <= lo < hi <= n_chunks):
+            raise ValueError(f"chunk_range {chunk_range} outside [0, {n_chunks}]")
+        r, hop = self.rate, chunk_size - overlap
+        # a shard also recomputes the chunk before its first one, so the cross-fade at its left seam
+        # is exact without any exchange between GPUs
+        c0 = max(lo - 1, 0)
+        cnt_all = hi - c0
+        if batch_chunks <= 0:
+            free, _ = torch.cuda.mem_get_info(self.device)
+            batch_chunks = min(cnt_all, self.max_batch(chunk_size, int(free * 0.6)), 1024)
+        y_all = torch.empty((cnt_all, 2, r * chunk_size), dtype=torch.float32, device=self.device)
+        buf = torch.empty((min(batch_chunks, cnt_all), 1, chunk_size), dtype=torch.float32, device=self.device)
+        for first in range(c0, hi, batch_chunks):
+            cnt = min(batch_chunks, hi - first)
+            _lib.check(L.ar_split_chunks(a.data_ptr(), N, buf.data_ptr(), first, cnt, chunk_size, overlap, self._stream()))
+            self.forward_chunks(buf[:cnt], y_all[first - c0:first - c0 + cnt])
+        # stitch chunks [c0, hi) as a virtual file, then keep this shard's span [lo*hop, hi*hop) (or to N)
+        n_virtual = N - c0 * hop if hi == n_chunks else (cnt_all - 1) * hop + chunk_size
+        out = torch.empty((2, r * n_virtual), dtype=torch.float32, device=self.device)
+        _lib.check(L.ar_overlap_add(y_all.data_ptr(), out.data_ptr(), n_virtual, cnt_all, 2, chunk_size, overlap, r,
+                                    self._stream()))
+        if chunk_range is None:
+            return out
+        begin = (lo - c0) * hop * r
+        end = r * n_virtual if hi == n_chunks else (hi - c0) * hop * r
+        return out[:, begin:end].contiguous()
+
+
+def restore_audio(
+    input_path: str,
+    output_path: str,
+    denoiser_checkpoint: str = 'models/checkpoints/best_model.pth',
+    super_res_checkpoint: str = 'models/checkpoints/super_resolution/best_model.pth',
+    stereo_checkpoint: str = 'models/checkpoints/stereo/best_model.pth',
+    sample_rate: int = 22050,
+    enable_super_resolution: bool = True,
+    device: str = 'cuda' if torch.cuda.is_available() else 'cpu',
+    mode: str = 'whole',
+    chunk_size: int = DEFAULT_CHUNK,
+    overlap: int = DEFAULT_OVERLAP,
+):
+    """Drop-in for the reference `restore_audio` (inference.py:17-108): same positional/keyword
+    arguments and progress prints; `mode`, `chunk_size`, `overlap` are additions (default
+    `mode='whole'` keeps the reference's whole-file semantics; `'chunked'` is the fast path).
+    """
+    if torch.device(device).type != 'cuda':
+        raise RuntimeError("restore_audio: device must be a CUDA device -- this build has no CPU fallback")
+    print(f"Processing: {input_path}")
+    print(f"Device: {device}")
+    print("Loading audio...")
+    audio, _ = load_audio(input_path, sample_rate=sample_rate, mono=True)
+    print("Loading denoiser model...")
+    den = _load_checkpoint(AudioDenoiser(), denoiser_checkpoint, device)
+    sr = None
+    if enable_super_resolution:
+        print("Loading super-resolution model...")
+        sr = _load_checkpoint(AudioSuperResolution(upscale_factor=2), super_res_checkpoint, device)
+    print("Loading stereo separator model...")
+    st = _load_checkpoint(StereoSeparator(), stereo_checkpoint, device)
+    pipe = RestorationPipeline(den, sr, st, device)
+    print("Applying denoising...")
+    if enable_super_resolution:
+        print("Applying bandwidth extension (22.05kHz -> 44.1kHz)...")
+    print("Applying stereo separation...")
+    stereo = pipe.restore(audio.pin_memory(), mode=mode, chunk_size=chunk_size, overlap=overlap)
+    out_rate = sample_rate * pipe.rate
+    print(f"Saving to: {output_path}")
+    save_audio(output_path, stereo, out_rate)
+    print("Restoration complete!")
+    suffix = " (bandwidth extended)" if enable_super_resolution else ""
+    print(f"Output sample rate: {out_rate}Hz{suffix}")
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description='Restore 78rpm record audio')
+    ap.add_argument('input', type=str, help='Input audio file path')
+    ap.add_argument('output', type=str, help='Output audio file path')
+    ap.add_argument('--denoiser', type=str, default='models/checkpoints/best_model.pth', help='Path to denoiser checkpoint')
+    ap.add_argument('--super-res', type=str, default='models/checkpoints/super_resolution/best_model.pth',
+                    help='Path to super-resolution checkpoint')
+    ap.add_argument('--stereo', type=str, default='models/checkpoints/stereo/best_model.pth',
+                    help='Path to stereo separator checkpoint')
+    ap.add_argument('--sample-rate', type=int, default=22050, help='Sample rate for processing')
+    ap.add_argument('--no-super-res', action='store_true', help='Disable bandwidth extension (super-resolution)')
+    ap.add_argument('--device', type=str, default='cuda' if torch.cuda.is_available() else 'cpu',
+                    help='Device to use (cuda or cpu)')
+    ap.add_argument('--mode', choices=('whole', 'chunked'), default='whole',
+                    help="'whole' = reference semantics; 'chunked' = batched 2 s chunks with overlap-add")
+    ap.add_argument('--chunk-size', type=int, default=DEFAULT_CHUNK)
+    ap.add_argument('--overlap', type=int, default=DEFAULT_OVERLAP)
+    a = ap.parse_args(argv)
+    restore_audio(a.input, a.output, denoiser_checkpoint=a.denoiser, super_res_checkpoint=a.super_res,
+                  stereo_checkpoint=a.stereo, sample_rate=a.sample_rate,
+                  enable_super_resolution=not a.no_super_res, device=a.device, mode=a.mode,
+                  chunk_size=a.chunk_size, overlap=a.overlap)
+
+
+if __name__ == "__main__":
+    main()

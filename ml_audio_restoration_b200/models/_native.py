@@ -1,0 +1,115 @@
+"""Shared host logic of the three drop-in modules: parameter container -> native handle.
+
+The modules keep real `nn.Parameter`s / buffers with the reference's exact `state_dict`
+keys so `load_state_dict(ckpt['model_state_dict'])` works unchanged
+(inference.py:52-53).  `forward` folds/packs them once per (device, parameter version) via
+`ar_model_create` and then runs `ar_model_forward` on the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+
+
+class _Workspace:
+    """Grow-only device scratch shared by all native modules on one device."""
+    _bufs: dict = {}
+
+    @classmethod
+    def get(cls, device: torch.device, nbytes: int) -> torch.Tensor:
+        key = (device.type, device.index)
+        buf = cls._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            cls._bufs[key] = None
+            buf = torch.empty(int(nbytes * 1.05) + 4096, dtype=torch.uint8, device=device)
+            cls._bufs[key] = buf
+        return buf
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class NativeModule(nn.Module):
+    KIND = -1
+
+    def __init__(self):
+        super().__init__()
+        self._handle = None
+        self._handle_key = None
+
+    # ------------------------------------------------------------------ handle management
+    def _param_key(self, device):
+        return (str(device),) + tuple((k, v._version, v.data_ptr()) for k, v in self.state_dict(keep_vars=True).items())
+
+    def native_handle(self, device: torch.device):
+        key = self._param_key(device)
+        if self._handle is not None and key == self._handle_key:
+            return self._handle
+        self._release()
+        L = _lib.lib()
+        sd = {k: v.detach().to("cpu", torch.float32).contiguous()
+              for k, v in self.state_dict().items() if v.dtype.is_floating_point}
+        arr = (_lib.ArTensor * len(sd))()
+        keep = []
+        for i, (k, v) in enumerate(sd.items()):
+            name = k.encode()
+            keep.append((name, v))
+            arr[i].name = name
+            arr[i].data = v.data_ptr()
+            arr[i].ndim = v.dim()
+            for d in range(v.dim()):
+                arr[i].shape[d] = v.shape[d]
+        h = C.c_void_p()
+        dev_index = device.index if device.index is not None else torch.cuda.current_device()
+        with torch.cuda.device(dev_index):
+            _lib.check(L.ar_model_create(self.KIND, arr, len(sd), dev_index, C.byref(h)))
+        self._handle, self._handle_key = h, key
+        return h
+
+    def _release(self):
+        if getattr(self, "_handle", None) is not None:
+            try:
+                _lib.lib().ar_model_destroy(self._handle)
+            except Exception:
+                pass
+            self._handle = None
+            self._handle_key = None
+
+    def __del__(self):
+        self._release()
+
+    # ------------------------------------------------------------------ forward plumbing
+    def _check_input(self, x: torch.Tensor) -> torch.Tensor:
+        if self.training:
+            raise NotImplementedError(
+                f"{type(self).__name__}: the B200 path implements eval-mode inference only "
+                "(call .eval(); training is out of scope, SURVEY.md section 2 #9)")
+        if not isinstance(x, torch.Tensor) or x.dim() != 3 or x.shape[1] != 1:
+            raise RuntimeError(f"expected input [batch, 1, samples], got {tuple(getattr(x, 'shape', ()))}")
+        if not x.is_cuda:
+            raise RuntimeError(f"{type(self).__name__}: input must be a CUDA tensor -- this build has no CPU fallback")
+        if x.dtype != torch.float32:
+            raise RuntimeError(f"expected float32 input, got {x.dtype}")
+        return x.contiguous()
+
+    def _out_shape(self, B: int, T: int):
+        raise NotImplementedError
+
+    def forward(self, x):
+        x = self._check_input(x)
+        B, _, T = x.shape
+        L = _lib.lib()
+        with torch.cuda.device(x.device):
+            h = self.native_handle(x.device)
+            need = C.c_size_t()
+            _lib.check(L.ar_model_workspace_bytes(h, B, T, C.byref(need)))
+            ws = _Workspace.get(x.device, need.value)
+            y = torch.empty(self._out_shape(B, T), dtype=torch.float32, device=x.device)
+            _lib.check(L.ar_model_forward(h, x.data_ptr(), y.data_ptr(), B, T, ws.data_ptr(), ws.numel(),
+                                          _stream_ptr(x.device)))
+        return y

@@ -1,0 +1,56 @@
+"""GPU: the two conv engines (tcgen05 implicit GEMM, CUDA-core cross-check) against torch conv1d
+on the CPU, layer shapes taken from the three models."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from ml_audio_restoration_b200 import _lib
+from gpu_util import debug_conv, assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def tf32(x):
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+SHAPES = [
+    # B, Cin, Cout, T,    k, dil   (where it occurs)
+    (2, 32, 32, 300, 3, 1),      # SR trunk / denoiser enc0
+    (1, 32, 64, 1000, 3, 1),     # stereo enc1a
+    (2, 64, 64, 257, 1, 1),      # stereo enc1b (k1)
+    (1, 64, 128, 640, 3, 2),     # stereo enc2a (dilation 2)
+    (1, 128, 128, 515, 3, 4),    # stereo enc3a
+    (1, 128, 128, 515, 3, 8),    # stereo enc4a (max reach)
+    (1, 128, 256, 129, 1, 1),    # LSTM input projection
+    (1, 64, 256, 400, 7, 1),     # fused L+R decoder layer 0
+    (1, 128, 64, 400, 7, 1),     # decoder layer 1
+    (1, 256, 256, 100, 3, 1),    # denoiser bottleneck
+    (3, 32, 32, 128, 5, 1),      # SR hf_emphasis, exactly one tile
+    (1, 16, 16, 8, 3, 1),        # tiny
+]
+
+
+@pytest.mark.parametrize("engine", [_lib.ENGINE_SIMT, _lib.ENGINE_UMMA], ids=["simt", "umma"])
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_conv_engine_matches_torch(engine, shape):
+    B, Cin, Cout, T, k, d = shape
+    g = torch.Generator().manual_seed(hash(shape) % (2 ** 31))
+    x = torch.randn(B, Cin, T, generator=g)
+    w = torch.randn(Cout, Cin, k, generator=g) / (Cin * k) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    y = debug_conv(x, w, b, dilation=d, lrelu=1, engine=engine)
+    # both engines see tf32-rounded operands (activations are rounded when stored, weights when packed)
+    ref = F.leaky_relu(F.conv1d(tf32(x).double(), tf32(w).double(), b.double(), padding=d * (k - 1) // 2, dilation=d), 0.2).float()
+    assert_close(ref, y, f"conv {shape}", max_abs=2e-5, min_snr=100.0)
+
+
+def test_engines_agree_bitwise_close():
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 64, 1000, generator=g)
+    w = torch.randn(128, 64, 3, generator=g) / 14
+    b = torch.randn(128, generator=g)
+    a = debug_conv(x, w, b, dilation=2, engine=_lib.ENGINE_SIMT)
+    c = debug_conv(x, w, b, dilation=2, engine=_lib.ENGINE_UMMA)
+    assert_close(a, c, "simt vs umma", max_abs=1e-5, min_snr=110.0)

@@ -1,0 +1,109 @@
+"""GPU: normalize / split / overlap-add kernels and the chunked + whole-file pipelines vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import pipeline as opipe
+from oracle.weights import make_input
+from ml_audio_restoration_b200 import RestorationPipeline, normalize_audio
+from gpu_util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pipe(state_dicts):
+    return RestorationPipeline.from_state_dicts(state_dicts["denoiser"], state_dicts["super_resolution"],
+                                                state_dicts["stereo"], "cuda")
+
+
+@pytest.fixture(scope="module")
+def pipe_nosr(state_dicts):
+    return RestorationPipeline.from_state_dicts(state_dicts["denoiser"], None, state_dicts["stereo"], "cuda")
+
+
+def test_normalize_matches_reference_golden(golden):
+    a = make_input(1, 4000)[0]
+    assert_close(torch.from_numpy(golden["normalize_plain"]), normalize_audio(a.cuda()), "normalize", 1e-6, 120.0)
+    z = torch.zeros(1, 100).cuda()
+    assert torch.equal(normalize_audio(z).cpu(), torch.zeros(1, 100))          # rms == 0 branch
+    spiky = a.clone() * 0.01
+    spiky[0, 17] = 5.0
+    assert_close(torch.from_numpy(golden["normalize_peak"]), normalize_audio(spiky.cuda()), "normalize peak-limit", 1e-6, 120.0)
+    st = make_input(2, 3000)[:, 0]
+    assert_close(torch.from_numpy(golden["normalize_stereo"]), normalize_audio(st.cuda()), "normalize stereo", 1e-6, 120.0)
+
+
+@pytest.mark.parametrize("n", [1, 3, 5, 1023, 100003])
+def test_normalize_odd_sizes(n):
+    a = make_input(1, n, seed=n)[0]
+    assert_close(opipe.normalize_audio(a), normalize_audio(a.cuda()), f"normalize n={n}", 1e-6, 110.0)
+
+
+def test_whole_file_chain_matches_reference_golden(pipe, pipe_nosr, golden):
+    audio = make_input(1, 3001, 1235, scale=0.3)[0]
+    assert_close(torch.from_numpy(golden["chain_whole"]), pipe.restore(audio, mode="whole"), "whole-file chain")
+    assert_close(torch.from_numpy(golden["chain_whole_nosr"]), pipe_nosr.restore(audio, mode="whole"), "whole-file chain (no SR)")
+
+
+def test_chunked_overlap0_matches_trainer_loop_golden(pipe, golden):
+    audio = make_input(1, 3001, 1235, scale=0.3)[0]
+    y = pipe.restore(audio, mode="chunked", chunk_size=1000, overlap=0, normalize=False)
+    assert_close(torch.from_numpy(golden["chain_trainer_chunks"]), y, "chunked overlap=0 vs trainer.py loop")
+
+
+@pytest.mark.parametrize("N,chunk,ov,batch", [(9000, 2048, 256, 2), (2048, 2048, 256, 0), (2049, 2048, 256, 0),
+                                              (7000, 2000, 1000, 3), (500, 2048, 0, 0)])
+def test_chunked_restore_vs_oracle(pipe, state_dicts, N, chunk, ov, batch):
+    audio = make_input(1, N, N, scale=0.2)[0]
+    ref = opipe.restore_chunked(state_dicts, audio, chunk_size=chunk, overlap=ov)
+    y = pipe.restore(audio, mode="chunked", chunk_size=chunk, overlap=ov, batch_chunks=batch)
+    assert_close(ref, y, f"chunked N={N} chunk={chunk} ov={ov}")
+
+
+def test_chunked_default_scheme_full_size_chunks(pipe, state_dicts):
+    """Three real 2 s chunks (44100 / overlap 2052) with a ragged tail."""
+    N = 2 * 42048 + 30000
+    audio = make_input(1, N, 99, scale=0.2)[0]
+    ref = opipe.restore_chunked(state_dicts, audio, batch=3)
+    y = pipe.restore(audio, mode="chunked")
+    assert y.shape == (2, 2 * N)
+    assert_close(ref, y, "chunked default scheme")
+
+
+def test_sharded_chunks_concatenate_to_unsharded(pipe):
+    from ml_audio_restoration_b200 import plan_chunks, shard_range
+    N, chunk, ov = 20000, 2048, 256
+    audio = make_input(1, N, 3, scale=0.2)[0].cuda()
+    full = pipe.restore(audio, mode="chunked", chunk_size=chunk, overlap=ov, normalize=False)
+    n = len(plan_chunks(N, chunk, ov))
+    for world in (2, 3):
+        parts = [pipe.restore(audio, mode="chunked", chunk_size=chunk, overlap=ov, normalize=False,
+                              chunk_range=shard_range(n, r, world)) for r in range(world)]
+        got = torch.cat(parts, dim=1)
+        assert got.shape == full.shape
+        assert torch.equal(got, full), f"world={world}: sharded stitch differs"
+
+
+def test_split_and_overlap_add_identities(pipe):
+    """Size-independent properties at the BASELINE chunk geometry: stitching chunks of a constant
+    signal gives the constant (windows sum to one); split then stitch at rate 1 is the identity."""
+    import ctypes as C
+    from ml_audio_restoration_b200 import _lib
+    L = _lib.lib()
+    N, chunk, ov = 10 * 42048 + 777, 44100, 2052
+    n = C.c_int()
+    _lib.check(L.ar_num_chunks(N, chunk, ov, C.byref(n)))
+    n = n.value
+    x = torch.randn(N, device="cuda")
+    chunks = torch.empty(n, 1, chunk, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.ar_split_chunks(x.data_ptr(), N, chunks.data_ptr(), 0, n, chunk, ov, s))
+    out = torch.empty(1, N, device="cuda")
+    _lib.check(L.ar_overlap_add(chunks.data_ptr(), out.data_ptr(), N, n, 1, chunk, ov, 1, s))
+    assert float((out[0] - x).abs().max()) <= 1e-6
+    ref_chunks = opipe.split_chunks(x.cpu()[None], chunk, ov)
+    assert torch.equal(ref_chunks, chunks.cpu())
+    with pytest.raises(ValueError):
+        _lib.check(L.ar_num_chunks(100, 10, 6, C.byref(C.c_int())))
