@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- restored source audio-seconds per second through the full chain
+(denoise -> super-res -> stereo, chunked with overlap-add, normalised) on N B200s.
+
+  python bench.py [--gpus N --steps K --warmup W]            this repo's CUDA path
+  python bench.py --impl reference [...]                     the reference's CPU path (oracle port)
+  torchrun-style launch for N > 1 (one rank per GPU, RANK/LOCAL_RANK/WORLD_SIZE from env).
+
+One "step" = one synthetic mono file of `--chunks-per-step` 2-second chunks per GPU pushed through
+`RestorationPipeline.restore(mode="chunked")` (input normalise, chunk, chain, overlap-add, output
+normalise).  It is a slice of BASELINE.json's 10-hour sweep: 592 chunks = 1128.8 s, so 32 steps
+are 10 h.  Files are independent => ranks share nothing (weak scaling, no collective on the data
+path; NCCL is used only for the timing barrier / max-over-ranks).
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 22050
+CHUNK, OVERLAP = 44100, 2052
+HOP = CHUNK - OVERLAP
+# algorithmic FLOPs (2 x MAC of the reference's conv / convT / LSTM terms) per source audio-second,
+# SURVEY.md 8(d) / BASELINE.md section 2
+CHAIN_GFLOP_PER_AUDIO_S = 51.661
+METRIC = "restored audio-sec/sec (full chain)"
+
+
+def synth_audio(n, seed, device):
+    """Music proxy (sines + chirp) with hiss and pops, ~ -20 dBFS (BASELINE config 4 recipe)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    t = torch.arange(n, device=device, dtype=torch.float32) / SR
+    x = 0.08 * torch.sin(2 * torch.pi * 220.0 * t) + 0.05 * torch.sin(2 * torch.pi * 554.4 * t + 0.3)
+    x += 0.04 * torch.sin(2 * torch.pi * (300.0 + 40.0 * torch.sin(2 * torch.pi * 0.25 * t)) * t)
+    x += 0.02 * torch.randn(n, device=device, generator=g)
+    pops = torch.rand(n, device=device, generator=g) < 2e-4
+    x += pops * (torch.rand(n, device=device, generator=g) - 0.5) * 1.2
+    return x.unsqueeze(0).contiguous()
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+    BAD = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown"}
+    NOTE = {0x4: "sw_power_cap", 0x80: "hw_power_brake"}
+
+    def __init__(self, device_index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.sm_max, self.ok = [], set(), None, False
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+                uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:  # NVML missing: report it rather than invent numbers
+            self.err = repr(e)
+
+    def run(self):
+        while self.ok and not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                r = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in {**self.BAD, **self.NOTE}.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def finish(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["nvml_unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "src": "measured"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback"}
+
+
+def cpu_chain_rate(n_chunks, threads=None):
+    """Oracle port of the reference chain on the host cores: audio-s/s over `n_chunks` 2 s chunks."""
+    import oracle
+    from oracle.weights import make_state_dict
+    if threads:
+        torch.set_num_threads(threads)
+    sds = {n: make_state_dict(n) for n in oracle.MODEL_NAMES}
+    n = (n_chunks - 1) * HOP + CHUNK
+    audio = synth_audio(n, 1, "cpu")
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        y = oracle.restore_chunked(sds, audio, CHUNK, OVERLAP, batch=n_chunks)
+        dt = time.perf_counter() - t0
+    assert y.shape == (2, 2 * n)
+    return (n / SR) / dt, dt, n / SR
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path (oracle port: same ATen CPU kernels the
+    reference modules dispatch to), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    cores = torch.get_num_threads()
+    nck = args.cpu_chunks
+    for _ in range(args.warmup):
+        cpu_chain_rate(1)
+    tot_audio, tot_t = 0.0, 0.0
+    for _ in range(args.steps):
+        _, dt, secs = cpu_chain_rate(nck)
+        tot_audio += secs
+        tot_t += dt
+    value = tot_audio / tot_t
+    sample = f"{nck} chunks ({nck * HOP / SR + OVERLAP / SR:.1f} s of audio) per step, oracle port on torch CPU"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "throughput sweep slice: synthetic 22.05 kHz mono, full chain denoise->super-res->stereo, "
+                        "chunk 44100 / overlap 2052 overlap-add, input+output normalize",
+            "chunks_per_step_per_gpu": args.chunks_per_step, "audio_s_per_step_per_gpu": round(step_samples(args) / SR, 2),
+            "batch_chunks": args.batch_chunks, "steps_for_10h": round(36000 / (step_samples(args) / SR), 1),
+            "partition": f"by file, {world} rank(s), no collective", "l2": "inputs and activations far larger than L2 (no flush needed)"}
+
+
+def step_samples(args):
+    return (args.chunks_per_step - 1) * HOP + CHUNK
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from ml_audio_restoration_b200 import RestorationPipeline, _lib
+    import oracle
+    from oracle.weights import make_state_dict
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    sds = {n: make_state_dict(n) for n in oracle.MODEL_NAMES}   # weights only: the oracle is not on the timed path
+    pipe = RestorationPipeline.from_state_dicts(sds["denoiser"], sds["super_resolution"], sds["stereo"], dev)
+    n = step_samples(args)
+    audio_s = n / SR
+    x_dev = synth_audio(n, 1000 + rank, dev)
+    x_host = x_dev.cpu().pin_memory()
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def step_resident():
+        return pipe.restore(x_dev, mode="chunked", chunk_size=CHUNK, overlap=OVERLAP, batch_chunks=args.batch_chunks,
+                            return_device=True)
+
+    def step_e2e():
+        return pipe.restore(x_host, mode="chunked", chunk_size=CHUNK, overlap=OVERLAP, batch_chunks=args.batch_chunks,
+                            reuse_output=True)
+
+    for _ in range(args.warmup):
+        y = step_resident()
+    assert y.shape == (2, 2 * n)
+    sync_all()
+
+    # ---- timed region: K steps, inputs resident in HBM, CUDA events on the launching stream
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    L.ar_profile_enable(1)
+    launches0 = L.ar_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        y = step_resident()
+    e1.record()
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    launches = L.ar_launch_count() - launches0
+    import ctypes as C
+    ncat = len(_lib.PROFILE_CATEGORIES)
+    p_ms, p_fl, p_ln = (C.c_double * ncat)(), (C.c_double * ncat)(), (C.c_longlong * ncat)()
+    _lib.check(L.ar_profile_read(p_ms, p_fl, p_ln, ncat))
+    L.ar_profile_enable(0)
+    clocks = sampler.finish()
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    t_s = float(ms.item()) / 1e3
+    value = world * audio_s * args.steps / t_s
+
+    # ---- end to end: host (pinned) input -> H2D -> chain -> D2H of the restored stereo, per step
+    step_e2e()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = step_e2e()
+    torch.cuda.synchronize(dev)
+    te = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * audio_s * args.steps / float(te.item())
+    assert out.shape == (2, 2 * n) and not out.is_cuda
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    cats = {name: {"ms": p_ms[i], "launches": int(p_ln[i]), "gflop": p_fl[i] / 1e9} for i, name in enumerate(_lib.PROFILE_CATEGORIES)}
+    conv = cats["conv"]
+    achieved = (conv["gflop"] / 1e3) / (conv["ms"] / 1e3) if conv["ms"] > 0 else 0.0
+    roofline = {
+        "kernel": "conv_umma_kernel (tcgen05 implicit-GEMM Conv1d, all conv/convT/LSTM-input layers)",
+        "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+        "frac": achieved / peaks["tflops"], "peak_source": f"{peaks['src']} bf16 dense (TF32 operands run at half that rate)",
+        "avg_launch_ms": conv["ms"] / max(1, conv["launches"]), "launches": conv["launches"],
+        "share_of_step": conv["ms"] / (1e3 * t_s), "traffic": None,
+        "per_category_ms_per_step": {k: v["ms"] / args.steps for k, v in cats.items()},
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "tf32", "data": "synthetic", "config": workload_config(args, world),
+        "realtime_factor_per_gpu": value / world,
+        "chain_tflops_per_gpu": value / world * CHAIN_GFLOP_PER_AUDIO_S / 1e3,
+        "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": 16 * n},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = torch.get_num_threads()
+        cpu_chain_rate(1)
+        v, dt, secs = cpu_chain_rate(args.cpu_chunks)
+        line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                                "sample": f"{args.cpu_chunks} chunks ({secs:.1f} s of audio) in {dt:.1f} s, oracle port on torch CPU"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
+    ap.add_argument("--chunks-per-step", type=int, default=592, help="2 s chunks per GPU per step (592 = 4 per SM)")
+    ap.add_argument("--batch-chunks", type=int, default=296, help="chunks per chain launch")
+    ap.add_argument("--cpu-chunks", type=int, default=8, help="chunks in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("for --gpus N > 1 launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N "
+                         "--master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -68,6 +68,7 @@ class RestorationPipeline:
         self._chain = None
         self._chain_key = None
         self._ws = None
+        self._host_out = None
         self._scratch = torch.empty(_lib.NORMALIZE_SCRATCH_BYTES, dtype=torch.uint8, device=self.device)
 
     @classmethod
@@ -148,7 +149,7 @@ class RestorationPipeline:
     @torch.no_grad()
     def restore(self, audio: torch.Tensor, mode: str = "auto", chunk_size: int = DEFAULT_CHUNK,
                 overlap: int = DEFAULT_OVERLAP, batch_chunks: int = 0, normalize: bool = True,
-                chunk_range=None, return_device: bool = False) -> torch.Tensor:
+                chunk_range=None, return_device: bool = False, reuse_output: bool = False) -> torch.Tensor:
         """Mono `[1,N]` (or `[N]`) float audio, host or device -> restored stereo `[2, rate*N]`.
 
         Host inputs are copied to the GPU (pinned memory makes the copy asynchronous) and the
@@ -185,7 +186,15 @@ class RestorationPipeline:
             if normalize:
                 self._normalize_(y)
             if was_host and not return_device:
-                return y.cpu()
+                if not reuse_output:
+                    return y.cpu()
+                # serving loop: D2H into a cached pinned buffer (valid until the next reuse_output call)
+                if self._host_out is None or self._host_out.numel() < y.numel():
+                    self._host_out = torch.empty(y.numel(), dtype=torch.float32).pin_memory()
+                host = self._host_out[:y.numel()].view(y.shape)
+                host.copy_(y, non_blocking=True)
+                torch.cuda.current_stream(self.device).synchronize()
+                return host
         return y
 
     def _restore_chunked(self, a, N, chunk_size, overlap, batch_chunks, chunk_range):
