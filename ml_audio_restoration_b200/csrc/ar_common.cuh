@@ -71,10 +71,11 @@ struct ConvParams {
   int Tin;               // valid input length; GEMM rows are input time positions
   int Cin;               // multiple of 8
   int taps, dil, pad_left;  // tap j reads input row t + j*dil - pad_left
-  // weights, packed for the UMMA B operand: [Cin/8][taps][2][N][4] (tf32-rounded fp32)
+  // weights, packed for the UMMA B operand: [n_slices][Cin/8][taps][2][N/n_slices][4] (tf32-rounded fp32)
   const float* w;
   const float* bias;     // [N]
   int N;                 // GEMM N, multiple of 16, <= 256
+  int n_slices;          // column slices the weights are packed in (each is one CTA's resident operand)
   // output (C4)
   int mode;              // MODE_SAME: out[t]; MODE_INTERLEAVE2: cols [0,N/2)->out[2t], [N/2,N)->out[2t+1]
   float* out;
@@ -101,8 +102,9 @@ __device__ __forceinline__ float to_tf32(float x) {
 
 // Fused epilogue for 4 consecutive GEMM columns [n0, n0+4) of GEMM row t (batch item b).
 // Must be called by all 32 lanes of a warp whose lanes hold consecutive rows (the pool
-// path exchanges neighbours with shuffles); `acc` is the raw accumulator.
-__device__ __forceinline__ void epilogue_chunk(const ConvParams& p, int b, int t, int n0, float4 acc) {
+// path exchanges neighbours with shuffles); `acc` is the raw accumulator, `resv` the residual
+// operand (ignored unless p.res is set; residual layers are MODE_SAME).
+__device__ __forceinline__ void epilogue_chunk(const ConvParams& p, int b, int t, int n0, float4 acc, float4 resv) {
   const float4 bias = *reinterpret_cast<const float4*>(p.bias + n0);
   float v[4] = {acc.x + bias.x, acc.y + bias.y, acc.z + bias.z, acc.w + bias.w};
   if (p.lrelu) {
@@ -120,9 +122,8 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, int b, int t
     chunk = (n0 - phase * half) >> 2;
   }
   const bool row_ok = (t < p.Tin) && (trow < p.Tout);
-  if (p.res != nullptr && row_ok) {
-    const float4 r = *reinterpret_cast<const float4*>(p.res + act_off(p.res_bs, p.res_Tp, b, p.res_coff4 + chunk, trow));
-    v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+  if (p.res != nullptr) {  // residual value supplied by the caller (same row / channels as the output)
+    v[0] += resv.x; v[1] += resv.y; v[2] += resv.z; v[3] += resv.w;
   }
   if (p.round_tf32) {
 #pragma unroll

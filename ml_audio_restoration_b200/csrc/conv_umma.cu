@@ -9,8 +9,12 @@
 //   exactly the canonical no-swizzle K-major UMMA layout ((8,m),(4,2)) with SBO = 128 B
 //   (8 rows x 16 B) and LBO = R*16 B.  Tap j (dilation d) is the same descriptor with its
 //   start address advanced by j*d*16 bytes -- no im2col, no per-tap reload.
-// * Weights are pre-packed per (channel block, tap) as [2][N][4] => LBO = N*16 B, SBO = 128 B;
-//   a stage's weights are one contiguous bulk copy.
+// * Weights are pre-packed per (channel block, tap) as [2][Ns][4] => LBO = Ns*16 B, SBO = 128 B and
+//   stay RESIDENT in shared memory for the whole (persistent) CTA: they are fetched once per CTA,
+//   not once per tile, so L2->SM traffic per tile is the activation tile only.  Layers whose
+//   weights exceed the budget are split along N into `n_slices` column slices (packed per slice on
+//   the host); CTA c owns slice c % n_slices and walks the tiles with stride grid/n_slices, so the
+//   CTAs that share an activation tile run side by side and the re-read hits L2.
 // * Warp roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer (also zeroes out-of-range
 //   rows of edge tiles = conv zero padding), warps 2..5 = epilogue (TMEM -> registers ->
 //   bias/LeakyReLU/residual/TF32-round -> coalesced float4 stores, + fused max-pool or
@@ -28,8 +32,10 @@ struct UmmaCfg {
   int kbs;          // 8-channel K blocks per pipeline stage
   int stages;
   int R;            // activation rows per chunk per tile
-  int a_bytes, w_bytes, stage_bytes;
-  int ncol;         // TMEM columns per accumulator buffer (pow2 >= N)
+  int a_bytes;      // bytes of one activation stage (= stage_bytes)
+  int w_bytes;      // resident weight slice: Cin*taps*Ns*4
+  int stage_bytes;
+  int ncol;         // TMEM columns per accumulator buffer (pow2 >= Ns)
   int tmem_cols;    // allocated columns (2 buffers)
   int nks;          // pipeline stages per tile = Cin / (8*kbs)
   int smem_bytes;
@@ -114,14 +120,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ UmmaCfg cfg, int num_tiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t smem_base = smem_u32(smem);
+  // shared memory: [resident weight slice][stages x activation stage][barriers]
+  const uint32_t w_base = smem_u32(smem);
+  const uint32_t smem_base = w_base + cfg.w_bytes;
+  uint8_t* const stage_ptr = smem + cfg.w_bytes;
   const uint32_t bar_base = smem_base + cfg.stages * cfg.stage_bytes;
-  // barrier slots (8 bytes each): full[stages], empty[stages], tmem_full[2], tmem_empty[2], tmem ptr
+  // barrier slots (8 bytes each): full[stages], empty[stages], tmem_full[2], tmem_empty[2], weights, tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (cfg.stages + s); };
   auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * cfg.stages + i); };
   auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * cfg.stages + 2 + i); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + cfg.stages * cfg.stage_bytes + 8 * (2 * cfg.stages + 4));
+  const uint32_t w_bar = bar_base + 8u * (2 * cfg.stages + 4);
+  volatile uint32_t* tmem_slot =
+      reinterpret_cast<volatile uint32_t*>(stage_ptr + cfg.stages * cfg.stage_bytes + 8 * (2 * cfg.stages + 5));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -135,6 +146,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ U
       mbar_init(tfull_bar(i), 1);
       mbar_init(tempty_bar(i), 4);
     }
+    mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), (uint32_t)cfg.tmem_cols);
@@ -145,12 +157,23 @@ conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ U
 
   const int tpi = p.tiles_per_item;
   const int R = cfg.R;
+  const int Ns = p.N / p.n_slices;                       // GEMM columns of this CTA's weight slice
+  const int slice = blockIdx.x % p.n_slices;
+  const int tile0 = blockIdx.x / p.n_slices;
+  const int tile_step = gridDim.x / p.n_slices;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
     if (lane == 0) {
+      // the weight slice, once per CTA
+      mbar_expect_tx(w_bar, (uint32_t)cfg.w_bytes);
+      const char* wsrc = reinterpret_cast<const char*>(p.w) + (size_t)slice * cfg.w_bytes;
+      for (int off = 0; off < cfg.w_bytes; off += 32768) {
+        const int n = cfg.w_bytes - off < 32768 ? cfg.w_bytes - off : 32768;
+        bulk_g2s(w_base + off, wsrc + off, (uint32_t)n, w_bar);
+      }
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int b = tile / tpi;
         const int t0 = (tile % tpi) * TILE_M;
         for (int ks = 0; ks < cfg.nks; ++ks, ++it) {
@@ -163,16 +186,16 @@ conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ U
           for (int c = 0; c < cfg.kbs * 2; ++c)
             bulk_g2s(a_dst + c * R * 16, p.in + act_off(p.in_bs, p.in_Tp, b, chunk0 + c, t0 - p.pad_left),
                      (uint32_t)(R * 16), full_bar(s));
-          bulk_g2s(a_dst + cfg.a_bytes, p.w + (size_t)ks * (cfg.w_bytes / 4), (uint32_t)cfg.w_bytes, full_bar(s));
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     // instruction descriptor: D=F32, A=B=TF32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Ns >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+    mbar_wait(w_bar, 0);
     int it = 0, tl = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tl) {
       const int t0 = (tile % tpi) * TILE_M;
       const int buf = tl & 1;
       const uint32_t aph = (uint32_t)(tl >> 1) & 1u;
@@ -185,7 +208,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ U
         const int s = it % cfg.stages;
         const uint32_t ph = (uint32_t)(it / cfg.stages) & 1u;
         mbar_wait(full_bar(s), ph);
-        uint8_t* a_ptr = smem + s * cfg.stage_bytes;
+        uint8_t* a_ptr = stage_ptr + s * cfg.stage_bytes;
         if (edge) {  // conv zero padding: rows outside [0, Tin) become zeros
           for (int r = lane; r < R; r += 32) {
             const int t = tfirst + r;
@@ -199,11 +222,11 @@ conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ U
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_s = smem_base + s * cfg.stage_bytes;
-          const uint32_t w_s = a_s + cfg.a_bytes;
+          const uint32_t w_s = w_base + (uint32_t)(ks * cfg.kbs * p.taps * Ns * 32);
           for (int kb = 0; kb < cfg.kbs; ++kb) {
             for (int j = 0; j < p.taps; ++j) {
               const uint64_t adesc = make_desc(a_s + (kb * 2 * R + j * p.dil) * 16, (uint32_t)(R * 16), 128u);
-              const uint64_t bdesc = make_desc(w_s + (kb * p.taps + j) * p.N * 32, (uint32_t)(p.N * 16), 128u);
+              const uint64_t bdesc = make_desc(w_s + (kb * p.taps + j) * Ns * 32, (uint32_t)(Ns * 16), 128u);
               umma_tf32(d_tmem, adesc, bdesc, idesc, (ks | kb | j) != 0 ? 1u : 0u);
             }
           }
@@ -216,23 +239,53 @@ conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ U
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int col_base = slice * Ns;
     int tl = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tl) {
       const int b = tile / tpi;
       const int t = (tile % tpi) * TILE_M + q * 32 + lane;
       const int buf = tl & 1;
       const uint32_t aph = (uint32_t)(tl >> 1) & 1u;
+      // residual operand (SR trunk, Ns <= 32): fetched before the accumulator is ready so the global-load
+      // latency hides behind the MMAs instead of serialising the epilogue
+      float4 resv[8];
+      const bool has_res = (p.res != nullptr);
+      if (has_res) {
+        const bool ok = (t < p.Tin);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          resv[c] = (ok && 4 * c < Ns)
+                        ? *reinterpret_cast<const float4*>(p.res + act_off(p.res_bs, p.res_Tp, b, p.res_coff4 + (col_base >> 2) + c, t))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       mbar_wait(tfull_bar(buf), aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * cfg.ncol);
-      for (int col0 = 0; col0 < p.N; col0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + col0, r);
+      if (has_res) {  // Ns <= 32: fully unrolled so resv[] stays in registers
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          epilogue_chunk(p, b, t, col0 + 4 * c,
-                         make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]),
-                                     __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3])));
+        for (int g = 0; g < 2; ++g) {
+          if (g * 16 < Ns) {
+            uint32_t r[16];
+            tmem_ld16(taddr + g * 16, r);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              epilogue_chunk(p, b, t, col_base + g * 16 + 4 * c,
+                             make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]),
+                                         __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3])),
+                             resv[g * 4 + c]);
+          }
+        }
+      } else {
+        for (int col0 = 0; col0 < Ns; col0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + col0, r);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            epilogue_chunk(p, b, t, col_base + col0 + 4 * c,
+                           make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]),
+                                       __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3])),
+                           make_float4(0.f, 0.f, 0.f, 0.f));
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -247,23 +300,24 @@ conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ U
 
 // ----------------------------------------------------------------------------- host side
 static bool pick_cfg(const ConvParams& p, UmmaCfg& c) {
+  const int Ns = p.N / p.n_slices;
   c.R = TILE_M + (p.taps - 1) * p.dil;
   int ncol = 32;
-  while (ncol < p.N) ncol <<= 1;
+  while (ncol < Ns) ncol <<= 1;
   c.ncol = ncol;
   c.tmem_cols = 2 * ncol;
+  c.w_bytes = p.Cin * p.taps * Ns * 4;
+  const int room = SMEM_BUDGET - BAR_BYTES - c.w_bytes;
   for (int kbs = 4; kbs >= 1; kbs >>= 1) {
     if (p.Cin % (8 * kbs)) continue;
     c.kbs = kbs;
-    c.a_bytes = kbs * 2 * c.R * 16;
-    c.w_bytes = kbs * p.taps * p.N * 32;
-    c.stage_bytes = c.a_bytes + c.w_bytes;
-    int stages = (SMEM_BUDGET - BAR_BYTES) / c.stage_bytes;
+    c.a_bytes = c.stage_bytes = kbs * 2 * c.R * 16;
+    int stages = room / c.stage_bytes;
     if (stages > 8) stages = 8;
-    if (stages >= 3 || (kbs == 1 && stages >= 2)) {
+    if (stages >= 4 || (kbs == 1 && stages >= 2)) {
       c.stages = stages;
       c.nks = p.Cin / (8 * kbs);
-      c.smem_bytes = stages * c.stage_bytes + BAR_BYTES;
+      c.smem_bytes = c.w_bytes + stages * c.stage_bytes + BAR_BYTES;
       return true;
     }
   }
@@ -282,7 +336,9 @@ int sm_count() {
 }
 
 int launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
-  AR_CHECK(p.Cin % 8 == 0 && p.N % 16 == 0 && p.N >= 16 && p.N <= 256, AR_ERR_INVALID, "conv_umma: unsupported channel counts");
+  AR_CHECK(p.Cin % 8 == 0 && p.n_slices >= 1 && p.N % (16 * p.n_slices) == 0 && p.N >= 16 && p.N <= 256, AR_ERR_INVALID,
+           "conv_umma: unsupported channel counts");
+  AR_CHECK(p.res == nullptr || p.N / p.n_slices <= 32, AR_ERR_INVALID, "conv_umma: residual epilogue supports at most 32 columns per slice");
   AR_CHECK(p.pad_left <= HALO && (p.taps - 1) * p.dil - p.pad_left <= HALO, AR_ERR_INVALID, "conv_umma: conv reach exceeds HALO");
   UmmaCfg cfg;
   AR_CHECK(pick_cfg(p, cfg), AR_ERR_INVALID, "conv_umma: no pipeline configuration fits shared memory");
@@ -292,7 +348,9 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
     max_smem_set = SMEM_BUDGET;
   }
   const int num_tiles = p.B * p.tiles_per_item;
-  const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
+  int groups = sm_count() / p.n_slices;                 // CTAs per slice
+  if (groups > num_tiles) groups = num_tiles;
+  const int grid = groups * p.n_slices;
   conv_umma_kernel<<<grid, UMMA_THREADS, cfg.smem_bytes, stream>>>(p, cfg, num_tiles);
   AR_CUDA_OK(cudaGetLastError());
   return AR_OK;

@@ -62,7 +62,16 @@ struct ConvLayer {  // device-resident packed layer
   int Cin, N, taps, dil, pad_left;
   size_t w_off, b_off;  // float offsets into the model blob
   double macs_per_row;  // algorithmic MACs of the reference op per input time step (structural zeros excluded)
+  int n_slices;         // column slices (each slice's weights stay resident in one CTA's shared memory)
 };
+
+// Resident-weight budget per CTA: leaves >= ~96 KB of the 227 KB for the activation ring.
+constexpr size_t W_SLICE_BUDGET = 128 * 1024;
+static int pick_slices(int Cin, int taps, int N) {
+  int s = 1;
+  while ((size_t)Cin * taps * (N / s) * 4 > W_SLICE_BUDGET && (N / (2 * s)) % 16 == 0) s *= 2;
+  return s;
+}
 
 struct Blob {
   std::vector<float> host;
@@ -73,15 +82,18 @@ struct Blob {
     return off;
   }
   size_t push(const std::vector<float>& v) { return push(v.data(), v.size()); }
-  ConvLayer push_gemm(Gemm& g) {  // [Cin/8][taps][2][N][4], tf32-rounded
+  ConvLayer push_gemm(Gemm& g) {  // [n_slices][Cin/8][taps][2][Ns][4], tf32-rounded
+    const int ns = pick_slices(g.Cin, g.taps, g.N), Ns = g.N / ns, KB = g.Cin / 8;
     std::vector<float> w((size_t)g.Cin * g.taps * g.N);
-    for (int kb = 0; kb < g.Cin / 8; ++kb)
-      for (int t = 0; t < g.taps; ++t)
-        for (int h = 0; h < 2; ++h)
-          for (int n = 0; n < g.N; ++n)
-            for (int j = 0; j < 4; ++j)
-              w[((((size_t)kb * g.taps + t) * 2 + h) * g.N + n) * 4 + j] = tf32_round_host(g.at(t, kb * 8 + h * 4 + j, n));
-    ConvLayer L{g.Cin, g.N, g.taps, g.dil, g.pad_left, 0, 0, 0.0};
+    for (int sl = 0; sl < ns; ++sl)
+      for (int kb = 0; kb < KB; ++kb)
+        for (int t = 0; t < g.taps; ++t)
+          for (int h = 0; h < 2; ++h)
+            for (int n = 0; n < Ns; ++n)
+              for (int j = 0; j < 4; ++j)
+                w[(((((size_t)sl * KB + kb) * g.taps + t) * 2 + h) * Ns + n) * 4 + j] =
+                    tf32_round_host(g.at(t, kb * 8 + h * 4 + j, sl * Ns + n));
+    ConvLayer L{g.Cin, g.N, g.taps, g.dil, g.pad_left, 0, 0, 0.0, ns};
     for (float v : g.G) L.macs_per_row += (v != 0.f) ? 1.0 : 0.0;  // == Cin*N*taps except the 2-phase ConvT
     L.w_off = push(w);
     L.b_off = push(g.bias);
@@ -402,7 +414,7 @@ static int run_conv(Ctx& c, const std::string& name, const Act& in, const Act& o
   std::memset(&p, 0, sizeof(p));
   p.in = in.base; p.in_bs = in.bs; p.in_Tp = in.Tp; p.in_coff4 = o.in_coff4;
   p.Tin = in.T; p.Cin = L.Cin; p.taps = L.taps; p.dil = L.dil; p.pad_left = L.pad_left;
-  p.w = c.m->blob + L.w_off; p.bias = c.m->blob + L.b_off; p.N = L.N;
+  p.w = c.m->blob + L.w_off; p.bias = c.m->blob + L.b_off; p.N = L.N; p.n_slices = L.n_slices;
   p.mode = o.mode;
   p.out = out.base; p.out_bs = out.bs; p.out_Tp = out.Tp; p.out_coff4 = o.out_coff4;
   p.Tout = o.Tout >= 0 ? o.Tout : out.T;
@@ -655,7 +667,7 @@ int debug_conv(const float* x, const float* w_host, const float* bias_host, floa
     ConvParams p;
     std::memset(&p, 0, sizeof(p));
     p.in = in.base; p.in_bs = in.bs; p.in_Tp = in.Tp; p.Tin = T; p.Cin = Cin; p.taps = k; p.dil = dil; p.pad_left = g.pad_left;
-    p.w = dblob + L.w_off; p.bias = dblob + L.b_off; p.N = Cout; p.mode = MODE_SAME;
+    p.w = dblob + L.w_off; p.bias = dblob + L.b_off; p.N = Cout; p.n_slices = L.n_slices; p.mode = MODE_SAME;
     p.out = out.base; p.out_bs = out.bs; p.out_Tp = out.Tp; p.Tout = T; p.lrelu = lrelu; p.round_tf32 = 0;
     p.B = B; p.tiles_per_item = (T + TILE_M - 1) / TILE_M;
     rc = engine == AR_ENGINE_SIMT ? launch_conv_simt(p, stream) : launch_conv_umma(p, stream);
