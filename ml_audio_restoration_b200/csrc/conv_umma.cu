@@ -24,9 +24,11 @@
 
 namespace ar {
 
-constexpr int UMMA_THREADS = 192;
+constexpr int EPI_WARPS = 8;                   // two per TMEM lane quarter, each takes half of the columns
+constexpr int UMMA_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int SMEM_BUDGET = 227 * 1024;
 constexpr int BAR_BYTES = 256;
+constexpr int BIAS_BYTES = 1024;              // bias of this CTA's column slice, staged in shared memory
 
 struct UmmaCfg {
   int kbs;          // 8-channel K blocks per pipeline stage
@@ -78,6 +80,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// One elected lane of a fully converged warp; ptxas maps this to ELECT and keeps the guarded region on
+// the uniform datapath, so tcgen05.mma / cp.async.bulk operands need no per-instruction broadcast loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -109,6 +122,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 // [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=0.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -117,6 +149,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 
 // ----------------------------------------------------------------------------- kernel
+// MODE / POOL / RES select the fused epilogue at compile time (ar_common.cuh: ConvMode; max-pool copy;
+// residual add); LeakyReLU slope and TF32 rounding stay runtime-uniform.
+template <int MODE, bool POOL, bool RES>
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ UmmaCfg cfg, int num_tiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -133,6 +168,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ U
   const uint32_t w_bar = bar_base + 8u * (2 * cfg.stages + 4);
   volatile uint32_t* tmem_slot =
       reinterpret_cast<volatile uint32_t*>(stage_ptr + cfg.stages * cfg.stage_bytes + 8 * (2 * cfg.stages + 5));
+  float* const s_bias = reinterpret_cast<float*>(stage_ptr + cfg.stages * cfg.stage_bytes + BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -144,12 +180,15 @@ conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ U
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar(i), 1);
-      mbar_init(tempty_bar(i), 4);
+      mbar_init(tempty_bar(i), EPI_WARPS);
     }
     mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), (uint32_t)cfg.tmem_cols);
+  const int Ns = p.N / p.n_slices;                       // GEMM columns of this CTA's weight slice
+  const int slice = blockIdx.x % p.n_slices;
+  for (int i = threadIdx.x; i < Ns; i += blockDim.x) s_bias[i] = p.bias[slice * Ns + i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -157,14 +196,12 @@ conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ U
 
   const int tpi = p.tiles_per_item;
   const int R = cfg.R;
-  const int Ns = p.N / p.n_slices;                       // GEMM columns of this CTA's weight slice
-  const int slice = blockIdx.x % p.n_slices;
   const int tile0 = blockIdx.x / p.n_slices;
   const int tile_step = gridDim.x / p.n_slices;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
-    if (lane == 0) {
+    if (elect_one()) {
       // the weight slice, once per CTA
       mbar_expect_tx(w_bar, (uint32_t)cfg.w_bytes);
       const char* wsrc = reinterpret_cast<const char*>(p.w) + (size_t)slice * cfg.w_bytes;
@@ -193,6 +230,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ U
     // ------------------------------------------------------------------ MMA issuer
     // instruction descriptor: D=F32, A=B=TF32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Ns >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+    const uint64_t a_desc_hi = make_desc(0u, (uint32_t)(R * 16), 128u);
+    const uint64_t b_desc_hi = make_desc(0u, (uint32_t)(Ns * 16), 128u);
     mbar_wait(w_bar, 0);
     int it = 0, tl = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tl) {
@@ -220,15 +259,18 @@ conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ U
           __syncwarp();
         }
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_s = smem_base + s * cfg.stage_bytes;
-          const uint32_t w_s = w_base + (uint32_t)(ks * cfg.kbs * p.taps * Ns * 32);
+        if (elect_one()) {
+          // descriptors differ only in their 14-bit start-address field (16-byte units)
+          uint32_t a_addr = (smem_base + s * cfg.stage_bytes) >> 4;
+          uint32_t b_addr = (w_base >> 4) + (uint32_t)(ks * cfg.kbs * p.taps * Ns * 2);
+          uint32_t accum = ks != 0 ? 1u : 0u;
           for (int kb = 0; kb < cfg.kbs; ++kb) {
             for (int j = 0; j < p.taps; ++j) {
-              const uint64_t adesc = make_desc(a_s + (kb * 2 * R + j * p.dil) * 16, (uint32_t)(R * 16), 128u);
-              const uint64_t bdesc = make_desc(w_s + (kb * p.taps + j) * Ns * 32, (uint32_t)(Ns * 16), 128u);
-              umma_tf32(d_tmem, adesc, bdesc, idesc, (ks | kb | j) != 0 ? 1u : 0u);
+              umma_tf32(d_tmem, a_desc_hi | (uint64_t)(a_addr + (uint32_t)(j * p.dil)), b_desc_hi | (uint64_t)b_addr, idesc, accum);
+              accum = 1u;
+              b_addr += (uint32_t)(Ns * 2);
             }
+            a_addr += (uint32_t)(2 * R);
           }
           umma_commit(empty_bar(s));                       // frees the smem stage when the MMAs retire
           if (ks == cfg.nks - 1) umma_commit(tfull_bar(buf));  // accumulator ready for the epilogue
@@ -237,54 +279,96 @@ conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ U
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int col_base = slice * Ns;
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    // Warp w may touch TMEM lanes [32*(w%4), +32) = GEMM rows; the two warps of a lane quarter split
+    // the columns.  Row addresses are hoisted per tile; per 4-column chunk the work is: bias add,
+    // LeakyReLU as max(v, slope*v), (residual), (TF32 round), one coalesced float4 store.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;                    // 0 or 1
+    const int wcols = Ns >= 32 ? Ns / 2 : Ns;            // columns this warp handles (multiple of 16)
+    const int col_lo = Ns >= 32 ? half * wcols : 0;
+    const bool active = Ns >= 32 || half == 0;
+    const float slope = p.lrelu ? LRELU_SLOPE : 1.0f;
+    const bool rnd = p.round_tf32 != 0;
+    const long long ostride = (long long)p.out_Tp * 4;   // floats between channel chunks
+    const int gcol0 = slice * Ns + col_lo;               // first global GEMM column of this warp
     int tl = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tl) {
       const int b = tile / tpi;
       const int t = (tile % tpi) * TILE_M + q * 32 + lane;
       const int buf = tl & 1;
       const uint32_t aph = (uint32_t)(tl >> 1) & 1u;
-      // residual operand (SR trunk, Ns <= 32): fetched before the accumulator is ready so the global-load
-      // latency hides behind the MMAs instead of serialising the epilogue
-      float4 resv[8];
-      const bool has_res = (p.res != nullptr);
-      if (has_res) {
-        const bool ok = (t < p.Tin);
+      const bool in_ok = t < p.Tin;
+      // hoisted output row pointers
+      float* orow0;
+      float* orow1 = nullptr;
+      bool ok0, ok1 = false;
+      int chunk0;
+      if (MODE == MODE_SAME) {
+        chunk0 = gcol0 >> 2;
+        orow0 = p.out + act_off(p.out_bs, p.out_Tp, b, p.out_coff4 + chunk0, t);
+        ok0 = in_ok && t < p.Tout;
+      } else {
+        // columns [0,N/2) -> row 2t, [N/2,N) -> row 2t+1; a warp's column range never straddles N/2
+        const int hN = p.N >> 1;
+        const int phase = gcol0 >= hN;
+        chunk0 = (gcol0 - phase * hN) >> 2;
+        orow0 = p.out + act_off(p.out_bs, p.out_Tp, b, p.out_coff4 + chunk0, 2 * t + phase);
+        ok0 = in_ok && (2 * t + phase) < p.Tout;
+        // right zero-pad column when the skip tensor is one sample longer (denoiser.py:121-122)
+        ok1 = (phase == 0) && (t == p.Tin - 1) && (2 * p.Tin < p.Tout);
+        orow1 = p.out + act_off(p.out_bs, p.out_Tp, b, p.out_coff4 + chunk0, 2 * p.Tin);
+      }
+      float* prow = nullptr;
+      bool pok = false;
+      if (POOL) {
+        prow = p.pool + act_off(p.pool_bs, p.pool_Tp, b, p.pool_coff4 + chunk0, t >> 1);
+        pok = ((t & 1) == 0) && (t + 1 < p.Tin);
+      }
+      // residual operand (SR trunk, Ns == 32 => 16 columns per warp): fetched before the accumulator is
+      // ready so the global-load latency hides behind the MMAs
+      float4 resv[4];
+      if (RES) {
+        const float* rrow = p.res + act_off(p.res_bs, p.res_Tp, b, p.res_coff4 + chunk0, t);
+        const long long rstride = (long long)p.res_Tp * 4;
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          resv[c] = (ok && 4 * c < Ns)
-                        ? *reinterpret_cast<const float4*>(p.res + act_off(p.res_bs, p.res_Tp, b, p.res_coff4 + (col_base >> 2) + c, t))
-                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < 4; ++c)
+          resv[c] = (in_ok && active) ? *reinterpret_cast<const float4*>(rrow + c * rstride) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       mbar_wait(tfull_bar(buf), aph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * cfg.ncol);
-      if (has_res) {  // Ns <= 32: fully unrolled so resv[] stays in registers
+      if (active) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * cfg.ncol + col_lo);
+        for (int cb = 0; cb < wcols; cb += 32) {
+          uint32_t r[32];
+          const int ncol = wcols - cb < 32 ? 16 : 32;     // wcols is 16 or a multiple of 32... or 48? no: 16,32,64,128
+          if (ncol == 32) tmem_ld32_nowait(taddr + cb, r);
+          else tmem_ld16_nowait(taddr + cb, r);
+          tmem_wait_ld();
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          if (g * 16 < Ns) {
-            uint32_t r[16];
-            tmem_ld16(taddr + g * 16, r);
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-              epilogue_chunk(p, b, t, col_base + g * 16 + 4 * c,
-                             make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]),
-                                         __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3])),
-                             resv[g * 4 + c]);
+          for (int c = 0; c < 8; ++c) {
+            if (4 * c < ncol) {
+              const float4 bz = *reinterpret_cast<const float4*>(s_bias + col_lo + cb + 4 * c);
+              float v0 = __uint_as_float(r[4 * c]) + bz.x, v1 = __uint_as_float(r[4 * c + 1]) + bz.y;
+              float v2 = __uint_as_float(r[4 * c + 2]) + bz.z, v3 = __uint_as_float(r[4 * c + 3]) + bz.w;
+              v0 = fmaxf(v0, slope * v0); v1 = fmaxf(v1, slope * v1);
+              v2 = fmaxf(v2, slope * v2); v3 = fmaxf(v3, slope * v3);
+              if (RES) { v0 += resv[c & 3].x; v1 += resv[c & 3].y; v2 += resv[c & 3].z; v3 += resv[c & 3].w; }
+              if (rnd) { v0 = to_tf32(v0); v1 = to_tf32(v1); v2 = to_tf32(v2); v3 = to_tf32(v3); }
+              const long long coff = (long long)((cb >> 2) + c) * ostride;
+              if (ok0) *reinterpret_cast<float4*>(orow0 + coff) = make_float4(v0, v1, v2, v3);
+              if (MODE == MODE_INTERLEAVE2) {
+                if (ok1) *reinterpret_cast<float4*>(orow1 + coff) = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+              if (POOL) {  // MaxPool1d(2,2), floor: rows (t, t+1) live in neighbouring lanes
+                const float m0 = fmaxf(v0, __shfl_down_sync(0xffffffffu, v0, 1));
+                const float m1 = fmaxf(v1, __shfl_down_sync(0xffffffffu, v1, 1));
+                const float m2 = fmaxf(v2, __shfl_down_sync(0xffffffffu, v2, 1));
+                const float m3 = fmaxf(v3, __shfl_down_sync(0xffffffffu, v3, 1));
+                if (pok) *reinterpret_cast<float4*>(prow + (long long)((cb >> 2) + c) * ((long long)p.pool_Tp * 4)) = make_float4(m0, m1, m2, m3);
+              }
+            }
           }
-        }
-      } else {
-        for (int col0 = 0; col0 < Ns; col0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(taddr + col0, r);
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            epilogue_chunk(p, b, t, col_base + col0 + 4 * c,
-                           make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]),
-                                       __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3])),
-                           make_float4(0.f, 0.f, 0.f, 0.f));
         }
       }
       tc_fence_before();
@@ -307,7 +391,7 @@ static bool pick_cfg(const ConvParams& p, UmmaCfg& c) {
   c.ncol = ncol;
   c.tmem_cols = 2 * ncol;
   c.w_bytes = p.Cin * p.taps * Ns * 4;
-  const int room = SMEM_BUDGET - BAR_BYTES - c.w_bytes;
+  const int room = SMEM_BUDGET - BAR_BYTES - BIAS_BYTES - c.w_bytes;
   for (int kbs = 4; kbs >= 1; kbs >>= 1) {
     if (p.Cin % (8 * kbs)) continue;
     c.kbs = kbs;
@@ -317,7 +401,7 @@ static bool pick_cfg(const ConvParams& p, UmmaCfg& c) {
     if (stages >= 4 || (kbs == 1 && stages >= 2)) {
       c.stages = stages;
       c.nks = p.Cin / (8 * kbs);
-      c.smem_bytes = c.w_bytes + stages * c.stage_bytes + BAR_BYTES;
+      c.smem_bytes = c.w_bytes + stages * c.stage_bytes + BAR_BYTES + BIAS_BYTES;
       return true;
     }
   }
@@ -342,16 +426,24 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
   AR_CHECK(p.pad_left <= HALO && (p.taps - 1) * p.dil - p.pad_left <= HALO, AR_ERR_INVALID, "conv_umma: conv reach exceeds HALO");
   UmmaCfg cfg;
   AR_CHECK(pick_cfg(p, cfg), AR_ERR_INVALID, "conv_umma: no pipeline configuration fits shared memory");
-  static int max_smem_set = 0;
-  if (max_smem_set < cfg.smem_bytes) {
-    AR_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
-    max_smem_set = SMEM_BUDGET;
-  }
+  AR_CHECK(p.mode == MODE_SAME || (p.pool == nullptr && p.res == nullptr), AR_ERR_INVALID, "conv_umma: interleave mode has no pool/residual epilogue");
+  AR_CHECK(p.mode == MODE_SAME || (p.N / 2) % (p.N / p.n_slices >= 32 ? p.N / p.n_slices / 2 : p.N / p.n_slices) == 0, AR_ERR_INVALID,
+           "conv_umma: interleave phases must align with the epilogue column split");
+  AR_CHECK(!(p.pool && p.res), AR_ERR_INVALID, "conv_umma: pool and residual epilogues are exclusive");
   const int num_tiles = p.B * p.tiles_per_item;
   int groups = sm_count() / p.n_slices;                 // CTAs per slice
   if (groups > num_tiles) groups = num_tiles;
   const int grid = groups * p.n_slices;
-  conv_umma_kernel<<<grid, UMMA_THREADS, cfg.smem_bytes, stream>>>(p, cfg, num_tiles);
+  using Kernel = void (*)(ConvParams, UmmaCfg, int);
+  static const Kernel kernels[4] = {conv_umma_kernel<MODE_SAME, false, false>, conv_umma_kernel<MODE_SAME, true, false>,
+                                    conv_umma_kernel<MODE_SAME, false, true>, conv_umma_kernel<MODE_INTERLEAVE2, false, false>};
+  static bool attr_set = false;
+  if (!attr_set) {
+    for (Kernel k : kernels) AR_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    attr_set = true;
+  }
+  const Kernel kernel = kernels[p.mode == MODE_INTERLEAVE2 ? 3 : (p.pool ? 1 : (p.res ? 2 : 0))];
+  kernel<<<grid, UMMA_THREADS, cfg.smem_bytes, stream>>>(p, cfg, num_tiles);
   AR_CUDA_OK(cudaGetLastError());
   return AR_OK;
 }
