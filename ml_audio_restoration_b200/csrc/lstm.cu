@@ -11,6 +11,7 @@
 // h that feeds the decoder convs is rounded to TF32.
 #include "ar_common.cuh"
 #include "pointwise.cuh"
+#include <cstdlib>
 
 namespace ar {
 
@@ -19,8 +20,18 @@ constexpr int LSTM_BLK = 8;  // steps per output flush / input prefetch block
 
 // ex2.approx-based gates: |rel err| ~ 2^-21, far below the TF32 noise of the surrounding convs,
 // and ~5x fewer issue slots than expf + IEEE division on the per-step critical path.
-__device__ __forceinline__ float sigmoid_f(float x) { return __frcp_rn(1.0f + __expf(-x)); }
-__device__ __forceinline__ float tanh_f(float x) { return 1.0f - 2.0f * __frcp_rn(__expf(2.0f * x) + 1.0f); }
+__device__ __forceinline__ float ex2_f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_f(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_f(1.0f + ex2_f(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_f(float x) { return 1.0f - 2.0f * rcp_f(ex2_f(2.8853900817779268f * x) + 1.0f); }
 
 // Packed 2-wide fp32 FMA (Blackwell FFMA2): halves the FMA issue slots of the 64-term dot product.
 __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
@@ -38,7 +49,7 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
 }
 
 template <int S>
-__global__ void __launch_bounds__(256, (S <= 2) ? 2 : 1)
+__global__ void __launch_bounds__(256, (S == 1) ? 2 : 1)
 lstm_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const float* __restrict__ whh,
             float* __restrict__ hout, long long h_bs, int h_Tp, int B, int T,
             const float* __restrict__ state_in, float* __restrict__ state_out) {
@@ -75,43 +86,55 @@ lstm_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const floa
   }
   __syncthreads();
 
-  float xn[S][LSTM_BLK];  // ring of prefetched pre-activations, each load in flight for 8 steps
+  // Pre-activations are prefetched one 8-step block ahead into a register set that is not live
+  // while the current block runs (two sets, ping-pong over a 16-step unrolled body), so the loads
+  // have a whole block (~8 steps) to land and never sit on the per-step critical path.
+  float xa[S][LSTM_BLK], xb[S][LSTM_BLK];
 #pragma unroll
   for (int s = 0; s < S; ++s)
 #pragma unroll
-    for (int k = 0; k < LSTM_BLK; ++k) xn[s][k] = __ldg(xrow[s] + 4 * min(k, T - 1));
+    for (int k = 0; k < LSTM_BLK; ++k) xa[s][k] = __ldg(xrow[s] + 4 * min(k, T - 1));
 
   int cur = 0;
   float hlast[S];
 #pragma unroll
   for (int s = 0; s < S; ++s) hlast[s] = 0.f;
-  for (int t0 = 0; t0 < T; t0 += LSTM_BLK) {
+
+  auto run_block = [&](float (&xc)[S][LSTM_BLK], float (&xnext)[S][LSTM_BLK], int t0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+      for (int k = 0; k < LSTM_BLK; ++k) xnext[s][k] = __ldg(xrow[s] + 4 * min(t0 + LSTM_BLK + k, T - 1));
     const int sb = (t0 / LSTM_BLK) & 1;
 #pragma unroll
     for (int k = 0; k < LSTM_BLK; ++k) {
       if (t0 + k < T) {  // uniform across the block
-        unsigned long long acc[S][2];
+        unsigned long long acc[S][4];
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-          acc[s][0] = pack2(xn[s][k], 0.f);
-          acc[s][1] = 0ull;
-          xn[s][k] = __ldg(xrow[s] + 4 * min(t0 + LSTM_BLK + k, T - 1));  // same slot, 8 steps ahead
+          acc[s][0] = pack2(xc[s][k], 0.f);
+          acc[s][1] = 0ull; acc[s][2] = 0ull; acc[s][3] = 0ull;
         }
 #pragma unroll
-        for (int j = 0; j < LSTM_H; j += 4) {
+        for (int j = 0; j < LSTM_H; j += 8) {
 #pragma unroll
           for (int s = 0; s < S; ++s) {
-            const ulonglong2 hv = *reinterpret_cast<const ulonglong2*>(&hbuf[cur][s][j]);
-            acc[s][0] = fma2(w2[j / 2], hv.x, acc[s][0]);
-            acc[s][1] = fma2(w2[j / 2 + 1], hv.y, acc[s][1]);
+            const ulonglong2 h0 = *reinterpret_cast<const ulonglong2*>(&hbuf[cur][s][j]);
+            const ulonglong2 h1 = *reinterpret_cast<const ulonglong2*>(&hbuf[cur][s][j + 4]);
+            acc[s][0] = fma2(w2[j / 2], h0.x, acc[s][0]);
+            acc[s][1] = fma2(w2[j / 2 + 1], h0.y, acc[s][1]);
+            acc[s][2] = fma2(w2[j / 2 + 2], h1.x, acc[s][2]);
+            acc[s][3] = fma2(w2[j / 2 + 3], h1.y, acc[s][3]);
           }
         }
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-          float a0, a1, a2, a3;
+          float a0, a1, a2, a3, a4, a5, a6, a7;
           unpack2(acc[s][0], a0, a1);
           unpack2(acc[s][1], a2, a3);
-          const float pre = (a0 + a1) + (a2 + a3);
+          unpack2(acc[s][2], a4, a5);
+          unpack2(acc[s][3], a6, a7);
+          const float pre = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
           const float a = (gate == 2) ? tanh_f(pre) : sigmoid_f(pre);
           const float af = __shfl_sync(0xffffffffu, a, (lane & 7) + 8);
           const float ag = __shfl_sync(0xffffffffu, a, (lane & 7) + 16);
@@ -140,6 +163,11 @@ lstm_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const floa
             make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
       }
     }
+  };
+
+  for (int t0 = 0; t0 < T; t0 += 2 * LSTM_BLK) {
+    run_block(xa, xb, t0);
+    if (t0 + LSTM_BLK < T) run_block(xb, xa, t0 + LSTM_BLK);
   }
   if (state_out != nullptr && gate == 0) {
 #pragma unroll
@@ -156,14 +184,21 @@ lstm_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const floa
 int launch_lstm(const Act& xp, const float* whh, const Act& h_out, int B, int T, const float* state_in, float* state_out,
                 cudaStream_t stream) {
   AR_CHECK(T >= 1 && B >= 1, AR_ERR_INVALID, "lstm: empty input");
-  const int sms = sm_count();
-  if (B <= 2 * sms) {
-    lstm_kernel<1><<<B, 256, 0, stream>>>(xp.base, xp.bs, xp.Tp, whh, h_out.base, h_out.bs, h_out.Tp, B, T, state_in, state_out);
-  } else if (B <= 4 * sms) {
-    lstm_kernel<2><<<(B + 1) / 2, 256, 0, stream>>>(xp.base, xp.bs, xp.Tp, whh, h_out.base, h_out.bs, h_out.Tp, B, T, state_in, state_out);
-  } else {
-    lstm_kernel<4><<<(B + 3) / 4, 256, 0, stream>>>(xp.base, xp.bs, xp.Tp, whh, h_out.base, h_out.bs, h_out.Tp, B, T, state_in, state_out);
+  // S sequences per CTA.  S=1 runs two CTAs per SM (register-limited); S=2/4 trade thread-level for
+  // instruction-level parallelism.  AR_LSTM_S overrides the heuristic (tuning knob).
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("AR_LSTM_S");
+    forced = e ? atoi(e) : 0;
   }
+  int S = forced ? forced : 1;
+#define AR_LSTM_LAUNCH(SS)                                                                                     \
+  lstm_kernel<SS><<<(B + SS - 1) / SS, 256, 0, stream>>>(xp.base, xp.bs, xp.Tp, whh, h_out.base, h_out.bs, h_out.Tp, B, T, \
+                                                         state_in, state_out)
+  if (S == 4) AR_LSTM_LAUNCH(4);
+  else if (S == 2) AR_LSTM_LAUNCH(2);
+  else AR_LSTM_LAUNCH(1);
+#undef AR_LSTM_LAUNCH
   AR_CUDA_OK(cudaGetLastError());
   return AR_OK;
 }
