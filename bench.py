@@ -150,7 +150,7 @@ def workload_config(args, world):
     return {"workload": "throughput sweep slice: synthetic 22.05 kHz mono, full chain denoise->super-res->stereo, "
                         "chunk 44100 / overlap 2052 overlap-add, input+output normalize",
             "chunks_per_step_per_gpu": args.chunks_per_step, "audio_s_per_step_per_gpu": round(step_samples(args) / SR, 2),
-            "batch_chunks": args.batch_chunks, "steps_for_10h": round(36000 / (step_samples(args) / SR), 1),
+            "batch_chunks": args.batch_chunks, "streams": args.streams, "steps_for_10h": round(36000 / (step_samples(args) / SR), 1),
             "partition": f"by file, {world} rank(s), no collective", "l2": "inputs and activations far larger than L2 (no flush needed)"}
 
 
@@ -186,11 +186,11 @@ def run_b200(args, rank, world, local_rank):
 
     def step_resident():
         return pipe.restore(x_dev, mode="chunked", chunk_size=CHUNK, overlap=OVERLAP, batch_chunks=args.batch_chunks,
-                            return_device=True)
+                            return_device=True, streams=args.streams)
 
     def step_e2e():
         return pipe.restore(x_host, mode="chunked", chunk_size=CHUNK, overlap=OVERLAP, batch_chunks=args.batch_chunks,
-                            reuse_output=True)
+                            reuse_output=True, streams=args.streams)
 
     for _ in range(args.warmup):
         y = step_resident()
@@ -277,7 +277,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
     ap.add_argument("--chunks-per-step", type=int, default=592, help="2 s chunks per GPU per step (592 = 4 per SM)")
-    ap.add_argument("--batch-chunks", type=int, default=296, help="chunks per chain launch")
+    ap.add_argument("--batch-chunks", type=int, default=296, help="chunks per chain launch (296 = two LSTM CTAs per SM)")
+    ap.add_argument("--streams", type=int, default=1, help="chunk batches in flight (LSTM of one overlaps convs of the next)")
     ap.add_argument("--cpu-chunks", type=int, default=8, help="chunks in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

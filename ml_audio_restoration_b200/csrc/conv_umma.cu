@@ -150,8 +150,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 
 // ----------------------------------------------------------------------------- kernel
 // MODE / POOL / RES select the fused epilogue at compile time (ar_common.cuh: ConvMode; max-pool copy;
-// residual add); LeakyReLU slope and TF32 rounding stay runtime-uniform.
-template <int MODE, bool POOL, bool RES>
+// residual add); LeakyReLU slope and TF32 rounding stay runtime-uniform.  TAPS is a template parameter
+// so the single issuing thread sees a fully unrolled tap loop: the MMAs of a K block go out back to back
+// instead of one per ~15 dependent integer instructions.
+template <int MODE, bool POOL, bool RES, int TAPS>
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ UmmaCfg cfg, int num_tiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -209,20 +211,27 @@ conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ U
         const int n = cfg.w_bytes - off < 32768 ? cfg.w_bytes - off : 32768;
         bulk_g2s(w_base + off, wsrc + off, (uint32_t)n, w_bar);
       }
-      int it = 0;
+      // per-stage work is kept to: wait, expect_tx, 2*kbs bulk copies, counter bump (no divisions)
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t row_bytes = (uint32_t)(R * 16);
+      const long long chunk_stride = (long long)p.in_Tp * 4;             // floats between channel chunks
+      const int chunks_per_stage = cfg.kbs * 2;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int b = tile / tpi;
-        const int t0 = (tile % tpi) * TILE_M;
-        for (int ks = 0; ks < cfg.nks; ++ks, ++it) {
-          const int s = it % cfg.stages;
-          const uint32_t ph = (uint32_t)(it / cfg.stages) & 1u;
+        const int t0 = (tile - b * tpi) * TILE_M;
+        const float* src = p.in + act_off(p.in_bs, p.in_Tp, b, p.in_coff4, t0 - p.pad_left);
+        for (int ks = 0; ks < cfg.nks; ++ks) {
+          const uint32_t fb = full_bar(s);
           mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_expect_tx(full_bar(s), (uint32_t)cfg.stage_bytes);
-          const uint32_t a_dst = smem_base + s * cfg.stage_bytes;
-          const int chunk0 = p.in_coff4 + ks * cfg.kbs * 2;
-          for (int c = 0; c < cfg.kbs * 2; ++c)
-            bulk_g2s(a_dst + c * R * 16, p.in + act_off(p.in_bs, p.in_Tp, b, chunk0 + c, t0 - p.pad_left),
-                     (uint32_t)(R * 16), full_bar(s));
+          mbar_expect_tx(fb, (uint32_t)cfg.stage_bytes);
+          uint32_t dst = smem_base + s * cfg.stage_bytes;
+          for (int c = 0; c < chunks_per_stage; ++c) {
+            bulk_g2s(dst, src, row_bytes, fb);
+            dst += row_bytes;
+            src += chunk_stride;
+          }
+          if (++s == cfg.stages) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -233,7 +242,12 @@ conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ U
     const uint64_t a_desc_hi = make_desc(0u, (uint32_t)(R * 16), 128u);
     const uint64_t b_desc_hi = make_desc(0u, (uint32_t)(Ns * 16), 128u);
     mbar_wait(w_bar, 0);
-    int it = 0, tl = 0;
+    int s = 0, tl = 0;
+    uint32_t ph = 0;
+    const uint32_t b_step = (uint32_t)(Ns * 2);            // descriptor units (16 B) between (kb,tap) weight blocks
+    const uint32_t a_step = (uint32_t)(2 * R);             // ... between 8-channel K blocks of a stage
+    const uint32_t w_addr0 = w_base >> 4;
+    const uint32_t dil_u = (uint32_t)p.dil;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tl) {
       const int t0 = (tile % tpi) * TILE_M;
       const int buf = tl & 1;
@@ -243,12 +257,12 @@ conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ U
       const int tfirst = t0 - p.pad_left;                 // time of local row 0
       const bool edge = (tfirst < 0) || (tfirst + R > p.Tin);
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * cfg.ncol);
-      for (int ks = 0; ks < cfg.nks; ++ks, ++it) {
-        const int s = it % cfg.stages;
-        const uint32_t ph = (uint32_t)(it / cfg.stages) & 1u;
+      uint32_t b_addr = w_addr0;
+      uint32_t accum = 0u;
+      for (int ks = 0; ks < cfg.nks; ++ks) {
         mbar_wait(full_bar(s), ph);
-        uint8_t* a_ptr = stage_ptr + s * cfg.stage_bytes;
-        if (edge) {  // conv zero padding: rows outside [0, Tin) become zeros
+        if (edge) {  // conv zero padding: rows outside [0, Tin) become zeros (first / last tiles only)
+          uint8_t* a_ptr = stage_ptr + s * cfg.stage_bytes;
           for (int r = lane; r < R; r += 32) {
             const int t = tfirst + r;
             if (t < 0 || t >= p.Tin)
@@ -262,20 +276,21 @@ conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ U
         if (elect_one()) {
           // descriptors differ only in their 14-bit start-address field (16-byte units)
           uint32_t a_addr = (smem_base + s * cfg.stage_bytes) >> 4;
-          uint32_t b_addr = (w_base >> 4) + (uint32_t)(ks * cfg.kbs * p.taps * Ns * 2);
-          uint32_t accum = ks != 0 ? 1u : 0u;
           for (int kb = 0; kb < cfg.kbs; ++kb) {
-            for (int j = 0; j < p.taps; ++j) {
-              umma_tf32(d_tmem, a_desc_hi | (uint64_t)(a_addr + (uint32_t)(j * p.dil)), b_desc_hi | (uint64_t)b_addr, idesc, accum);
-              accum = 1u;
-              b_addr += (uint32_t)(Ns * 2);
+#pragma unroll
+            for (int j = 0; j < TAPS; ++j) {
+              umma_tf32(d_tmem, a_desc_hi | (uint64_t)(a_addr + (uint32_t)j * dil_u), b_desc_hi | (uint64_t)(b_addr + (uint32_t)j * b_step),
+                        idesc, (j == 0) ? accum : 1u);
             }
-            a_addr += (uint32_t)(2 * R);
+            accum = 1u;
+            b_addr += (uint32_t)TAPS * b_step;
+            a_addr += a_step;
           }
           umma_commit(empty_bar(s));                       // frees the smem stage when the MMAs retire
           if (ks == cfg.nks - 1) umma_commit(tfull_bar(buf));  // accumulator ready for the epilogue
         }
         __syncwarp();
+        if (++s == cfg.stages) { s = 0; ph ^= 1u; }
       }
     }
   } else {
@@ -435,14 +450,23 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
   if (groups > num_tiles) groups = num_tiles;
   const int grid = groups * p.n_slices;
   using Kernel = void (*)(ConvParams, UmmaCfg, int);
-  static const Kernel kernels[4] = {conv_umma_kernel<MODE_SAME, false, false>, conv_umma_kernel<MODE_SAME, true, false>,
-                                    conv_umma_kernel<MODE_SAME, false, true>, conv_umma_kernel<MODE_INTERLEAVE2, false, false>};
+  struct Entry { int variant, taps; Kernel k; };   // variant: 0 plain, 1 pool, 2 residual, 3 interleave
+  static const Entry table[] = {
+      {0, 1, conv_umma_kernel<MODE_SAME, false, false, 1>}, {0, 3, conv_umma_kernel<MODE_SAME, false, false, 3>},
+      {0, 5, conv_umma_kernel<MODE_SAME, false, false, 5>}, {0, 7, conv_umma_kernel<MODE_SAME, false, false, 7>},
+      {1, 3, conv_umma_kernel<MODE_SAME, true, false, 3>},  {2, 3, conv_umma_kernel<MODE_SAME, false, true, 3>},
+      {3, 1, conv_umma_kernel<MODE_INTERLEAVE2, false, false, 1>}, {3, 3, conv_umma_kernel<MODE_INTERLEAVE2, false, false, 3>},
+  };
   static bool attr_set = false;
   if (!attr_set) {
-    for (Kernel k : kernels) AR_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    for (const Entry& e : table) AR_CUDA_OK(cudaFuncSetAttribute(e.k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
     attr_set = true;
   }
-  const Kernel kernel = kernels[p.mode == MODE_INTERLEAVE2 ? 3 : (p.pool ? 1 : (p.res ? 2 : 0))];
+  const int variant = p.mode == MODE_INTERLEAVE2 ? 3 : (p.pool ? 1 : (p.res ? 2 : 0));
+  Kernel kernel = nullptr;
+  for (const Entry& e : table)
+    if (e.variant == variant && e.taps == p.taps) kernel = e.k;
+  AR_CHECK(kernel != nullptr, AR_ERR_INVALID, "conv_umma: no kernel instantiated for this (epilogue, taps) combination");
   kernel<<<grid, UMMA_THREADS, cfg.smem_bytes, stream>>>(p, cfg, num_tiles);
   AR_CUDA_OK(cudaGetLastError());
   return AR_OK;

@@ -65,8 +65,9 @@ struct ConvLayer {  // device-resident packed layer
   int n_slices;         // column slices (each slice's weights stay resident in one CTA's shared memory)
 };
 
-// Resident-weight budget per CTA: leaves >= ~96 KB of the 227 KB for the activation ring.
-constexpr size_t W_SLICE_BUDGET = 128 * 1024;
+// Resident-weight budget per CTA: fewest column slices that still leave >= ~28 KB of the 227 KB for the
+// activation ring (a 128x128 k3 layer, 192 KB, stays unsliced: full-N MMAs beat a deeper ring).
+constexpr size_t W_SLICE_BUDGET = 197 * 1024;
 static int pick_slices(int Cin, int taps, int N) {
   int s = 1;
   while ((size_t)Cin * taps * (N / s) * 4 > W_SLICE_BUDGET && (N / (2 * s)) % 16 == 0) s *= 2;

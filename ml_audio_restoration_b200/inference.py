@@ -68,6 +68,7 @@ class RestorationPipeline:
         self._chain = None
         self._chain_key = None
         self._ws = None
+        self._streams = None
         self._host_out = None
         self._scratch = torch.empty(_lib.NORMALIZE_SCRATCH_BYTES, dtype=torch.uint8, device=self.device)
 
@@ -110,26 +111,34 @@ class RestorationPipeline:
         except Exception:
             pass
 
-    def _workspace(self, nbytes):
-        if self._ws is None or self._ws.numel() < nbytes:
-            self._ws = None
-            self._ws = torch.empty(nbytes + 4096, dtype=torch.uint8, device=self.device)
-        return self._ws
+    def _workspace(self, nbytes, slot=0):
+        if self._ws is None:
+            self._ws = {}
+        buf = self._ws.get(slot)
+        if buf is None or buf.numel() < nbytes:
+            self._ws[slot] = None
+            buf = self._ws[slot] = torch.empty(nbytes + 4096, dtype=torch.uint8, device=self.device)
+        return buf
+
+    def _side_streams(self, n):
+        if self._streams is None or len(self._streams) < n:
+            self._streams = [torch.cuda.Stream(self.device) for _ in range(n)]
+        return self._streams[:n]
 
     def _normalize_(self, t: torch.Tensor, target_db: float = -20.0):
         _lib.check(_lib.lib().ar_normalize(t.data_ptr(), t.numel(), target_db, self._scratch.data_ptr(), self._stream()))
         return t
 
     # ------------------------------------------------------------------ batched chain on chunks
-    def forward_chunks(self, chunks: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
-        """`[B,1,T]` device chunks -> `[B,2,rate*T]` (one `ar_chain_forward`)."""
+    def forward_chunks(self, chunks: torch.Tensor, out: torch.Tensor = None, slot: int = 0) -> torch.Tensor:
+        """`[B,1,T]` device chunks -> `[B,2,rate*T]` (one `ar_chain_forward` on the current stream)."""
         B, _, T = chunks.shape
         L = _lib.lib()
         with torch.cuda.device(self.device):
             c = self.chain()
             need = C.c_size_t()
             _lib.check(L.ar_chain_workspace_bytes(c, B, T, C.byref(need)))
-            ws = self._workspace(need.value)
+            ws = self._workspace(need.value, slot)
             if out is None:
                 out = torch.empty((B, 2, self.rate * T), dtype=torch.float32, device=self.device)
             _lib.check(L.ar_chain_forward(c, chunks.data_ptr(), out.data_ptr(), B, T, ws.data_ptr(), ws.numel(),
@@ -149,7 +158,8 @@ class RestorationPipeline:
     @torch.no_grad()
     def restore(self, audio: torch.Tensor, mode: str = "auto", chunk_size: int = DEFAULT_CHUNK,
                 overlap: int = DEFAULT_OVERLAP, batch_chunks: int = 0, normalize: bool = True,
-                chunk_range=None, return_device: bool = False, reuse_output: bool = False) -> torch.Tensor:
+                chunk_range=None, return_device: bool = False, reuse_output: bool = False,
+                streams: int = 1) -> torch.Tensor:
         """Mono `[1,N]` (or `[N]`) float audio, host or device -> restored stereo `[2, rate*N]`.
 
         Host inputs are copied to the GPU (pinned memory makes the copy asynchronous) and the
@@ -180,7 +190,7 @@ class RestorationPipeline:
             if mode == "whole":
                 y = self.forward_chunks(a.view(1, 1, N))[0]
             elif mode == "chunked":
-                y = self._restore_chunked(a, N, chunk_size, overlap, batch_chunks, chunk_range)
+                y = self._restore_chunked(a, N, chunk_size, overlap, batch_chunks, chunk_range, streams)
             else:
                 raise ValueError(f"unknown mode {mode!r}")
             if normalize:
@@ -197,7 +207,7 @@ class RestorationPipeline:
                 return host
         return y
 
-    def _restore_chunked(self, a, N, chunk_size, overlap, batch_chunks, chunk_range):
+    def _restore_chunked(self, a, N, chunk_size, overlap, batch_chunks, chunk_range, streams=1):
         L = _lib.lib()
         n_chunks = C.c_int()
         _lib.check(L.ar_num_chunks(N, chunk_size, overlap, C.byref(n_chunks)))
@@ -211,14 +221,43 @@ class RestorationPipeline:
         c0 = max(lo - 1, 0)
         cnt_all = hi - c0
         if batch_chunks <= 0:
+            # two chunks per SM: the LSTM scan (one CTA per sequence, two CTAs per SM) is then fully occupied;
+            # bounded by what the workspace of `streams` concurrent batches may take
             free, _ = torch.cuda.mem_get_info(self.device)
-            batch_chunks = min(cnt_all, self.max_batch(chunk_size, int(free * 0.6)), 1024)
+            sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+            batch_chunks = min(cnt_all, 2 * sms, self.max_batch(chunk_size, int(free * 0.6) // max(1, streams)))
         y_all = torch.empty((cnt_all, 2, r * chunk_size), dtype=torch.float32, device=self.device)
-        buf = torch.empty((min(batch_chunks, cnt_all), 1, chunk_size), dtype=torch.float32, device=self.device)
-        for first in range(c0, hi, batch_chunks):
-            cnt = min(batch_chunks, hi - first)
-            _lib.check(L.ar_split_chunks(a.data_ptr(), N, buf.data_ptr(), first, cnt, chunk_size, overlap, self._stream()))
-            self.forward_chunks(buf[:cnt], y_all[first - c0:first - c0 + cnt])
+        firsts = list(range(c0, hi, batch_chunks))
+        n_streams = max(1, min(streams, len(firsts)))
+        main = torch.cuda.current_stream(self.device)
+        if n_streams == 1:
+            buf = torch.empty((min(batch_chunks, cnt_all), 1, chunk_size), dtype=torch.float32, device=self.device)
+            for first in firsts:
+                cnt = min(batch_chunks, hi - first)
+                _lib.check(L.ar_split_chunks(a.data_ptr(), N, buf.data_ptr(), first, cnt, chunk_size, overlap, self._stream()))
+                self.forward_chunks(buf[:cnt], y_all[first - c0:first - c0 + cnt])
+        else:
+            # Batches of chunks are independent: issue them round-robin on side streams (own workspace each)
+            # so the latency-bound LSTM scan of one batch runs under the tensor-core convs of the next.
+            side = self._side_streams(n_streams)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            bufs = [torch.empty((min(batch_chunks, cnt_all), 1, chunk_size), dtype=torch.float32, device=self.device)
+                    for _ in range(n_streams)]
+            for j, first in enumerate(firsts):
+                k = j % n_streams
+                cnt = min(batch_chunks, hi - first)
+                if j < n_streams:
+                    side[k].wait_event(ready)
+                with torch.cuda.stream(side[k]):
+                    _lib.check(L.ar_split_chunks(a.data_ptr(), N, bufs[k].data_ptr(), first, cnt, chunk_size, overlap,
+                                                 side[k].cuda_stream))
+                    self.forward_chunks(bufs[k][:cnt], y_all[first - c0:first - c0 + cnt], slot=k)
+            for st in side:
+                main.wait_stream(st)
+            for t in bufs + [a, y_all]:
+                for st in side:
+                    t.record_stream(st)
         # stitch chunks [c0, hi) as a virtual file, then keep this shard's span [lo*hop, hi*hop) (or to N)
         n_virtual = N - c0 * hop if hi == n_chunks else (cnt_all - 1) * hop + chunk_size
         out = torch.empty((2, r * n_virtual), dtype=torch.float32, device=self.device)
