@@ -101,12 +101,20 @@ def load_peaks():
         return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback"}
 
 
-def cpu_chain_rate(n_chunks, threads=None):
+def host_threads():
+    """All host threads this process may use (torchrun pins OMP_NUM_THREADS=1, undo that for the CPU arm)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def cpu_chain_rate(n_chunks):
     """Oracle port of the reference chain on the host cores: audio-s/s over `n_chunks` 2 s chunks."""
     import oracle
     from oracle.weights import make_state_dict
-    if threads:
-        torch.set_num_threads(threads)
     sds = {n: make_state_dict(n) for n in oracle.MODEL_NAMES}
     n = (n_chunks - 1) * HOP + CHUNK
     audio = synth_audio(n, 1, "cpu")
@@ -123,7 +131,7 @@ def run_reference(args, rank, world):
     reference modules dispatch to), all host threads, bounded sample per step."""
     if rank != 0:
         return
-    cores = torch.get_num_threads()
+    cores = host_threads()
     nck = args.cpu_chunks
     for _ in range(args.warmup):
         cpu_chain_rate(1)
@@ -260,7 +268,7 @@ def run_b200(args, rank, world, local_rank):
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
     }
     if world == 1 and not args.no_cpu_baseline:
-        cores = torch.get_num_threads()
+        cores = host_threads()
         cpu_chain_rate(1)
         v, dt, secs = cpu_chain_rate(args.cpu_chunks)
         line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
