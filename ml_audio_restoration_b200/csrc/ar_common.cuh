@@ -76,6 +76,7 @@ struct ConvParams {
   const float* bias;     // [N]
   int N;                 // GEMM N, multiple of 16, <= 256
   int n_slices;          // column slices the weights are packed in (each is one CTA's resident operand)
+  int cta2;              // packed for the 2-CTA engine: slices (2i, 2i+1) are the two halves of pair-slice i
   // output (C4)
   int mode;              // MODE_SAME: out[t]; MODE_INTERLEAVE2: cols [0,N/2)->out[2t], [N/2,N)->out[2t+1]
   float* out;
@@ -151,6 +152,7 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, int b, int t
 
 // ----------------------------------------------------------------------------- launchers
 int launch_conv_umma(const ConvParams& p, cudaStream_t stream);
+int launch_conv_umma2(const ConvParams& p, cudaStream_t stream);   // cta_group::2 engine (needs p.cta2)
 int launch_conv_simt(const ConvParams& p, cudaStream_t stream);
 int sm_count();
 

@@ -1,0 +1,365 @@
+// 2-CTA (cta_group::2) variant of the tcgen05 implicit-GEMM Conv1d engine.
+//
+// A cluster of two CTAs (an SM pair) computes TWO adjacent 128-row time tiles with ONE instruction
+// stream: D[256 x Ns] += A[256 x 8] * B[8 x Ns] per `tcgen05.mma.cta_group::2`.  Each CTA keeps in its
+// own shared memory (a) the activation rows of its own tile (same C4 / no-swizzle K-major layout and
+// tap-shift trick as conv_umma.cu) and (b) HALF of the weight columns (Ns/2), and in its own TMEM the
+// 128 accumulator rows of its tile.  Compared with the 1-CTA kernel this halves the number of MMA
+// instructions per tile (the layers here are bound by the fixed per-MMA operand fetch, not by FLOPs)
+// and halves the resident weight bytes per CTA, so 128->128 k3, 128->64 k7 ... layers need no N-slices.
+//
+// Roles per CTA: warp 0 = bulk-copy (TMA) producer for its own rows, warp 1 = "MMA warp", warps 2..9 =
+// epilogue for its own 128 rows.  Only the leader CTA's (rank 0) MMA warp issues tcgen05.mma; the
+// peer's MMA warp zero-pads its edge rows and then tells the leader, per pipeline stage, that its half
+// of the operands is in place (remote mbarrier arrive).  Stage release (empty) and accumulator-ready
+// (tmem_full) are multicast commits that arrive in both CTAs; accumulator-drained (tmem_empty) is
+// collected in the leader from the epilogue warps of both CTAs.
+#include "ar_common.cuh"
+#include "umma_ptx.cuh"
+
+namespace ar {
+
+constexpr int EPI2_WARPS = 8;
+constexpr int UMMA2_THREADS = 64 + 32 * EPI2_WARPS;
+constexpr int SMEM2_BUDGET = 227 * 1024;
+constexpr int BAR2_BYTES = 512;
+constexpr int BIAS2_BYTES = 1024;
+
+struct Umma2Cfg {
+  int kbs, stages, R;
+  int w_bytes;      // resident weights per CTA: Cin*taps*(Ns/2)*4
+  int stage_bytes;  // activation stage per CTA
+  int ncol, tmem_cols, nks, smem_bytes;
+};
+
+template <int MODE, bool POOL, bool RES, int TAPS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UMMA2_THREADS, 1)
+conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ Umma2Cfg cfg, int num_pairs) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // shared memory (identical offsets in both CTAs): [weight half][stages x activation stage][barriers][bias]
+  const uint32_t w_base = smem_u32(smem);
+  const uint32_t smem_base = w_base + cfg.w_bytes;
+  uint8_t* const stage_ptr = smem + cfg.w_bytes;
+  const uint32_t bar_base = smem_base + cfg.stages * cfg.stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (cfg.stages + s); };
+  auto peer_bar = [&](int s) { return bar_base + 8u * (2 * cfg.stages + s); };   // used in the leader only
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (3 * cfg.stages + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (3 * cfg.stages + 2 + i); };  // used in the leader only
+  const uint32_t w_bar = bar_base + 8u * (3 * cfg.stages + 4);
+  volatile uint32_t* tmem_slot =
+      reinterpret_cast<volatile uint32_t*>(stage_ptr + cfg.stages * cfg.stage_bytes + 8 * (3 * cfg.stages + 5));
+  float* const s_bias = reinterpret_cast<float*>(stage_ptr + cfg.stages * cfg.stage_bytes + BAR2_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < cfg.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(peer_bar(s), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar(i), 1);
+      mbar_init(tempty_bar(i), 2 * EPI2_WARPS);
+    }
+    mbar_init(w_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc2(smem_u32((const void*)tmem_slot), (uint32_t)cfg.tmem_cols);
+  const int nsl = p.n_slices >> 1;                       // pair-slices (p.n_slices counts per-CTA halves)
+  const int Ns = p.N / nsl;                              // GEMM columns of this pair's weight slice
+  const int Nh = Ns >> 1;                                // weight columns resident in this CTA
+  const int cid = blockIdx.x >> 1;                       // cluster index
+  const int slice = cid % nsl;
+  for (int i = threadIdx.x; i < Ns; i += blockDim.x) s_bias[i] = p.bias[slice * Ns + i];
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                    // barriers of both CTAs initialised before any remote use
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tpi = p.tiles_per_item;
+  const int ppi = (tpi + 1) >> 1;                        // tile pairs per batch item
+  const int R = cfg.R;
+  const int pair0 = cid / nsl;
+  const int pair_step = (gridDim.x >> 1) / nsl;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer (own rows, own weight half)
+    if (elect_one()) {
+      mbar_expect_tx(w_bar, (uint32_t)cfg.w_bytes);
+      const char* wsrc = reinterpret_cast<const char*>(p.w) + ((size_t)slice * 2 + rank) * cfg.w_bytes;
+      for (int off = 0; off < cfg.w_bytes; off += 32768) {
+        const int n = cfg.w_bytes - off < 32768 ? cfg.w_bytes - off : 32768;
+        bulk_g2s(w_base + off, wsrc + off, (uint32_t)n, w_bar);
+      }
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t row_bytes = (uint32_t)(R * 16);
+      const long long chunk_stride = (long long)p.in_Tp * 4;
+      const int chunks_per_stage = cfg.kbs * 2;
+      for (int pr = pair0; pr < num_pairs; pr += pair_step) {
+        const int b = pr / ppi;
+        int tl_in_item = (pr - b * ppi) * 2 + (int)rank;
+        if (tl_in_item > tpi - 1) tl_in_item = tpi - 1;   // odd tile count: the idle half re-reads a valid tile (all its rows get zeroed)
+        const int t0 = tl_in_item * TILE_M;
+        const float* src = p.in + act_off(p.in_bs, p.in_Tp, b, p.in_coff4, t0 - p.pad_left);
+        for (int ks = 0; ks < cfg.nks; ++ks) {
+          const uint32_t fb = full_bar(s);
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_expect_tx(fb, (uint32_t)cfg.stage_bytes);
+          uint32_t dst = smem_base + s * cfg.stage_bytes;
+          for (int c = 0; c < chunks_per_stage; ++c) {
+            bulk_g2s(dst, src, row_bytes, fb);
+            dst += row_bytes;
+            src += chunk_stride;
+          }
+          if (++s == cfg.stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA warp
+    // idesc: D=F32, A=B=TF32, K-major, N>>3 at [17,23), M>>4 at [24,29) with M = 256 (both CTAs)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Ns >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    const uint64_t a_desc_hi = make_desc(0u, (uint32_t)(R * 16), 128u);
+    const uint64_t b_desc_hi = make_desc(0u, (uint32_t)(Nh * 16), 128u);
+    mbar_wait(w_bar, 0);
+    int s = 0, tl = 0;
+    uint32_t ph = 0;
+    const uint32_t b_step = (uint32_t)(Nh * 2);
+    const uint32_t a_step = (uint32_t)(2 * R);
+    const uint32_t w_addr0 = w_base >> 4;
+    const uint32_t dil_u = (uint32_t)p.dil;
+    for (int pr = pair0; pr < num_pairs; pr += pair_step, ++tl) {
+      const int b = pr / ppi;
+      const int tl_in_item = (pr - b * ppi) * 2 + (int)rank;
+      const int t_true = tl_in_item * TILE_M;                          // true first output row of this CTA's tile
+      const int t0 = (tl_in_item > tpi - 1 ? tpi - 1 : tl_in_item) * TILE_M;  // tile that was actually loaded
+      const int tfirst = t0 - p.pad_left;
+      const bool dead = tl_in_item > tpi - 1;                          // no such tile: contribute zeros
+      const bool edge = dead || (tfirst < 0) || (tfirst + R > p.Tin);
+      const int buf = tl & 1;
+      const uint32_t aph = (uint32_t)(tl >> 1) & 1u;
+      (void)t_true;
+      if (leader) {
+        mbar_wait(tempty_bar(buf), aph ^ 1u);                          // both epilogues drained this accumulator
+        tc_fence_after();
+      }
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * cfg.ncol);
+      uint32_t b_addr = w_addr0;
+      uint32_t accum = 0u;
+      for (int ks = 0; ks < cfg.nks; ++ks) {
+        mbar_wait(full_bar(s), ph);
+        if (edge) {  // conv zero padding of this CTA's rows
+          uint8_t* a_ptr = stage_ptr + s * cfg.stage_bytes;
+          for (int r = lane; r < R; r += 32) {
+            const int t = tfirst + r;
+            if (dead || t < 0 || t >= p.Tin)
+              for (int c = 0; c < cfg.kbs * 2; ++c)
+                *reinterpret_cast<float4*>(a_ptr + (c * R + r) * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          fence_async_smem();
+          __syncwarp();
+        }
+        if (!leader) {
+          // my half of this stage (rows + resident weights) is in place: tell the leader
+          if (elect_one()) {
+            if (edge) mbar_arrive_remote_release(mapa_u32(peer_bar(s), 0));   // zero-padding writes must be visible
+            else mbar_arrive_remote(mapa_u32(peer_bar(s), 0));
+          }
+          __syncwarp();
+        } else {
+          mbar_wait(peer_bar(s), ph);
+          tc_fence_after();
+          if (elect_one()) {
+            uint32_t a_addr = (smem_base + s * cfg.stage_bytes) >> 4;
+            for (int kb = 0; kb < cfg.kbs; ++kb) {
+#pragma unroll
+              for (int j = 0; j < TAPS; ++j)
+                umma2_tf32(d_tmem, a_desc_hi | (uint64_t)(a_addr + (uint32_t)j * dil_u),
+                           b_desc_hi | (uint64_t)(b_addr + (uint32_t)j * b_step), idesc, (j == 0) ? accum : 1u);
+              accum = 1u;
+              b_addr += (uint32_t)TAPS * b_step;
+              a_addr += a_step;
+            }
+            umma_commit2(empty_bar(s));                          // both CTAs' stage s is free once these MMAs retire
+            if (ks == cfg.nks - 1) umma_commit2(tfull_bar(buf));   // both accumulator halves ready
+          }
+          __syncwarp();
+        }
+        if (++s == cfg.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..9), own 128 rows
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int wcols = Ns >= 32 ? Ns / 2 : Ns;
+    const int col_lo = Ns >= 32 ? half * wcols : 0;
+    const bool active = Ns >= 32 || half == 0;
+    const float slope = p.lrelu ? LRELU_SLOPE : 1.0f;
+    const bool rnd = p.round_tf32 != 0;
+    const long long ostride = (long long)p.out_Tp * 4;
+    const int gcol0 = slice * Ns + col_lo;
+    const uint32_t tempty_leader0 = mapa_u32(tempty_bar(0), 0);
+    const uint32_t tempty_leader1 = mapa_u32(tempty_bar(1), 0);
+    int tl = 0;
+    for (int pr = pair0; pr < num_pairs; pr += pair_step, ++tl) {
+      const int b = pr / ppi;
+      const int tl_in_item = (pr - b * ppi) * 2 + (int)rank;
+      const int t = tl_in_item * TILE_M + q * 32 + lane;   // >= Tin for a dead tile => every store is masked
+      const int buf = tl & 1;
+      const uint32_t aph = (uint32_t)(tl >> 1) & 1u;
+      const bool in_ok = t < p.Tin;
+      float* orow0;
+      float* orow1 = nullptr;
+      bool ok0, ok1 = false;
+      int chunk0;
+      if (MODE == MODE_SAME) {
+        chunk0 = gcol0 >> 2;
+        orow0 = p.out + act_off(p.out_bs, p.out_Tp, b, p.out_coff4 + chunk0, in_ok ? t : 0);
+        ok0 = in_ok && t < p.Tout;
+      } else {
+        const int hN = p.N >> 1;
+        const int phase = gcol0 >= hN;
+        chunk0 = (gcol0 - phase * hN) >> 2;
+        orow0 = p.out + act_off(p.out_bs, p.out_Tp, b, p.out_coff4 + chunk0, in_ok ? 2 * t + phase : 0);
+        ok0 = in_ok && (2 * t + phase) < p.Tout;
+        ok1 = (phase == 0) && (t == p.Tin - 1) && (2 * p.Tin < p.Tout);
+        orow1 = p.out + act_off(p.out_bs, p.out_Tp, b, p.out_coff4 + chunk0, 2 * p.Tin);
+      }
+      float* prow = nullptr;
+      bool pok = false;
+      if (POOL) {
+        prow = p.pool + act_off(p.pool_bs, p.pool_Tp, b, p.pool_coff4 + chunk0, in_ok ? (t >> 1) : 0);
+        pok = ((t & 1) == 0) && (t + 1 < p.Tin);
+      }
+      float4 resv[4];
+      if (RES) {
+        const float* rrow = p.res + act_off(p.res_bs, p.res_Tp, b, p.res_coff4 + chunk0, in_ok ? t : 0);
+        const long long rstride = (long long)p.res_Tp * 4;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          resv[c] = (in_ok && active) ? *reinterpret_cast<const float4*>(rrow + c * rstride) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      mbar_wait(tfull_bar(buf), aph);
+      tc_fence_after();
+      if (active) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * cfg.ncol + col_lo);
+        for (int cb = 0; cb < wcols; cb += 32) {
+          uint32_t r[32];
+          const int ncol = wcols - cb < 32 ? 16 : 32;
+          if (ncol == 32) tmem_ld32_nowait(taddr + cb, r);
+          else tmem_ld16_nowait(taddr + cb, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            if (4 * c < ncol) {
+              const float4 bz = *reinterpret_cast<const float4*>(s_bias + col_lo + cb + 4 * c);
+              float v0 = __uint_as_float(r[4 * c]) + bz.x, v1 = __uint_as_float(r[4 * c + 1]) + bz.y;
+              float v2 = __uint_as_float(r[4 * c + 2]) + bz.z, v3 = __uint_as_float(r[4 * c + 3]) + bz.w;
+              v0 = fmaxf(v0, slope * v0); v1 = fmaxf(v1, slope * v1);
+              v2 = fmaxf(v2, slope * v2); v3 = fmaxf(v3, slope * v3);
+              if (RES) { v0 += resv[c & 3].x; v1 += resv[c & 3].y; v2 += resv[c & 3].z; v3 += resv[c & 3].w; }
+              if (rnd) { v0 = to_tf32(v0); v1 = to_tf32(v1); v2 = to_tf32(v2); v3 = to_tf32(v3); }
+              const long long coff = (long long)((cb >> 2) + c) * ostride;
+              if (ok0) *reinterpret_cast<float4*>(orow0 + coff) = make_float4(v0, v1, v2, v3);
+              if (MODE == MODE_INTERLEAVE2) {
+                if (ok1) *reinterpret_cast<float4*>(orow1 + coff) = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+              if (POOL) {
+                const float m0 = fmaxf(v0, __shfl_down_sync(0xffffffffu, v0, 1));
+                const float m1 = fmaxf(v1, __shfl_down_sync(0xffffffffu, v1, 1));
+                const float m2 = fmaxf(v2, __shfl_down_sync(0xffffffffu, v2, 1));
+                const float m3 = fmaxf(v3, __shfl_down_sync(0xffffffffu, v3, 1));
+                if (pok) *reinterpret_cast<float4*>(prow + (long long)((cb >> 2) + c) * ((long long)p.pool_Tp * 4)) = make_float4(m0, m1, m2, m3);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(buf ? tempty_leader1 : tempty_leader0);   // leader collects 2 x 8 warps
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer may still touch it
+  if (warp == 1) tmem_dealloc2(tmem_base, (uint32_t)cfg.tmem_cols);
+}
+
+// ----------------------------------------------------------------------------- host side
+static bool pick_cfg2(const ConvParams& p, Umma2Cfg& c) {
+  const int Ns = p.N / (p.n_slices / 2);
+  c.R = TILE_M + (p.taps - 1) * p.dil;
+  int ncol = 32;
+  while (ncol < Ns) ncol <<= 1;
+  c.ncol = ncol;
+  c.tmem_cols = 2 * ncol;
+  c.w_bytes = p.Cin * p.taps * (Ns / 2) * 4;
+  const int room = SMEM2_BUDGET - BAR2_BYTES - BIAS2_BYTES - c.w_bytes;
+  for (int kbs = 4; kbs >= 1; kbs >>= 1) {
+    if (p.Cin % (8 * kbs)) continue;
+    c.kbs = kbs;
+    c.stage_bytes = kbs * 2 * c.R * 16;
+    int stages = room / c.stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages >= 4 || (kbs == 1 && stages >= 2)) {
+      c.stages = stages;
+      c.nks = p.Cin / (8 * kbs);
+      c.smem_bytes = c.w_bytes + stages * c.stage_bytes + BAR2_BYTES + BIAS2_BYTES;
+      return true;
+    }
+  }
+  return false;
+}
+
+int launch_conv_umma2(const ConvParams& p, cudaStream_t stream) {
+  AR_CHECK(p.cta2 && p.n_slices >= 2 && (p.n_slices & 1) == 0, AR_ERR_INVALID, "conv_umma2: layer is not packed for the 2-CTA engine");
+  const int nsl = p.n_slices / 2;
+  const int Ns = p.N / nsl;
+  AR_CHECK(p.Cin % 8 == 0 && p.N % (32 * nsl) == 0 && Ns >= 32 && Ns <= 256, AR_ERR_INVALID, "conv_umma2: unsupported channel counts");
+  AR_CHECK(p.res == nullptr || Ns <= 32, AR_ERR_INVALID, "conv_umma2: residual epilogue supports at most 32 columns per slice");
+  AR_CHECK(p.pad_left <= HALO && (p.taps - 1) * p.dil - p.pad_left <= HALO, AR_ERR_INVALID, "conv_umma2: conv reach exceeds HALO");
+  AR_CHECK(p.mode == MODE_SAME || (p.pool == nullptr && p.res == nullptr), AR_ERR_INVALID, "conv_umma2: interleave mode has no pool/residual epilogue");
+  AR_CHECK(p.mode == MODE_SAME || (p.N / 2) % (Ns / 2) == 0, AR_ERR_INVALID, "conv_umma2: interleave phases must align with the epilogue column split");
+  AR_CHECK(!(p.pool && p.res), AR_ERR_INVALID, "conv_umma2: pool and residual epilogues are exclusive");
+  Umma2Cfg cfg;
+  AR_CHECK(pick_cfg2(p, cfg), AR_ERR_INVALID, "conv_umma2: no pipeline configuration fits shared memory");
+  using Kernel = void (*)(ConvParams, Umma2Cfg, int);
+  struct Entry { int variant, taps; Kernel k; };
+  static const Entry table[] = {
+      {0, 1, conv_umma2_kernel<MODE_SAME, false, false, 1>}, {0, 3, conv_umma2_kernel<MODE_SAME, false, false, 3>},
+      {0, 5, conv_umma2_kernel<MODE_SAME, false, false, 5>}, {0, 7, conv_umma2_kernel<MODE_SAME, false, false, 7>},
+      {1, 3, conv_umma2_kernel<MODE_SAME, true, false, 3>},  {2, 3, conv_umma2_kernel<MODE_SAME, false, true, 3>},
+      {3, 1, conv_umma2_kernel<MODE_INTERLEAVE2, false, false, 1>}, {3, 3, conv_umma2_kernel<MODE_INTERLEAVE2, false, false, 3>},
+  };
+  static bool attr_set = false;
+  if (!attr_set) {
+    for (const Entry& e : table) AR_CUDA_OK(cudaFuncSetAttribute(e.k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BUDGET));
+    attr_set = true;
+  }
+  const int variant = p.mode == MODE_INTERLEAVE2 ? 3 : (p.pool ? 1 : (p.res ? 2 : 0));
+  Kernel kernel = nullptr;
+  for (const Entry& e : table)
+    if (e.variant == variant && e.taps == p.taps) kernel = e.k;
+  AR_CHECK(kernel != nullptr, AR_ERR_INVALID, "conv_umma2: no kernel instantiated for this (epilogue, taps) combination");
+  const int ppi = (p.tiles_per_item + 1) / 2;
+  const int num_pairs = p.B * ppi;
+  int groups = (sm_count() / 2) / nsl;                   // clusters per pair-slice
+  if (groups > num_pairs) groups = num_pairs;
+  if (groups < 1) groups = 1;
+  const int grid = groups * nsl * 2;
+  kernel<<<grid, UMMA2_THREADS, cfg.smem_bytes, stream>>>(p, cfg, num_pairs);
+  AR_CUDA_OK(cudaGetLastError());
+  return AR_OK;
+}
+
+}  // namespace ar

@@ -1,6 +1,7 @@
 // Host side of libaudiorestore_sm100: state_dict -> folded / packed device weights, the
 // workspace planner, and the three model forwards + the chain expressed as kernel sequences.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -63,6 +64,7 @@ struct ConvLayer {  // device-resident packed layer
   size_t w_off, b_off;  // float offsets into the model blob
   double macs_per_row;  // algorithmic MACs of the reference op per input time step (structural zeros excluded)
   int n_slices;         // column slices (each slice's weights stay resident in one CTA's shared memory)
+  int cta2;             // slices come in (2i, 2i+1) pairs: the two halves of a 2-CTA pair-slice
 };
 
 // Resident-weight budget per CTA: fewest column slices that still leave >= ~28 KB of the 227 KB for the
@@ -72,6 +74,16 @@ static int pick_slices(int Cin, int taps, int N) {
   int s = 1;
   while ((size_t)Cin * taps * (N / s) * 4 > W_SLICE_BUDGET && (N / (2 * s)) % 16 == 0) s *= 2;
   return s;
+}
+// 2-CTA engine: every layer with N >= 32 is packed as pair-slices of two halves (one per CTA of the pair);
+// AR_CTA2=0 (read at model creation) packs for the 1-CTA engine instead.
+static bool want_cta2(int N) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("AR_CTA2");
+    on = e ? atoi(e) : 1;
+  }
+  return on && N >= 32 && N % 32 == 0;
 }
 
 struct Blob {
@@ -84,7 +96,11 @@ struct Blob {
   }
   size_t push(const std::vector<float>& v) { return push(v.data(), v.size()); }
   ConvLayer push_gemm(Gemm& g) {  // [n_slices][Cin/8][taps][2][Ns][4], tf32-rounded
-    const int ns = pick_slices(g.Cin, g.taps, g.N), Ns = g.N / ns, KB = g.Cin / 8;
+    const bool cta2 = want_cta2(g.N);
+    // per-CTA slices: for the 2-CTA engine split every pair-slice once more (the budget applies per CTA)
+    int ns = pick_slices(g.Cin, g.taps, g.N);
+    if (cta2 && ns == 1) ns = 2;
+    const int Ns = g.N / ns, KB = g.Cin / 8;
     std::vector<float> w((size_t)g.Cin * g.taps * g.N);
     for (int sl = 0; sl < ns; ++sl)
       for (int kb = 0; kb < KB; ++kb)
@@ -94,7 +110,7 @@ struct Blob {
               for (int j = 0; j < 4; ++j)
                 w[(((((size_t)sl * KB + kb) * g.taps + t) * 2 + h) * Ns + n) * 4 + j] =
                     tf32_round_host(g.at(t, kb * 8 + h * 4 + j, sl * Ns + n));
-    ConvLayer L{g.Cin, g.N, g.taps, g.dil, g.pad_left, 0, 0, 0.0, ns};
+    ConvLayer L{g.Cin, g.N, g.taps, g.dil, g.pad_left, 0, 0, 0.0, ns, cta2 ? 1 : 0};
     for (float v : g.G) L.macs_per_row += (v != 0.f) ? 1.0 : 0.0;  // == Cin*N*taps except the 2-phase ConvT
     L.w_off = push(w);
     L.b_off = push(g.bias);
@@ -415,7 +431,7 @@ static int run_conv(Ctx& c, const std::string& name, const Act& in, const Act& o
   std::memset(&p, 0, sizeof(p));
   p.in = in.base; p.in_bs = in.bs; p.in_Tp = in.Tp; p.in_coff4 = o.in_coff4;
   p.Tin = in.T; p.Cin = L.Cin; p.taps = L.taps; p.dil = L.dil; p.pad_left = L.pad_left;
-  p.w = c.m->blob + L.w_off; p.bias = c.m->blob + L.b_off; p.N = L.N; p.n_slices = L.n_slices;
+  p.w = c.m->blob + L.w_off; p.bias = c.m->blob + L.b_off; p.N = L.N; p.n_slices = L.n_slices; p.cta2 = L.cta2;
   p.mode = o.mode;
   p.out = out.base; p.out_bs = out.bs; p.out_Tp = out.Tp; p.out_coff4 = o.out_coff4;
   p.Tout = o.Tout >= 0 ? o.Tout : out.T;
@@ -425,7 +441,8 @@ static int run_conv(Ctx& c, const std::string& name, const Act& in, const Act& o
   p.B = c.B;
   p.tiles_per_item = (in.T + TILE_M - 1) / TILE_M;
   ProfScope ps(CAT_CONV, c.stream, 2.0 * L.macs_per_row * (double)c.B * (double)in.T);
-  return c.m->engine == AR_ENGINE_SIMT ? launch_conv_simt(p, c.stream) : launch_conv_umma(p, c.stream);
+  if (c.m->engine == AR_ENGINE_SIMT) return launch_conv_simt(p, c.stream);
+  return p.cta2 ? launch_conv_umma2(p, c.stream) : launch_conv_umma(p, c.stream);
 }
 
 // ---------------------------------------------------------------------------- denoiser.py:88-144
@@ -668,10 +685,10 @@ int debug_conv(const float* x, const float* w_host, const float* bias_host, floa
     ConvParams p;
     std::memset(&p, 0, sizeof(p));
     p.in = in.base; p.in_bs = in.bs; p.in_Tp = in.Tp; p.Tin = T; p.Cin = Cin; p.taps = k; p.dil = dil; p.pad_left = g.pad_left;
-    p.w = dblob + L.w_off; p.bias = dblob + L.b_off; p.N = Cout; p.n_slices = L.n_slices; p.mode = MODE_SAME;
+    p.w = dblob + L.w_off; p.bias = dblob + L.b_off; p.N = Cout; p.n_slices = L.n_slices; p.cta2 = L.cta2; p.mode = MODE_SAME;
     p.out = out.base; p.out_bs = out.bs; p.out_Tp = out.Tp; p.Tout = T; p.lrelu = lrelu; p.round_tf32 = 0;
     p.B = B; p.tiles_per_item = (T + TILE_M - 1) / TILE_M;
-    rc = engine == AR_ENGINE_SIMT ? launch_conv_simt(p, stream) : launch_conv_umma(p, stream);
+    rc = engine == AR_ENGINE_SIMT ? launch_conv_simt(p, stream) : (p.cta2 ? launch_conv_umma2(p, stream) : launch_conv_umma(p, stream));
   }
   if (rc == AR_OK) rc = launch_c4_to_plain(out, B, Cout, T, y, stream);
   cudaError_t e = cudaStreamSynchronize(stream);
