@@ -285,7 +285,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
     ap.add_argument("--chunks-per-step", type=int, default=592, help="2 s chunks per GPU per step (592 = 4 per SM)")
-    ap.add_argument("--batch-chunks", type=int, default=296, help="chunks per chain launch (296 = two LSTM CTAs per SM)")
+    ap.add_argument("--batch-chunks", type=int, default=592, help="chunks per chain launch (592 = 4 per SM: one tensor-core LSTM launch per step)")
     ap.add_argument("--streams", type=int, default=1, help="chunk batches in flight (LSTM of one overlaps convs of the next)")
     ap.add_argument("--cpu-chunks", type=int, default=8, help="chunks in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -48,8 +48,8 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
   return d;
 }
 
-template <int S>
-__global__ void __launch_bounds__(256, (S == 1) ? 2 : 1)
+template <int S, int PF>
+__global__ void __launch_bounds__(256, (S <= 2) ? 2 : 1)
 lstm_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const float* __restrict__ whh,
             float* __restrict__ hout, long long h_bs, int h_Tp, int B, int T,
             const float* __restrict__ state_in, float* __restrict__ state_out) {
@@ -86,29 +86,29 @@ lstm_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const floa
   }
   __syncthreads();
 
-  // Pre-activations are prefetched one 8-step block ahead into a register set that is not live
-  // while the current block runs (two sets, ping-pong over a 16-step unrolled body), so the loads
-  // have a whole block (~8 steps) to land and never sit on the per-step critical path.
-  float xa[S][LSTM_BLK], xb[S][LSTM_BLK];
+  // Pre-activations are prefetched PF steps ahead into a register set that is not live while the current
+  // PF steps run (two sets, ping-pong over a 2*PF-step unrolled body), so the loads have PF steps to land
+  // and never sit on the per-step critical path.
+  float xa[S][PF], xb[S][PF];
 #pragma unroll
   for (int s = 0; s < S; ++s)
 #pragma unroll
-    for (int k = 0; k < LSTM_BLK; ++k) xa[s][k] = __ldg(xrow[s] + 4 * min(k, T - 1));
+    for (int k = 0; k < PF; ++k) xa[s][k] = __ldg(xrow[s] + 4 * min(k, T - 1));
 
   int cur = 0;
   float hlast[S];
 #pragma unroll
   for (int s = 0; s < S; ++s) hlast[s] = 0.f;
 
-  auto run_block = [&](float (&xc)[S][LSTM_BLK], float (&xnext)[S][LSTM_BLK], int t0) {
+  auto run_block = [&](float (&xc)[S][PF], float (&xnext)[S][PF], int t0) {
 #pragma unroll
     for (int s = 0; s < S; ++s)
 #pragma unroll
-      for (int k = 0; k < LSTM_BLK; ++k) xnext[s][k] = __ldg(xrow[s] + 4 * min(t0 + LSTM_BLK + k, T - 1));
-    const int sb = (t0 / LSTM_BLK) & 1;
+      for (int k = 0; k < PF; ++k) xnext[s][k] = __ldg(xrow[s] + 4 * min(t0 + PF + k, T - 1));
 #pragma unroll
-    for (int k = 0; k < LSTM_BLK; ++k) {
-      if (t0 + k < T) {  // uniform across the block
+    for (int k = 0; k < PF; ++k) {
+      const int t = t0 + k;
+      if (t < T) {  // uniform across the block
         unsigned long long acc[S][4];
 #pragma unroll
         for (int s = 0; s < S; ++s) {
@@ -127,6 +127,7 @@ lstm_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const floa
             acc[s][3] = fma2(w2[j / 2 + 3], h1.y, acc[s][3]);
           }
         }
+        const int sb = (t >> 3) & 1;
 #pragma unroll
         for (int s = 0; s < S; ++s) {
           float a0, a1, a2, a3, a4, a5, a6, a7;
@@ -144,30 +145,34 @@ lstm_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const floa
             const float h = ao * tanh_f(c[s]);
             hlast[s] = h;
             hbuf[cur ^ 1][s][unit] = h;
-            hstage[sb][s][k][unit] = h;
+            hstage[sb][s][t & 7][unit] = h;
           }
         }
         __syncthreads();
         cur ^= 1;
-      }
-    }
-    // flush this block's hidden states: [16 chunks][<=8 steps] float4 per sequence, coalesced along time
-    for (int i = tid; i < S * 16 * LSTM_BLK; i += 256) {
-      const int s = i / (16 * LSTM_BLK);
-      const int ch = (i / LSTM_BLK) % 16;
-      const int k = i % LSTM_BLK;
-      const int b = seq0 + s;
-      if (b < B && t0 + k < T) {
-        const float4 v = *reinterpret_cast<const float4*>(&hstage[sb][s][k][4 * ch]);
-        *reinterpret_cast<float4*>(hout + act_off(h_bs, h_Tp, b, ch, t0 + k)) =
-            make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+        if ((t & 7) == 7 || t == T - 1) {
+          // flush up to 8 finished steps: [16 chunks][steps] float4 per sequence, coalesced along time
+          const int tb = t & ~7;
+          const int nst = t - tb + 1;
+          for (int i = tid; i < S * 16 * LSTM_BLK; i += 256) {
+            const int s = i / (16 * LSTM_BLK);
+            const int ch = (i / LSTM_BLK) % 16;
+            const int kk = i % LSTM_BLK;
+            const int b = seq0 + s;
+            if (b < B && kk < nst) {
+              const float4 v = *reinterpret_cast<const float4*>(&hstage[sb][s][kk][4 * ch]);
+              *reinterpret_cast<float4*>(hout + act_off(h_bs, h_Tp, b, ch, tb + kk)) =
+                  make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+            }
+          }
+        }
       }
     }
   };
 
-  for (int t0 = 0; t0 < T; t0 += 2 * LSTM_BLK) {
+  for (int t0 = 0; t0 < T; t0 += 2 * PF) {
     run_block(xa, xb, t0);
-    if (t0 + LSTM_BLK < T) run_block(xb, xa, t0 + LSTM_BLK);
+    if (t0 + PF < T) run_block(xb, xa, t0 + PF);
   }
   if (state_out != nullptr && gate == 0) {
 #pragma unroll
@@ -181,23 +186,199 @@ lstm_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const floa
   }
 }
 
+// ============================================================================ tensor-core recurrence
+// Eight sequences per CTA: the recurrent mat-vec of a step becomes a [256 x 64] x [64 x 8] product run on
+// warp-level tensor-core MMAs (mma.sync m16n8k8, TF32 operands, fp32 accumulate).  W_hh is rounded to TF32
+// like every other weight of the model and h is rounded to TF32 before it is fed back -- it is the same
+// rounded value the decoder convs consume -- while the cell state c, the gate pre-activations and all gate
+// math stay fp32 (measured on the oracle: output SNR > 100 dB vs the all-fp32 recurrence, tests/ check it).
+// Warp w owns hidden units [8w, 8w+8): its two 16-row MMA tiles hold rows (i,f) and (g,o) of those units, so
+// in the accumulator layout one thread ends up with all four gates of ONE unit for TWO sequences and the
+// cell update needs no cross-thread exchange.  h goes through shared memory ([seq][unit], stride 68 floats:
+// conflict-free both for the update's stores and for the B-fragment loads); one block barrier per step.
+constexpr int LM_SEQ = 8;       // sequences per CTA
+constexpr int LM_HS = 68;       // padded row stride of the h exchange buffer
+
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int LM_XS = 260;                        // padded per-sequence stride of a staged pre-activation row (floats)
+constexpr int LM_XSTEP = LM_SEQ * LM_XS;          // floats per staged step
+constexpr int LM_XBUF = LSTM_BLK * LM_XSTEP;      // floats per 8-step buffer
+constexpr int LM_SMEM = (2 * LM_XBUF + 2 * LM_SEQ * LM_HS + 2 * LSTM_BLK * LM_SEQ * LSTM_H) * 4;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 1)
+lstm_mma_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const float* __restrict__ whh,
+                float* __restrict__ hout, long long h_bs, int h_Tp, int B, int T,
+                const float* __restrict__ state_in, float* __restrict__ state_out) {
+  extern __shared__ __align__(16) float lm_smem[];
+  float* const xs = lm_smem;                                   // [2][8 steps][8 seq][260]: staged gate pre-activations
+  float* const hbuf = xs + 2 * LM_XBUF;                        // [2][8 seq][68]
+  float* const hstage = hbuf + 2 * LM_SEQ * LM_HS;             // [2][8 steps][8 seq][64]
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int gid = lane >> 2, tig = lane & 3;        // mma fragment coordinates
+  const int unit = warp * 8 + gid;                  // hidden unit whose 4 gates this thread finishes
+  const int seq0 = blockIdx.x * LM_SEQ;
+  const int sa = 2 * tig, sb2 = 2 * tig + 1;        // the two sequences (columns) this thread finishes
+
+  // A fragments: tile 0 = rows (i | f), tile 1 = rows (g | o) of this warp's 8 units; 8 k-tiles each.
+  uint32_t wfrag[2][8][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const int row_lo = (2 * mt) * LSTM_H + warp * 8 + gid;       // gate i (mt=0) / g (mt=1)
+    const int row_hi = (2 * mt + 1) * LSTM_H + warp * 8 + gid;   // gate f / o
+#pragma unroll
+    for (int kt = 0; kt < 8; ++kt) {
+      wfrag[mt][kt][0] = __float_as_uint(to_tf32(whh[row_lo * LSTM_H + kt * 8 + tig]));
+      wfrag[mt][kt][1] = __float_as_uint(to_tf32(whh[row_hi * LSTM_H + kt * 8 + tig]));
+      wfrag[mt][kt][2] = __float_as_uint(to_tf32(whh[row_lo * LSTM_H + kt * 8 + tig + 4]));
+      wfrag[mt][kt][3] = __float_as_uint(to_tf32(whh[row_hi * LSTM_H + kt * 8 + tig + 4]));
+    }
+  }
+
+  // per-thread state: (unit, seq sa) and (unit, seq sb2)
+  const int ba = min(seq0 + sa, B - 1), bb = min(seq0 + sb2, B - 1);
+  float c0 = 0.f, c1 = 0.f, hl0 = 0.f, hl1 = 0.f;
+  if (state_in != nullptr) {
+    c0 = state_in[(long long)ba * 2 * LSTM_H + LSTM_H + unit];
+    c1 = state_in[(long long)bb * 2 * LSTM_H + LSTM_H + unit];
+    hl0 = state_in[(long long)ba * 2 * LSTM_H + unit];
+    hl1 = state_in[(long long)bb * 2 * LSTM_H + unit];
+  }
+  hbuf[sa * LM_HS + unit] = to_tf32(hl0);
+  hbuf[sb2 * LM_HS + unit] = to_tf32(hl1);
+
+  // Staging of the gate pre-activations: 8 steps x 8 sequences x 64 chunks of 16 bytes per block, copied with
+  // cp.async (16 pieces per thread, consecutive threads = consecutive steps of one (sequence, chunk) run =>
+  // 128-byte coalesced reads), one block ahead of its use.
+  const uint32_t xs_u32 = (uint32_t)__cvta_generic_to_shared(xs);
+  auto stage_block = [&](int blk) {
+    const int t0 = blk * LSTM_BLK;
+    const uint32_t dst0 = xs_u32 + (uint32_t)((blk & 1) * LM_XBUF * 4);
+#pragma unroll 4
+    for (int m = 0; m < 16; ++m) {
+      const int i = tid + 256 * m;
+      const int k = i & 7, run = i >> 3;
+      const int sq = run >> 6, ch = run & 63;
+      const int b = min(seq0 + sq, B - 1);
+      const int t = min(t0 + k, T - 1);
+      cp_async16(dst0 + (uint32_t)((k * LM_XSTEP + sq * LM_XS + ch * 4) * 4), xp + act_off(xp_bs, xp_Tp, b, ch, t));
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage_block(0);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  int cur = 0;
+  const int nblk = (T + LSTM_BLK - 1) / LSTM_BLK;
+  for (int blk = 0; blk < nblk; ++blk) {
+    if (blk + 1 < nblk) stage_block(blk + 1);
+    const float* xb = xs + (blk & 1) * LM_XBUF;
+    float* hst = hstage + (blk & 1) * (LSTM_BLK * LM_SEQ * LSTM_H);
+    const int t0 = blk * LSTM_BLK;
+    const int nst = min(LSTM_BLK, T - t0);
+#pragma unroll
+    for (int k = 0; k < LSTM_BLK; ++k) {
+      if (k < nst) {  // uniform
+        float acc[2][2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[mt][h][i] = 0.f;
+        const float* hb = hbuf + cur * (LM_SEQ * LM_HS) + gid * LM_HS + tig;
+#pragma unroll
+        for (int kt = 0; kt < 8; ++kt) {
+          const uint32_t b0 = __float_as_uint(hb[kt * 8]);
+          const uint32_t b1 = __float_as_uint(hb[kt * 8 + 4]);
+          mma_tf32_16x8x8(acc[0][kt & 1], wfrag[0][kt], b0, b1);
+          mma_tf32_16x8x8(acc[1][kt & 1], wfrag[1][kt], b0, b1);
+        }
+        const float* xa = xb + k * LM_XSTEP + sa * LM_XS + unit;
+        const float* xbq = xa + LM_XS;
+        // accumulator layout: [0]=(row gid, col 2tig) [1]=(gid, 2tig+1) [2]=(gid+8, 2tig) [3]=(gid+8, 2tig+1)
+        const float pi0 = acc[0][0][0] + acc[0][1][0] + xa[0], pi1 = acc[0][0][1] + acc[0][1][1] + xbq[0];
+        const float pf0 = acc[0][0][2] + acc[0][1][2] + xa[64], pf1 = acc[0][0][3] + acc[0][1][3] + xbq[64];
+        const float pg0 = acc[1][0][0] + acc[1][1][0] + xa[128], pg1 = acc[1][0][1] + acc[1][1][1] + xbq[128];
+        const float po0 = acc[1][0][2] + acc[1][1][2] + xa[192], po1 = acc[1][0][3] + acc[1][1][3] + xbq[192];
+        c0 = sigmoid_f(pf0) * c0 + sigmoid_f(pi0) * tanh_f(pg0);
+        c1 = sigmoid_f(pf1) * c1 + sigmoid_f(pi1) * tanh_f(pg1);
+        hl0 = sigmoid_f(po0) * tanh_f(c0);
+        hl1 = sigmoid_f(po1) * tanh_f(c1);
+        const float hr0 = to_tf32(hl0), hr1 = to_tf32(hl1);
+        float* hn = hbuf + (cur ^ 1) * (LM_SEQ * LM_HS);
+        hn[sa * LM_HS + unit] = hr0;
+        hn[sb2 * LM_HS + unit] = hr1;
+        hst[(k * LM_SEQ + sa) * LSTM_H + unit] = hr0;
+        hst[(k * LM_SEQ + sb2) * LSTM_H + unit] = hr1;
+        if (k == nst - 1) asm volatile("cp.async.wait_group 0;" ::: "memory");   // next block's staging has landed
+        __syncthreads();
+        cur ^= 1;
+      }
+    }
+    // flush the block's hidden states: per sequence 16 chunks x steps float4, coalesced along time
+    for (int i = tid; i < LM_SEQ * 16 * LSTM_BLK; i += 256) {
+      const int s = i / (16 * LSTM_BLK);
+      const int ch = (i / LSTM_BLK) % 16;
+      const int kk = i % LSTM_BLK;
+      const int b = seq0 + s;
+      if (b < B && kk < nst)
+        *reinterpret_cast<float4*>(hout + act_off(h_bs, h_Tp, b, ch, t0 + kk)) =
+            *reinterpret_cast<const float4*>(&hst[(kk * LM_SEQ + s) * LSTM_H + 4 * ch]);
+    }
+  }
+  if (state_out != nullptr) {
+    if (seq0 + sa < B) {
+      state_out[(long long)(seq0 + sa) * 2 * LSTM_H + unit] = hl0;
+      state_out[(long long)(seq0 + sa) * 2 * LSTM_H + LSTM_H + unit] = c0;
+    }
+    if (seq0 + sb2 < B) {
+      state_out[(long long)(seq0 + sb2) * 2 * LSTM_H + unit] = hl1;
+      state_out[(long long)(seq0 + sb2) * 2 * LSTM_H + LSTM_H + unit] = c1;
+    }
+  }
+}
+
 int launch_lstm(const Act& xp, const float* whh, const Act& h_out, int B, int T, const float* state_in, float* state_out,
                 cudaStream_t stream) {
   AR_CHECK(T >= 1 && B >= 1, AR_ERR_INVALID, "lstm: empty input");
-  // S sequences per CTA.  S=1 runs two CTAs per SM (register-limited); S=2/4 trade thread-level for
-  // instruction-level parallelism.  AR_LSTM_S overrides the heuristic (tuning knob).
+  // AR_LSTM_S=1|2|4 selects the CUDA-core kernel with S sequences per CTA (cross-check / tuning knob).
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("AR_LSTM_S");
     forced = e ? atoi(e) : 0;
   }
+  // Heuristic: the CUDA-core kernel (one sequence per CTA, two CTAs per SM) while that covers the batch;
+  // beyond two sequences per SM the tensor-core kernel (eight sequences per CTA) wins.  AR_LSTM_S overrides.
+  if (forced == 8 || (forced == 0 && B > 2 * sm_count())) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      AR_CUDA_OK(cudaFuncSetAttribute(lstm_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_SMEM));
+      attr_set = true;
+    }
+    lstm_mma_kernel<<<(B + LM_SEQ - 1) / LM_SEQ, 256, LM_SMEM, stream>>>(xp.base, xp.bs, xp.Tp, whh, h_out.base, h_out.bs, h_out.Tp, B, T,
+                                                                  state_in, state_out);
+    AR_CUDA_OK(cudaGetLastError());
+    return AR_OK;
+  }
   int S = forced ? forced : 1;
-#define AR_LSTM_LAUNCH(SS)                                                                                     \
-  lstm_kernel<SS><<<(B + SS - 1) / SS, 256, 0, stream>>>(xp.base, xp.bs, xp.Tp, whh, h_out.base, h_out.bs, h_out.Tp, B, T, \
-                                                         state_in, state_out)
-  if (S == 4) AR_LSTM_LAUNCH(4);
-  else if (S == 2) AR_LSTM_LAUNCH(2);
-  else AR_LSTM_LAUNCH(1);
+#define AR_LSTM_LAUNCH(SS, PF)                                                                                 \
+  lstm_kernel<SS, PF><<<(B + SS - 1) / SS, 256, 0, stream>>>(xp.base, xp.bs, xp.Tp, whh, h_out.base, h_out.bs, h_out.Tp, B, \
+                                                             T, state_in, state_out)
+  if (S == 4) AR_LSTM_LAUNCH(4, 4);
+  else if (S == 2) AR_LSTM_LAUNCH(2, 4);
+  else AR_LSTM_LAUNCH(1, 8);
 #undef AR_LSTM_LAUNCH
   AR_CUDA_OK(cudaGetLastError());
   return AR_OK;
