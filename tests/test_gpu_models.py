@@ -93,6 +93,19 @@ def test_lstm_state_carry_equals_whole_sequence(models, state_dicts):
     assert_close(cn[0], st[:, 1], "carried c", max_abs=1e-3, min_snr=50.0)
 
 
+def test_stereo_large_batch_tensor_core_lstm(models, state_dicts):
+    """More than two sequences per SM switches the recurrence to the tensor-core (mma.sync TF32) kernel;
+    ragged length (not a multiple of the 8-step block) and a batch that is not a multiple of 8."""
+    m = models("stereo", "umma")
+    x = make_input(301, 203, seed=11)
+    ref, (hn, cn) = oracle.stereo_forward(state_dicts["stereo"], x, return_state=True)
+    with torch.no_grad():
+        y, st = m.forward_with_state(x.cuda())
+    assert_close(ref, y, "stereo B=301 T=203 (tensor-core LSTM)")
+    assert_close(hn[0], st[:, 0], "carried h (tensor-core LSTM)", max_abs=1e-3, min_snr=50.0)
+    assert_close(cn[0], st[:, 1], "carried c (tensor-core LSTM)", max_abs=1e-3, min_snr=50.0)
+
+
 def test_error_behaviour(models, state_dicts):
     den = models("denoiser", "umma")
     with pytest.raises(RuntimeError):          # reference: RuntimeError from max_pool1d for T < 8
