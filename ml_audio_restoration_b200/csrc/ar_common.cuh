@@ -1,6 +1,7 @@
 // Shared definitions for libaudiorestore_sm100: activation layout, conv parameters,
 // the fused conv epilogue and error plumbing.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
@@ -33,67 +34,60 @@ void set_error(const std::string& msg);
   } while (0)
 
 // ----------------------------------------------------------------------------- layout
-// Internal activations are "C4" channel-blocked:  [B][C/4][Tp][4] fp32, where
+// Internal activations are "H8" channel-blocked half precision:  [B][C/8][Tp][8] fp16, where
 //   Tp = HALO + round_up(T, TILE_M) + HALO   rows of 16 bytes,
-// row (HALO + t) of chunk c holds channels 4c..4c+3 at time t.  One conv tap of an
-// implicit-GEMM tile is then a contiguous run of rows, so a tile is fetched with one bulk
-// (TMA) copy per channel chunk and every tap is a 16-byte-granular shift of the UMMA
-// shared-memory descriptor.  Rows outside [0,T) hold garbage in HBM; consumers zero them
-// in shared memory (conv zero padding), producers never write them.
+// row (HALO + t) of chunk c holds channels 8c..8c+7 at time t.  One conv tap of an implicit-GEMM tile is
+// then a contiguous run of rows, so a tile is fetched with one bulk (TMA) copy per channel chunk and every
+// tap is a 16-byte-granular shift of the UMMA shared-memory descriptor.  fp16 carries the same 11-bit
+// significand as TF32 (the tensor core would drop the rest anyway) at half the bytes and twice the K per
+// MMA; values are rounded to nearest and clamped to the fp16 range when stored.  Rows outside [0,T) hold
+// garbage in HBM; consumers zero them in shared memory (conv zero padding), producers never write them.
+// The only fp32 activation tensor is the LSTM gate pre-activation ("C4": [B][C/4][Tp][4] fp32).
 constexpr int TILE_M = 128;
 constexpr int HALO = 8;  // >= max one-sided conv reach: dilation 8 * (3-1)/2
 constexpr float LRELU_SLOPE = 0.2f;
+constexpr float HALF_MAX = 65504.0f;
 
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 __host__ __device__ inline int padded_rows(int T) { return HALO + round_up(T, TILE_M) + HALO; }
 
-struct Act {      // a C4 activation tensor (or a channel window of one)
-  float* base = nullptr;  // element (b=0, chunk 0, row 0 == t=-HALO)
+struct Act {      // an H8 (fp16) activation tensor, or -- when f32 is set -- the C4 fp32 variant
+  void* base = nullptr;   // element (b=0, chunk 0, row 0 == t=-HALO)
   int C = 0;              // channels of the whole buffer
   int T = 0;              // valid length
   int Tp = 0;             // padded rows per chunk
-  long long bs = 0;       // floats between batch items = (C/4)*Tp*4
-  __host__ __device__ size_t floats_per_item() const { return (size_t)(C / 4) * Tp * 4; }
+  long long bs = 0;       // ELEMENTS between batch items = C*Tp
+  int f32 = 0;
+  __host__ __device__ __half* h() const { return reinterpret_cast<__half*>(base); }
+  __host__ __device__ float* f() const { return reinterpret_cast<float*>(base); }
 };
 
-__device__ __forceinline__ long long act_off(long long bs, int Tp, int b, int chunk, int t) {
+// element offsets; `chunk` counts 8-channel (H8) / 4-channel (C4) groups
+__device__ __forceinline__ long long act_off(long long bs, int Tp, int b, int chunk, int t) {        // H8
+  return (long long)b * bs + ((long long)chunk * Tp + (HALO + t)) * 8;
+}
+__device__ __forceinline__ long long act_off4(long long bs, int Tp, int b, int chunk, int t) {       // C4 fp32
   return (long long)b * bs + ((long long)chunk * Tp + (HALO + t)) * 4;
 }
 
-// ----------------------------------------------------------------------------- conv params
-enum ConvMode { MODE_SAME = 0, MODE_INTERLEAVE2 = 1 };
-
-struct ConvParams {
-  // input (C4)
-  const float* in;
-  long long in_bs;
-  int in_Tp, in_coff4;   // chunk offset of the first input channel
-  int Tin;               // valid input length; GEMM rows are input time positions
-  int Cin;               // multiple of 8
-  int taps, dil, pad_left;  // tap j reads input row t + j*dil - pad_left
-  // weights, packed for the UMMA B operand: [n_slices][Cin/8][taps][2][N/n_slices][4] (tf32-rounded fp32)
-  const float* w;
-  const float* bias;     // [N]
-  int N;                 // GEMM N, multiple of 16, <= 256
-  int n_slices;          // column slices the weights are packed in (each is one CTA's resident operand)
-  int cta2;              // packed for the 2-CTA engine: slices (2i, 2i+1) are the two halves of pair-slice i
-  // output (C4)
-  int mode;              // MODE_SAME: out[t]; MODE_INTERLEAVE2: cols [0,N/2)->out[2t], [N/2,N)->out[2t+1]
-  float* out;
-  long long out_bs;
-  int out_Tp, out_coff4;
-  int Tout;              // valid output length
-  float* pool;           // optional max-pool(2,2) copy of the output (MODE_SAME only)
-  long long pool_bs;
-  int pool_Tp, pool_coff4;
-  const float* res;      // optional residual added after the activation (same geometry as out)
-  long long res_bs;
-  int res_Tp, res_coff4;
-  int lrelu;             // LeakyReLU(0.2) after bias
-  int round_tf32;        // round stored values to TF32 (they feed a tensor-core conv)
-  int B;
-  int tiles_per_item;    // ceil(Tin / TILE_M)
-};
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {  // round to nearest, clamp to the fp16 range
+  a = fminf(fmaxf(a, -HALF_MAX), HALF_MAX);
+  b = fminf(fmaxf(b, -HALF_MAX), HALF_MAX);
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint4 pack_half8(const float (&v)[8]) {
+  return make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
+}
+__device__ __forceinline__ void unpack_half8(uint4 u, float (&v)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
 
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t u;
@@ -101,52 +95,83 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float(u);
 }
 
-// Fused epilogue for 4 consecutive GEMM columns [n0, n0+4) of GEMM row t (batch item b).
-// Must be called by all 32 lanes of a warp whose lanes hold consecutive rows (the pool
-// path exchanges neighbours with shuffles); `acc` is the raw accumulator, `resv` the residual
-// operand (ignored unless p.res is set; residual layers are MODE_SAME).
-__device__ __forceinline__ void epilogue_chunk(const ConvParams& p, int b, int t, int n0, float4 acc, float4 resv) {
-  const float4 bias = *reinterpret_cast<const float4*>(p.bias + n0);
-  float v[4] = {acc.x + bias.x, acc.y + bias.y, acc.z + bias.z, acc.w + bias.w};
-  if (p.lrelu) {
+// ----------------------------------------------------------------------------- conv params
+enum ConvMode { MODE_SAME = 0, MODE_INTERLEAVE2 = 1 };
+
+struct ConvParams {
+  // input (H8)
+  const __half* in;
+  long long in_bs;
+  int in_Tp, in_coff8;   // chunk offset of the first input channel
+  int Tin;               // valid input length; GEMM rows are input time positions
+  int Cin;               // multiple of 16
+  int taps, dil, pad_left;  // tap j reads input row t + j*dil - pad_left
+  // weights, packed for the UMMA B operand: [n_slices][Cin/16][taps][2][N/n_slices][8] fp16
+  const __half* w;
+  const float* bias;     // [N] fp32
+  int N;                 // GEMM N, multiple of 16, <= 256
+  int n_slices;          // column slices the weights are packed in (each is one CTA's resident operand)
+  int cta2;              // packed for the 2-CTA engine: slices (2i, 2i+1) are the two halves of pair-slice i
+  // output: H8 fp16, or C4 fp32 when out_f32 (LSTM gate pre-activations)
+  int mode;              // MODE_SAME: out[t]; MODE_INTERLEAVE2: cols [0,N/2)->out[2t], [N/2,N)->out[2t+1]
+  void* out;
+  int out_f32;
+  long long out_bs;
+  int out_Tp, out_coff8; // chunk offset in 8-channel units (in 4-channel units when out_f32)
+  int Tout;              // valid output length
+  __half* pool;          // optional max-pool(2,2) copy of the output (MODE_SAME only), H8
+  long long pool_bs;
+  int pool_Tp, pool_coff8;
+  const __half* res;     // optional residual added after the activation (same geometry as out), H8
+  long long res_bs;
+  int res_Tp, res_coff8;
+  int lrelu;             // LeakyReLU(0.2) after bias
+  int B;
+  int tiles_per_item;    // ceil(Tin / TILE_M)
+};
+
+// Fused epilogue for 8 consecutive GEMM columns [n0, n0+8) of GEMM row t (batch item b), shared by the
+// CUDA-core cross-check engine.  Must be called by all 32 lanes of a warp whose lanes hold consecutive rows
+// (the pool path exchanges neighbours with shuffles); `acc` = raw accumulators, `resv` = residual operand.
+__device__ __forceinline__ void epilogue_chunk8(const ConvParams& p, int b, int t, int n0, const float (&acc)[8], const float (&resv)[8]) {
+  float v[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = v[i] > 0.f ? v[i] : LRELU_SLOPE * v[i];
+  for (int i = 0; i < 8; ++i) {
+    v[i] = acc[i] + p.bias[n0 + i];
+    if (p.lrelu) v[i] = v[i] > 0.f ? v[i] : LRELU_SLOPE * v[i];
+    if (p.res != nullptr) v[i] += resv[i];
   }
-  int trow, chunk;
+  int trow, col;
   if (p.mode == MODE_SAME) {
     trow = t;
-    chunk = n0 >> 2;
+    col = n0;
   } else {
     const int half = p.N >> 1;
     const int phase = n0 >= half;
     trow = 2 * t + phase;
-    chunk = (n0 - phase * half) >> 2;
+    col = n0 - phase * half;
   }
   const bool row_ok = (t < p.Tin) && (trow < p.Tout);
-  if (p.res != nullptr) {  // residual value supplied by the caller (same row / channels as the output)
-    v[0] += resv.x; v[1] += resv.y; v[2] += resv.z; v[3] += resv.w;
+  if (p.out_f32) {
+    float* o = reinterpret_cast<float*>(p.out);
+    if (row_ok) {
+      *reinterpret_cast<float4*>(o + act_off4(p.out_bs, p.out_Tp, b, p.out_coff8 + (col >> 2), trow)) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(o + act_off4(p.out_bs, p.out_Tp, b, p.out_coff8 + (col >> 2) + 1, trow)) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    return;
   }
-  if (p.round_tf32) {
+  __half* o = reinterpret_cast<__half*>(p.out);
+  const uint4 packed = pack_half8(v);
+  if (row_ok) *reinterpret_cast<uint4*>(o + act_off(p.out_bs, p.out_Tp, b, p.out_coff8 + (col >> 3), trow)) = packed;
+  if (p.mode == MODE_INTERLEAVE2 && t == p.Tin - 1 && 2 * p.Tin < p.Tout && n0 < (p.N >> 1))
+    *reinterpret_cast<uint4*>(o + act_off(p.out_bs, p.out_Tp, b, p.out_coff8 + (col >> 3), 2 * p.Tin)) = make_uint4(0u, 0u, 0u, 0u);
+  if (p.pool != nullptr) {  // MaxPool1d(2,2), floor; max of the ROUNDED values == rounded max (rounding is monotonic)
+    float r[8], m[8];
+    unpack_half8(packed, r);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = to_tf32(v[i]);
-  }
-  if (row_ok)
-    *reinterpret_cast<float4*>(p.out + act_off(p.out_bs, p.out_Tp, b, p.out_coff4 + chunk, trow)) =
-        make_float4(v[0], v[1], v[2], v[3]);
-  if (p.mode == MODE_INTERLEAVE2 && t == p.Tin - 1 && 2 * p.Tin < p.Tout) {
-    // right zero-pad column of the up-sampled half when the skip is one sample longer
-    // (denoiser.py:121-122); written once per chunk by the phase-0 call.
-    if (n0 < (p.N >> 1))
-      *reinterpret_cast<float4*>(p.out + act_off(p.out_bs, p.out_Tp, b, p.out_coff4 + chunk, 2 * p.Tin)) =
-          make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  if (p.pool != nullptr) {  // MaxPool1d(2,2), floor (denoiser.py:18,107)
-    float m[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) m[i] = fmaxf(v[i], __shfl_down_sync(0xffffffffu, v[i], 1));
+    for (int i = 0; i < 8; ++i) m[i] = fmaxf(r[i], __shfl_down_sync(0xffffffffu, r[i], 1));
     if (((t & 1) == 0) && (t + 1 < p.Tin))
-      *reinterpret_cast<float4*>(p.pool + act_off(p.pool_bs, p.pool_Tp, b, p.pool_coff4 + chunk, t >> 1)) =
-          make_float4(m[0], m[1], m[2], m[3]);
+      *reinterpret_cast<uint4*>(p.pool + act_off(p.pool_bs, p.pool_Tp, b, p.pool_coff8 + (col >> 3), t >> 1)) = pack_half8(m);
   }
 }
 

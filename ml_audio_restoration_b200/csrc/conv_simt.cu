@@ -1,5 +1,5 @@
-// CUDA-core fp32 conv engine on C4 activations.  Debug cross-check for the tcgen05 engine
-// (AR_ENGINE_SIMT); same ConvParams, same packed weights, same fused epilogue.
+// CUDA-core conv engine on H8 (fp16) activations with fp32 accumulation.  Debug cross-check for the
+// tcgen05 engines (AR_ENGINE_SIMT): same ConvParams, same packed fp16 weights, same fused epilogue.
 #include "ar_common.cuh"
 
 namespace ar {
@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(TILE_M) conv_simt_kernel(const ConvParams p) {
 #pragma unroll
   for (int i = 0; i < SIMT_NB; ++i) acc[i] = 0.f;
 
-  const int kblocks = p.Cin / 8;
+  const int kblocks = p.Cin / 16;
   const int Ns = p.N / p.n_slices;
   const int slice = n_base / Ns, n_loc = n_base % Ns;  // SIMT_NB divides Ns (both multiples of 16)
   for (int kb = 0; kb < kblocks; ++kb) {
@@ -24,27 +24,30 @@ __global__ void __launch_bounds__(TILE_M) conv_simt_kernel(const ConvParams p) {
       const bool ok = (ti >= 0) && (ti < p.Tin);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok) a = *reinterpret_cast<const float4*>(p.in + act_off(p.in_bs, p.in_Tp, b, p.in_coff4 + kb * 2 + h, ti));
-        const float4* w4 = reinterpret_cast<const float4*>(p.w) +
-                           ((size_t)(((slice * kblocks + kb) * p.taps + tap) * 2 + h) * Ns + n_loc);
+        float a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = 0.f;
+        if (ok) unpack_half8(*reinterpret_cast<const uint4*>(p.in + act_off(p.in_bs, p.in_Tp, b, p.in_coff8 + kb * 2 + h, ti)), a);
+        const uint4* w8 = reinterpret_cast<const uint4*>(p.w) +
+                          ((size_t)(((slice * kblocks + kb) * p.taps + tap) * 2 + h) * Ns + n_loc);
 #pragma unroll
         for (int i = 0; i < SIMT_NB; ++i) {
-          const float4 w = __ldg(w4 + i);
-          acc[i] = fmaf(a.x, w.x, acc[i]);
-          acc[i] = fmaf(a.y, w.y, acc[i]);
-          acc[i] = fmaf(a.z, w.z, acc[i]);
-          acc[i] = fmaf(a.w, w.w, acc[i]);
+          float w[8];
+          unpack_half8(__ldg(w8 + i), w);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i] = fmaf(a[j], w[j], acc[i]);
         }
       }
     }
   }
 #pragma unroll
-  for (int c = 0; c < SIMT_NB / 4; ++c) {
-    float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = 0; c < SIMT_NB / 8; ++c) {
+    float rv[8], av[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { rv[i] = 0.f; av[i] = acc[8 * c + i]; }
     if (p.res != nullptr && t < p.Tin)
-      rv = *reinterpret_cast<const float4*>(p.res + act_off(p.res_bs, p.res_Tp, b, p.res_coff4 + ((n_base + 4 * c) >> 2), t));
-    epilogue_chunk(p, b, t, n_base + 4 * c, make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]), rv);
+      unpack_half8(*reinterpret_cast<const uint4*>(p.res + act_off(p.res_bs, p.res_Tp, b, p.res_coff8 + ((n_base + 8 * c) >> 3), t)), rv);
+    epilogue_chunk8(p, b, t, n_base + 8 * c, av, rv);
   }
 }
 

@@ -1,12 +1,12 @@
 // tcgen05 implicit-GEMM Conv1d engine for sm_100a.
 //
 //   D[128 time rows, N out channels] (fp32, TMEM) += sum over taps j, input-channel blocks kb
-//        A_j,kb[128 x 8] (tf32, smem, K-major, no swizzle)  x  B_j,kb[8 x N] (tf32, smem, K-major)
+//        A_j,kb[128 x 16] (fp16, smem, K-major, no swizzle)  x  B_j,kb[16 x N] (fp16, smem, K-major)
 //
-// * Activations live in HBM as C4 ([C/4][Tp][4], see ar_common.cuh), so the rows a tile needs
-//   for ALL taps of one 4-channel chunk are one contiguous run: one cp.async.bulk (TMA, UBLKCP)
+// * Activations live in HBM as H8 ([C/8][Tp][8] fp16, see ar_common.cuh), so the rows a tile needs
+//   for ALL taps of one 8-channel chunk are one contiguous run: one cp.async.bulk (TMA, UBLKCP)
 //   per chunk.  In shared memory chunk c of a stage sits at c*R*16 bytes (R = 128 + reach), which is
-//   exactly the canonical no-swizzle K-major UMMA layout ((8,m),(4,2)) with SBO = 128 B
+//   exactly the canonical no-swizzle K-major UMMA layout ((8,m),(8,2)) with SBO = 128 B
 //   (8 rows x 16 B) and LBO = R*16 B.  Tap j (dilation d) is the same descriptor with its
 //   start address advanced by j*d*16 bytes -- no im2col, no per-tap reload.
 // * Weights are pre-packed per (channel block, tap) as [2][Ns][4] => LBO = Ns*16 B, SBO = 128 B and
@@ -22,6 +22,7 @@
 //   overlaps the MMAs of tile i+1.  Persistent grid: one CTA per SM, static tile striding.
 #include "ar_common.cuh"
 #include "umma_ptx.cuh"
+#include "umma_epilogue.cuh"
 
 namespace ar {
 
@@ -49,7 +50,7 @@ struct UmmaCfg {
 // residual add); LeakyReLU slope and TF32 rounding stay runtime-uniform.  TAPS is a template parameter
 // so the single issuing thread sees a fully unrolled tap loop: the MMAs of a K block go out back to back
 // instead of one per ~15 dependent integer instructions.
-template <int MODE, bool POOL, bool RES, int TAPS>
+template <int MODE, bool POOL, bool RES, bool OUTF32, int TAPS>
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ UmmaCfg cfg, int num_tiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -111,12 +112,12 @@ conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ U
       int s = 0;
       uint32_t ph = 0;
       const uint32_t row_bytes = (uint32_t)(R * 16);
-      const long long chunk_stride = (long long)p.in_Tp * 4;             // floats between channel chunks
+      const long long chunk_stride = (long long)p.in_Tp * 8;             // halves between 8-channel chunks
       const int chunks_per_stage = cfg.kbs * 2;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int b = tile / tpi;
         const int t0 = (tile - b * tpi) * TILE_M;
-        const float* src = p.in + act_off(p.in_bs, p.in_Tp, b, p.in_coff4, t0 - p.pad_left);
+        const __half* src = p.in + act_off(p.in_bs, p.in_Tp, b, p.in_coff8, t0 - p.pad_left);
         for (int ks = 0; ks < cfg.nks; ++ks) {
           const uint32_t fb = full_bar(s);
           mbar_wait(empty_bar(s), ph ^ 1u);
@@ -133,8 +134,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ U
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    // instruction descriptor: D=F32, A=B=TF32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Ns >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+    const uint32_t idesc = make_idesc_f16(TILE_M, Ns);
     const uint64_t a_desc_hi = make_desc(0u, (uint32_t)(R * 16), 128u);
     const uint64_t b_desc_hi = make_desc(0u, (uint32_t)(Ns * 16), 128u);
     mbar_wait(w_bar, 0);
@@ -175,7 +175,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ U
           for (int kb = 0; kb < cfg.kbs; ++kb) {
 #pragma unroll
             for (int j = 0; j < TAPS; ++j) {
-              umma_tf32(d_tmem, a_desc_hi | (uint64_t)(a_addr + (uint32_t)j * dil_u), b_desc_hi | (uint64_t)(b_addr + (uint32_t)j * b_step),
+              umma_f16(d_tmem, a_desc_hi | (uint64_t)(a_addr + (uint32_t)j * dil_u), b_desc_hi | (uint64_t)(b_addr + (uint32_t)j * b_step),
                         idesc, (j == 0) ? accum : 1u);
             }
             accum = 1u;
@@ -200,8 +200,6 @@ conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ U
     const int col_lo = Ns >= 32 ? half * wcols : 0;
     const bool active = Ns >= 32 || half == 0;
     const float slope = p.lrelu ? LRELU_SLOPE : 1.0f;
-    const bool rnd = p.round_tf32 != 0;
-    const long long ostride = (long long)p.out_Tp * 4;   // floats between channel chunks
     const int gcol0 = slice * Ns + col_lo;               // first global GEMM column of this warp
     int tl = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tl) {
@@ -209,78 +207,14 @@ conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ U
       const int t = (tile % tpi) * TILE_M + q * 32 + lane;
       const int buf = tl & 1;
       const uint32_t aph = (uint32_t)(tl >> 1) & 1u;
-      const bool in_ok = t < p.Tin;
-      // hoisted output row pointers
-      float* orow0;
-      float* orow1 = nullptr;
-      bool ok0, ok1 = false;
-      int chunk0;
-      if (MODE == MODE_SAME) {
-        chunk0 = gcol0 >> 2;
-        orow0 = p.out + act_off(p.out_bs, p.out_Tp, b, p.out_coff4 + chunk0, t);
-        ok0 = in_ok && t < p.Tout;
-      } else {
-        // columns [0,N/2) -> row 2t, [N/2,N) -> row 2t+1; a warp's column range never straddles N/2
-        const int hN = p.N >> 1;
-        const int phase = gcol0 >= hN;
-        chunk0 = (gcol0 - phase * hN) >> 2;
-        orow0 = p.out + act_off(p.out_bs, p.out_Tp, b, p.out_coff4 + chunk0, 2 * t + phase);
-        ok0 = in_ok && (2 * t + phase) < p.Tout;
-        // right zero-pad column when the skip tensor is one sample longer (denoiser.py:121-122)
-        ok1 = (phase == 0) && (t == p.Tin - 1) && (2 * p.Tin < p.Tout);
-        orow1 = p.out + act_off(p.out_bs, p.out_Tp, b, p.out_coff4 + chunk0, 2 * p.Tin);
-      }
-      float* prow = nullptr;
-      bool pok = false;
-      if (POOL) {
-        prow = p.pool + act_off(p.pool_bs, p.pool_Tp, b, p.pool_coff4 + chunk0, t >> 1);
-        pok = ((t & 1) == 0) && (t + 1 < p.Tin);
-      }
-      // residual operand (SR trunk, Ns == 32 => 16 columns per warp): fetched before the accumulator is
-      // ready so the global-load latency hides behind the MMAs
-      float4 resv[4];
-      if (RES) {
-        const float* rrow = p.res + act_off(p.res_bs, p.res_Tp, b, p.res_coff4 + chunk0, t);
-        const long long rstride = (long long)p.res_Tp * 4;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          resv[c] = (in_ok && active) ? *reinterpret_cast<const float4*>(rrow + c * rstride) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      const EpiRow row = epi_row<MODE, POOL, RES, OUTF32>(p, b, t, gcol0);
+      uint4 resv[2];
+      epi_prefetch_res<RES>(row, active, resv);
       mbar_wait(tfull_bar(buf), aph);
       tc_fence_after();
       if (active) {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * cfg.ncol + col_lo);
-        for (int cb = 0; cb < wcols; cb += 32) {
-          uint32_t r[32];
-          const int ncol = wcols - cb < 32 ? 16 : 32;     // wcols is 16 or a multiple of 32... or 48? no: 16,32,64,128
-          if (ncol == 32) tmem_ld32_nowait(taddr + cb, r);
-          else tmem_ld16_nowait(taddr + cb, r);
-          tmem_wait_ld();
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            if (4 * c < ncol) {
-              const float4 bz = *reinterpret_cast<const float4*>(s_bias + col_lo + cb + 4 * c);
-              float v0 = __uint_as_float(r[4 * c]) + bz.x, v1 = __uint_as_float(r[4 * c + 1]) + bz.y;
-              float v2 = __uint_as_float(r[4 * c + 2]) + bz.z, v3 = __uint_as_float(r[4 * c + 3]) + bz.w;
-              v0 = fmaxf(v0, slope * v0); v1 = fmaxf(v1, slope * v1);
-              v2 = fmaxf(v2, slope * v2); v3 = fmaxf(v3, slope * v3);
-              if (RES) { v0 += resv[c & 3].x; v1 += resv[c & 3].y; v2 += resv[c & 3].z; v3 += resv[c & 3].w; }
-              if (rnd) { v0 = to_tf32(v0); v1 = to_tf32(v1); v2 = to_tf32(v2); v3 = to_tf32(v3); }
-              const long long coff = (long long)((cb >> 2) + c) * ostride;
-              if (ok0) *reinterpret_cast<float4*>(orow0 + coff) = make_float4(v0, v1, v2, v3);
-              if (MODE == MODE_INTERLEAVE2) {
-                if (ok1) *reinterpret_cast<float4*>(orow1 + coff) = make_float4(0.f, 0.f, 0.f, 0.f);
-              }
-              if (POOL) {  // MaxPool1d(2,2), floor: rows (t, t+1) live in neighbouring lanes
-                const float m0 = fmaxf(v0, __shfl_down_sync(0xffffffffu, v0, 1));
-                const float m1 = fmaxf(v1, __shfl_down_sync(0xffffffffu, v1, 1));
-                const float m2 = fmaxf(v2, __shfl_down_sync(0xffffffffu, v2, 1));
-                const float m3 = fmaxf(v3, __shfl_down_sync(0xffffffffu, v3, 1));
-                if (pok) *reinterpret_cast<float4*>(prow + (long long)((cb >> 2) + c) * ((long long)p.pool_Tp * 4)) = make_float4(m0, m1, m2, m3);
-              }
-            }
-          }
-        }
+        epi_store<MODE, POOL, RES, OUTF32>(row, s_bias + col_lo, taddr, wcols, slope, resv);
       }
       tc_fence_before();
       __syncwarp();
@@ -301,17 +235,17 @@ static bool pick_cfg(const ConvParams& p, UmmaCfg& c) {
   while (ncol < Ns) ncol <<= 1;
   c.ncol = ncol;
   c.tmem_cols = 2 * ncol;
-  c.w_bytes = p.Cin * p.taps * Ns * 4;
+  c.w_bytes = p.Cin * p.taps * Ns * 2;
   const int room = SMEM_BUDGET - BAR_BYTES - BIAS_BYTES - c.w_bytes;
   for (int kbs = 4; kbs >= 1; kbs >>= 1) {
-    if (p.Cin % (8 * kbs)) continue;
+    if (p.Cin % (16 * kbs)) continue;
     c.kbs = kbs;
     c.a_bytes = c.stage_bytes = kbs * 2 * c.R * 16;
     int stages = room / c.stage_bytes;
     if (stages > 8) stages = 8;
     if (stages >= 4 || (kbs == 1 && stages >= 2)) {
       c.stages = stages;
-      c.nks = p.Cin / (8 * kbs);
+      c.nks = p.Cin / (16 * kbs);
       c.smem_bytes = c.w_bytes + stages * c.stage_bytes + BAR_BYTES + BIAS_BYTES;
       return true;
     }
@@ -331,7 +265,7 @@ int sm_count() {
 }
 
 int launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
-  AR_CHECK(p.Cin % 8 == 0 && p.n_slices >= 1 && p.N % (16 * p.n_slices) == 0 && p.N >= 16 && p.N <= 256, AR_ERR_INVALID,
+  AR_CHECK(p.Cin % 16 == 0 && p.n_slices >= 1 && p.N % (16 * p.n_slices) == 0 && p.N >= 16 && p.N <= 256, AR_ERR_INVALID,
            "conv_umma: unsupported channel counts");
   AR_CHECK(p.res == nullptr || p.N / p.n_slices <= 32, AR_ERR_INVALID, "conv_umma: residual epilogue supports at most 32 columns per slice");
   AR_CHECK(p.pad_left <= HALO && (p.taps - 1) * p.dil - p.pad_left <= HALO, AR_ERR_INVALID, "conv_umma: conv reach exceeds HALO");
@@ -346,19 +280,21 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
   if (groups > num_tiles) groups = num_tiles;
   const int grid = groups * p.n_slices;
   using Kernel = void (*)(ConvParams, UmmaCfg, int);
-  struct Entry { int variant, taps; Kernel k; };   // variant: 0 plain, 1 pool, 2 residual, 3 interleave
+  struct Entry { int variant, taps; Kernel k; };
   static const Entry table[] = {
-      {0, 1, conv_umma_kernel<MODE_SAME, false, false, 1>}, {0, 3, conv_umma_kernel<MODE_SAME, false, false, 3>},
-      {0, 5, conv_umma_kernel<MODE_SAME, false, false, 5>}, {0, 7, conv_umma_kernel<MODE_SAME, false, false, 7>},
-      {1, 3, conv_umma_kernel<MODE_SAME, true, false, 3>},  {2, 3, conv_umma_kernel<MODE_SAME, false, true, 3>},
-      {3, 1, conv_umma_kernel<MODE_INTERLEAVE2, false, false, 1>}, {3, 3, conv_umma_kernel<MODE_INTERLEAVE2, false, false, 3>},
+      {EV_PLAIN, 1, conv_umma_kernel<MODE_SAME, false, false, false, 1>}, {EV_PLAIN, 3, conv_umma_kernel<MODE_SAME, false, false, false, 3>},
+      {EV_PLAIN, 5, conv_umma_kernel<MODE_SAME, false, false, false, 5>}, {EV_PLAIN, 7, conv_umma_kernel<MODE_SAME, false, false, false, 7>},
+      {EV_POOL, 3, conv_umma_kernel<MODE_SAME, true, false, false, 3>},   {EV_RES, 3, conv_umma_kernel<MODE_SAME, false, true, false, 3>},
+      {EV_INTERLEAVE, 1, conv_umma_kernel<MODE_INTERLEAVE2, false, false, false, 1>},
+      {EV_INTERLEAVE, 3, conv_umma_kernel<MODE_INTERLEAVE2, false, false, false, 3>},
+      {EV_F32, 1, conv_umma_kernel<MODE_SAME, false, false, true, 1>},
   };
   static bool attr_set = false;
   if (!attr_set) {
     for (const Entry& e : table) AR_CUDA_OK(cudaFuncSetAttribute(e.k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
     attr_set = true;
   }
-  const int variant = p.mode == MODE_INTERLEAVE2 ? 3 : (p.pool ? 1 : (p.res ? 2 : 0));
+  const int variant = epi_variant(p);
   Kernel kernel = nullptr;
   for (const Entry& e : table)
     if (e.variant == variant && e.taps == p.taps) kernel = e.k;

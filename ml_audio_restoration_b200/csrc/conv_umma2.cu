@@ -1,8 +1,8 @@
 // 2-CTA (cta_group::2) variant of the tcgen05 implicit-GEMM Conv1d engine.
 //
 // A cluster of two CTAs (an SM pair) computes TWO adjacent 128-row time tiles with ONE instruction
-// stream: D[256 x Ns] += A[256 x 8] * B[8 x Ns] per `tcgen05.mma.cta_group::2`.  Each CTA keeps in its
-// own shared memory (a) the activation rows of its own tile (same C4 / no-swizzle K-major layout and
+// stream: D[256 x Ns] (fp32, TMEM) += A[256 x 16] * B[16 x Ns] (fp16) per `tcgen05.mma.cta_group::2.kind::f16`.  Each CTA keeps in its
+// own shared memory (a) the activation rows of its own tile (same H8 / no-swizzle K-major layout and
 // tap-shift trick as conv_umma.cu) and (b) HALF of the weight columns (Ns/2), and in its own TMEM the
 // 128 accumulator rows of its tile.  Compared with the 1-CTA kernel this halves the number of MMA
 // instructions per tile (the layers here are bound by the fixed per-MMA operand fetch, not by FLOPs)
@@ -16,6 +16,7 @@
 // collected in the leader from the epilogue warps of both CTAs.
 #include "ar_common.cuh"
 #include "umma_ptx.cuh"
+#include "umma_epilogue.cuh"
 
 namespace ar {
 
@@ -27,12 +28,12 @@ constexpr int BIAS2_BYTES = 1024;
 
 struct Umma2Cfg {
   int kbs, stages, R;
-  int w_bytes;      // resident weights per CTA: Cin*taps*(Ns/2)*4
+  int w_bytes;      // resident weights per CTA: Cin*taps*(Ns/2)*2
   int stage_bytes;  // activation stage per CTA
   int ncol, tmem_cols, nks, smem_bytes;
 };
 
-template <int MODE, bool POOL, bool RES, int TAPS>
+template <int MODE, bool POOL, bool RES, bool OUTF32, int TAPS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UMMA2_THREADS, 1)
 conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ Umma2Cfg cfg, int num_pairs) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -100,14 +101,14 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
       int s = 0;
       uint32_t ph = 0;
       const uint32_t row_bytes = (uint32_t)(R * 16);
-      const long long chunk_stride = (long long)p.in_Tp * 4;
+      const long long chunk_stride = (long long)p.in_Tp * 8;             // halves between 8-channel chunks
       const int chunks_per_stage = cfg.kbs * 2;
       for (int pr = pair0; pr < num_pairs; pr += pair_step) {
         const int b = pr / ppi;
         int tl_in_item = (pr - b * ppi) * 2 + (int)rank;
         if (tl_in_item > tpi - 1) tl_in_item = tpi - 1;   // odd tile count: the idle half re-reads a valid tile (all its rows get zeroed)
         const int t0 = tl_in_item * TILE_M;
-        const float* src = p.in + act_off(p.in_bs, p.in_Tp, b, p.in_coff4, t0 - p.pad_left);
+        const __half* src = p.in + act_off(p.in_bs, p.in_Tp, b, p.in_coff8, t0 - p.pad_left);
         for (int ks = 0; ks < cfg.nks; ++ks) {
           const uint32_t fb = full_bar(s);
           mbar_wait(empty_bar(s), ph ^ 1u);
@@ -124,8 +125,7 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA warp
-    // idesc: D=F32, A=B=TF32, K-major, N>>3 at [17,23), M>>4 at [24,29) with M = 256 (both CTAs)
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Ns >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    const uint32_t idesc = make_idesc_f16(256, Ns);          // M = 256: both CTAs' 128 rows
     const uint64_t a_desc_hi = make_desc(0u, (uint32_t)(R * 16), 128u);
     const uint64_t b_desc_hi = make_desc(0u, (uint32_t)(Nh * 16), 128u);
     mbar_wait(w_bar, 0);
@@ -181,7 +181,7 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
             for (int kb = 0; kb < cfg.kbs; ++kb) {
 #pragma unroll
               for (int j = 0; j < TAPS; ++j)
-                umma2_tf32(d_tmem, a_desc_hi | (uint64_t)(a_addr + (uint32_t)j * dil_u),
+                umma2_f16(d_tmem, a_desc_hi | (uint64_t)(a_addr + (uint32_t)j * dil_u),
                            b_desc_hi | (uint64_t)(b_addr + (uint32_t)j * b_step), idesc, (j == 0) ? accum : 1u);
               accum = 1u;
               b_addr += (uint32_t)TAPS * b_step;
@@ -203,8 +203,6 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
     const int col_lo = Ns >= 32 ? half * wcols : 0;
     const bool active = Ns >= 32 || half == 0;
     const float slope = p.lrelu ? LRELU_SLOPE : 1.0f;
-    const bool rnd = p.round_tf32 != 0;
-    const long long ostride = (long long)p.out_Tp * 4;
     const int gcol0 = slice * Ns + col_lo;
     const uint32_t tempty_leader0 = mapa_u32(tempty_bar(0), 0);
     const uint32_t tempty_leader1 = mapa_u32(tempty_bar(1), 0);
@@ -215,73 +213,14 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
       const int t = tl_in_item * TILE_M + q * 32 + lane;   // >= Tin for a dead tile => every store is masked
       const int buf = tl & 1;
       const uint32_t aph = (uint32_t)(tl >> 1) & 1u;
-      const bool in_ok = t < p.Tin;
-      float* orow0;
-      float* orow1 = nullptr;
-      bool ok0, ok1 = false;
-      int chunk0;
-      if (MODE == MODE_SAME) {
-        chunk0 = gcol0 >> 2;
-        orow0 = p.out + act_off(p.out_bs, p.out_Tp, b, p.out_coff4 + chunk0, in_ok ? t : 0);
-        ok0 = in_ok && t < p.Tout;
-      } else {
-        const int hN = p.N >> 1;
-        const int phase = gcol0 >= hN;
-        chunk0 = (gcol0 - phase * hN) >> 2;
-        orow0 = p.out + act_off(p.out_bs, p.out_Tp, b, p.out_coff4 + chunk0, in_ok ? 2 * t + phase : 0);
-        ok0 = in_ok && (2 * t + phase) < p.Tout;
-        ok1 = (phase == 0) && (t == p.Tin - 1) && (2 * p.Tin < p.Tout);
-        orow1 = p.out + act_off(p.out_bs, p.out_Tp, b, p.out_coff4 + chunk0, 2 * p.Tin);
-      }
-      float* prow = nullptr;
-      bool pok = false;
-      if (POOL) {
-        prow = p.pool + act_off(p.pool_bs, p.pool_Tp, b, p.pool_coff4 + chunk0, in_ok ? (t >> 1) : 0);
-        pok = ((t & 1) == 0) && (t + 1 < p.Tin);
-      }
-      float4 resv[4];
-      if (RES) {
-        const float* rrow = p.res + act_off(p.res_bs, p.res_Tp, b, p.res_coff4 + chunk0, in_ok ? t : 0);
-        const long long rstride = (long long)p.res_Tp * 4;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          resv[c] = (in_ok && active) ? *reinterpret_cast<const float4*>(rrow + c * rstride) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      const EpiRow row = epi_row<MODE, POOL, RES, OUTF32>(p, b, t, gcol0);
+      uint4 resv[2];
+      epi_prefetch_res<RES>(row, active, resv);
       mbar_wait(tfull_bar(buf), aph);
       tc_fence_after();
       if (active) {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * cfg.ncol + col_lo);
-        for (int cb = 0; cb < wcols; cb += 32) {
-          uint32_t r[32];
-          const int ncol = wcols - cb < 32 ? 16 : 32;
-          if (ncol == 32) tmem_ld32_nowait(taddr + cb, r);
-          else tmem_ld16_nowait(taddr + cb, r);
-          tmem_wait_ld();
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            if (4 * c < ncol) {
-              const float4 bz = *reinterpret_cast<const float4*>(s_bias + col_lo + cb + 4 * c);
-              float v0 = __uint_as_float(r[4 * c]) + bz.x, v1 = __uint_as_float(r[4 * c + 1]) + bz.y;
-              float v2 = __uint_as_float(r[4 * c + 2]) + bz.z, v3 = __uint_as_float(r[4 * c + 3]) + bz.w;
-              v0 = fmaxf(v0, slope * v0); v1 = fmaxf(v1, slope * v1);
-              v2 = fmaxf(v2, slope * v2); v3 = fmaxf(v3, slope * v3);
-              if (RES) { v0 += resv[c & 3].x; v1 += resv[c & 3].y; v2 += resv[c & 3].z; v3 += resv[c & 3].w; }
-              if (rnd) { v0 = to_tf32(v0); v1 = to_tf32(v1); v2 = to_tf32(v2); v3 = to_tf32(v3); }
-              const long long coff = (long long)((cb >> 2) + c) * ostride;
-              if (ok0) *reinterpret_cast<float4*>(orow0 + coff) = make_float4(v0, v1, v2, v3);
-              if (MODE == MODE_INTERLEAVE2) {
-                if (ok1) *reinterpret_cast<float4*>(orow1 + coff) = make_float4(0.f, 0.f, 0.f, 0.f);
-              }
-              if (POOL) {
-                const float m0 = fmaxf(v0, __shfl_down_sync(0xffffffffu, v0, 1));
-                const float m1 = fmaxf(v1, __shfl_down_sync(0xffffffffu, v1, 1));
-                const float m2 = fmaxf(v2, __shfl_down_sync(0xffffffffu, v2, 1));
-                const float m3 = fmaxf(v3, __shfl_down_sync(0xffffffffu, v3, 1));
-                if (pok) *reinterpret_cast<float4*>(prow + (long long)((cb >> 2) + c) * ((long long)p.pool_Tp * 4)) = make_float4(m0, m1, m2, m3);
-              }
-            }
-          }
-        }
+        epi_store<MODE, POOL, RES, OUTF32>(row, s_bias + col_lo, taddr, wcols, slope, resv);
       }
       tc_fence_before();
       __syncwarp();
@@ -303,17 +242,17 @@ static bool pick_cfg2(const ConvParams& p, Umma2Cfg& c) {
   while (ncol < Ns) ncol <<= 1;
   c.ncol = ncol;
   c.tmem_cols = 2 * ncol;
-  c.w_bytes = p.Cin * p.taps * (Ns / 2) * 4;
+  c.w_bytes = p.Cin * p.taps * (Ns / 2) * 2;
   const int room = SMEM2_BUDGET - BAR2_BYTES - BIAS2_BYTES - c.w_bytes;
   for (int kbs = 4; kbs >= 1; kbs >>= 1) {
-    if (p.Cin % (8 * kbs)) continue;
+    if (p.Cin % (16 * kbs)) continue;
     c.kbs = kbs;
     c.stage_bytes = kbs * 2 * c.R * 16;
     int stages = room / c.stage_bytes;
     if (stages > 8) stages = 8;
     if (stages >= 4 || (kbs == 1 && stages >= 2)) {
       c.stages = stages;
-      c.nks = p.Cin / (8 * kbs);
+      c.nks = p.Cin / (16 * kbs);
       c.smem_bytes = c.w_bytes + stages * c.stage_bytes + BAR2_BYTES + BIAS2_BYTES;
       return true;
     }
@@ -325,7 +264,7 @@ int launch_conv_umma2(const ConvParams& p, cudaStream_t stream) {
   AR_CHECK(p.cta2 && p.n_slices >= 2 && (p.n_slices & 1) == 0, AR_ERR_INVALID, "conv_umma2: layer is not packed for the 2-CTA engine");
   const int nsl = p.n_slices / 2;
   const int Ns = p.N / nsl;
-  AR_CHECK(p.Cin % 8 == 0 && p.N % (32 * nsl) == 0 && Ns >= 32 && Ns <= 256, AR_ERR_INVALID, "conv_umma2: unsupported channel counts");
+  AR_CHECK(p.Cin % 16 == 0 && p.N % (32 * nsl) == 0 && Ns >= 32 && Ns <= 256, AR_ERR_INVALID, "conv_umma2: unsupported channel counts");
   AR_CHECK(p.res == nullptr || Ns <= 32, AR_ERR_INVALID, "conv_umma2: residual epilogue supports at most 32 columns per slice");
   AR_CHECK(p.pad_left <= HALO && (p.taps - 1) * p.dil - p.pad_left <= HALO, AR_ERR_INVALID, "conv_umma2: conv reach exceeds HALO");
   AR_CHECK(p.mode == MODE_SAME || (p.pool == nullptr && p.res == nullptr), AR_ERR_INVALID, "conv_umma2: interleave mode has no pool/residual epilogue");
@@ -336,17 +275,19 @@ int launch_conv_umma2(const ConvParams& p, cudaStream_t stream) {
   using Kernel = void (*)(ConvParams, Umma2Cfg, int);
   struct Entry { int variant, taps; Kernel k; };
   static const Entry table[] = {
-      {0, 1, conv_umma2_kernel<MODE_SAME, false, false, 1>}, {0, 3, conv_umma2_kernel<MODE_SAME, false, false, 3>},
-      {0, 5, conv_umma2_kernel<MODE_SAME, false, false, 5>}, {0, 7, conv_umma2_kernel<MODE_SAME, false, false, 7>},
-      {1, 3, conv_umma2_kernel<MODE_SAME, true, false, 3>},  {2, 3, conv_umma2_kernel<MODE_SAME, false, true, 3>},
-      {3, 1, conv_umma2_kernel<MODE_INTERLEAVE2, false, false, 1>}, {3, 3, conv_umma2_kernel<MODE_INTERLEAVE2, false, false, 3>},
+      {EV_PLAIN, 1, conv_umma2_kernel<MODE_SAME, false, false, false, 1>}, {EV_PLAIN, 3, conv_umma2_kernel<MODE_SAME, false, false, false, 3>},
+      {EV_PLAIN, 5, conv_umma2_kernel<MODE_SAME, false, false, false, 5>}, {EV_PLAIN, 7, conv_umma2_kernel<MODE_SAME, false, false, false, 7>},
+      {EV_POOL, 3, conv_umma2_kernel<MODE_SAME, true, false, false, 3>},   {EV_RES, 3, conv_umma2_kernel<MODE_SAME, false, true, false, 3>},
+      {EV_INTERLEAVE, 1, conv_umma2_kernel<MODE_INTERLEAVE2, false, false, false, 1>},
+      {EV_INTERLEAVE, 3, conv_umma2_kernel<MODE_INTERLEAVE2, false, false, false, 3>},
+      {EV_F32, 1, conv_umma2_kernel<MODE_SAME, false, false, true, 1>},
   };
   static bool attr_set = false;
   if (!attr_set) {
     for (const Entry& e : table) AR_CUDA_OK(cudaFuncSetAttribute(e.k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BUDGET));
     attr_set = true;
   }
-  const int variant = p.mode == MODE_INTERLEAVE2 ? 3 : (p.pool ? 1 : (p.res ? 2 : 0));
+  const int variant = epi_variant(p);
   Kernel kernel = nullptr;
   for (const Entry& e : table)
     if (e.variant == variant && e.taps == p.taps) kernel = e.k;

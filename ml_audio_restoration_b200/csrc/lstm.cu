@@ -51,7 +51,7 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
 template <int S, int PF>
 __global__ void __launch_bounds__(256, (S <= 2) ? 2 : 1)
 lstm_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const float* __restrict__ whh,
-            float* __restrict__ hout, long long h_bs, int h_Tp, int B, int T,
+            __half* __restrict__ hout, long long h_bs, int h_Tp, int B, int T,
             const float* __restrict__ state_in, float* __restrict__ state_out) {
   __shared__ __align__(16) float hbuf[2][S][LSTM_H];
   __shared__ __align__(16) float hstage[2][S][LSTM_BLK][LSTM_H];
@@ -82,7 +82,7 @@ lstm_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const floa
       c[s] = state_in[(long long)b * 2 * LSTM_H + LSTM_H + unit];
     }
     if (gate == 0) hbuf[0][s][unit] = h0;
-    xrow[s] = xp + act_off(xp_bs, xp_Tp, b, row >> 2, 0) + (row & 3);
+    xrow[s] = xp + act_off4(xp_bs, xp_Tp, b, row >> 2, 0) + (row & 3);
   }
   __syncthreads();
 
@@ -151,18 +151,19 @@ lstm_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const floa
         __syncthreads();
         cur ^= 1;
         if ((t & 7) == 7 || t == T - 1) {
-          // flush up to 8 finished steps: [16 chunks][steps] float4 per sequence, coalesced along time
+          // flush up to 8 finished steps: [8 chunks][steps] x 16 bytes per sequence, coalesced along time
           const int tb = t & ~7;
           const int nst = t - tb + 1;
-          for (int i = tid; i < S * 16 * LSTM_BLK; i += 256) {
-            const int s = i / (16 * LSTM_BLK);
-            const int ch = (i / LSTM_BLK) % 16;
+          for (int i = tid; i < S * 8 * LSTM_BLK; i += 256) {
+            const int s = i / (8 * LSTM_BLK);
+            const int ch = (i / LSTM_BLK) % 8;
             const int kk = i % LSTM_BLK;
             const int b = seq0 + s;
             if (b < B && kk < nst) {
-              const float4 v = *reinterpret_cast<const float4*>(&hstage[sb][s][kk][4 * ch]);
-              *reinterpret_cast<float4*>(hout + act_off(h_bs, h_Tp, b, ch, tb + kk)) =
-                  make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+              const float4 v0 = *reinterpret_cast<const float4*>(&hstage[sb][s][kk][8 * ch]);
+              const float4 v1 = *reinterpret_cast<const float4*>(&hstage[sb][s][kk][8 * ch + 4]);
+              const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+              *reinterpret_cast<uint4*>(hout + act_off(h_bs, h_Tp, b, ch, tb + kk)) = pack_half8(v);
             }
           }
         }
@@ -217,7 +218,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 
 __global__ void __launch_bounds__(256, 1)
 lstm_mma_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const float* __restrict__ whh,
-                float* __restrict__ hout, long long h_bs, int h_Tp, int B, int T,
+                __half* __restrict__ hout, long long h_bs, int h_Tp, int B, int T,
                 const float* __restrict__ state_in, float* __restrict__ state_out) {
   extern __shared__ __align__(16) float lm_smem[];
   float* const xs = lm_smem;                                   // [2][8 steps][8 seq][260]: staged gate pre-activations
@@ -271,7 +272,7 @@ lstm_mma_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const 
       const int sq = run >> 6, ch = run & 63;
       const int b = min(seq0 + sq, B - 1);
       const int t = min(t0 + k, T - 1);
-      cp_async16(dst0 + (uint32_t)((k * LM_XSTEP + sq * LM_XS + ch * 4) * 4), xp + act_off(xp_bs, xp_Tp, b, ch, t));
+      cp_async16(dst0 + (uint32_t)((k * LM_XSTEP + sq * LM_XS + ch * 4) * 4), xp + act_off4(xp_bs, xp_Tp, b, ch, t));
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -316,7 +317,8 @@ lstm_mma_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const 
         c1 = sigmoid_f(pf1) * c1 + sigmoid_f(pi1) * tanh_f(pg1);
         hl0 = sigmoid_f(po0) * tanh_f(c0);
         hl1 = sigmoid_f(po1) * tanh_f(c1);
-        const float hr0 = to_tf32(hl0), hr1 = to_tf32(hl1);
+        // fed-back h == the fp16-rounded value the decoder convs will read (exactly representable in TF32)
+        const float hr0 = __half2float(__float2half_rn(hl0)), hr1 = __half2float(__float2half_rn(hl1));
         float* hn = hbuf + (cur ^ 1) * (LM_SEQ * LM_HS);
         hn[sa * LM_HS + unit] = hr0;
         hn[sb2 * LM_HS + unit] = hr1;
@@ -327,15 +329,19 @@ lstm_mma_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const 
         cur ^= 1;
       }
     }
-    // flush the block's hidden states: per sequence 16 chunks x steps float4, coalesced along time
-    for (int i = tid; i < LM_SEQ * 16 * LSTM_BLK; i += 256) {
-      const int s = i / (16 * LSTM_BLK);
-      const int ch = (i / LSTM_BLK) % 16;
+    // flush the block's hidden states: per sequence 8 chunks x steps x 16 bytes, coalesced along time
+    for (int i = tid; i < LM_SEQ * 8 * LSTM_BLK; i += 256) {
+      const int s = i / (8 * LSTM_BLK);
+      const int ch = (i / LSTM_BLK) % 8;
       const int kk = i % LSTM_BLK;
       const int b = seq0 + s;
-      if (b < B && kk < nst)
-        *reinterpret_cast<float4*>(hout + act_off(h_bs, h_Tp, b, ch, t0 + kk)) =
-            *reinterpret_cast<const float4*>(&hst[(kk * LM_SEQ + s) * LSTM_H + 4 * ch]);
+      if (b < B && kk < nst) {
+        const float* src = &hst[(kk * LM_SEQ + s) * LSTM_H + 8 * ch];
+        const float4 v0 = *reinterpret_cast<const float4*>(src);
+        const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
+        const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        *reinterpret_cast<uint4*>(hout + act_off(h_bs, h_Tp, b, ch, t0 + kk)) = pack_half8(v);
+      }
     }
   }
   if (state_out != nullptr) {
@@ -367,14 +373,14 @@ int launch_lstm(const Act& xp, const float* whh, const Act& h_out, int B, int T,
       AR_CUDA_OK(cudaFuncSetAttribute(lstm_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_SMEM));
       attr_set = true;
     }
-    lstm_mma_kernel<<<(B + LM_SEQ - 1) / LM_SEQ, 256, LM_SMEM, stream>>>(xp.base, xp.bs, xp.Tp, whh, h_out.base, h_out.bs, h_out.Tp, B, T,
+    lstm_mma_kernel<<<(B + LM_SEQ - 1) / LM_SEQ, 256, LM_SMEM, stream>>>(xp.f(), xp.bs, xp.Tp, whh, h_out.h(), h_out.bs, h_out.Tp, B, T,
                                                                   state_in, state_out);
     AR_CUDA_OK(cudaGetLastError());
     return AR_OK;
   }
   int S = forced ? forced : 1;
 #define AR_LSTM_LAUNCH(SS, PF)                                                                                 \
-  lstm_kernel<SS, PF><<<(B + SS - 1) / SS, 256, 0, stream>>>(xp.base, xp.bs, xp.Tp, whh, h_out.base, h_out.bs, h_out.Tp, B, \
+  lstm_kernel<SS, PF><<<(B + SS - 1) / SS, 256, 0, stream>>>(xp.f(), xp.bs, xp.Tp, whh, h_out.h(), h_out.bs, h_out.Tp, B, \
                                                              T, state_in, state_out)
   if (S == 4) AR_LSTM_LAUNCH(4, 4);
   else if (S == 2) AR_LSTM_LAUNCH(2, 4);

@@ -1,6 +1,7 @@
 // Host side of libaudiorestore_sm100: state_dict -> folded / packed device weights, the
 // workspace planner, and the three model forwards + the chain expressed as kernel sequences.
 #include <cmath>
+#include <cuda_fp16.h>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -25,12 +26,13 @@ int set_engine(int e) {
 }
 
 // ============================================================================ weight folding / packing
-static float tf32_round_host(float x) {  // round-to-nearest (ties away), like cvt.rna.tf32.f32
-  uint32_t u;
-  std::memcpy(&u, &x, 4);
-  if ((u & 0x7F800000u) != 0x7F800000u) u = (u + 0x1000u) & 0xFFFFE000u;
-  std::memcpy(&x, &u, 4);
-  return x;
+static uint16_t half_bits_host(float x) {  // fp32 -> fp16, round to nearest even, clamped to the finite range
+  if (x > 65504.f) x = 65504.f;
+  if (x < -65504.f) x = -65504.f;
+  const __half h = __float2half_rn(x);
+  uint16_t b;
+  std::memcpy(&b, &h, 2);
+  return b;
 }
 
 struct Table {
@@ -67,12 +69,12 @@ struct ConvLayer {  // device-resident packed layer
   int cta2;             // slices come in (2i, 2i+1) pairs: the two halves of a 2-CTA pair-slice
 };
 
-// Resident-weight budget per CTA: fewest column slices that still leave >= ~28 KB of the 227 KB for the
-// activation ring (a 128x128 k3 layer, 192 KB, stays unsliced: full-N MMAs beat a deeper ring).
-constexpr size_t W_SLICE_BUDGET = 197 * 1024;
+// Resident-weight budget per CTA (fp16 weights): leaves >= ~96 KB of the 227 KB for the activation ring.
+// With the 2-CTA engine every layer of the three models fits unsliced (largest: 256x256 k3 = 192 KB / CTA).
+constexpr size_t W_SLICE_BUDGET = 128 * 1024;
 static int pick_slices(int Cin, int taps, int N) {
   int s = 1;
-  while ((size_t)Cin * taps * (N / s) * 4 > W_SLICE_BUDGET && (N / (2 * s)) % 16 == 0) s *= 2;
+  while ((size_t)Cin * taps * (N / s) * 2 > W_SLICE_BUDGET && (N / (2 * s)) % 16 == 0) s *= 2;
   return s;
 }
 // 2-CTA engine: every layer with N >= 32 is packed as pair-slices of two halves (one per CTA of the pair);
@@ -95,24 +97,26 @@ struct Blob {
     return off;
   }
   size_t push(const std::vector<float>& v) { return push(v.data(), v.size()); }
-  ConvLayer push_gemm(Gemm& g) {  // [n_slices][Cin/8][taps][2][Ns][4], tf32-rounded
+  ConvLayer push_gemm(Gemm& g) {  // fp16 [n_slices][Cin/16][taps][2][Ns][8]
     const bool cta2 = want_cta2(g.N);
     // per-CTA slices: for the 2-CTA engine split every pair-slice once more (the budget applies per CTA)
     int ns = pick_slices(g.Cin, g.taps, g.N);
     if (cta2 && ns == 1) ns = 2;
-    const int Ns = g.N / ns, KB = g.Cin / 8;
-    std::vector<float> w((size_t)g.Cin * g.taps * g.N);
+    const int Ns = g.N / ns, KB = g.Cin / 16;
+    std::vector<uint16_t> w((size_t)g.Cin * g.taps * g.N);
     for (int sl = 0; sl < ns; ++sl)
       for (int kb = 0; kb < KB; ++kb)
         for (int t = 0; t < g.taps; ++t)
           for (int h = 0; h < 2; ++h)
             for (int n = 0; n < Ns; ++n)
-              for (int j = 0; j < 4; ++j)
-                w[(((((size_t)sl * KB + kb) * g.taps + t) * 2 + h) * Ns + n) * 4 + j] =
-                    tf32_round_host(g.at(t, kb * 8 + h * 4 + j, sl * Ns + n));
+              for (int j = 0; j < 8; ++j)
+                w[(((((size_t)sl * KB + kb) * g.taps + t) * 2 + h) * Ns + n) * 8 + j] =
+                    half_bits_host(g.at(t, kb * 16 + h * 8 + j, sl * Ns + n));
     ConvLayer L{g.Cin, g.N, g.taps, g.dil, g.pad_left, 0, 0, 0.0, ns, cta2 ? 1 : 0};
     for (float v : g.G) L.macs_per_row += (v != 0.f) ? 1.0 : 0.0;  // == Cin*N*taps except the 2-phase ConvT
-    L.w_off = push(w);
+    std::vector<float> raw((w.size() + 1) / 2);
+    std::memcpy(raw.data(), w.data(), w.size() * 2);
+    L.w_off = push(raw);
     L.b_off = push(g.bias);
     return L;
   }
@@ -393,12 +397,12 @@ struct Arena {
         return;
       }
   }
-  Act act(int B, int C, int T) {
+  Act act(int B, int C, int T, bool f32 = false) {
     Act a;
-    a.C = C; a.T = T; a.Tp = padded_rows(T);
-    a.bs = (long long)(C / 4) * a.Tp * 4;
-    const size_t off = alloc((size_t)B * a.bs * sizeof(float));
-    a.base = reinterpret_cast<float*>(base + off);
+    a.C = C; a.T = T; a.Tp = padded_rows(T); a.f32 = f32 ? 1 : 0;
+    a.bs = (long long)C * a.Tp;
+    const size_t off = alloc((size_t)B * a.bs * (f32 ? 4 : 2));
+    a.base = base + off;
     return a;
   }
   void release(const Act& a) { release((size_t)(reinterpret_cast<char*>(a.base) - base)); }
@@ -414,9 +418,9 @@ struct Ctx {
 };
 
 struct ConvOpt {
-  int in_coff4 = 0, out_coff4 = 0;
+  int in_coff8 = 0, out_coff8 = 0;   // channel offsets in units of 8 channels
   int mode = MODE_SAME;
-  int lrelu = 1, round_tf32 = 1;
+  int lrelu = 1;
   const Act* pool = nullptr;
   const Act* res = nullptr;
   int Tout = -1;
@@ -429,15 +433,15 @@ static int run_conv(Ctx& c, const std::string& name, const Act& in, const Act& o
   const ConvLayer& L = it->second;
   ConvParams p;
   std::memset(&p, 0, sizeof(p));
-  p.in = in.base; p.in_bs = in.bs; p.in_Tp = in.Tp; p.in_coff4 = o.in_coff4;
+  p.in = in.h(); p.in_bs = in.bs; p.in_Tp = in.Tp; p.in_coff8 = o.in_coff8;
   p.Tin = in.T; p.Cin = L.Cin; p.taps = L.taps; p.dil = L.dil; p.pad_left = L.pad_left;
-  p.w = c.m->blob + L.w_off; p.bias = c.m->blob + L.b_off; p.N = L.N; p.n_slices = L.n_slices; p.cta2 = L.cta2;
+  p.w = reinterpret_cast<const __half*>(c.m->blob + L.w_off); p.bias = c.m->blob + L.b_off; p.N = L.N; p.n_slices = L.n_slices; p.cta2 = L.cta2;
   p.mode = o.mode;
-  p.out = out.base; p.out_bs = out.bs; p.out_Tp = out.Tp; p.out_coff4 = o.out_coff4;
+  p.out = out.base; p.out_f32 = out.f32; p.out_bs = out.bs; p.out_Tp = out.Tp; p.out_coff8 = o.out_coff8;
   p.Tout = o.Tout >= 0 ? o.Tout : out.T;
-  if (o.pool) { p.pool = o.pool->base; p.pool_bs = o.pool->bs; p.pool_Tp = o.pool->Tp; p.pool_coff4 = 0; }
-  if (o.res) { p.res = o.res->base; p.res_bs = o.res->bs; p.res_Tp = o.res->Tp; p.res_coff4 = 0; }
-  p.lrelu = o.lrelu; p.round_tf32 = o.round_tf32;
+  if (o.pool) { p.pool = o.pool->h(); p.pool_bs = o.pool->bs; p.pool_Tp = o.pool->Tp; p.pool_coff8 = 0; }
+  if (o.res) { p.res = o.res->h(); p.res_bs = o.res->bs; p.res_Tp = o.res->Tp; p.res_coff8 = 0; }
+  p.lrelu = o.lrelu;
   p.B = c.B;
   p.tiles_per_item = (in.T + TILE_M - 1) / TILE_M;
   ProfScope ps(CAT_CONV, c.stream, 2.0 * L.macs_per_row * (double)c.B * (double)in.T);
@@ -480,7 +484,7 @@ static int denoiser_forward(Ctx& c, const float* x, float* y, int T) {
   AR_TRY(run_conv(c, "bot_b", b0, b1));
   A.release(b0);
   // decoder level 0: up-conv writes the upper channel half of the concat buffer (skip first, :124)
-  o = ConvOpt(); o.mode = MODE_INTERLEAVE2; o.lrelu = 0; o.out_coff4 = 128 / 4; o.Tout = T2;
+  o = ConvOpt(); o.mode = MODE_INTERLEAVE2; o.lrelu = 0; o.out_coff8 = 128 / 8; o.Tout = T2;
   AR_TRY(run_conv(c, "up0", b1, cat2, o));
   A.release(b1);
   Act d0a = A.act(B, 128, T2);
@@ -489,7 +493,7 @@ static int denoiser_forward(Ctx& c, const float* x, float* y, int T) {
   Act d0b = A.act(B, 128, T2);
   AR_TRY(run_conv(c, "dec0b", d0a, d0b));
   A.release(d0a);
-  o = ConvOpt(); o.mode = MODE_INTERLEAVE2; o.lrelu = 0; o.out_coff4 = 64 / 4; o.Tout = T1;
+  o = ConvOpt(); o.mode = MODE_INTERLEAVE2; o.lrelu = 0; o.out_coff8 = 64 / 8; o.Tout = T1;
   AR_TRY(run_conv(c, "up1", d0b, cat1, o));
   A.release(d0b);
   Act d1a = A.act(B, 64, T1);
@@ -498,15 +502,14 @@ static int denoiser_forward(Ctx& c, const float* x, float* y, int T) {
   Act d1b = A.act(B, 64, T1);
   AR_TRY(run_conv(c, "dec1b", d1a, d1b));
   A.release(d1a);
-  o = ConvOpt(); o.mode = MODE_INTERLEAVE2; o.lrelu = 0; o.out_coff4 = 32 / 4; o.Tout = T;
+  o = ConvOpt(); o.mode = MODE_INTERLEAVE2; o.lrelu = 0; o.out_coff8 = 32 / 8; o.Tout = T;
   AR_TRY(run_conv(c, "up2", d1b, cat0, o));
   A.release(d1b);
   Act d2a = A.act(B, 32, T);
   AR_TRY(run_conv(c, "dec2a", cat0, d2a));
   A.release(cat0);
   Act f = A.act(B, 32, T);
-  o = ConvOpt(); o.round_tf32 = 0;  // feeds the fp32 CUDA-core tail
-  AR_TRY(run_conv(c, "dec2b", d2a, f, o));
+  AR_TRY(run_conv(c, "dec2b", d2a, f));
   A.release(d2a);
   if (!A.dry) {
     DenTailW w{m.blob + m.td_w0, m.blob + m.td_b0, m.blob + m.td_w1, m.blob + m.td_b1, m.blob + m.td_w2, m.blob + m.td_wf, m.td_b2, m.td_bf};
@@ -549,8 +552,7 @@ static int sr_forward(Ctx& c, const float* x, float* y, int T) {
   AR_TRY(run_conv(c, "up", mid, u, o));
   A.release(mid);
   Act h = A.act(B, 32, 2 * T);
-  o = ConvOpt(); o.round_tf32 = 0;
-  AR_TRY(run_conv(c, "hf", u, h, o));
+  AR_TRY(run_conv(c, "hf", u, h));
   A.release(u);
   if (!A.dry) {
     const int coff[1] = {0};
@@ -583,8 +585,8 @@ static int stereo_forward(Ctx& c, const float* x, float* y, int T, const float* 
     A.release(a);
     cur = b;
   }
-  Act xp = A.act(B, 256, T);
-  ConvOpt o; o.lrelu = 0; o.round_tf32 = 0;  // gate pre-activations stay fp32
+  Act xp = A.act(B, 256, T, /*f32=*/true);   // gate pre-activations stay fp32 (C4 layout)
+  ConvOpt o; o.lrelu = 0;
   AR_TRY(run_conv(c, "xproj", cur, xp, o));
   A.release(cur);
   Act h = A.act(B, 64, T);
@@ -597,19 +599,19 @@ static int stereo_forward(Ctx& c, const float* x, float* y, int T, const float* 
   AR_TRY(run_conv(c, "dec0", h, d0));
   A.release(h);
   Act d1 = A.act(B, 128, T);
-  o = ConvOpt(); o.in_coff4 = 0; o.out_coff4 = 0;
+  o = ConvOpt(); o.in_coff8 = 0; o.out_coff8 = 0;
   AR_TRY(run_conv(c, "dec1L", d0, d1, o));
-  o.in_coff4 = 128 / 4; o.out_coff4 = 64 / 4;
+  o.in_coff8 = 128 / 8; o.out_coff8 = 64 / 8;
   AR_TRY(run_conv(c, "dec1R", d0, d1, o));
   A.release(d0);
   Act d2 = A.act(B, 64, T);
-  o = ConvOpt(); o.round_tf32 = 0;
+  o = ConvOpt();
   AR_TRY(run_conv(c, "dec2L", d1, d2, o));
-  o.in_coff4 = 64 / 4; o.out_coff4 = 32 / 4;
+  o.in_coff8 = 64 / 8; o.out_coff8 = 32 / 8;
   AR_TRY(run_conv(c, "dec2R", d1, d2, o));
   A.release(d1);
   if (!A.dry) {
-    const int coff[2] = {0, 32 / 4};
+    const int coff[2] = {0, 32 / 8};
     const float* w[2] = {m.blob + m.fin_w[0], m.blob + m.fin_w[1]};
     ProfScope ps(CAT_TAIL, c.stream, 2.0 * 448 * (double)B * T);
     AR_TRY(launch_final_k7(d2, coff, w, m.fin_b, 2, y, B, T, nullptr, c.stream));
@@ -659,7 +661,7 @@ int model_kind(const Model* m) { return m->kind; }
 int debug_conv(const float* x, const float* w_host, const float* bias_host, float* y, int B, int Cin, int Cout, int T, int k,
                int dil, int lrelu, int engine, cudaStream_t stream) {
   AR_CHECK(x && w_host && bias_host && y && B >= 1 && T >= 1, AR_ERR_INVALID, "debug_conv: bad argument");
-  AR_CHECK(Cin % 8 == 0 && Cout % 16 == 0 && Cout <= 256 && (k & 1) == 1 && dil * (k - 1) / 2 <= HALO, AR_ERR_INVALID,
+  AR_CHECK(Cin % 16 == 0 && Cout % 16 == 0 && Cout <= 256 && (k & 1) == 1 && dil * (k - 1) / 2 <= HALO, AR_ERR_INVALID,
            "debug_conv: unsupported shape");
   Gemm g;
   g.init(Cin, Cout, k, dil, dil * (k - 1) / 2);
@@ -678,15 +680,15 @@ int debug_conv(const float* x, const float* w_host, const float* bias_host, floa
   AR_CUDA_OK(cudaMalloc(&dblob, blob.host.size() * sizeof(float)));
   AR_CUDA_OK(cudaMalloc(&dws, A.peak));
   AR_CUDA_OK(cudaMemcpyAsync(dblob, blob.host.data(), blob.host.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
-  in.base = reinterpret_cast<float*>(dws + (reinterpret_cast<char*>(in.base) - (char*)nullptr));
-  out.base = reinterpret_cast<float*>(dws + (reinterpret_cast<char*>(out.base) - (char*)nullptr));
+  in.base = dws + (reinterpret_cast<char*>(in.base) - (char*)nullptr);
+  out.base = dws + (reinterpret_cast<char*>(out.base) - (char*)nullptr);
   int rc = launch_plain_to_c4(x, B, Cin, T, in, stream);
   if (rc == AR_OK) {
     ConvParams p;
     std::memset(&p, 0, sizeof(p));
-    p.in = in.base; p.in_bs = in.bs; p.in_Tp = in.Tp; p.Tin = T; p.Cin = Cin; p.taps = k; p.dil = dil; p.pad_left = g.pad_left;
-    p.w = dblob + L.w_off; p.bias = dblob + L.b_off; p.N = Cout; p.n_slices = L.n_slices; p.cta2 = L.cta2; p.mode = MODE_SAME;
-    p.out = out.base; p.out_bs = out.bs; p.out_Tp = out.Tp; p.Tout = T; p.lrelu = lrelu; p.round_tf32 = 0;
+    p.in = in.h(); p.in_bs = in.bs; p.in_Tp = in.Tp; p.Tin = T; p.Cin = Cin; p.taps = k; p.dil = dil; p.pad_left = g.pad_left;
+    p.w = reinterpret_cast<const __half*>(dblob + L.w_off); p.bias = dblob + L.b_off; p.N = Cout; p.n_slices = L.n_slices; p.cta2 = L.cta2; p.mode = MODE_SAME;
+    p.out = out.base; p.out_bs = out.bs; p.out_Tp = out.Tp; p.Tout = T; p.lrelu = lrelu;
     p.B = B; p.tiles_per_item = (T + TILE_M - 1) / TILE_M;
     rc = engine == AR_ENGINE_SIMT ? launch_conv_simt(p, stream) : (p.cta2 ? launch_conv_umma2(p, stream) : launch_conv_umma(p, stream));
   }

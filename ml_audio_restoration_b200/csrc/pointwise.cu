@@ -8,11 +8,11 @@
 namespace ar {
 
 // ============================================================================ stem: Cin = 1
-// x[B][T] plain -> C4 out (32 channels): conv(k taps, pad k/2) + folded BN bias + LeakyReLU.
+// x[B][T] plain fp32 -> H8 fp16 out (32 channels): conv(k taps, pad k/2) + folded BN bias + LeakyReLU.
 // denoiser.py:54 (encoder.0.0), super_resolution.py:25 (initial.0), stereo_separator.py:25.
 template <int TAPS>
 __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ x, int T, const float* __restrict__ w /*[32][TAPS]*/,
-                                                   const float* __restrict__ bias, float* __restrict__ out,
+                                                   const float* __restrict__ bias, __half* __restrict__ out,
                                                    long long out_bs, int out_Tp, int lrelu) {
   __shared__ float sw[32 * TAPS];
   __shared__ float sb[32];
@@ -30,17 +30,17 @@ __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ x, 
     xin[j] = (ti >= 0 && ti < T) ? __ldg(xb + ti) : 0.f;
   }
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    float v[4];
+  for (int c = 0; c < 4; ++c) {
+    float v[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float a = sb[4 * c + i];
+    for (int i = 0; i < 8; ++i) {
+      float a = sb[8 * c + i];
 #pragma unroll
-      for (int j = 0; j < TAPS; ++j) a = fmaf(sw[(4 * c + i) * TAPS + j], xin[j], a);
+      for (int j = 0; j < TAPS; ++j) a = fmaf(sw[(8 * c + i) * TAPS + j], xin[j], a);
       if (lrelu) a = a > 0.f ? a : LRELU_SLOPE * a;
-      v[i] = to_tf32(a);
+      v[i] = a;
     }
-    *reinterpret_cast<float4*>(out + act_off(out_bs, out_Tp, b, c, t)) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<uint4*>(out + act_off(out_bs, out_Tp, b, c, t)) = pack_half8(v);
   }
 }
 
@@ -48,9 +48,9 @@ int launch_stem(const float* x, int B, int T, int taps, const float* w, const fl
                 cudaStream_t stream) {
   dim3 grid((T + 127) / 128, B);
   if (taps == 3)
-    stem_kernel<3><<<grid, 128, 0, stream>>>(x, T, w, bias, out.base, out.bs, out.Tp, lrelu);
+    stem_kernel<3><<<grid, 128, 0, stream>>>(x, T, w, bias, out.h(), out.bs, out.Tp, lrelu);
   else if (taps == 7)
-    stem_kernel<7><<<grid, 128, 0, stream>>>(x, T, w, bias, out.base, out.bs, out.Tp, lrelu);
+    stem_kernel<7><<<grid, 128, 0, stream>>>(x, T, w, bias, out.h(), out.bs, out.Tp, lrelu);
   else {
     set_error("stem: unsupported tap count");
     return AR_ERR_INVALID;
@@ -64,10 +64,10 @@ int launch_stem(const float* x, int B, int T, int taps, const float* w, const fl
 // super_resolution.py:62,96-99 (reconstruction + F.interpolate residual, App. B.3);
 // stereo_separator.py:81 ({left,right}_decoder.9) with blockIdx.z selecting the side.
 struct FinalArgs {
-  const float* in;
+  const __half* in;
   long long in_bs;
   int in_Tp;
-  int in_coff4[2];
+  int in_coff8[2];
   const float* w[2];     // [32][7] each (c-major)
   float bias[2];
   float* y;              // [B][nout][T]
@@ -90,12 +90,11 @@ __global__ void __launch_bounds__(128) final_k7_kernel(const FinalArgs a) {
     const int ti = t + j - 3;
     if (ti < 0 || ti >= a.T) continue;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float4 v = *reinterpret_cast<const float4*>(a.in + act_off(a.in_bs, a.in_Tp, b, a.in_coff4[o] + c, ti));
-      acc = fmaf(v.x, sw[j][4 * c + 0], acc);
-      acc = fmaf(v.y, sw[j][4 * c + 1], acc);
-      acc = fmaf(v.z, sw[j][4 * c + 2], acc);
-      acc = fmaf(v.w, sw[j][4 * c + 3], acc);
+    for (int c = 0; c < 4; ++c) {
+      float v[8];
+      unpack_half8(*reinterpret_cast<const uint4*>(a.in + act_off(a.in_bs, a.in_Tp, b, a.in_coff8[o] + c, ti)), v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc = fmaf(v[i], sw[j][8 * c + i], acc);
     }
   }
   if (a.x_lr != nullptr) {
@@ -116,11 +115,11 @@ __global__ void __launch_bounds__(128) final_k7_kernel(const FinalArgs a) {
   a.y[((long long)b * a.nout + o) * a.T + t] = acc;
 }
 
-int launch_final_k7(const Act& in, const int* in_coff4, const float* const* w, const float* bias, int nout, float* y,
+int launch_final_k7(const Act& in, const int* in_coff8, const float* const* w, const float* bias, int nout, float* y,
                     int B, int T, const float* x_lr, cudaStream_t stream) {
   FinalArgs a;
-  a.in = in.base; a.in_bs = in.bs; a.in_Tp = in.Tp;
-  for (int i = 0; i < nout; ++i) { a.in_coff4[i] = in_coff4[i]; a.w[i] = w[i]; a.bias[i] = bias[i]; }
+  a.in = in.h(); a.in_bs = in.bs; a.in_Tp = in.Tp;
+  for (int i = 0; i < nout; ++i) { a.in_coff8[i] = in_coff8[i]; a.w[i] = w[i]; a.bias[i] = bias[i]; }
   a.y = y; a.nout = nout; a.T = T; a.x_lr = x_lr;
   dim3 grid((T + 127) / 128, B, nout);
   final_k7_kernel<<<grid, 128, 0, stream>>>(a);
@@ -138,7 +137,7 @@ int launch_final_k7(const Act& in, const int* in_coff4, const float* const* w, c
 constexpr int DT = 128;  // outputs per block
 
 
-__global__ void __launch_bounds__(DT) den_tail_kernel(const float* __restrict__ fin, long long f_bs, int f_Tp,
+__global__ void __launch_bounds__(DT) den_tail_kernel(const __half* __restrict__ fin, long long f_bs, int f_Tp,
                                                       const float* __restrict__ x, float* __restrict__ y, int T,
                                                       const DenTailW w) {
   __shared__ float4 sf[8][DT + 6];
@@ -157,12 +156,13 @@ __global__ void __launch_bounds__(DT) den_tail_kernel(const float* __restrict__ 
   if (tid < 24) sw2[tid] = w.w2[tid];
   if (tid < 32) swf[tid] = w.wf[tid];
   // f tile: rows t0-3 .. t0+DT+2
-  for (int i = tid; i < 8 * (DT + 6); i += DT) {
-    const int c = i / (DT + 6), r = i % (DT + 6);
+  for (int i = tid; i < 4 * (DT + 6); i += DT) {
+    const int c = i / (DT + 6), r = i % (DT + 6);   // c: 8-channel chunk of the H8 input
     const int t = t0 - 3 + r;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t >= 0 && t < T) v = *reinterpret_cast<const float4*>(fin + act_off(f_bs, f_Tp, b, c, t));
-    sf[c][r] = v;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (t >= 0 && t < T) unpack_half8(*reinterpret_cast<const uint4*>(fin + act_off(f_bs, f_Tp, b, c, t)), v);
+    sf[2 * c][r] = make_float4(v[0], v[1], v[2], v[3]);
+    sf[2 * c + 1][r] = make_float4(v[4], v[5], v[6], v[7]);
   }
   __syncthreads();
   // td0: 32 -> 16 at rows t0-2 .. t0+DT+1 (local r in [0, DT+4)), input rows r..r+2 of sf
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(DT) den_tail_kernel(const float* __restrict__ 
 
 int launch_den_tail(const Act& f, const float* x, float* y, int B, int T, const DenTailW& w, cudaStream_t stream) {
   dim3 grid((T + DT - 1) / DT, B);
-  den_tail_kernel<<<grid, DT, 0, stream>>>(f.base, f.bs, f.Tp, x, y, T, w);
+  den_tail_kernel<<<grid, DT, 0, stream>>>(f.h(), f.bs, f.Tp, x, y, T, w);
   AR_CUDA_OK(cudaGetLastError());
   return AR_OK;
 }
@@ -399,31 +399,31 @@ int launch_ola(const float* y, float* out, long long n, int n_chunks, int channe
 }
 
 // ============================================================================ layout converters (debug conv)
-__global__ void plain_to_c4_kernel(const float* __restrict__ x, int C, int T, float* __restrict__ out, long long bs, int Tp) {
-  const int b = blockIdx.z, c4 = blockIdx.y;
+__global__ void plain_to_h8_kernel(const float* __restrict__ x, int C, int T, __half* __restrict__ out, long long bs, int Tp) {
+  const int b = blockIdx.z, c8 = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
-  float v[4];
-  for (int i = 0; i < 4; ++i) v[i] = to_tf32(x[((long long)b * C + c4 * 4 + i) * T + t]);
-  *reinterpret_cast<float4*>(out + act_off(bs, Tp, b, c4, t)) = make_float4(v[0], v[1], v[2], v[3]);
+  float v[8];
+  for (int i = 0; i < 8; ++i) v[i] = x[((long long)b * C + c8 * 8 + i) * T + t];
+  *reinterpret_cast<uint4*>(out + act_off(bs, Tp, b, c8, t)) = pack_half8(v);
 }
-__global__ void c4_to_plain_kernel(const float* __restrict__ in, long long bs, int Tp, int C, int T, float* __restrict__ y) {
-  const int b = blockIdx.z, c4 = blockIdx.y;
+__global__ void h8_to_plain_kernel(const __half* __restrict__ in, long long bs, int Tp, int C, int T, float* __restrict__ y) {
+  const int b = blockIdx.z, c8 = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
-  const float4 v = *reinterpret_cast<const float4*>(in + act_off(bs, Tp, b, c4, t));
-  const float a[4] = {v.x, v.y, v.z, v.w};
-  for (int i = 0; i < 4; ++i) y[((long long)b * C + c4 * 4 + i) * T + t] = a[i];
+  float v[8];
+  unpack_half8(*reinterpret_cast<const uint4*>(in + act_off(bs, Tp, b, c8, t)), v);
+  for (int i = 0; i < 8; ++i) y[((long long)b * C + c8 * 8 + i) * T + t] = v[i];
 }
 int launch_plain_to_c4(const float* x, int B, int C, int T, const Act& out, cudaStream_t stream) {
-  dim3 grid((T + 127) / 128, C / 4, B);
-  plain_to_c4_kernel<<<grid, 128, 0, stream>>>(x, C, T, out.base, out.bs, out.Tp);
+  dim3 grid((T + 127) / 128, C / 8, B);
+  plain_to_h8_kernel<<<grid, 128, 0, stream>>>(x, C, T, out.h(), out.bs, out.Tp);
   AR_CUDA_OK(cudaGetLastError());
   return AR_OK;
 }
 int launch_c4_to_plain(const Act& in, int B, int C, int T, float* y, cudaStream_t stream) {
-  dim3 grid((T + 127) / 128, C / 4, B);
-  c4_to_plain_kernel<<<grid, 128, 0, stream>>>(in.base, in.bs, in.Tp, C, T, y);
+  dim3 grid((T + 127) / 128, C / 8, B);
+  h8_to_plain_kernel<<<grid, 128, 0, stream>>>(in.h(), in.bs, in.Tp, C, T, y);
   AR_CUDA_OK(cudaGetLastError());
   return AR_OK;
 }

@@ -1,0 +1,138 @@
+// Fused epilogue shared by the 1-CTA and 2-CTA tcgen05 conv kernels.
+// One warp owns 32 GEMM rows (TMEM lanes = time steps) and `wcols` accumulator columns; per 8-column chunk
+// the work is: bias add, LeakyReLU as max(v, slope*v), (residual add), round to fp16 and ONE coalesced 16-byte
+// store per thread (consecutive lanes = consecutive rows = consecutive 16 bytes of the H8 layout), plus the
+// fused max-pool copy / 2x interleave ("pixel shuffle") / right zero-pad column where the layer needs them.
+// Output row addresses are hoisted per tile.  OUTF32 writes fp32 C4 instead (LSTM gate pre-activations).
+#pragma once
+#include "ar_common.cuh"
+#include "umma_ptx.cuh"
+
+namespace ar {
+
+struct EpiRow {
+  char* o0;            // output row of this thread, first chunk of this warp's column range
+  char* o1;            // interleave mode: the right zero-pad row (written when ok1)
+  char* prow;          // pooled row
+  const __half* rrow;  // residual row
+  long long ostride;   // bytes between consecutive output chunks
+  long long pstride;
+  long long rstride;   // halves
+  bool ok0, ok1, pok, in_ok;
+};
+
+template <int MODE, bool POOL, bool RES, bool OUTF32>
+__device__ __forceinline__ EpiRow epi_row(const ConvParams& p, int b, int t, int gcol0) {
+  EpiRow r;
+  r.in_ok = t < p.Tin;
+  r.o1 = nullptr; r.prow = nullptr; r.rrow = nullptr; r.ok1 = false; r.pok = false;
+  r.pstride = 0; r.rstride = 0;
+  const int tt = r.in_ok ? t : 0;   // keep the address arithmetic in range for masked rows
+  if (OUTF32) {
+    r.ostride = (long long)p.out_Tp * 16;   // 4 floats per row
+    r.o0 = reinterpret_cast<char*>(p.out) + 4 * act_off4(p.out_bs, p.out_Tp, b, p.out_coff8 + (gcol0 >> 2), tt);
+    r.ok0 = r.in_ok && t < p.Tout;
+    return r;
+  }
+  r.ostride = (long long)p.out_Tp * 16;     // 8 halves per row
+  __half* out = reinterpret_cast<__half*>(p.out);
+  int chunk0;
+  if (MODE == MODE_SAME) {
+    chunk0 = gcol0 >> 3;
+    r.o0 = reinterpret_cast<char*>(out + act_off(p.out_bs, p.out_Tp, b, p.out_coff8 + chunk0, tt));
+    r.ok0 = r.in_ok && t < p.Tout;
+  } else {
+    // columns [0,N/2) -> row 2t, [N/2,N) -> row 2t+1; a warp's column range never straddles N/2
+    const int hN = p.N >> 1;
+    const int phase = gcol0 >= hN;
+    chunk0 = (gcol0 - phase * hN) >> 3;
+    r.o0 = reinterpret_cast<char*>(out + act_off(p.out_bs, p.out_Tp, b, p.out_coff8 + chunk0, 2 * tt + phase));
+    r.ok0 = r.in_ok && (2 * t + phase) < p.Tout;
+    // right zero-pad column when the skip tensor is one sample longer (denoiser.py:121-122)
+    r.ok1 = (phase == 0) && (t == p.Tin - 1) && (2 * p.Tin < p.Tout);
+    r.o1 = reinterpret_cast<char*>(out + act_off(p.out_bs, p.out_Tp, b, p.out_coff8 + chunk0, 2 * p.Tin));
+  }
+  if (POOL) {
+    r.prow = reinterpret_cast<char*>(p.pool + act_off(p.pool_bs, p.pool_Tp, b, p.pool_coff8 + chunk0, tt >> 1));
+    r.pstride = (long long)p.pool_Tp * 16;
+    r.pok = ((t & 1) == 0) && (t + 1 < p.Tin);
+  }
+  if (RES) {
+    r.rrow = p.res + act_off(p.res_bs, p.res_Tp, b, p.res_coff8 + chunk0, tt);
+    r.rstride = (long long)p.res_Tp * 8;
+  }
+  return r;
+}
+
+// residual operand of this warp's (<= 16) columns, fetched BEFORE the accumulator is ready
+template <bool RES>
+__device__ __forceinline__ void epi_prefetch_res(const EpiRow& r, bool active, uint4 (&resv)[2]) {
+  if (RES) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+      resv[c] = (r.in_ok && active) ? *reinterpret_cast<const uint4*>(r.rrow + c * r.rstride) : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+template <int MODE, bool POOL, bool RES, bool OUTF32>
+__device__ __forceinline__ void epi_store(const EpiRow& r, const float* s_bias_w /* bias of this warp's first column */, uint32_t taddr,
+                                          int wcols, float slope, const uint4 (&resv)[2]) {
+  for (int cb = 0; cb < wcols; cb += 32) {
+    uint32_t a[32];
+    const int ncol = wcols - cb < 32 ? 16 : 32;     // wcols is 16 or a multiple of 32
+    if (ncol == 32) tmem_ld32_nowait(taddr + cb, a);
+    else tmem_ld16_nowait(taddr + cb, a);
+    tmem_wait_ld();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (8 * c < ncol) {
+        const float4 b0 = *reinterpret_cast<const float4*>(s_bias_w + cb + 8 * c);
+        const float4 b1 = *reinterpret_cast<const float4*>(s_bias_w + cb + 8 * c + 4);
+        float v[8] = {__uint_as_float(a[8 * c]) + b0.x,     __uint_as_float(a[8 * c + 1]) + b0.y,
+                      __uint_as_float(a[8 * c + 2]) + b0.z, __uint_as_float(a[8 * c + 3]) + b0.w,
+                      __uint_as_float(a[8 * c + 4]) + b1.x, __uint_as_float(a[8 * c + 5]) + b1.y,
+                      __uint_as_float(a[8 * c + 6]) + b1.z, __uint_as_float(a[8 * c + 7]) + b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], slope * v[i]);
+        if (RES) {
+          float rr[8];
+          unpack_half8(resv[c & 1], rr);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] += rr[i];
+        }
+        const int ch = (cb >> 3) + c;               // 8-column chunk index within this warp's range
+        if (OUTF32) {
+          if (r.ok0) {
+            *reinterpret_cast<float4*>(r.o0 + (long long)(2 * ch) * r.ostride) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(r.o0 + (long long)(2 * ch + 1) * r.ostride) = make_float4(v[4], v[5], v[6], v[7]);
+          }
+        } else {
+          const uint4 packed = pack_half8(v);
+          if (r.ok0) *reinterpret_cast<uint4*>(r.o0 + (long long)ch * r.ostride) = packed;
+          if (MODE == MODE_INTERLEAVE2) {
+            if (r.ok1) *reinterpret_cast<uint4*>(r.o1 + (long long)ch * r.ostride) = make_uint4(0u, 0u, 0u, 0u);
+          }
+          if (POOL) {  // MaxPool1d(2,2), floor: rows (t, t+1) live in neighbouring lanes; max of rounded == rounded max
+            float q[8], m[8];
+            unpack_half8(packed, q);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) m[i] = fmaxf(q[i], __shfl_down_sync(0xffffffffu, q[i], 1));
+            if (r.pok) *reinterpret_cast<uint4*>(r.prow + (long long)ch * r.pstride) = pack_half8(m);
+          }
+        }
+      }
+    }
+  }
+}
+
+// (variant, taps) -> kernel instantiation table shared by both engines' launchers
+enum EpiVariant { EV_PLAIN = 0, EV_POOL = 1, EV_RES = 2, EV_INTERLEAVE = 3, EV_F32 = 4 };
+__host__ inline int epi_variant(const ConvParams& p) {
+  if (p.out_f32) return EV_F32;
+  if (p.mode == MODE_INTERLEAVE2) return EV_INTERLEAVE;
+  if (p.pool) return EV_POOL;
+  if (p.res) return EV_RES;
+  return EV_PLAIN;
+}
+
+}  // namespace ar

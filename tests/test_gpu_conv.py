@@ -11,8 +11,8 @@ pytestmark = pytest.mark.gpu
 
 
 def tf32(x):
-    i = x.contiguous().view(torch.int32)
-    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+    """Operand rounding of the engines: fp16 (same 11-bit significand as TF32), round to nearest."""
+    return x.half().float()
 
 
 SHAPES = [
@@ -41,9 +41,10 @@ def test_conv_engine_matches_torch(engine, shape):
     w = torch.randn(Cout, Cin, k, generator=g) / (Cin * k) ** 0.5
     b = torch.randn(Cout, generator=g)
     y = debug_conv(x, w, b, dilation=d, lrelu=1, engine=engine)
-    # both engines see tf32-rounded operands (activations are rounded when stored, weights when packed)
+    # both engines see fp16-rounded operands (activations are rounded when stored, weights when packed);
+    # the debug hook also returns the result through the fp16 activation layout
     ref = F.leaky_relu(F.conv1d(tf32(x).double(), tf32(w).double(), b.double(), padding=d * (k - 1) // 2, dilation=d), 0.2).float()
-    assert_close(ref, y, f"conv {shape}", max_abs=2e-5, min_snr=100.0)
+    assert_close(ref.half().float(), y, f"conv {shape}", max_abs=1e-2, min_snr=66.0)  # 1 fp16 ulp at |y|~8 is 7.8e-3
 
 
 def test_engines_agree_bitwise_close():
@@ -53,4 +54,4 @@ def test_engines_agree_bitwise_close():
     b = torch.randn(128, generator=g)
     a = debug_conv(x, w, b, dilation=2, engine=_lib.ENGINE_SIMT)
     c = debug_conv(x, w, b, dilation=2, engine=_lib.ENGINE_UMMA)
-    assert_close(a, c, "simt vs umma", max_abs=1e-5, min_snr=110.0)
+    assert_close(a, c, "simt vs umma", max_abs=1e-2, min_snr=66.0)   # both outputs are fp16-rounded
