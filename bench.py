@@ -8,7 +8,7 @@
 
 One "step" = one synthetic mono file of `--chunks-per-step` 2-second chunks per GPU pushed through
 `RestorationPipeline.restore(mode="chunked")` (input normalise, chunk, chain, overlap-add, output
-normalise).  It is a slice of BASELINE.json's 10-hour sweep: 592 chunks = 1128.8 s, so 32 steps
+normalise).  It is a slice of BASELINE.json's 10-hour sweep: 1184 chunks = 2257.7 s, so 16 steps
 are 10 h.  Files are independent => ranks share nothing (weak scaling, no collective on the data
 path; NCCL is used only for the timing barrier / max-over-ranks).
 Prints ONE JSON line (rank 0).
@@ -253,7 +253,7 @@ def run_b200(args, rank, world, local_rank):
     roofline = {
         "kernel": "conv_umma_kernel (tcgen05 implicit-GEMM Conv1d, all conv/convT/LSTM-input layers)",
         "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-        "frac": achieved / peaks["tflops"], "peak_source": f"{peaks['src']} bf16 dense (TF32 operands run at half that rate)",
+        "frac": achieved / peaks["tflops"], "peak_source": f"{peaks['src']} bf16 dense sustained (fp16 operands run at the same rate)",
         "avg_launch_ms": conv["ms"] / max(1, conv["launches"]), "launches": conv["launches"],
         "share_of_step": conv["ms"] / (1e3 * t_s), "traffic": None,
         "per_category_ms_per_step": {k: v["ms"] / args.steps for k, v in cats.items()},
@@ -261,7 +261,7 @@ def run_b200(args, rank, world, local_rank):
     line = {
         "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "tf32", "data": "synthetic", "config": workload_config(args, world),
+        "dtype": "f16 operands, f32 accumulate", "data": "synthetic", "config": workload_config(args, world),
         "realtime_factor_per_gpu": value / world,
         "chain_tflops_per_gpu": value / world * CHAIN_GFLOP_PER_AUDIO_S / 1e3,
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": 16 * n},
@@ -284,8 +284,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
-    ap.add_argument("--chunks-per-step", type=int, default=592, help="2 s chunks per GPU per step (592 = 4 per SM)")
-    ap.add_argument("--batch-chunks", type=int, default=592, help="chunks per chain launch (592 = 4 per SM: one tensor-core LSTM launch per step)")
+    ap.add_argument("--chunks-per-step", type=int, default=1184, help="2 s chunks per GPU per step (1184 = 8 per SM)")
+    ap.add_argument("--batch-chunks", type=int, default=1184, help="chunks per chain launch (1184 = 8 per SM: one full-chip tensor-core LSTM launch)")
     ap.add_argument("--streams", type=int, default=1, help="chunk batches in flight (LSTM of one overlaps convs of the next)")
     ap.add_argument("--cpu-chunks", type=int, default=8, help="chunks in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -42,7 +42,6 @@ void set_error(const std::string& msg);
 // significand as TF32 (the tensor core would drop the rest anyway) at half the bytes and twice the K per
 // MMA; values are rounded to nearest and clamped to the fp16 range when stored.  Rows outside [0,T) hold
 // garbage in HBM; consumers zero them in shared memory (conv zero padding), producers never write them.
-// The only fp32 activation tensor is the LSTM gate pre-activation ("C4": [B][C/4][Tp][4] fp32).
 constexpr int TILE_M = 128;
 constexpr int HALO = 8;  // >= max one-sided conv reach: dilation 8 * (3-1)/2
 constexpr float LRELU_SLOPE = 0.2f;
@@ -51,23 +50,18 @@ constexpr float HALF_MAX = 65504.0f;
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 __host__ __device__ inline int padded_rows(int T) { return HALO + round_up(T, TILE_M) + HALO; }
 
-struct Act {      // an H8 (fp16) activation tensor, or -- when f32 is set -- the C4 fp32 variant
+struct Act {      // an H8 (fp16) activation tensor
   void* base = nullptr;   // element (b=0, chunk 0, row 0 == t=-HALO)
   int C = 0;              // channels of the whole buffer
   int T = 0;              // valid length
   int Tp = 0;             // padded rows per chunk
-  long long bs = 0;       // ELEMENTS between batch items = C*Tp
-  int f32 = 0;
+  long long bs = 0;       // halves between batch items = C*Tp
   __host__ __device__ __half* h() const { return reinterpret_cast<__half*>(base); }
-  __host__ __device__ float* f() const { return reinterpret_cast<float*>(base); }
 };
 
-// element offsets; `chunk` counts 8-channel (H8) / 4-channel (C4) groups
-__device__ __forceinline__ long long act_off(long long bs, int Tp, int b, int chunk, int t) {        // H8
+// element (half) offset; `chunk` counts 8-channel groups
+__device__ __forceinline__ long long act_off(long long bs, int Tp, int b, int chunk, int t) {
   return (long long)b * bs + ((long long)chunk * Tp + (HALO + t)) * 8;
-}
-__device__ __forceinline__ long long act_off4(long long bs, int Tp, int b, int chunk, int t) {       // C4 fp32
-  return (long long)b * bs + ((long long)chunk * Tp + (HALO + t)) * 4;
 }
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {  // round to nearest, clamp to the fp16 range
@@ -112,12 +106,11 @@ struct ConvParams {
   int N;                 // GEMM N, multiple of 16, <= 256
   int n_slices;          // column slices the weights are packed in (each is one CTA's resident operand)
   int cta2;              // packed for the 2-CTA engine: slices (2i, 2i+1) are the two halves of pair-slice i
-  // output: H8 fp16, or C4 fp32 when out_f32 (LSTM gate pre-activations)
+  // output (H8)
   int mode;              // MODE_SAME: out[t]; MODE_INTERLEAVE2: cols [0,N/2)->out[2t], [N/2,N)->out[2t+1]
-  void* out;
-  int out_f32;
+  __half* out;
   long long out_bs;
-  int out_Tp, out_coff8; // chunk offset in 8-channel units (in 4-channel units when out_f32)
+  int out_Tp, out_coff8;
   int Tout;              // valid output length
   __half* pool;          // optional max-pool(2,2) copy of the output (MODE_SAME only), H8
   long long pool_bs;
@@ -152,15 +145,7 @@ __device__ __forceinline__ void epilogue_chunk8(const ConvParams& p, int b, int 
     col = n0 - phase * half;
   }
   const bool row_ok = (t < p.Tin) && (trow < p.Tout);
-  if (p.out_f32) {
-    float* o = reinterpret_cast<float*>(p.out);
-    if (row_ok) {
-      *reinterpret_cast<float4*>(o + act_off4(p.out_bs, p.out_Tp, b, p.out_coff8 + (col >> 2), trow)) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(o + act_off4(p.out_bs, p.out_Tp, b, p.out_coff8 + (col >> 2) + 1, trow)) = make_float4(v[4], v[5], v[6], v[7]);
-    }
-    return;
-  }
-  __half* o = reinterpret_cast<__half*>(p.out);
+  __half* o = p.out;
   const uint4 packed = pack_half8(v);
   if (row_ok) *reinterpret_cast<uint4*>(o + act_off(p.out_bs, p.out_Tp, b, p.out_coff8 + (col >> 3), trow)) = packed;
   if (p.mode == MODE_INTERLEAVE2 && t == p.Tin - 1 && 2 * p.Tin < p.Tout && n0 < (p.N >> 1))

@@ -50,7 +50,7 @@ struct UmmaCfg {
 // residual add); LeakyReLU slope and TF32 rounding stay runtime-uniform.  TAPS is a template parameter
 // so the single issuing thread sees a fully unrolled tap loop: the MMAs of a K block go out back to back
 // instead of one per ~15 dependent integer instructions.
-template <int MODE, bool POOL, bool RES, bool OUTF32, int TAPS>
+template <int MODE, bool POOL, bool RES, int TAPS>
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ UmmaCfg cfg, int num_tiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -207,14 +207,14 @@ conv_umma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ U
       const int t = (tile % tpi) * TILE_M + q * 32 + lane;
       const int buf = tl & 1;
       const uint32_t aph = (uint32_t)(tl >> 1) & 1u;
-      const EpiRow row = epi_row<MODE, POOL, RES, OUTF32>(p, b, t, gcol0);
+      const EpiRow row = epi_row<MODE, POOL, RES>(p, b, t, gcol0);
       uint4 resv[2];
       epi_prefetch_res<RES>(row, active, resv);
       mbar_wait(tfull_bar(buf), aph);
       tc_fence_after();
       if (active) {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * cfg.ncol + col_lo);
-        epi_store<MODE, POOL, RES, OUTF32>(row, s_bias + col_lo, taddr, wcols, slope, resv);
+        epi_store<MODE, POOL, RES>(row, s_bias + col_lo, taddr, wcols, slope, resv);
       }
       tc_fence_before();
       __syncwarp();
@@ -282,12 +282,11 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
   using Kernel = void (*)(ConvParams, UmmaCfg, int);
   struct Entry { int variant, taps; Kernel k; };
   static const Entry table[] = {
-      {EV_PLAIN, 1, conv_umma_kernel<MODE_SAME, false, false, false, 1>}, {EV_PLAIN, 3, conv_umma_kernel<MODE_SAME, false, false, false, 3>},
-      {EV_PLAIN, 5, conv_umma_kernel<MODE_SAME, false, false, false, 5>}, {EV_PLAIN, 7, conv_umma_kernel<MODE_SAME, false, false, false, 7>},
-      {EV_POOL, 3, conv_umma_kernel<MODE_SAME, true, false, false, 3>},   {EV_RES, 3, conv_umma_kernel<MODE_SAME, false, true, false, 3>},
-      {EV_INTERLEAVE, 1, conv_umma_kernel<MODE_INTERLEAVE2, false, false, false, 1>},
-      {EV_INTERLEAVE, 3, conv_umma_kernel<MODE_INTERLEAVE2, false, false, false, 3>},
-      {EV_F32, 1, conv_umma_kernel<MODE_SAME, false, false, true, 1>},
+      {EV_PLAIN, 1, conv_umma_kernel<MODE_SAME, false, false, 1>}, {EV_PLAIN, 3, conv_umma_kernel<MODE_SAME, false, false, 3>},
+      {EV_PLAIN, 5, conv_umma_kernel<MODE_SAME, false, false, 5>}, {EV_PLAIN, 7, conv_umma_kernel<MODE_SAME, false, false, 7>},
+      {EV_POOL, 3, conv_umma_kernel<MODE_SAME, true, false, 3>},   {EV_RES, 3, conv_umma_kernel<MODE_SAME, false, true, 3>},
+      {EV_INTERLEAVE, 1, conv_umma_kernel<MODE_INTERLEAVE2, false, false, 1>},
+      {EV_INTERLEAVE, 3, conv_umma_kernel<MODE_INTERLEAVE2, false, false, 3>},
   };
   static bool attr_set = false;
   if (!attr_set) {

@@ -33,7 +33,7 @@ struct Umma2Cfg {
   int ncol, tmem_cols, nks, smem_bytes;
 };
 
-template <int MODE, bool POOL, bool RES, bool OUTF32, int TAPS>
+template <int MODE, bool POOL, bool RES, int TAPS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UMMA2_THREADS, 1)
 conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ Umma2Cfg cfg, int num_pairs) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -213,14 +213,14 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
       const int t = tl_in_item * TILE_M + q * 32 + lane;   // >= Tin for a dead tile => every store is masked
       const int buf = tl & 1;
       const uint32_t aph = (uint32_t)(tl >> 1) & 1u;
-      const EpiRow row = epi_row<MODE, POOL, RES, OUTF32>(p, b, t, gcol0);
+      const EpiRow row = epi_row<MODE, POOL, RES>(p, b, t, gcol0);
       uint4 resv[2];
       epi_prefetch_res<RES>(row, active, resv);
       mbar_wait(tfull_bar(buf), aph);
       tc_fence_after();
       if (active) {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * cfg.ncol + col_lo);
-        epi_store<MODE, POOL, RES, OUTF32>(row, s_bias + col_lo, taddr, wcols, slope, resv);
+        epi_store<MODE, POOL, RES>(row, s_bias + col_lo, taddr, wcols, slope, resv);
       }
       tc_fence_before();
       __syncwarp();
@@ -275,12 +275,11 @@ int launch_conv_umma2(const ConvParams& p, cudaStream_t stream) {
   using Kernel = void (*)(ConvParams, Umma2Cfg, int);
   struct Entry { int variant, taps; Kernel k; };
   static const Entry table[] = {
-      {EV_PLAIN, 1, conv_umma2_kernel<MODE_SAME, false, false, false, 1>}, {EV_PLAIN, 3, conv_umma2_kernel<MODE_SAME, false, false, false, 3>},
-      {EV_PLAIN, 5, conv_umma2_kernel<MODE_SAME, false, false, false, 5>}, {EV_PLAIN, 7, conv_umma2_kernel<MODE_SAME, false, false, false, 7>},
-      {EV_POOL, 3, conv_umma2_kernel<MODE_SAME, true, false, false, 3>},   {EV_RES, 3, conv_umma2_kernel<MODE_SAME, false, true, false, 3>},
-      {EV_INTERLEAVE, 1, conv_umma2_kernel<MODE_INTERLEAVE2, false, false, false, 1>},
-      {EV_INTERLEAVE, 3, conv_umma2_kernel<MODE_INTERLEAVE2, false, false, false, 3>},
-      {EV_F32, 1, conv_umma2_kernel<MODE_SAME, false, false, true, 1>},
+      {EV_PLAIN, 1, conv_umma2_kernel<MODE_SAME, false, false, 1>}, {EV_PLAIN, 3, conv_umma2_kernel<MODE_SAME, false, false, 3>},
+      {EV_PLAIN, 5, conv_umma2_kernel<MODE_SAME, false, false, 5>}, {EV_PLAIN, 7, conv_umma2_kernel<MODE_SAME, false, false, 7>},
+      {EV_POOL, 3, conv_umma2_kernel<MODE_SAME, true, false, 3>},   {EV_RES, 3, conv_umma2_kernel<MODE_SAME, false, true, 3>},
+      {EV_INTERLEAVE, 1, conv_umma2_kernel<MODE_INTERLEAVE2, false, false, 1>},
+      {EV_INTERLEAVE, 3, conv_umma2_kernel<MODE_INTERLEAVE2, false, false, 3>},
   };
   static bool attr_set = false;
   if (!attr_set) {

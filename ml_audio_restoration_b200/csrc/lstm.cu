@@ -50,7 +50,7 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
 
 template <int S, int PF>
 __global__ void __launch_bounds__(256, (S <= 2) ? 2 : 1)
-lstm_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const float* __restrict__ whh,
+lstm_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, const float* __restrict__ whh,
             __half* __restrict__ hout, long long h_bs, int h_Tp, int B, int T,
             const float* __restrict__ state_in, float* __restrict__ state_out) {
   __shared__ __align__(16) float hbuf[2][S][LSTM_H];
@@ -71,7 +71,7 @@ lstm_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const floa
   }
 
   float c[S];
-  const float* xrow[S];
+  const __half* xrow[S];
 #pragma unroll
   for (int s = 0; s < S; ++s) {
     const int b = min(seq0 + s, B - 1);  // surplus slots replay the last sequence, stores are masked
@@ -82,7 +82,7 @@ lstm_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const floa
       c[s] = state_in[(long long)b * 2 * LSTM_H + LSTM_H + unit];
     }
     if (gate == 0) hbuf[0][s][unit] = h0;
-    xrow[s] = xp + act_off4(xp_bs, xp_Tp, b, row >> 2, 0) + (row & 3);
+    xrow[s] = xp + act_off(xp_bs, xp_Tp, b, row >> 3, 0) + (row & 7);
   }
   __syncthreads();
 
@@ -93,7 +93,7 @@ lstm_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const floa
 #pragma unroll
   for (int s = 0; s < S; ++s)
 #pragma unroll
-    for (int k = 0; k < PF; ++k) xa[s][k] = __ldg(xrow[s] + 4 * min(k, T - 1));
+    for (int k = 0; k < PF; ++k) xa[s][k] = __half2float(__ldg(xrow[s] + 8 * min(k, T - 1)));
 
   int cur = 0;
   float hlast[S];
@@ -104,7 +104,7 @@ lstm_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const floa
 #pragma unroll
     for (int s = 0; s < S; ++s)
 #pragma unroll
-      for (int k = 0; k < PF; ++k) xnext[s][k] = __ldg(xrow[s] + 4 * min(t0 + PF + k, T - 1));
+      for (int k = 0; k < PF; ++k) xnext[s][k] = __half2float(__ldg(xrow[s] + 8 * min(t0 + PF + k, T - 1)));
 #pragma unroll
     for (int k = 0; k < PF; ++k) {
       const int t = t0 + k;
@@ -207,22 +207,22 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-constexpr int LM_XS = 260;                        // padded per-sequence stride of a staged pre-activation row (floats)
-constexpr int LM_XSTEP = LM_SEQ * LM_XS;          // floats per staged step
-constexpr int LM_XBUF = LSTM_BLK * LM_XSTEP;      // floats per 8-step buffer
-constexpr int LM_SMEM = (2 * LM_XBUF + 2 * LM_SEQ * LM_HS + 2 * LSTM_BLK * LM_SEQ * LSTM_H) * 4;
+constexpr int LM_XS = 264;                        // padded per-sequence stride of a staged pre-activation row (halves)
+constexpr int LM_XSTEP = LM_SEQ * LM_XS;          // halves per staged step
+constexpr int LM_XBUF = LSTM_BLK * LM_XSTEP;      // halves per 8-step buffer
+constexpr int LM_SMEM = 2 * LM_XBUF * 2 + (2 * LM_SEQ * LM_HS + 2 * LSTM_BLK * LM_SEQ * LSTM_H) * 4;
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
 __global__ void __launch_bounds__(256, 1)
-lstm_mma_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const float* __restrict__ whh,
+lstm_mma_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, const float* __restrict__ whh,
                 __half* __restrict__ hout, long long h_bs, int h_Tp, int B, int T,
                 const float* __restrict__ state_in, float* __restrict__ state_out) {
   extern __shared__ __align__(16) float lm_smem[];
-  float* const xs = lm_smem;                                   // [2][8 steps][8 seq][260]: staged gate pre-activations
-  float* const hbuf = xs + 2 * LM_XBUF;                        // [2][8 seq][68]
+  __half* const xs = reinterpret_cast<__half*>(lm_smem);       // [2][8 steps][8 seq][264] fp16: staged gate pre-activations
+  float* const hbuf = lm_smem + LM_XBUF;                       // [2][8 seq][68]   (2*LM_XBUF halves == LM_XBUF floats)
   float* const hstage = hbuf + 2 * LM_SEQ * LM_HS;             // [2][8 steps][8 seq][64]
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -258,21 +258,21 @@ lstm_mma_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const 
   hbuf[sa * LM_HS + unit] = to_tf32(hl0);
   hbuf[sb2 * LM_HS + unit] = to_tf32(hl1);
 
-  // Staging of the gate pre-activations: 8 steps x 8 sequences x 64 chunks of 16 bytes per block, copied with
-  // cp.async (16 pieces per thread, consecutive threads = consecutive steps of one (sequence, chunk) run =>
+  // Staging of the gate pre-activations: 8 steps x 8 sequences x 32 chunks of 16 bytes per block, copied with
+  // cp.async (8 pieces per thread, consecutive threads = consecutive steps of one (sequence, chunk) run =>
   // 128-byte coalesced reads), one block ahead of its use.
   const uint32_t xs_u32 = (uint32_t)__cvta_generic_to_shared(xs);
   auto stage_block = [&](int blk) {
     const int t0 = blk * LSTM_BLK;
-    const uint32_t dst0 = xs_u32 + (uint32_t)((blk & 1) * LM_XBUF * 4);
+    const uint32_t dst0 = xs_u32 + (uint32_t)((blk & 1) * LM_XBUF * 2);
 #pragma unroll 4
-    for (int m = 0; m < 16; ++m) {
+    for (int m = 0; m < 8; ++m) {
       const int i = tid + 256 * m;
       const int k = i & 7, run = i >> 3;
-      const int sq = run >> 6, ch = run & 63;
+      const int sq = run >> 5, ch = run & 31;
       const int b = min(seq0 + sq, B - 1);
       const int t = min(t0 + k, T - 1);
-      cp_async16(dst0 + (uint32_t)((k * LM_XSTEP + sq * LM_XS + ch * 4) * 4), xp + act_off4(xp_bs, xp_Tp, b, ch, t));
+      cp_async16(dst0 + (uint32_t)((k * LM_XSTEP + sq * LM_XS + ch * 8) * 2), xp + act_off(xp_bs, xp_Tp, b, ch, t));
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -284,7 +284,7 @@ lstm_mma_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const 
   const int nblk = (T + LSTM_BLK - 1) / LSTM_BLK;
   for (int blk = 0; blk < nblk; ++blk) {
     if (blk + 1 < nblk) stage_block(blk + 1);
-    const float* xb = xs + (blk & 1) * LM_XBUF;
+    const __half* xb = xs + (blk & 1) * LM_XBUF;
     float* hst = hstage + (blk & 1) * (LSTM_BLK * LM_SEQ * LSTM_H);
     const int t0 = blk * LSTM_BLK;
     const int nst = min(LSTM_BLK, T - t0);
@@ -306,13 +306,13 @@ lstm_mma_kernel(const float* __restrict__ xp, long long xp_bs, int xp_Tp, const 
           mma_tf32_16x8x8(acc[0][kt & 1], wfrag[0][kt], b0, b1);
           mma_tf32_16x8x8(acc[1][kt & 1], wfrag[1][kt], b0, b1);
         }
-        const float* xa = xb + k * LM_XSTEP + sa * LM_XS + unit;
-        const float* xbq = xa + LM_XS;
+        const __half* xa = xb + k * LM_XSTEP + sa * LM_XS + unit;
+        const __half* xbq = xa + LM_XS;
         // accumulator layout: [0]=(row gid, col 2tig) [1]=(gid, 2tig+1) [2]=(gid+8, 2tig) [3]=(gid+8, 2tig+1)
-        const float pi0 = acc[0][0][0] + acc[0][1][0] + xa[0], pi1 = acc[0][0][1] + acc[0][1][1] + xbq[0];
-        const float pf0 = acc[0][0][2] + acc[0][1][2] + xa[64], pf1 = acc[0][0][3] + acc[0][1][3] + xbq[64];
-        const float pg0 = acc[1][0][0] + acc[1][1][0] + xa[128], pg1 = acc[1][0][1] + acc[1][1][1] + xbq[128];
-        const float po0 = acc[1][0][2] + acc[1][1][2] + xa[192], po1 = acc[1][0][3] + acc[1][1][3] + xbq[192];
+        const float pi0 = acc[0][0][0] + acc[0][1][0] + __half2float(xa[0]), pi1 = acc[0][0][1] + acc[0][1][1] + __half2float(xbq[0]);
+        const float pf0 = acc[0][0][2] + acc[0][1][2] + __half2float(xa[64]), pf1 = acc[0][0][3] + acc[0][1][3] + __half2float(xbq[64]);
+        const float pg0 = acc[1][0][0] + acc[1][1][0] + __half2float(xa[128]), pg1 = acc[1][0][1] + acc[1][1][1] + __half2float(xbq[128]);
+        const float po0 = acc[1][0][2] + acc[1][1][2] + __half2float(xa[192]), po1 = acc[1][0][3] + acc[1][1][3] + __half2float(xbq[192]);
         c0 = sigmoid_f(pf0) * c0 + sigmoid_f(pi0) * tanh_f(pg0);
         c1 = sigmoid_f(pf1) * c1 + sigmoid_f(pi1) * tanh_f(pg1);
         hl0 = sigmoid_f(po0) * tanh_f(c0);
@@ -373,14 +373,14 @@ int launch_lstm(const Act& xp, const float* whh, const Act& h_out, int B, int T,
       AR_CUDA_OK(cudaFuncSetAttribute(lstm_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_SMEM));
       attr_set = true;
     }
-    lstm_mma_kernel<<<(B + LM_SEQ - 1) / LM_SEQ, 256, LM_SMEM, stream>>>(xp.f(), xp.bs, xp.Tp, whh, h_out.h(), h_out.bs, h_out.Tp, B, T,
+    lstm_mma_kernel<<<(B + LM_SEQ - 1) / LM_SEQ, 256, LM_SMEM, stream>>>(xp.h(), xp.bs, xp.Tp, whh, h_out.h(), h_out.bs, h_out.Tp, B, T,
                                                                   state_in, state_out);
     AR_CUDA_OK(cudaGetLastError());
     return AR_OK;
   }
   int S = forced ? forced : 1;
 #define AR_LSTM_LAUNCH(SS, PF)                                                                                 \
-  lstm_kernel<SS, PF><<<(B + SS - 1) / SS, 256, 0, stream>>>(xp.f(), xp.bs, xp.Tp, whh, h_out.h(), h_out.bs, h_out.Tp, B, \
+  lstm_kernel<SS, PF><<<(B + SS - 1) / SS, 256, 0, stream>>>(xp.h(), xp.bs, xp.Tp, whh, h_out.h(), h_out.bs, h_out.Tp, B, \
                                                              T, state_in, state_out)
   if (S == 4) AR_LSTM_LAUNCH(4, 4);
   else if (S == 2) AR_LSTM_LAUNCH(2, 4);

@@ -27,7 +27,7 @@ int launch_ola(const float* y, float* out, long long n, int n_chunks, int channe
 int launch_plain_to_c4(const float* x, int B, int C, int T, const Act& out, cudaStream_t stream);
 int launch_c4_to_plain(const Act& in, int B, int C, int T, float* y, cudaStream_t stream);
 
-// xp: C4 fp32 [B][256 ch] gate pre-activations (W_ih x + b_ih + b_hh, rows i|f|g|o), whh: [256][64] device,
+// xp: H8 fp16 [B][256 ch] gate pre-activations (W_ih x + b_ih + b_hh, rows i|f|g|o), whh: [256][64] device,
 // h_out: H8 fp16 [B][64 ch]; state_in/out: [B][2][64] (h, c) or nullptr.
 int launch_lstm(const Act& xp, const float* whh, const Act& h_out, int B, int T, const float* state_in, float* state_out,
                 cudaStream_t stream);

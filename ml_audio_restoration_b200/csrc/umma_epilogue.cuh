@@ -3,7 +3,7 @@
 // the work is: bias add, LeakyReLU as max(v, slope*v), (residual add), round to fp16 and ONE coalesced 16-byte
 // store per thread (consecutive lanes = consecutive rows = consecutive 16 bytes of the H8 layout), plus the
 // fused max-pool copy / 2x interleave ("pixel shuffle") / right zero-pad column where the layer needs them.
-// Output row addresses are hoisted per tile.  OUTF32 writes fp32 C4 instead (LSTM gate pre-activations).
+// Output row addresses are hoisted per tile.
 #pragma once
 #include "ar_common.cuh"
 #include "umma_ptx.cuh"
@@ -21,21 +21,15 @@ struct EpiRow {
   bool ok0, ok1, pok, in_ok;
 };
 
-template <int MODE, bool POOL, bool RES, bool OUTF32>
+template <int MODE, bool POOL, bool RES>
 __device__ __forceinline__ EpiRow epi_row(const ConvParams& p, int b, int t, int gcol0) {
   EpiRow r;
   r.in_ok = t < p.Tin;
   r.o1 = nullptr; r.prow = nullptr; r.rrow = nullptr; r.ok1 = false; r.pok = false;
   r.pstride = 0; r.rstride = 0;
   const int tt = r.in_ok ? t : 0;   // keep the address arithmetic in range for masked rows
-  if (OUTF32) {
-    r.ostride = (long long)p.out_Tp * 16;   // 4 floats per row
-    r.o0 = reinterpret_cast<char*>(p.out) + 4 * act_off4(p.out_bs, p.out_Tp, b, p.out_coff8 + (gcol0 >> 2), tt);
-    r.ok0 = r.in_ok && t < p.Tout;
-    return r;
-  }
   r.ostride = (long long)p.out_Tp * 16;     // 8 halves per row
-  __half* out = reinterpret_cast<__half*>(p.out);
+  __half* out = p.out;
   int chunk0;
   if (MODE == MODE_SAME) {
     chunk0 = gcol0 >> 3;
@@ -74,7 +68,7 @@ __device__ __forceinline__ void epi_prefetch_res(const EpiRow& r, bool active, u
   }
 }
 
-template <int MODE, bool POOL, bool RES, bool OUTF32>
+template <int MODE, bool POOL, bool RES>
 __device__ __forceinline__ void epi_store(const EpiRow& r, const float* s_bias_w /* bias of this warp's first column */, uint32_t taddr,
                                           int wcols, float slope, const uint4 (&resv)[2]) {
   for (int cb = 0; cb < wcols; cb += 32) {
@@ -101,12 +95,7 @@ __device__ __forceinline__ void epi_store(const EpiRow& r, const float* s_bias_w
           for (int i = 0; i < 8; ++i) v[i] += rr[i];
         }
         const int ch = (cb >> 3) + c;               // 8-column chunk index within this warp's range
-        if (OUTF32) {
-          if (r.ok0) {
-            *reinterpret_cast<float4*>(r.o0 + (long long)(2 * ch) * r.ostride) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(r.o0 + (long long)(2 * ch + 1) * r.ostride) = make_float4(v[4], v[5], v[6], v[7]);
-          }
-        } else {
+        {
           const uint4 packed = pack_half8(v);
           if (r.ok0) *reinterpret_cast<uint4*>(r.o0 + (long long)ch * r.ostride) = packed;
           if (MODE == MODE_INTERLEAVE2) {
@@ -126,9 +115,8 @@ __device__ __forceinline__ void epi_store(const EpiRow& r, const float* s_bias_w
 }
 
 // (variant, taps) -> kernel instantiation table shared by both engines' launchers
-enum EpiVariant { EV_PLAIN = 0, EV_POOL = 1, EV_RES = 2, EV_INTERLEAVE = 3, EV_F32 = 4 };
+enum EpiVariant { EV_PLAIN = 0, EV_POOL = 1, EV_RES = 2, EV_INTERLEAVE = 3 };
 __host__ inline int epi_variant(const ConvParams& p) {
-  if (p.out_f32) return EV_F32;
   if (p.mode == MODE_INTERLEAVE2) return EV_INTERLEAVE;
   if (p.pool) return EV_POOL;
   if (p.res) return EV_RES;

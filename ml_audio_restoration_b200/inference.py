@@ -221,11 +221,11 @@ class RestorationPipeline:
         c0 = max(lo - 1, 0)
         cnt_all = hi - c0
         if batch_chunks <= 0:
-            # four chunks per SM: one launch of the tensor-core LSTM scan (8 sequences per CTA) then covers the
-            # batch; bounded by what the workspace of `streams` concurrent batches may take
+            # eight chunks per SM: one launch of the tensor-core LSTM scan (8 sequences per CTA) then fills the
+            # chip; bounded by what the workspace of `streams` concurrent batches may take
             free, _ = torch.cuda.mem_get_info(self.device)
             sms = torch.cuda.get_device_properties(self.device).multi_processor_count
-            batch_chunks = min(cnt_all, 4 * sms, self.max_batch(chunk_size, int(free * 0.6) // max(1, streams)))
+            batch_chunks = min(cnt_all, 8 * sms, self.max_batch(chunk_size, int(free * 0.6) // max(1, streams)))
         y_all = torch.empty((cnt_all, 2, r * chunk_size), dtype=torch.float32, device=self.device)
         firsts = list(range(c0, hi, batch_chunks))
         n_streams = max(1, min(streams, len(firsts)))
