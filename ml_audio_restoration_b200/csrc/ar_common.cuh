@@ -64,6 +64,14 @@ __device__ __forceinline__ long long act_off(long long bs, int Tp, int b, int ch
   return (long long)b * bs + ((long long)chunk * Tp + (HALO + t)) * 8;
 }
 
+// Time-blocked H8 ("TB8"): [B][Tp/8][C/8][8 steps][8] -- all channels of 8 consecutive time steps are one
+// contiguous (C*16)-byte run.  Used for the LSTM gate pre-activations only: the recurrence streams a
+// sequence strictly in time order, and 4 KB runs are what HBM likes (plain H8 would be 128-byte pieces).
+__device__ __forceinline__ long long act_off_tb(long long bs, int C8, int b, int chunk, int t) {
+  const int tr = HALO + t;
+  return (long long)b * bs + (((long long)(tr >> 3) * C8 + chunk) * 8 + (tr & 7)) * 8;
+}
+
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {  // round to nearest, clamp to the fp16 range
   a = fminf(fmaxf(a, -HALF_MAX), HALF_MAX);
   b = fminf(fmaxf(b, -HALF_MAX), HALF_MAX);
@@ -111,6 +119,7 @@ struct ConvParams {
   __half* out;
   long long out_bs;
   int out_Tp, out_coff8;
+  int out_tblock;        // write the time-blocked variant of H8 (act_off_tb) instead -- LSTM gate pre-activations
   int Tout;              // valid output length
   __half* pool;          // optional max-pool(2,2) copy of the output (MODE_SAME only), H8
   long long pool_bs;
@@ -147,7 +156,11 @@ __device__ __forceinline__ void epilogue_chunk8(const ConvParams& p, int b, int 
   const bool row_ok = (t < p.Tin) && (trow < p.Tout);
   __half* o = p.out;
   const uint4 packed = pack_half8(v);
-  if (row_ok) *reinterpret_cast<uint4*>(o + act_off(p.out_bs, p.out_Tp, b, p.out_coff8 + (col >> 3), trow)) = packed;
+  if (row_ok) {
+    const long long off = p.out_tblock ? act_off_tb(p.out_bs, p.N >> 3, b, col >> 3, trow)
+                                       : act_off(p.out_bs, p.out_Tp, b, p.out_coff8 + (col >> 3), trow);
+    *reinterpret_cast<uint4*>(o + off) = packed;
+  }
   if (p.mode == MODE_INTERLEAVE2 && t == p.Tin - 1 && 2 * p.Tin < p.Tout && n0 < (p.N >> 1))
     *reinterpret_cast<uint4*>(o + act_off(p.out_bs, p.out_Tp, b, p.out_coff8 + (col >> 3), 2 * p.Tin)) = make_uint4(0u, 0u, 0u, 0u);
   if (p.pool != nullptr) {  // MaxPool1d(2,2), floor; max of the ROUNDED values == rounded max (rounding is monotonic)

@@ -30,6 +30,25 @@ __device__ __forceinline__ float rcp_f(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// One LSTM cell update with 5 ex2 + 2 rcp (the special-function unit, 16 lanes/clk/SM, is the throughput limit of
+// the tensor-core recurrence kernel): the three gate functions of the cell state share ONE reciprocal,
+//   s(f) c + s(i) tanh(g) = [ c (1+b)(1+d) + (1-d)(1+a) ] / [ (1+a)(1+b)(1+d) ],  a=e^-f, b=e^-i, d=e^-2g,
+// and so do s(o) tanh(c').  Pre-activations are clamped to +-20 (changes a gate by < 3e-9) so the product of
+// three exponentials stays finite.
+__device__ __forceinline__ void lstm_cell(float pi, float pf, float pg, float po, float& c, float& h) {
+  const float L2E = 1.4426950408889634f;
+  pi = fminf(fmaxf(pi, -20.f), 20.f);
+  pf = fminf(fmaxf(pf, -20.f), 20.f);
+  pg = fminf(fmaxf(pg, -20.f), 20.f);
+  po = fminf(fmaxf(po, -20.f), 20.f);
+  const float a = ex2_f(-L2E * pf), b = ex2_f(-L2E * pi), d = ex2_f(-2.f * L2E * pg);
+  const float bd = (1.f + b) * (1.f + d);
+  const float num = fmaf(c, bd, (1.f - d) * (1.f + a));
+  c = num * rcp_f((1.f + a) * bd);
+  const float cc = fminf(fmaxf(c, -20.f), 20.f);
+  const float q = ex2_f(-L2E * po), e = ex2_f(-2.f * L2E * cc);
+  h = (1.f - e) * rcp_f((1.f + q) * (1.f + e));
+}
 __device__ __forceinline__ float sigmoid_f(float x) { return rcp_f(1.0f + ex2_f(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float tanh_f(float x) { return 1.0f - 2.0f * rcp_f(ex2_f(2.8853900817779268f * x) + 1.0f); }
 
@@ -46,6 +65,12 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
   unsigned long long d;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
+}
+
+// offset (halves) of time step t inside one sequence of the time-blocked 256-channel pre-activation tensor
+__device__ __forceinline__ long long tb_off(int t) {
+  const int tr = HALO + t;
+  return (long long)(tr >> 3) * (32 * 64) + (tr & 7) * 8;
 }
 
 template <int S, int PF>
@@ -82,7 +107,8 @@ lstm_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, const flo
       c[s] = state_in[(long long)b * 2 * LSTM_H + LSTM_H + unit];
     }
     if (gate == 0) hbuf[0][s][unit] = h0;
-    xrow[s] = xp + act_off(xp_bs, xp_Tp, b, row >> 3, 0) + (row & 7);
+    const int xcol = unit * 4 + gate;   // pre-activation channels are stored [unit][gate], time-blocked (act_off_tb)
+    xrow[s] = xp + (long long)b * xp_bs + (xcol >> 3) * 64 + (xcol & 7);
   }
   __syncthreads();
 
@@ -93,7 +119,7 @@ lstm_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, const flo
 #pragma unroll
   for (int s = 0; s < S; ++s)
 #pragma unroll
-    for (int k = 0; k < PF; ++k) xa[s][k] = __half2float(__ldg(xrow[s] + 8 * min(k, T - 1)));
+    for (int k = 0; k < PF; ++k) xa[s][k] = __half2float(__ldg(xrow[s] + tb_off(min(k, T - 1))));
 
   int cur = 0;
   float hlast[S];
@@ -104,7 +130,7 @@ lstm_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, const flo
 #pragma unroll
     for (int s = 0; s < S; ++s)
 #pragma unroll
-      for (int k = 0; k < PF; ++k) xnext[s][k] = __half2float(__ldg(xrow[s] + 8 * min(t0 + PF + k, T - 1)));
+      for (int k = 0; k < PF; ++k) xnext[s][k] = __half2float(__ldg(xrow[s] + tb_off(min(t0 + PF + k, T - 1))));
 #pragma unroll
     for (int k = 0; k < PF; ++k) {
       const int t = t0 + k;
@@ -189,20 +215,20 @@ lstm_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, const flo
 
 // ============================================================================ tensor-core recurrence
 // Eight sequences per CTA: the recurrent mat-vec of a step becomes a [256 x 64] x [64 x 8] product run on
-// warp-level tensor-core MMAs (mma.sync m16n8k8, TF32 operands, fp32 accumulate).  W_hh is rounded to TF32
-// like every other weight of the model and h is rounded to TF32 before it is fed back -- it is the same
+// warp-level tensor-core MMAs (mma.sync m16n8k16, fp16 operands, fp32 accumulate).  W_hh is rounded to fp16
+// like every other weight of the model and h is rounded to fp16 before it is fed back -- it is the same
 // rounded value the decoder convs consume -- while the cell state c, the gate pre-activations and all gate
 // math stay fp32 (measured on the oracle: output SNR > 100 dB vs the all-fp32 recurrence, tests/ check it).
 // Warp w owns hidden units [8w, 8w+8): its two 16-row MMA tiles hold rows (i,f) and (g,o) of those units, so
 // in the accumulator layout one thread ends up with all four gates of ONE unit for TWO sequences and the
-// cell update needs no cross-thread exchange.  h goes through shared memory ([seq][unit], stride 68 floats:
-// conflict-free both for the update's stores and for the B-fragment loads); one block barrier per step.
+// cell update needs no cross-thread exchange.  h goes through shared memory ([seq][unit] fp16, stride 72
+// halves: conflict-free B-fragment loads); one block barrier per step.
 constexpr int LM_SEQ = 8;       // sequences per CTA
-constexpr int LM_HS = 68;       // padded row stride of the h exchange buffer
+constexpr int LM_HS = 80;       // padded row stride of the h exchange buffer (halves): conflict-free 8-byte fragment loads
 
-__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void mma_f16_16x8x16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -210,149 +236,162 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&
 constexpr int LM_XS = 264;                        // padded per-sequence stride of a staged pre-activation row (halves)
 constexpr int LM_XSTEP = LM_SEQ * LM_XS;          // halves per staged step
 constexpr int LM_XBUF = LSTM_BLK * LM_XSTEP;      // halves per 8-step buffer
-constexpr int LM_SMEM = 2 * LM_XBUF * 2 + (2 * LM_SEQ * LM_HS + 2 * LSTM_BLK * LM_SEQ * LSTM_H) * 4;
+constexpr int LM_HST = 68;      // padded [seq] row stride of the hidden-state staging buffer (floats): conflict-free stores
+constexpr int LM_SMEM = 2 * LM_XBUF * 2 + 2 * LM_SEQ * LM_HS * 2 + 2 * LSTM_BLK * LM_SEQ * LM_HST * 4;
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
-__global__ void __launch_bounds__(256, 1)
+// 16 warps: warp w owns hidden units [4w, 4w+4) = ONE 16-row MMA tile ordered (i | g | f | o) x 4 units.  In
+// the accumulator layout lane (gid, tig) then holds gates (i,f) [gid < 4] or (g,o) [gid >= 4] of unit 4w+(gid&3)
+// for sequences 2tig and 2tig+1; one shuffle pair with lane^16 gives every thread all four gates of ONE
+// (unit, sequence), so the 512 threads each carry one cell.  The per-step dependent chain per warp is short
+// (4 MMAs, 5 gate functions) and four warps per scheduler interleave -- the kernel is latency-bound.
+constexpr int LM_THREADS = 512;
+
+__global__ void __launch_bounds__(LM_THREADS, 1)
 lstm_mma_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, const float* __restrict__ whh,
                 __half* __restrict__ hout, long long h_bs, int h_Tp, int B, int T,
                 const float* __restrict__ state_in, float* __restrict__ state_out) {
   extern __shared__ __align__(16) float lm_smem[];
   __half* const xs = reinterpret_cast<__half*>(lm_smem);       // [2][8 steps][8 seq][264] fp16: staged gate pre-activations
-  float* const hbuf = lm_smem + LM_XBUF;                       // [2][8 seq][68]   (2*LM_XBUF halves == LM_XBUF floats)
-  float* const hstage = hbuf + 2 * LM_SEQ * LM_HS;             // [2][8 steps][8 seq][64]
+  float* const hstage = lm_smem + LM_XBUF;                     // [2][8 steps][8 seq][64] fp32 (2*LM_XBUF halves == LM_XBUF floats)
+  __half* const hbuf = reinterpret_cast<__half*>(hstage + 2 * LSTM_BLK * LM_SEQ * LM_HST);   // [2][8 seq][80] fp16
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int gid = lane >> 2, tig = lane & 3;        // mma fragment coordinates
-  const int unit = warp * 8 + gid;                  // hidden unit whose 4 gates this thread finishes
+  const bool lowhalf = gid < 4;                     // holds (i,f); the partner lane^16 holds (g,o)
+  const int unit = warp * 4 + (gid & 3);            // the cell this thread carries: (unit, seq)
+  const int seq = 2 * tig + (lowhalf ? 0 : 1);
   const int seq0 = blockIdx.x * LM_SEQ;
-  const int sa = 2 * tig, sb2 = 2 * tig + 1;        // the two sequences (columns) this thread finishes
+  const int bq = min(seq0 + seq, B - 1);            // surplus columns replay the last sequence, stores are masked
 
-  // A fragments: tile 0 = rows (i | f), tile 1 = rows (g | o) of this warp's 8 units; 8 k-tiles each.
-  uint32_t wfrag[2][8][4];
+  // A fragment rows of this lane: gid -> (gate i or g), gid+8 -> (gate f or o) of unit 4w + (gid & 3)
+  uint32_t wfrag[4][4];
+  {
+    const int u = warp * 4 + (gid & 3);
+    const int row_lo = (lowhalf ? 0 : 2) * LSTM_H + u;     // i or g
+    const int row_hi = (lowhalf ? 1 : 3) * LSTM_H + u;     // f or o
+    auto w2 = [&](int row, int k) {
+      const __half2 h = __floats2half2_rn(whh[row * LSTM_H + k], whh[row * LSTM_H + k + 1]);
+      return *reinterpret_cast<const uint32_t*>(&h);
+    };
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
-    const int row_lo = (2 * mt) * LSTM_H + warp * 8 + gid;       // gate i (mt=0) / g (mt=1)
-    const int row_hi = (2 * mt + 1) * LSTM_H + warp * 8 + gid;   // gate f / o
-#pragma unroll
-    for (int kt = 0; kt < 8; ++kt) {
-      wfrag[mt][kt][0] = __float_as_uint(to_tf32(whh[row_lo * LSTM_H + kt * 8 + tig]));
-      wfrag[mt][kt][1] = __float_as_uint(to_tf32(whh[row_hi * LSTM_H + kt * 8 + tig]));
-      wfrag[mt][kt][2] = __float_as_uint(to_tf32(whh[row_lo * LSTM_H + kt * 8 + tig + 4]));
-      wfrag[mt][kt][3] = __float_as_uint(to_tf32(whh[row_hi * LSTM_H + kt * 8 + tig + 4]));
+    for (int kt = 0; kt < 4; ++kt) {
+      wfrag[kt][0] = w2(row_lo, kt * 16 + 2 * tig);
+      wfrag[kt][1] = w2(row_hi, kt * 16 + 2 * tig);
+      wfrag[kt][2] = w2(row_lo, kt * 16 + 2 * tig + 8);
+      wfrag[kt][3] = w2(row_hi, kt * 16 + 2 * tig + 8);
     }
   }
 
-  // per-thread state: (unit, seq sa) and (unit, seq sb2)
-  const int ba = min(seq0 + sa, B - 1), bb = min(seq0 + sb2, B - 1);
-  float c0 = 0.f, c1 = 0.f, hl0 = 0.f, hl1 = 0.f;
+  float c = 0.f, hl = 0.f;
   if (state_in != nullptr) {
-    c0 = state_in[(long long)ba * 2 * LSTM_H + LSTM_H + unit];
-    c1 = state_in[(long long)bb * 2 * LSTM_H + LSTM_H + unit];
-    hl0 = state_in[(long long)ba * 2 * LSTM_H + unit];
-    hl1 = state_in[(long long)bb * 2 * LSTM_H + unit];
+    hl = state_in[(long long)bq * 2 * LSTM_H + unit];
+    c = state_in[(long long)bq * 2 * LSTM_H + LSTM_H + unit];
   }
-  hbuf[sa * LM_HS + unit] = to_tf32(hl0);
-  hbuf[sb2 * LM_HS + unit] = to_tf32(hl1);
+  // position of hidden unit `unit` inside its sequence row: within each 16-unit k-tile the pairs (2j, 2j+1) and
+  // (2j+8, 2j+9) that form one thread's B fragment (b0, b1) are made adjacent => one 8-byte load per k-tile
+  const int upos = (unit & ~15) + ((((unit & 7) >> 1) * 2 + ((unit >> 3) & 1)) * 2) + (unit & 1);
+  hbuf[seq * LM_HS + upos] = __float2half_rn(hl);
 
   // Staging of the gate pre-activations: 8 steps x 8 sequences x 32 chunks of 16 bytes per block, copied with
-  // cp.async (8 pieces per thread, consecutive threads = consecutive steps of one (sequence, chunk) run =>
+  // cp.async (4 pieces per thread, consecutive threads = consecutive steps of one (sequence, chunk) run =>
   // 128-byte coalesced reads), one block ahead of its use.
   const uint32_t xs_u32 = (uint32_t)__cvta_generic_to_shared(xs);
-  auto stage_block = [&](int blk) {
+  auto stage_piece = [&](int blk, int m) {          // piece m (0..3) of this thread's share of block blk
     const int t0 = blk * LSTM_BLK;
     const uint32_t dst0 = xs_u32 + (uint32_t)((blk & 1) * LM_XBUF * 2);
-#pragma unroll 4
-    for (int m = 0; m < 8; ++m) {
-      const int i = tid + 256 * m;
-      const int k = i & 7, run = i >> 3;
-      const int sq = run >> 5, ch = run & 31;
-      const int b = min(seq0 + sq, B - 1);
-      const int t = min(t0 + k, T - 1);
-      cp_async16(dst0 + (uint32_t)((k * LM_XSTEP + sq * LM_XS + ch * 8) * 2), xp + act_off(xp_bs, xp_Tp, b, ch, t));
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    // 8 steps x 32 chunks of one sequence are ONE contiguous 4 KB run (HALO == 8 keeps blocks aligned):
+    // consecutive threads take consecutive 16-byte pieces of it
+    const int i = tid + LM_THREADS * m;           // 0..2047
+    const int sq = i >> 8, piece = i & 255;       // piece = chunk*8 + step
+    const int ch = piece >> 3, k = piece & 7;
+    const int b = min(seq0 + sq, B - 1);
+    cp_async16(dst0 + (uint32_t)((k * LM_XSTEP + sq * LM_XS + ch * 8) * 2), xp + act_off_tb(xp_bs, 32, b, ch, t0 + k));
   };
-  stage_block(0);
+  // one hidden-state item per thread per block: [8 seq][8 chunks][8 steps] x 16 bytes, coalesced along time
+  auto flush_item = [&](int blk) {
+    const float* hst = hstage + (blk & 1) * (LSTM_BLK * LM_SEQ * LM_HST);
+    const int t0 = blk * LSTM_BLK;
+    const int s = tid / (8 * LSTM_BLK);              // LM_SEQ * 8 * LSTM_BLK == 512 == LM_THREADS
+    const int ch = (tid / LSTM_BLK) % 8;
+    const int kk = tid % LSTM_BLK;
+    const int b = seq0 + s;
+    if (b < B && t0 + kk < T) {
+      const float* src = &hst[(kk * LM_SEQ + s) * LM_HST + 8 * ch];
+      const float4 v0 = *reinterpret_cast<const float4*>(src);
+      const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
+      const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      *reinterpret_cast<uint4*>(hout + act_off(h_bs, h_Tp, b, ch, t0 + kk)) = pack_half8(v);
+    }
+  };
+#pragma unroll
+  for (int m = 0; m < 4; ++m) stage_piece(0, m);
+  asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
+  // The staging of block blk+1 and the write-back of block blk-1 are spread over the steps of block blk (one
+  // cp.async every other step, one warp-pair flushing per step) instead of bursting at the block boundary,
+  // where all 16 warps would queue on the memory pipe at once.
   int cur = 0;
   const int nblk = (T + LSTM_BLK - 1) / LSTM_BLK;
+  const int my_flush_step = warp & 7;
   for (int blk = 0; blk < nblk; ++blk) {
-    if (blk + 1 < nblk) stage_block(blk + 1);
+    const bool more = blk + 1 < nblk;
     const __half* xb = xs + (blk & 1) * LM_XBUF;
-    float* hst = hstage + (blk & 1) * (LSTM_BLK * LM_SEQ * LSTM_H);
+    float* hst = hstage + (blk & 1) * (LSTM_BLK * LM_SEQ * LM_HST);
     const int t0 = blk * LSTM_BLK;
     const int nst = min(LSTM_BLK, T - t0);
+    if (!more && blk > 0) flush_item(blk - 1);       // last (possibly short) block: write the previous one up front
 #pragma unroll
     for (int k = 0; k < LSTM_BLK; ++k) {
       if (k < nst) {  // uniform
-        float acc[2][2][4];
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[mt][h][i] = 0.f;
-        const float* hb = hbuf + cur * (LM_SEQ * LM_HS) + gid * LM_HS + tig;
-#pragma unroll
-        for (int kt = 0; kt < 8; ++kt) {
-          const uint32_t b0 = __float_as_uint(hb[kt * 8]);
-          const uint32_t b1 = __float_as_uint(hb[kt * 8 + 4]);
-          mma_tf32_16x8x8(acc[0][kt & 1], wfrag[0][kt], b0, b1);
-          mma_tf32_16x8x8(acc[1][kt & 1], wfrag[1][kt], b0, b1);
+        if (more) {
+          if ((k & 1) == 0) stage_piece(blk + 1, k >> 1);
+          if (k == 6) asm volatile("cp.async.commit_group;" ::: "memory");
+          if (blk > 0 && k == my_flush_step) flush_item(blk - 1);
         }
-        const __half* xa = xb + k * LM_XSTEP + sa * LM_XS + unit;
-        const __half* xbq = xa + LM_XS;
-        // accumulator layout: [0]=(row gid, col 2tig) [1]=(gid, 2tig+1) [2]=(gid+8, 2tig) [3]=(gid+8, 2tig+1)
-        const float pi0 = acc[0][0][0] + acc[0][1][0] + __half2float(xa[0]), pi1 = acc[0][0][1] + acc[0][1][1] + __half2float(xbq[0]);
-        const float pf0 = acc[0][0][2] + acc[0][1][2] + __half2float(xa[64]), pf1 = acc[0][0][3] + acc[0][1][3] + __half2float(xbq[64]);
-        const float pg0 = acc[1][0][0] + acc[1][1][0] + __half2float(xa[128]), pg1 = acc[1][0][1] + acc[1][1][1] + __half2float(xbq[128]);
-        const float po0 = acc[1][0][2] + acc[1][1][2] + __half2float(xa[192]), po1 = acc[1][0][3] + acc[1][1][3] + __half2float(xbq[192]);
-        c0 = sigmoid_f(pf0) * c0 + sigmoid_f(pi0) * tanh_f(pg0);
-        c1 = sigmoid_f(pf1) * c1 + sigmoid_f(pi1) * tanh_f(pg1);
-        hl0 = sigmoid_f(po0) * tanh_f(c0);
-        hl1 = sigmoid_f(po1) * tanh_f(c1);
-        // fed-back h == the fp16-rounded value the decoder convs will read (exactly representable in TF32)
-        const float hr0 = __half2float(__float2half_rn(hl0)), hr1 = __half2float(__float2half_rn(hl1));
-        float* hn = hbuf + (cur ^ 1) * (LM_SEQ * LM_HS);
-        hn[sa * LM_HS + unit] = hr0;
-        hn[sb2 * LM_HS + unit] = hr1;
-        hst[(k * LM_SEQ + sa) * LSTM_H + unit] = hr0;
-        hst[(k * LM_SEQ + sb2) * LSTM_H + unit] = hr1;
-        if (k == nst - 1) asm volatile("cp.async.wait_group 0;" ::: "memory");   // next block's staging has landed
+        float acc[2][4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[h][i] = 0.f;
+        const uint2* hb = reinterpret_cast<const uint2*>(hbuf + cur * (LM_SEQ * LM_HS) + gid * LM_HS) + tig;
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt) {
+          const uint2 bf = hb[kt * 4];           // .x = h[16kt + 2tig, +1], .y = h[16kt + 2tig + 8, +9] of sequence gid
+          mma_f16_16x8x16(acc[kt & 1], wfrag[kt], bf.x, bf.y);
+        }
+        // [0]=(row gid, seq 2tig) [1]=(gid, 2tig+1) [2]=(gid+8, 2tig) [3]=(gid+8, 2tig+1)
+        const float v0 = acc[0][0] + acc[1][0], v1 = acc[0][1] + acc[1][1];
+        const float v2 = acc[0][2] + acc[1][2], v3 = acc[0][3] + acc[1][3];
+        // lowhalf keeps sequence 2tig (needs g,o of it), the partner keeps 2tig+1 (needs i,f of it)
+        const float r0 = __shfl_xor_sync(0xffffffffu, lowhalf ? v1 : v0, 16);
+        const float r1 = __shfl_xor_sync(0xffffffffu, lowhalf ? v3 : v2, 16);
+        const uint2 q = *reinterpret_cast<const uint2*>(xb + k * LM_XSTEP + seq * LM_XS + unit * 4);   // [unit][i,f,g,o]
+        const float2 x_if = __half22float2(*reinterpret_cast<const __half2*>(&q.x));
+        const float2 x_go = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+        const float pi = (lowhalf ? v0 : r0) + x_if.x;
+        const float pf = (lowhalf ? v2 : r1) + x_if.y;
+        const float pg = (lowhalf ? r0 : v1) + x_go.x;
+        const float po = (lowhalf ? r1 : v3) + x_go.y;
+        lstm_cell(pi, pf, pg, po, c, hl);
+        // fed-back h == the fp16-rounded value the decoder convs will read
+        hbuf[(cur ^ 1) * (LM_SEQ * LM_HS) + seq * LM_HS + upos] = __float2half_rn(hl);
+        hst[(k * LM_SEQ + seq) * LM_HST + unit] = hl;     // rounded to fp16 (the same value) when flushed
+        if (more && k == LSTM_BLK - 1) asm volatile("cp.async.wait_group 0;" ::: "memory");   // next block's staging has landed
         __syncthreads();
         cur ^= 1;
       }
     }
-    // flush the block's hidden states: per sequence 8 chunks x steps x 16 bytes, coalesced along time
-    for (int i = tid; i < LM_SEQ * 8 * LSTM_BLK; i += 256) {
-      const int s = i / (8 * LSTM_BLK);
-      const int ch = (i / LSTM_BLK) % 8;
-      const int kk = i % LSTM_BLK;
-      const int b = seq0 + s;
-      if (b < B && kk < nst) {
-        const float* src = &hst[(kk * LM_SEQ + s) * LSTM_H + 8 * ch];
-        const float4 v0 = *reinterpret_cast<const float4*>(src);
-        const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
-        const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        *reinterpret_cast<uint4*>(hout + act_off(h_bs, h_Tp, b, ch, t0 + kk)) = pack_half8(v);
-      }
-    }
   }
-  if (state_out != nullptr) {
-    if (seq0 + sa < B) {
-      state_out[(long long)(seq0 + sa) * 2 * LSTM_H + unit] = hl0;
-      state_out[(long long)(seq0 + sa) * 2 * LSTM_H + LSTM_H + unit] = c0;
-    }
-    if (seq0 + sb2 < B) {
-      state_out[(long long)(seq0 + sb2) * 2 * LSTM_H + unit] = hl1;
-      state_out[(long long)(seq0 + sb2) * 2 * LSTM_H + LSTM_H + unit] = c1;
-    }
+  flush_item(nblk - 1);
+  if (state_out != nullptr && seq0 + seq < B) {
+    state_out[(long long)(seq0 + seq) * 2 * LSTM_H + unit] = hl;
+    state_out[(long long)(seq0 + seq) * 2 * LSTM_H + LSTM_H + unit] = c;
   }
 }
 
@@ -373,8 +412,8 @@ int launch_lstm(const Act& xp, const float* whh, const Act& h_out, int B, int T,
       AR_CUDA_OK(cudaFuncSetAttribute(lstm_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_SMEM));
       attr_set = true;
     }
-    lstm_mma_kernel<<<(B + LM_SEQ - 1) / LM_SEQ, 256, LM_SMEM, stream>>>(xp.h(), xp.bs, xp.Tp, whh, h_out.h(), h_out.bs, h_out.Tp, B, T,
-                                                                  state_in, state_out);
+    lstm_mma_kernel<<<(B + LM_SEQ - 1) / LM_SEQ, LM_THREADS, LM_SMEM, stream>>>(xp.h(), xp.bs, xp.Tp, whh, h_out.h(), h_out.bs, h_out.Tp,
+                                                                         B, T, state_in, state_out);
     AR_CUDA_OK(cudaGetLastError());
     return AR_OK;
   }

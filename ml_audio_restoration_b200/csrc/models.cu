@@ -300,11 +300,14 @@ static bool build_stereo(const Table& t, Blob& blob, Model& m) {
   const float* bih = t.get("lstm.bias_ih_l0", {256});
   const float* bhh = t.get("lstm.bias_hh_l0", {256});
   if (!Wih || !Whh || !bih || !bhh) return false;
+  // Output channels are permuted to [unit][gate] (gate order i,f,g,o) so that the four gate pre-activations a
+  // recurrence thread needs are 8 contiguous bytes of the H8 tensor.
   Gemm g;
   g.init(128, 256, 1, 1, 0);
   for (int o = 0; o < 256; ++o) {
-    for (int c = 0; c < 128; ++c) g.at(0, c, o) = Wih[o * 128 + c];
-    g.bias[o] = bih[o] + bhh[o];
+    const int op = (o % 64) * 4 + o / 64;
+    for (int c = 0; c < 128; ++c) g.at(0, c, op) = Wih[o * 128 + c];
+    g.bias[op] = bih[o] + bhh[o];
   }
   m.conv["xproj"] = blob.push_gemm(g);
   m.whh_off = blob.push(Whh, 256 * 64);
@@ -421,6 +424,7 @@ struct ConvOpt {
   int in_coff8 = 0, out_coff8 = 0;   // channel offsets in units of 8 channels
   int mode = MODE_SAME;
   int lrelu = 1;
+  int out_tblock = 0;
   const Act* pool = nullptr;
   const Act* res = nullptr;
   int Tout = -1;
@@ -442,6 +446,7 @@ static int run_conv(Ctx& c, const std::string& name, const Act& in, const Act& o
   if (o.pool) { p.pool = o.pool->h(); p.pool_bs = o.pool->bs; p.pool_Tp = o.pool->Tp; p.pool_coff8 = 0; }
   if (o.res) { p.res = o.res->h(); p.res_bs = o.res->bs; p.res_Tp = o.res->Tp; p.res_coff8 = 0; }
   p.lrelu = o.lrelu;
+  p.out_tblock = o.out_tblock;
   p.B = c.B;
   p.tiles_per_item = (in.T + TILE_M - 1) / TILE_M;
   ProfScope ps(CAT_CONV, c.stream, 2.0 * L.macs_per_row * (double)c.B * (double)in.T);
@@ -586,7 +591,7 @@ static int stereo_forward(Ctx& c, const float* x, float* y, int T, const float* 
     cur = b;
   }
   Act xp = A.act(B, 256, T);   // gate pre-activations (fp16 storage costs < 0.1 dB, halves the LSTM's HBM stream)
-  ConvOpt o; o.lrelu = 0;
+  ConvOpt o; o.lrelu = 0; o.out_tblock = 1;   // time-blocked layout: the recurrence streams it in 4 KB runs
   AR_TRY(run_conv(c, "xproj", cur, xp, o));
   A.release(cur);
   Act h = A.act(B, 64, T);

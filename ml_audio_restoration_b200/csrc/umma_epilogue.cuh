@@ -33,7 +33,12 @@ __device__ __forceinline__ EpiRow epi_row(const ConvParams& p, int b, int t, int
   int chunk0;
   if (MODE == MODE_SAME) {
     chunk0 = gcol0 >> 3;
-    r.o0 = reinterpret_cast<char*>(out + act_off(p.out_bs, p.out_Tp, b, p.out_coff8 + chunk0, tt));
+    if (p.out_tblock) {   // time-blocked output (LSTM pre-activations): chunks of one time block are 128 bytes apart
+      r.o0 = reinterpret_cast<char*>(out + act_off_tb(p.out_bs, p.N >> 3, b, chunk0, tt));
+      r.ostride = 128;
+    } else {
+      r.o0 = reinterpret_cast<char*>(out + act_off(p.out_bs, p.out_Tp, b, p.out_coff8 + chunk0, tt));
+    }
     r.ok0 = r.in_ok && t < p.Tout;
   } else {
     // columns [0,N/2) -> row 2t, [N/2,N) -> row 2t+1; a warp's column range never straddles N/2
