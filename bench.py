@@ -34,6 +34,32 @@ CHAIN_GFLOP_PER_AUDIO_S = 51.661
 METRIC = "restored audio-sec/sec (full chain)"
 
 
+def conv_algorithmic_bytes_per_audio_s():
+    """fp16 activation bytes (inputs read + outputs written, incl. pooled copies and residual operands) that the
+    conv engine's 41 layer launches must move per source audio-second when layers are not fused."""
+    r = SR                                   # denoiser / SR input rate; stereo runs at 2r
+    den = [(160, r), (192, r // 2), (320, r // 2), (384, r // 4), (640, r // 4), (768, r // 8), (1024, r // 8),
+           (512, r // 8), (256, r // 4), (768, r // 4), (512, r // 4), (256, r // 4), (128, r // 2), (384, r // 2),
+           (256, r // 2), (128, r // 2), (64, r), (192, r), (128, r)]
+    sr = [(128, r)] * 4 + [(192, r)] * 5 + [(64, r), (64, 2 * r), (128, 2 * r)]
+    st = [(192, 2 * r), (256, 2 * r), (384, 2 * r), (512, 2 * r)] + [(512, 2 * r)] * 4 + [(768, 2 * r), (640, 2 * r),
+          (384, 2 * r), (384, 2 * r), (192, 2 * r), (192, 2 * r)]
+    return float(sum(b * n for b, n in den + sr + st))
+
+
+def load_conv_traffic(args):
+    """Measured DRAM bytes per conv launch from the committed ncu capture, if it was taken at this configuration."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "conv_traffic_r01.json")) as f:
+            t = json.load(f)
+        c = t["config"]
+        if c["chunks_per_step_per_gpu"] == args.chunks_per_step and c["batch_chunks"] == args.batch_chunks:
+            return t["dram_bytes_per_launch_avg"]
+    except Exception:
+        pass
+    return None
+
+
 def synth_audio(n, seed, device):
     """Music proxy (sines + chirp) with hiss and pops, ~ -20 dBFS (BASELINE config 4 recipe)."""
     g = torch.Generator(device=device).manual_seed(seed)
@@ -250,12 +276,17 @@ def run_b200(args, rank, world, local_rank):
     cats = {name: {"ms": p_ms[i], "launches": int(p_ln[i]), "gflop": p_fl[i] / 1e9} for i, name in enumerate(_lib.PROFILE_CATEGORIES)}
     conv = cats["conv"]
     achieved = (conv["gflop"] / 1e3) / (conv["ms"] / 1e3) if conv["ms"] > 0 else 0.0
+    conv_bytes = conv_algorithmic_bytes_per_audio_s() * audio_s * args.steps      # algorithmic, this rank
+    hbm_gbs = (conv_bytes / 1e9) / (conv["ms"] / 1e3) if conv["ms"] > 0 else 0.0
     roofline = {
-        "kernel": "conv_umma_kernel (tcgen05 implicit-GEMM Conv1d, all conv/convT/LSTM-input layers)",
+        "kernel": "conv_umma2_kernel (2-CTA tcgen05 implicit-GEMM Conv1d: all conv / convT / LSTM-input layers)",
         "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
         "frac": achieved / peaks["tflops"], "peak_source": f"{peaks['src']} bf16 dense sustained (fp16 operands run at the same rate)",
         "avg_launch_ms": conv["ms"] / max(1, conv["launches"]), "launches": conv["launches"],
-        "share_of_step": conv["ms"] / (1e3 * t_s), "traffic": None,
+        "share_of_step": conv["ms"] / (1e3 * t_s), "traffic": load_conv_traffic(args),
+        "algorithmic_bytes_per_launch": conv_bytes / max(1, conv["launches"]),
+        "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_gbs / peaks["hbm_gbs"],
+                "note": "same launches against the HBM roofline (unfused layers: algorithmic activation bytes)"},
         "per_category_ms_per_step": {k: v["ms"] / args.steps for k, v in cats.items()},
     }
     line = {

@@ -39,7 +39,7 @@ extern "C" {
 #define AR_MODEL_SUPER_RES 1 /* AudioSuperResolution(upscale_factor=2) super_resolution.py:6 */
 #define AR_MODEL_STEREO 2    /* StereoSeparator(32, 64, 1)            stereo_separator.py:5  */
 
-#define AR_ENGINE_UMMA 0 /* tcgen05 implicit-GEMM conv engine (product path)                 */
+#define AR_ENGINE_UMMA 0 /* tcgen05 implicit-GEMM conv engines (product path)                */
 #define AR_ENGINE_SIMT 1 /* CUDA-core fp32 conv engine (debug cross-check only)              */
 
 typedef struct ar_model_s* ar_model_t;
@@ -62,7 +62,7 @@ int ar_set_conv_engine(int engine);
 
 /* Replaces: model construction + torch.load + load_state_dict(strict) + .to(device) + .eval()
  * (inference.py:51-55, 66-70, 85-89).  Folds eval-mode BatchNorm into the conv weights,
- * rounds tensor-core operands to TF32, packs into the kernels' layouts, uploads.  */
+ * rounds tensor-core operands to fp16 (the 11-bit significand TF32 would keep), packs into the kernels' layouts, uploads.  */
 int ar_model_create(int kind, const ar_tensor_t* tensors, int n_tensors, int device, ar_model_t* out);
 void ar_model_destroy(ar_model_t m);
 int ar_model_kind(ar_model_t m);

@@ -10,7 +10,7 @@ from gpu_util import debug_conv, assert_close
 pytestmark = pytest.mark.gpu
 
 
-def tf32(x):
+def operand_round(x):
     """Operand rounding of the engines: fp16 (same 11-bit significand as TF32), round to nearest."""
     return x.half().float()
 
@@ -43,7 +43,7 @@ def test_conv_engine_matches_torch(engine, shape):
     y = debug_conv(x, w, b, dilation=d, lrelu=1, engine=engine)
     # both engines see fp16-rounded operands (activations are rounded when stored, weights when packed);
     # the debug hook also returns the result through the fp16 activation layout
-    ref = F.leaky_relu(F.conv1d(tf32(x).double(), tf32(w).double(), b.double(), padding=d * (k - 1) // 2, dilation=d), 0.2).float()
+    ref = F.leaky_relu(F.conv1d(operand_round(x).double(), operand_round(w).double(), b.double(), padding=d * (k - 1) // 2, dilation=d), 0.2).float()
     assert_close(ref.half().float(), y, f"conv {shape}", max_abs=1e-2, min_snr=66.0)  # 1 fp16 ulp at |y|~8 is 7.8e-3
 
 

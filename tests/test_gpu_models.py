@@ -94,7 +94,7 @@ def test_lstm_state_carry_equals_whole_sequence(models, state_dicts):
 
 
 def test_stereo_large_batch_tensor_core_lstm(models, state_dicts):
-    """More than two sequences per SM switches the recurrence to the tensor-core (mma.sync TF32) kernel;
+    """More than two sequences per SM switches the recurrence to the tensor-core (mma.sync fp16) kernel;
     ragged length (not a multiple of the 8-step block) and a batch that is not a multiple of 8."""
     m = models("stereo", "umma")
     x = make_input(301, 203, seed=11)

@@ -175,3 +175,25 @@ def test_two_rank_gloo_shards_cover_file(tmp_path):
                          capture_output=True, text=True, env=env, timeout=240)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count("ok") == 2
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (CPU oracle port) prints one JSON line with the contract's keys."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-chunks", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
+
+
+def test_bench_algorithmic_constants():
+    sys.path.insert(0, ROOT)
+    import bench
+    # SURVEY.md 8(d): 51.661 GFLOP per source audio-second; unfused fp16 conv traffic ~354 MB per audio-second
+    assert bench.CHAIN_GFLOP_PER_AUDIO_S == pytest.approx(2e-9 * (148504 * 22050 + 42656 * 22050 + 490144 * 44100), rel=1e-4)
+    assert bench.conv_algorithmic_bytes_per_audio_s() == pytest.approx(354.2e6, rel=1e-3)
