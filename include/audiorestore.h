@@ -60,6 +60,12 @@ int ar_version(void);
 /* Select the conv engine used by subsequently created models (default AR_ENGINE_UMMA). */
 int ar_set_conv_engine(int engine);
 
+/* Enable (default) / disable fused multi-layer launches (e.g. the StereoSeparator's dilated block
+ * conv k3 -> conv k1 [-> LSTM input projection], stereo_separator.py:49-64,104-106, as one kernel whose
+ * intermediates stay in shared memory) for subsequently created models.  Cross-check knob: both settings
+ * compute the same fp16-rounded intermediates. */
+int ar_set_fusion(int on);
+
 /* Replaces: model construction + torch.load + load_state_dict(strict) + .to(device) + .eval()
  * (inference.py:51-55, 66-70, 85-89).  Folds eval-mode BatchNorm into the conv weights,
  * rounds tensor-core operands to fp16 (the 11-bit significand TF32 would keep), packs into the kernels' layouts, uploads.  */

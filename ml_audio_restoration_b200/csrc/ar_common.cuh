@@ -173,7 +173,20 @@ __device__ __forceinline__ void epilogue_chunk8(const ConvParams& p, int b, int 
   }
 }
 
+// A fused chain (conv_chain.cu): first GEMM = `p` (k-tap conv, input geometry, W1, bias1), then n_gemms-1 pointwise
+// convs whose inputs never leave the SM.  `pl` carries the output geometry of the LAST stage (out*, Tout,
+// out_tblock, N = N[n_gemms-1]); every stage's weights are packed as one 2-CTA pair-slice (two column halves).
+struct ChainParams {
+  ConvParams p, pl;
+  int n_gemms;
+  const __half* w[3];
+  const float* bias[3];
+  int N[3];
+  int lrelu[3];
+};
+
 // ----------------------------------------------------------------------------- launchers
+int launch_conv_chain(const ChainParams& cp, cudaStream_t stream);  // fused k-tap conv -> pointwise conv(s), 2-CTA engine
 int launch_conv_umma(const ConvParams& p, cudaStream_t stream);
 int launch_conv_umma2(const ConvParams& p, cudaStream_t stream);   // cta_group::2 engine (needs p.cta2)
 int launch_conv_simt(const ConvParams& p, cudaStream_t stream);

@@ -31,6 +31,7 @@ struct Umma2Cfg {
   int w_bytes;      // resident weights per CTA: Cin*taps*(Ns/2)*2
   int stage_bytes;  // activation stage per CTA
   int ncol, tmem_cols, nks, smem_bytes;
+  int nbuf;         // TMEM accumulator buffers (2..8): how many tile pairs the MMAs may run ahead of the epilogue
 };
 
 template <int MODE, bool POOL, bool RES, int TAPS>
@@ -46,10 +47,10 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
   auto empty_bar = [&](int s) { return bar_base + 8u * (cfg.stages + s); };
   auto peer_bar = [&](int s) { return bar_base + 8u * (2 * cfg.stages + s); };   // used in the leader only
   auto tfull_bar = [&](int i) { return bar_base + 8u * (3 * cfg.stages + i); };
-  auto tempty_bar = [&](int i) { return bar_base + 8u * (3 * cfg.stages + 2 + i); };  // used in the leader only
-  const uint32_t w_bar = bar_base + 8u * (3 * cfg.stages + 4);
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (3 * cfg.stages + 8 + i); };  // used in the leader only
+  const uint32_t w_bar = bar_base + 8u * (3 * cfg.stages + 16);
   volatile uint32_t* tmem_slot =
-      reinterpret_cast<volatile uint32_t*>(stage_ptr + cfg.stages * cfg.stage_bytes + 8 * (3 * cfg.stages + 5));
+      reinterpret_cast<volatile uint32_t*>(stage_ptr + cfg.stages * cfg.stage_bytes + 8 * (3 * cfg.stages + 17));
   float* const s_bias = reinterpret_cast<float*>(stage_ptr + cfg.stages * cfg.stage_bytes + BAR2_BYTES);
 
   const int warp = threadIdx.x >> 5;
@@ -63,7 +64,7 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
       mbar_init(empty_bar(s), 1);
       mbar_init(peer_bar(s), 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < cfg.nbuf; ++i) {
       mbar_init(tfull_bar(i), 1);
       mbar_init(tempty_bar(i), 2 * EPI2_WARPS);
     }
@@ -129,13 +130,13 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
     const uint64_t a_desc_hi = make_desc(0u, (uint32_t)(R * 16), 128u);
     const uint64_t b_desc_hi = make_desc(0u, (uint32_t)(Nh * 16), 128u);
     mbar_wait(w_bar, 0);
-    int s = 0, tl = 0;
-    uint32_t ph = 0;
+    int s = 0, buf = 0;
+    uint32_t ph = 0, aph = 0;
     const uint32_t b_step = (uint32_t)(Nh * 2);
     const uint32_t a_step = (uint32_t)(2 * R);
     const uint32_t w_addr0 = w_base >> 4;
     const uint32_t dil_u = (uint32_t)p.dil;
-    for (int pr = pair0; pr < num_pairs; pr += pair_step, ++tl) {
+    for (int pr = pair0; pr < num_pairs; pr += pair_step) {
       const int b = pr / ppi;
       const int tl_in_item = (pr - b * ppi) * 2 + (int)rank;
       const int t_true = tl_in_item * TILE_M;                          // true first output row of this CTA's tile
@@ -143,8 +144,6 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
       const int tfirst = t0 - p.pad_left;
       const bool dead = tl_in_item > tpi - 1;                          // no such tile: contribute zeros
       const bool edge = dead || (tfirst < 0) || (tfirst + R > p.Tin);
-      const int buf = tl & 1;
-      const uint32_t aph = (uint32_t)(tl >> 1) & 1u;
       (void)t_true;
       if (leader) {
         mbar_wait(tempty_bar(buf), aph ^ 1u);                          // both epilogues drained this accumulator
@@ -194,6 +193,7 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
         }
         if (++s == cfg.stages) { s = 0; ph ^= 1u; }
       }
+      if (++buf == cfg.nbuf) { buf = 0; aph ^= 1u; }
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9), own 128 rows
@@ -204,15 +204,13 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
     const bool active = Ns >= 32 || half == 0;
     const float slope = p.lrelu ? LRELU_SLOPE : 1.0f;
     const int gcol0 = slice * Ns + col_lo;
-    const uint32_t tempty_leader0 = mapa_u32(tempty_bar(0), 0);
-    const uint32_t tempty_leader1 = mapa_u32(tempty_bar(1), 0);
-    int tl = 0;
-    for (int pr = pair0; pr < num_pairs; pr += pair_step, ++tl) {
+    const uint32_t tempty_leader0 = mapa_u32(tempty_bar(0), 0);   // barriers are 8 bytes apart in the leader too
+    int buf = 0;
+    uint32_t aph = 0;
+    for (int pr = pair0; pr < num_pairs; pr += pair_step) {
       const int b = pr / ppi;
       const int tl_in_item = (pr - b * ppi) * 2 + (int)rank;
       const int t = tl_in_item * TILE_M + q * 32 + lane;   // >= Tin for a dead tile => every store is masked
-      const int buf = tl & 1;
-      const uint32_t aph = (uint32_t)(tl >> 1) & 1u;
       const EpiRow row = epi_row<MODE, POOL, RES>(p, b, t, gcol0);
       uint4 resv[2];
       epi_prefetch_res<RES>(row, active, resv);
@@ -224,7 +222,8 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_remote(buf ? tempty_leader1 : tempty_leader0);   // leader collects 2 x 8 warps
+      if (lane == 0) mbar_arrive_remote(tempty_leader0 + 8u * buf);   // leader collects 2 x 8 warps
+      if (++buf == cfg.nbuf) { buf = 0; aph ^= 1u; }
     }
   }
 
@@ -241,7 +240,8 @@ static bool pick_cfg2(const ConvParams& p, Umma2Cfg& c) {
   int ncol = 32;
   while (ncol < Ns) ncol <<= 1;
   c.ncol = ncol;
-  c.tmem_cols = 2 * ncol;
+  c.nbuf = 512 / ncol > 8 ? 8 : 512 / ncol;
+  c.tmem_cols = c.nbuf * ncol;
   c.w_bytes = p.Cin * p.taps * (Ns / 2) * 2;
   const int room = SMEM2_BUDGET - BAR2_BYTES - BIAS2_BYTES - c.w_bytes;
   for (int kbs = 4; kbs >= 1; kbs >>= 1) {

@@ -234,10 +234,12 @@ __device__ __forceinline__ void mma_f16_16x8x16(float (&d)[4], const uint32_t (&
 }
 
 constexpr int LM_XS = 264;                        // padded per-sequence stride of a staged pre-activation row (halves)
-constexpr int LM_XSTEP = LM_SEQ * LM_XS;          // halves per staged step
+constexpr int LM_XSTEP = LM_SEQ * LM_XS + 8;      // halves per staged step; +16 bytes so the 8 steps that consecutive lanes stage
+                                                  // with one cp.async land in 8 different bank groups (a multiple of 128 B would be 8-way conflicted)
 constexpr int LM_XBUF = LSTM_BLK * LM_XSTEP;      // halves per 8-step buffer
 constexpr int LM_HST = 68;      // padded [seq] row stride of the hidden-state staging buffer (floats): conflict-free stores
-constexpr int LM_SMEM = 2 * LM_XBUF * 2 + 2 * LM_SEQ * LM_HS * 2 + 2 * LSTM_BLK * LM_SEQ * LM_HST * 4;
+constexpr int LM_HSTEP = LM_SEQ * LM_HST + 4;     // floats per staged step of hidden states; +16 bytes: the flush reads 8 steps with consecutive lanes
+constexpr int LM_SMEM = 2 * LM_XBUF * 2 + 2 * LM_SEQ * LM_HS * 2 + 2 * LSTM_BLK * LM_HSTEP * 4;
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -257,7 +259,7 @@ lstm_mma_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, const
   extern __shared__ __align__(16) float lm_smem[];
   __half* const xs = reinterpret_cast<__half*>(lm_smem);       // [2][8 steps][8 seq][264] fp16: staged gate pre-activations
   float* const hstage = lm_smem + LM_XBUF;                     // [2][8 steps][8 seq][64] fp32 (2*LM_XBUF halves == LM_XBUF floats)
-  __half* const hbuf = reinterpret_cast<__half*>(hstage + 2 * LSTM_BLK * LM_SEQ * LM_HST);   // [2][8 seq][80] fp16
+  __half* const hbuf = reinterpret_cast<__half*>(hstage + 2 * LSTM_BLK * LM_HSTEP);   // [2][8 seq][80] fp16
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int gid = lane >> 2, tig = lane & 3;        // mma fragment coordinates
@@ -313,14 +315,14 @@ lstm_mma_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, const
   };
   // one hidden-state item per thread per block: [8 seq][8 chunks][8 steps] x 16 bytes, coalesced along time
   auto flush_item = [&](int blk) {
-    const float* hst = hstage + (blk & 1) * (LSTM_BLK * LM_SEQ * LM_HST);
+    const float* hst = hstage + (blk & 1) * (LSTM_BLK * LM_HSTEP);
     const int t0 = blk * LSTM_BLK;
     const int s = tid / (8 * LSTM_BLK);              // LM_SEQ * 8 * LSTM_BLK == 512 == LM_THREADS
     const int ch = (tid / LSTM_BLK) % 8;
     const int kk = tid % LSTM_BLK;
     const int b = seq0 + s;
     if (b < B && t0 + kk < T) {
-      const float* src = &hst[(kk * LM_SEQ + s) * LM_HST + 8 * ch];
+      const float* src = &hst[kk * LM_HSTEP + s * LM_HST + 8 * ch];
       const float4 v0 = *reinterpret_cast<const float4*>(src);
       const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
       const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
@@ -342,7 +344,7 @@ lstm_mma_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, const
   for (int blk = 0; blk < nblk; ++blk) {
     const bool more = blk + 1 < nblk;
     const __half* xb = xs + (blk & 1) * LM_XBUF;
-    float* hst = hstage + (blk & 1) * (LSTM_BLK * LM_SEQ * LM_HST);
+    float* hst = hstage + (blk & 1) * (LSTM_BLK * LM_HSTEP);
     const int t0 = blk * LSTM_BLK;
     const int nst = min(LSTM_BLK, T - t0);
     if (!more && blk > 0) flush_item(blk - 1);       // last (possibly short) block: write the previous one up front
@@ -381,7 +383,7 @@ lstm_mma_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, const
         lstm_cell(pi, pf, pg, po, c, hl);
         // fed-back h == the fp16-rounded value the decoder convs will read
         hbuf[(cur ^ 1) * (LM_SEQ * LM_HS) + seq * LM_HS + upos] = __float2half_rn(hl);
-        hst[(k * LM_SEQ + seq) * LM_HST + unit] = hl;     // rounded to fp16 (the same value) when flushed
+        hst[k * LM_HSTEP + seq * LM_HST + unit] = hl;     // rounded to fp16 (the same value) when flushed
         if (more && k == LSTM_BLK - 1) asm volatile("cp.async.wait_group 0;" ::: "memory");   // next block's staging has landed
         __syncthreads();
         cur ^= 1;

@@ -24,6 +24,19 @@ int set_engine(int e) {
   g_engine = e;
   return AR_OK;
 }
+// Layer fusion (conv_chain.cu) for subsequently created models; AR_FUSE=0 in the environment turns it off too.
+static int g_fuse = -1;
+int set_fusion(int on) {
+  g_fuse = on ? 1 : 0;
+  return AR_OK;
+}
+static int fusion_default() {
+  if (g_fuse < 0) {
+    const char* e = getenv("AR_FUSE");
+    g_fuse = e ? (atoi(e) != 0) : 1;
+  }
+  return g_fuse;
+}
 
 // ============================================================================ weight folding / packing
 static uint16_t half_bits_host(float x) {  // fp32 -> fp16, round to nearest even, clamped to the finite range
@@ -170,6 +183,7 @@ struct StemW { size_t w_off, b_off; int taps; };
 
 struct Model {
   int kind = -1, device = 0, engine = AR_ENGINE_UMMA;
+  int fuse = 1;   // fused conv chains where the engine has them (tcgen05 engine, 2-CTA packing)
   float* blob = nullptr;
   std::map<std::string, ConvLayer> conv;
   StemW stem{};
@@ -345,6 +359,7 @@ int model_create(int kind, const ar_tensor_t* tensors, int n, int device, Model*
   m->kind = kind;
   m->device = device;
   m->engine = g_engine;
+  m->fuse = fusion_default() && g_engine == AR_ENGINE_UMMA;
   Blob blob;
   bool ok = false;
   if (kind == AR_MODEL_DENOISER) ok = build_denoiser(t, blob, *m);
@@ -452,6 +467,59 @@ static int run_conv(Ctx& c, const std::string& name, const Act& in, const Act& o
   ProfScope ps(CAT_CONV, c.stream, 2.0 * L.macs_per_row * (double)c.B * (double)in.T);
   if (c.m->engine == AR_ENGINE_SIMT) return launch_conv_simt(p, c.stream);
   return p.cta2 ? launch_conv_umma2(p, c.stream) : launch_conv_umma(p, c.stream);
+}
+
+// A k-tap conv followed by one or two pointwise convs as ONE fused launch (conv_chain.cu).  `o` describes the
+// LAST stage's output (lrelu, time-blocked layout); intermediate stages apply LeakyReLU (they are
+// `_dilated_block` halves, stereo_separator.py:49-64).
+static bool can_chain(const Ctx& c, std::initializer_list<const char*> names) {
+  if (!c.m->fuse || c.m->engine != AR_ENGINE_UMMA) return false;
+  bool first = true;
+  int prevN = 0;
+  for (const char* n : names) {
+    auto it = c.m->conv.find(n);
+    if (it == c.m->conv.end()) return false;
+    const ConvLayer& L = it->second;
+    if (!L.cta2 || L.n_slices != 2) return false;
+    if (!first && (L.taps != 1 || L.Cin != prevN)) return false;
+    prevN = L.N;
+    first = false;
+  }
+  return true;
+}
+
+static int run_chain(Ctx& c, std::initializer_list<const char*> names, const Act& in, const Act& out, const ConvOpt& o = ConvOpt()) {
+  if (c.ar.dry) return AR_OK;
+  ChainParams cp;
+  std::memset(&cp, 0, sizeof(cp));
+  double macs = 0.0;
+  int g = 0;
+  for (const char* n : names) {
+    const ConvLayer& L = c.m->conv.find(n)->second;
+    if (g == 0) {
+      ConvParams& p = cp.p;
+      p.in = in.h(); p.in_bs = in.bs; p.in_Tp = in.Tp; p.in_coff8 = o.in_coff8;
+      p.Tin = in.T; p.Cin = L.Cin; p.taps = L.taps; p.dil = L.dil; p.pad_left = L.pad_left;
+      p.N = L.N; p.n_slices = L.n_slices; p.cta2 = 1; p.mode = MODE_SAME; p.lrelu = 1;
+      p.B = c.B; p.tiles_per_item = (in.T + TILE_M - 1) / TILE_M;
+    }
+    cp.w[g] = reinterpret_cast<const __half*>(c.m->blob + L.w_off);
+    cp.bias[g] = c.m->blob + L.b_off;
+    cp.N[g] = L.N;
+    cp.lrelu[g] = 1;
+    macs += L.macs_per_row;
+    ++g;
+  }
+  cp.n_gemms = g;
+  cp.lrelu[g - 1] = o.lrelu;
+  cp.p.w = cp.w[0]; cp.p.bias = cp.bias[0];
+  cp.pl = cp.p;
+  cp.pl.N = cp.N[g - 1]; cp.pl.bias = cp.bias[g - 1]; cp.pl.lrelu = o.lrelu;
+  cp.pl.out = out.h(); cp.pl.out_bs = out.bs; cp.pl.out_Tp = out.Tp; cp.pl.out_coff8 = o.out_coff8;
+  cp.pl.Tout = o.Tout >= 0 ? o.Tout : out.T;
+  cp.pl.out_tblock = o.out_tblock;
+  ProfScope ps(CAT_CONV, c.stream, 2.0 * macs * (double)c.B * (double)in.T);
+  return launch_conv_chain(cp, c.stream);
 }
 
 // ---------------------------------------------------------------------------- denoiser.py:88-144
@@ -581,19 +649,38 @@ static int stereo_forward(Ctx& c, const float* x, float* y, int T, const float* 
     AR_TRY(launch_stem(x, B, T, 7, m.blob + m.stem.w_off, m.blob + m.stem.b_off, cur, 1, c.stream));
   }
   const int widths[4] = {64, 128, 128, 128};
+  static const char* const NA[4] = {"enc1a", "enc2a", "enc3a", "enc4a"};
+  static const char* const NB[4] = {"enc1b", "enc2b", "enc3b", "enc4b"};
+  ConvOpt oxp; oxp.lrelu = 0; oxp.out_tblock = 1;   // gate pre-activations, time-blocked: the recurrence streams 4 KB runs
+  Act xp{};
+  bool xp_done = false;
   for (int i = 0; i < 4; ++i) {
-    Act a = A.act(B, widths[i], T);
-    AR_TRY(run_conv(c, "enc" + std::to_string(i + 1) + "a", cur, a));
-    A.release(cur);
-    Act b = A.act(B, widths[i], T);
-    AR_TRY(run_conv(c, "enc" + std::to_string(i + 1) + "b", a, b));
-    A.release(a);
-    cur = b;
+    if (i == 3 && can_chain(c, {NA[i], NB[i], "xproj"})) {
+      // last dilated block + LSTM input projection: 128 -k3 d8-> 128 -k1-> 128 -k1-> 256 in one launch
+      xp = A.act(B, 256, T);
+      AR_TRY(run_chain(c, {NA[i], NB[i], "xproj"}, cur, xp, oxp));
+      A.release(cur);
+      xp_done = true;
+    } else if (can_chain(c, {NA[i], NB[i]})) {
+      Act b = A.act(B, widths[i], T);
+      AR_TRY(run_chain(c, {NA[i], NB[i]}, cur, b));
+      A.release(cur);
+      cur = b;
+    } else {
+      Act a = A.act(B, widths[i], T);
+      AR_TRY(run_conv(c, NA[i], cur, a));
+      A.release(cur);
+      Act b = A.act(B, widths[i], T);
+      AR_TRY(run_conv(c, NB[i], a, b));
+      A.release(a);
+      cur = b;
+    }
   }
-  Act xp = A.act(B, 256, T);   // gate pre-activations (fp16 storage costs < 0.1 dB, halves the LSTM's HBM stream)
-  ConvOpt o; o.lrelu = 0; o.out_tblock = 1;   // time-blocked layout: the recurrence streams it in 4 KB runs
-  AR_TRY(run_conv(c, "xproj", cur, xp, o));
-  A.release(cur);
+  if (!xp_done) {
+    xp = A.act(B, 256, T);   // fp16 storage costs < 0.1 dB, halves the LSTM's HBM stream
+    AR_TRY(run_conv(c, "xproj", cur, xp, oxp));
+    A.release(cur);
+  }
   Act h = A.act(B, 64, T);
   if (!A.dry) {
     ProfScope ps(CAT_LSTM, c.stream, 2.0 * 16384 * (double)B * T);
@@ -604,7 +691,7 @@ static int stereo_forward(Ctx& c, const float* x, float* y, int T, const float* 
   AR_TRY(run_conv(c, "dec0", h, d0));
   A.release(h);
   Act d1 = A.act(B, 128, T);
-  o = ConvOpt(); o.in_coff8 = 0; o.out_coff8 = 0;
+  ConvOpt o;
   AR_TRY(run_conv(c, "dec1L", d0, d1, o));
   o.in_coff8 = 128 / 8; o.out_coff8 = 64 / 8;
   AR_TRY(run_conv(c, "dec1R", d0, d1, o));

@@ -11,16 +11,18 @@ MAX_ABS = 1e-3      # north_star tolerance: max abs error <= 1e-3 ...
 MIN_SNR_DB = 60.0   # ... or >= 60 dB SNR; the tests demand both unless stated
 
 
-def make_model(name, sd, engine=_lib.ENGINE_UMMA, device="cuda"):
+def make_model(name, sd, engine=_lib.ENGINE_UMMA, device="cuda", fusion=True):
     m = CLS[name]()
     m.load_state_dict(sd, strict=True)
     m = m.to(device).eval()
     L = _lib.lib()
     _lib.check(L.ar_set_conv_engine(engine))
+    _lib.check(L.ar_set_fusion(1 if fusion else 0))
     try:
         m.native_handle(torch.device("cuda", torch.cuda.current_device()))
     finally:
         L.ar_set_conv_engine(_lib.ENGINE_UMMA)
+        L.ar_set_fusion(1)
     return m
 
 

@@ -106,6 +106,22 @@ def test_stereo_large_batch_tensor_core_lstm(models, state_dicts):
     assert_close(cn[0], st[:, 1], "carried c (tensor-core LSTM)", max_abs=1e-3, min_snr=50.0)
 
 
+@pytest.mark.parametrize("B,T", [(1, 100), (3, 129), (2, 1500), (5, 4099), (160, 1000)])
+def test_fused_chains_match_layer_by_layer(state_dicts, B, T):
+    """The fused dilated-block launches (conv k3 -> conv k1 [-> LSTM input projection], conv_chain.cu) compute the
+    same fp16-rounded intermediates as the layer-by-layer launches: outputs agree far inside the tolerance, and
+    both agree with the oracle.  B=160 gives every SM pair several tile pairs (steady-state pipeline)."""
+    fused = make_model("stereo", state_dicts["stereo"], fusion=True)
+    plain = make_model("stereo", state_dicts["stereo"], fusion=False)
+    x = make_input(B, T, seed=B * 7 + T)
+    with torch.no_grad():
+        yf = fused(x.cuda())
+        yp = plain(x.cuda())
+    assert_close(yp, yf, f"stereo fused vs layer-by-layer B={B} T={T}", max_abs=2e-5, min_snr=90.0)
+    if B <= 5:
+        assert_close(oracle.stereo_forward(state_dicts["stereo"], x), yf, f"stereo fused vs oracle B={B} T={T}")
+
+
 def test_error_behaviour(models, state_dicts):
     den = models("denoiser", "umma")
     with pytest.raises(RuntimeError):          # reference: RuntimeError from max_pool1d for T < 8
