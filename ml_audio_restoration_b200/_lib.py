@@ -47,6 +47,7 @@ _SIGNATURES = {
     "ar_profile_enable": (C.c_int, [C.c_int]),
     "ar_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]),
     "ar_launch_count": (C.c_longlong, []),
+    "ar_debug_chain_trace": (C.c_int, [C.c_void_p]),
     "ar_debug_conv1d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }

@@ -183,6 +183,7 @@ struct ChainParams {
   const float* bias[3];
   int N[3];
   int lrelu[3];
+  long long* trace;   // optional pipeline trace buffer (ar_debug_chain_trace), else nullptr
 };
 
 // ----------------------------------------------------------------------------- launchers

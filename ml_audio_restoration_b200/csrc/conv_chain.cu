@@ -10,28 +10,35 @@
 //   E2: last stage: the usual fused epilogue to HBM (H8 or time-blocked);  otherwise -> I2 and G3 / E3.
 //
 // The unfused layers of these blocks are HBM-bound (k1 128->128: 512 B of activation traffic per row for
-// 32 K MACs), so removing the intermediate write + read halves the time of a block; the three-GEMM chain
+// 32 K MACs), so removing the intermediate write + read halves the traffic of a block; the three-GEMM chain
 // (128 -k3-> 128 -k1-> 128 -k1-> 256) moves 768 B per row instead of 1 792.
 //
-// Same roles as conv_umma2.cu: warp 0 = bulk-copy producer, warp 1 = MMA warp (leader CTA issues; the peer
-// zero-pads its edge rows and forwards "my half is ready" arrivals), warps 2..9 = epilogues.  The GEMMs of
-// consecutive tile pairs are software-pipelined so the tensor pipe does not idle while an epilogue turns an
-// accumulator into the next operand:
-//   two GEMMs  : slot s issues G1(s), G2(s-1); accumulators and I1 double-buffered
-//   three GEMMs: slot s issues G3(s-2), G2(s-1), G1(s); every buffer single (TMEM: 128+128+256 = 512 columns) --
-//                in that order each epilogue has a full GEMM of another tile to hide behind.
+// Warp roles (every stage of the chain has its own issuer and its own epilogue group, so no warp ever
+// waits for a result that depends on work it still has to issue -- a pipeline trace of the first version,
+// where one MMA warp and one epilogue group walked all stages, showed the tensor pipe idle half of the time
+// behind that warp's serial waits):
+//   warp 0            bulk-copy (TMA) producer: resident weights of all stages, then the activation ring of G1
+//   warp 1 .. NG      issuer of GEMM g = warp-1 (leader CTA issues tcgen05.mma.cta_group::2; the peer's warp zero-pads
+//                     its edge rows / forwards "my operand half is ready" arrivals to the leader)
+//   then NG groups    epilogue group g drains the accumulator of GEMM g: to shared memory (g < NG-1) or to HBM (last)
+// Buffers: two GEMMs -> accumulators and I1 double-buffered; three GEMMs -> single (TMEM 128+128+256 = 512 columns).
 #include "ar_common.cuh"
 #include "umma_ptx.cuh"
 #include "umma_epilogue.cuh"
+#include <cstdlib>
 
 namespace ar {
 
-constexpr int CH_EPI_WARPS = 8;
-constexpr int CH_THREADS = 64 + 32 * CH_EPI_WARPS;
 constexpr int CH_SMEM_BUDGET = 227 * 1024;
-constexpr int CH_BAR_BYTES = 512;
+constexpr int CH_BAR_BYTES = 768;
 constexpr int CH_BIAS_BYTES = 2048;      // <= 512 fp32 biases over all stages
 constexpr int CH_RI = TILE_M;            // rows of an intermediate operand (pointwise follow-up convs: no halo)
+constexpr int CH_MAX_STAGES = 16;
+constexpr int CH_PREFETCH = 4;           // tile pairs the L2 prefetch runs ahead of the shared-memory ring
+
+// epilogue warps per stage
+__host__ __device__ constexpr int ch_group_warps(int NG, int g) { return NG == 2 ? 8 : (g == 2 ? 8 : 4); }
+__host__ __device__ constexpr int ch_threads(int NG) { return 32 * (1 + NG) + 32 * 16; }
 
 struct ChainCfg {
   int kbs, stages, R, nks, stage_bytes;  // activation ring of the first GEMM
@@ -42,12 +49,37 @@ struct ChainCfg {
   int stage_off, bar_off, bias_off, smem_bytes;
 };
 
+// Optional pipeline trace (ar_debug_chain_trace): CTA 0 records clock64() at pipeline events of its first
+// CH_TRACE_TILES tile pairs; slots: 0/1 G1 issue begin/end, 2/3 G2 operands ready / issued, 4/5 E1 begin/end,
+// 6/7 E_last begin/end, 8 first stage landed, 9 peer's first stage ready, 10/11 G3 ready / issued, 12/13 E2(mid) begin/end.
+constexpr int CH_TRACE_TILES = 64;
+__device__ __forceinline__ void trace_ev(long long* tr, int it, int ev) {
+  if (tr != nullptr && blockIdx.x == 0 && it < CH_TRACE_TILES && (threadIdx.x & 31) == 0) tr[it * 16 + ev] = clock64();
+}
+
 // buffer index / mbarrier phase of the it-th use of a set of nb (1 or 2) buffers
 __device__ __forceinline__ int buf_of(int it, int nb) { return it & (nb - 1); }
 __device__ __forceinline__ uint32_t phase_of(int it, int nb) { return (uint32_t)(it >> (nb - 1)) & 1u; }
 
+// walks the tile pairs of one cluster (pair0, pair0 + step, ...) without divisions in the loop
+struct PairIter {
+  int b, pi;            // batch item, pair index inside the item
+  int step_b, step_p, ppi;
+  __device__ PairIter(int pair0, int pair_step, int ppi_) : ppi(ppi_) {
+    b = pair0 / ppi_;
+    pi = pair0 - b * ppi_;
+    step_b = pair_step / ppi_;
+    step_p = pair_step - step_b * ppi_;
+  }
+  __device__ __forceinline__ void next() {
+    b += step_b;
+    pi += step_p;
+    if (pi >= ppi) { pi -= ppi; ++b; }
+  }
+};
+
 template <int TAPS, int NG>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ch_threads(NG), 1)
 conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant__ ChainCfg cfg, int num_pairs) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const ConvParams& p = cp.p;
@@ -56,15 +88,14 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
   uint8_t* const stage_ptr = smem + cfg.stage_off;
   const uint32_t bar_base = sbase + cfg.bar_off;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
-  auto peer_bar = [&](int s) { return bar_base + 8u * (16 + s); };            // leader only
-  auto tfull_bar = [&](int g, int b) { return bar_base + 8u * (24 + g * 2 + b); };
-  auto tempty_bar = [&](int g, int b) { return bar_base + 8u * (30 + g * 2 + b); };   // leader only
-  auto ifull_bar = [&](int g, int b) { return bar_base + 8u * (36 + g * 2 + b); };    // own epilogue warps -> own MMA warp
-  auto ipeer_bar = [&](int g, int b) { return bar_base + 8u * (40 + g * 2 + b); };    // peer's MMA warp -> leader
-  auto iempty_bar = [&](int g, int b) { return bar_base + 8u * (44 + g * 2 + b); };
-  const uint32_t w_bar = bar_base + 8u * 48;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + cfg.bar_off + 8 * 49);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (CH_MAX_STAGES + s); };
+  constexpr int B0 = 3 * CH_MAX_STAGES;
+  auto tfull_bar = [&](int g, int b) { return bar_base + 8u * (B0 + g * 2 + b); };
+  auto tempty_bar = [&](int g, int b) { return bar_base + 8u * (B0 + 6 + g * 2 + b); };      // leader only
+  auto ifull_bar = [&](int g, int b) { return bar_base + 8u * (B0 + 12 + g * 2 + b); };      // leader only: epilogue group g of BOTH CTAs -> issuer g+1
+  auto iempty_bar = [&](int g, int b) { return bar_base + 8u * (B0 + 20 + g * 2 + b); };
+  const uint32_t w_bar = bar_base + 8u * (B0 + 24);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + cfg.bar_off + 8 * (B0 + 25));
   float* const s_bias = reinterpret_cast<float*>(smem + cfg.bias_off);
 
   const int warp = threadIdx.x >> 5;
@@ -74,19 +105,18 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < cfg.stages; ++s) {
-      mbar_init(full_bar(s), 1);
+      // the leader's "stage full" also collects the peer's "my rows have landed" arrive: one wait per stage for the issuer
+      mbar_init(full_bar(s), leader ? 2 : 1);
       mbar_init(empty_bar(s), 1);
-      mbar_init(peer_bar(s), 1);
     }
     for (int g = 0; g < NG; ++g)
       for (int b = 0; b < 2; ++b) {
         mbar_init(tfull_bar(g, b), 1);
-        mbar_init(tempty_bar(g, b), 2 * CH_EPI_WARPS);
+        mbar_init(tempty_bar(g, b), 2 * ch_group_warps(NG, g));
       }
     for (int g = 0; g < NG - 1; ++g)
       for (int b = 0; b < 2; ++b) {
-        mbar_init(ifull_bar(g, b), CH_EPI_WARPS);
-        mbar_init(ipeer_bar(g, b), 1);
+        mbar_init(ifull_bar(g, b), 2 * ch_group_warps(NG, g));
         mbar_init(iempty_bar(g, b), 1);
       }
     mbar_init(w_bar, 1);
@@ -131,13 +161,23 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
       const uint32_t row_bytes = (uint32_t)(R * 16);
       const long long chunk_stride = (long long)p.in_Tp * 8;
       const int chunks_per_stage = cfg.kbs * 2;
-      for (int it = 0; it < n_local; ++it) {
-        const int pr = pair0 + it * pair_step;
-        const int b = pr / ppi;
-        int tl_in_item = (pr - b * ppi) * 2 + (int)rank;
+      PairIter pit(pair0, pair_step, ppi), pre(pair0, pair_step, ppi);
+      auto tile_src = [&](const PairIter& pi_) {
+        int tl_in_item = pi_.pi * 2 + (int)rank;
         if (tl_in_item > tpi - 1) tl_in_item = tpi - 1;   // odd tile count: the idle half re-reads a valid tile (rows get zeroed)
-        const int t0 = tl_in_item * TILE_M;
-        const __half* src = p.in + act_off(p.in_bs, p.in_Tp, b, p.in_coff8, t0 - p.pad_left);
+        return p.in + act_off(p.in_bs, p.in_Tp, pi_.b, p.in_coff8, tl_in_item * TILE_M - p.pad_left);
+      };
+      const int n_chunks = p.Cin >> 3;
+      // L2 prefetch runs CH_PREFETCH tile pairs ahead of the ring
+      for (int d = 0; d < CH_PREFETCH && d < n_local; ++d, pre.next()) {
+        const __half* ps = tile_src(pre);
+        for (int c = 0; c < n_chunks; ++c, ps += chunk_stride) bulk_prefetch_l2(ps, row_bytes);
+      }
+      for (int it = 0; it < n_local; ++it, pit.next()) {
+        const __half* src = tile_src(pit);
+        const bool do_pre = it + CH_PREFETCH < n_local;
+        const __half* ps = do_pre ? tile_src(pre) : nullptr;
+        if (do_pre) pre.next();
         for (int ks = 0; ks < cfg.nks; ++ks) {
           const uint32_t fb = full_bar(s);
           mbar_wait(empty_bar(s), ph ^ 1u);
@@ -145,6 +185,7 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
           uint32_t dst = stage_base + s * cfg.stage_bytes;
           for (int c = 0; c < chunks_per_stage; ++c) {
             bulk_g2s(dst, src, row_bytes, fb);
+            if (do_pre) { bulk_prefetch_l2(ps, row_bytes); ps += chunk_stride; }
             dst += row_bytes;
             src += chunk_stride;
           }
@@ -153,36 +194,40 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA warp
+    // ------------------------------------------------------------------ issuer of G1: k-tap conv, rows streamed through the ring
     mbar_wait(w_bar, 0);
     int s = 0;
     uint32_t ph = 0;
-    // first GEMM of tile pair `it`: k-tap conv, rows streamed through the ring
-    auto gemm_first = [&](int it) {
-      const int N1 = cp.N[0], Nh = N1 >> 1;
-      const uint32_t idesc = make_idesc_f16(256, N1);
-      const uint64_t a_desc_hi = make_desc(0u, (uint32_t)(R * 16), 128u);
-      const uint64_t b_desc_hi = make_desc(0u, (uint32_t)(Nh * 16), 128u);
-      const uint32_t b_step = (uint32_t)(Nh * 2);
-      const uint32_t a_step = (uint32_t)(2 * R);
-      const uint32_t dil_u = (uint32_t)p.dil;
-      const int pr = pair0 + it * pair_step;
-      const int b = pr / ppi;
-      const int tl_in_item = (pr - b * ppi) * 2 + (int)rank;
+    const int N1 = cp.N[0], Nh = N1 >> 1;
+    const uint32_t idesc = make_idesc_f16(256, N1);
+    const uint64_t a_desc_hi = make_desc(0u, (uint32_t)(R * 16), 128u);
+    const uint64_t b_desc_hi = make_desc(0u, (uint32_t)(Nh * 16), 128u);
+    const uint32_t b_step = (uint32_t)(Nh * 2);
+    const uint32_t a_step = (uint32_t)(2 * R);
+    const uint32_t dil_u = (uint32_t)p.dil;
+    const uint32_t w_addr0 = (sbase + cfg.w_off[0]) >> 4;
+    const int nbA = cfg.nbA[0];
+    const uint32_t full0_leader = mapa_u32(full_bar(0), 0);
+    PairIter pit(pair0, pair_step, ppi);
+    for (int it = 0; it < n_local; ++it, pit.next()) {
+      const int tl_in_item = pit.pi * 2 + (int)rank;
       const int t0 = (tl_in_item > tpi - 1 ? tpi - 1 : tl_in_item) * TILE_M;
       const int tfirst = t0 - p.pad_left;
       const bool dead = tl_in_item > tpi - 1;
       const bool edge = dead || (tfirst < 0) || (tfirst + R > p.Tin);
-      const int buf = buf_of(it, cfg.nbA[0]);
+      const int buf = buf_of(it, nbA);
       if (leader) {
-        mbar_wait(tempty_bar(0, buf), phase_of(it, cfg.nbA[0]) ^ 1u);
+        mbar_wait(tempty_bar(0, buf), phase_of(it, nbA) ^ 1u);
         tc_fence_after();
       }
+      trace_ev(cp.trace, it, 0);
       const uint32_t d_tmem = tmem_base + (uint32_t)(cfg.acc_col[0] + buf * N1);
-      uint32_t b_addr = (sbase + cfg.w_off[0]) >> 4;
+      uint32_t b_addr = w_addr0;
       uint32_t accum = 0u;
       for (int ks = 0; ks < cfg.nks; ++ks) {
         mbar_wait(full_bar(s), ph);
+        if (ks == 0) trace_ev(cp.trace, it, 8);
+        if (ks == cfg.nks - 1) trace_ev(cp.trace, it, 14);
         if (edge) {  // conv zero padding of this CTA's rows
           uint8_t* a_ptr = stage_ptr + s * cfg.stage_bytes;
           for (int r = lane; r < R; r += 32) {
@@ -196,13 +241,14 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
         }
         if (!leader) {
           if (elect_one()) {
-            if (edge) mbar_arrive_remote_release(mapa_u32(peer_bar(s), 0));
-            else mbar_arrive_remote(mapa_u32(peer_bar(s), 0));
+            if (edge) mbar_arrive_remote_release(full0_leader + 8u * s);   // zero-padding writes must be visible
+            else mbar_arrive_remote(full0_leader + 8u * s);
           }
           __syncwarp();
         } else {
-          mbar_wait(peer_bar(s), ph);
           tc_fence_after();
+          if (ks == 0) trace_ev(cp.trace, it, 9);
+          if (ks == cfg.nks - 1) trace_ev(cp.trace, it, 15);
           if (elect_one()) {
             uint32_t a_addr = (stage_base + s * cfg.stage_bytes) >> 4;
             for (int kb = 0; kb < cfg.kbs; ++kb) {
@@ -221,29 +267,33 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
         }
         if (++s == cfg.stages) { s = 0; ph ^= 1u; }
       }
-    };
-    // pointwise GEMM g (1 or 2) of tile pair `it`: A = intermediate operand written by the epilogue of GEMM g-1
-    auto gemm_next = [&](int g, int it) {
-      const int K = cp.N[g - 1], Ng = cp.N[g], Nh = Ng >> 1;
-      const int bi = buf_of(it, cfg.nbI[g - 1]);
-      const uint32_t iph = phase_of(it, cfg.nbI[g - 1]);
-      mbar_wait(ifull_bar(g - 1, bi), iph);                 // this CTA's 128 operand rows are in shared memory
-      if (!leader) {
-        if (elect_one()) mbar_arrive_remote_release(mapa_u32(ipeer_bar(g - 1, bi), 0));
-        __syncwarp();
-        return;
-      }
-      mbar_wait_cluster(ipeer_bar(g - 1, bi), iph);
-      const int buf = buf_of(it, cfg.nbA[g]);
-      mbar_wait(tempty_bar(g, buf), phase_of(it, cfg.nbA[g]) ^ 1u);
+      trace_ev(cp.trace, it, 1);
+    }
+  } else if (warp <= NG) {
+    // ------------------------------------------------------------------ issuer of pointwise GEMM g: A = operand written by epilogue group g-1
+    const int g = warp - 1;
+    mbar_wait(w_bar, 0);
+    const int K = cp.N[g - 1], Ng = cp.N[g], Nh = Ng >> 1;
+    const int nbI = cfg.nbI[g - 1], nbA = cfg.nbA[g];
+    const uint32_t idesc = make_idesc_f16(256, Ng);
+    const uint64_t a_desc_hi = make_desc(0u, (uint32_t)(CH_RI * 16), 128u);
+    const uint64_t b_desc_hi = make_desc(0u, (uint32_t)(Nh * 16), 128u);
+    const uint32_t w_addr0 = (sbase + cfg.w_off[g]) >> 4;
+    // Only the leader issues.  The operand rows each CTA wrote for itself are published by its epilogue warps
+    // (fence.proxy.async, then an arrive on the LEADER's barrier -- same relaxed remote arrive as the per-stage
+    // "my half is in place" handshake of G1: the data is read by the writer's own SM, only the trigger is remote).
+    for (int it = 0; leader && it < n_local; ++it) {
+      const int bi = buf_of(it, nbI);
+      mbar_wait(ifull_bar(g - 1, bi), phase_of(it, nbI));   // both CTAs' 128 operand rows are in their shared memory
+      if (NG == 2) trace_ev(cp.trace, it, 10);
+      const int buf = buf_of(it, nbA);
+      mbar_wait(tempty_bar(g, buf), phase_of(it, nbA) ^ 1u);
       tc_fence_after();
+      trace_ev(cp.trace, it, g == 1 ? 2 : 10);
       if (elect_one()) {
-        const uint32_t idesc = make_idesc_f16(256, Ng);
-        const uint64_t a_desc_hi = make_desc(0u, (uint32_t)(CH_RI * 16), 128u);
-        const uint64_t b_desc_hi = make_desc(0u, (uint32_t)(Nh * 16), 128u);
         const uint32_t d_tmem = tmem_base + (uint32_t)(cfg.acc_col[g] + buf * Ng);
         uint32_t a_addr = (sbase + cfg.i_off[g - 1] + bi * cfg.i_bytes[g - 1]) >> 4;
-        uint32_t b_addr = (sbase + cfg.w_off[g]) >> 4;
+        uint32_t b_addr = w_addr0;
         for (int kb = 0; kb < K / 16; ++kb) {
           umma2_f16(d_tmem, a_desc_hi | (uint64_t)a_addr, b_desc_hi | (uint64_t)b_addr, idesc, kb ? 1u : 0u);
           a_addr += (uint32_t)(2 * CH_RI);
@@ -253,94 +303,81 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
         umma_commit2(tfull_bar(g, buf));
       }
       __syncwarp();
-    };
-    for (int slot = 0; slot < n_local + NG - 1; ++slot) {
-      if (NG == 2) {
-        if (slot < n_local) gemm_first(slot);
-        if (slot >= 1) gemm_next(1, slot - 1);
-      } else {
-        if (slot >= 2) gemm_next(2, slot - 2);
-        if (slot >= 1 && slot - 1 < n_local) gemm_next(1, slot - 1);
-        if (slot < n_local) gemm_first(slot);
-      }
+      trace_ev(cp.trace, it, g == 1 ? 3 : 11);
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps: own 128 rows
-    const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    // accumulator of GEMM g -> bias, LeakyReLU, fp16 -> this CTA's operand rows of GEMM g+1
-    auto epi_mid = [&](int g, int it, int bias_off) {
-      const int Ng = cp.N[g];
-      const int wcols = Ng >> 1, col_lo = half * wcols;      // Ng >= 32
-      const float slope = cp.lrelu[g] ? LRELU_SLOPE : 1.0f;
-      const int buf = buf_of(it, cfg.nbA[g]);
-      const int bi = buf_of(it, cfg.nbI[g]);
-      mbar_wait(tfull_bar(g, buf), phase_of(it, cfg.nbA[g]));
-      mbar_wait(iempty_bar(g, bi), phase_of(it, cfg.nbI[g]) ^ 1u);   // GEMM g+1 of the previous user has read the buffer
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cfg.acc_col[g] + buf * Ng + col_lo);
-      uint8_t* const dst = smem + cfg.i_off[g] + bi * cfg.i_bytes[g] + (q * 32 + lane) * 16;
-      const float* bw = s_bias + bias_off + col_lo;
-      for (int cb = 0; cb < wcols; cb += 32) {
-        uint32_t a[32];
-        const int ncol = wcols - cb < 32 ? 16 : 32;
-        if (ncol == 32) tmem_ld32_nowait(taddr + cb, a);
-        else tmem_ld16_nowait(taddr + cb, a);
-        tmem_wait_ld();
+    // ------------------------------------------------------------------ epilogue groups: own 128 rows of one stage's accumulator
+    int g = 0, w0 = 1 + NG;
+    while (g < NG - 1 && warp >= w0 + ch_group_warps(NG, g)) { w0 += ch_group_warps(NG, g); ++g; }
+    const int gw = ch_group_warps(NG, g);
+    const int q = warp & 3;                                  // TMEM lane quarter this warp may read
+    const int part = (warp - w0) >> 2, nparts = gw >> 2;     // column part
+    const int Ng = cp.N[g];
+    const int wcols = Ng / nparts < 16 ? 16 : Ng / nparts;
+    const int col_lo = part * wcols;
+    const bool active = col_lo < Ng;
+    const float slope = cp.lrelu[g] ? LRELU_SLOPE : 1.0f;
+    int bias_off = 0;
+    for (int i = 0; i < g; ++i) bias_off += cp.N[i];
+    const float* bw = s_bias + bias_off + col_lo;
+    const int nbA = cfg.nbA[g];
+    const uint32_t tempty0_leader = mapa_u32(tempty_bar(g, 0), 0);
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cfg.acc_col[g] + col_lo);
+    const bool tracer = (warp == w0);
+    if (g < NG - 1) {
+      // accumulator -> bias, LeakyReLU, fp16 -> this CTA's operand rows of GEMM g+1
+      const float ca = 0.5f * (1.0f + slope), cbk = 0.5f * (1.0f - slope);
+      const int nbI = cfg.nbI[g];
+      const uint32_t ifull0_leader = mapa_u32(ifull_bar(g, 0), 0);
+      for (int it = 0; it < n_local; ++it) {
+        const int buf = buf_of(it, nbA);
+        const int bi = buf_of(it, nbI);
+        mbar_wait(tfull_bar(g, buf), phase_of(it, nbA));
+        mbar_wait(iempty_bar(g, bi), phase_of(it, nbI) ^ 1u);   // GEMM g+1 of the previous user has read the buffer
+        tc_fence_after();
+        if (tracer) trace_ev(cp.trace, it, g == 0 ? 4 : 12);
+        const uint32_t taddr = taddr0 + (uint32_t)(buf * Ng);
+        uint8_t* const dst = smem + cfg.i_off[g] + bi * cfg.i_bytes[g] + (q * 32 + lane) * 16;
+        for (int cb = 0; active && cb < wcols; cb += 32) {
+          uint32_t a[32];
+          const int ncol = wcols - cb < 32 ? 16 : 32;
+          if (ncol == 32) tmem_ld32_nowait(taddr + cb, a);
+          else tmem_ld16_nowait(taddr + cb, a);
+          tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (8 * c < ncol) {
-            const float4 b0 = *reinterpret_cast<const float4*>(bw + cb + 8 * c);
-            const float4 b1 = *reinterpret_cast<const float4*>(bw + cb + 8 * c + 4);
-            float v[8] = {__uint_as_float(a[8 * c]) + b0.x,     __uint_as_float(a[8 * c + 1]) + b0.y,
-                          __uint_as_float(a[8 * c + 2]) + b0.z, __uint_as_float(a[8 * c + 3]) + b0.w,
-                          __uint_as_float(a[8 * c + 4]) + b1.x, __uint_as_float(a[8 * c + 5]) + b1.y,
-                          __uint_as_float(a[8 * c + 6]) + b1.z, __uint_as_float(a[8 * c + 7]) + b1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], slope * v[i]);
-            const int chunk = ((col_lo + cb) >> 3) + c;
-            *reinterpret_cast<uint4*>(dst + chunk * (CH_RI * 16)) = pack_half8(v);
+          for (int c = 0; c < 4; ++c) {
+            if (8 * c < ncol) {
+              const int chunk = ((col_lo + cb) >> 3) + c;
+              *reinterpret_cast<uint4*>(dst + chunk * (CH_RI * 16)) = epi_chunk8<false>(a + 8 * c, bw + cb + 8 * c, ca, cbk, make_uint4(0u, 0u, 0u, 0u));
+            }
           }
         }
+        tc_fence_before();
+        fence_async_smem();                                    // generic-proxy writes -> visible to the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_remote(tempty0_leader + 8u * buf);
+          mbar_arrive_remote(ifull0_leader + 8u * bi);
+        }
+        if (tracer) trace_ev(cp.trace, it, g == 0 ? 5 : 13);
       }
-      tc_fence_before();
-      fence_async_smem();                                    // generic-proxy writes -> visible to the tensor core's async proxy
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive_remote(mapa_u32(tempty_bar(g, buf), 0));
-        mbar_arrive(ifull_bar(g, bi));
-      }
-    };
-    // accumulator of the last GEMM -> the usual fused epilogue to HBM
-    auto epi_last = [&](int it, int bias_off) {
-      const int g = NG - 1;
-      const int Ng = cp.N[g];
-      const int wcols = Ng >> 1, col_lo = half * wcols;
-      const float slope = cp.lrelu[g] ? LRELU_SLOPE : 1.0f;
-      const int pr = pair0 + it * pair_step;
-      const int b = pr / ppi;
-      const int tl_in_item = (pr - b * ppi) * 2 + (int)rank;
-      const int t = tl_in_item * TILE_M + q * 32 + lane;     // >= Tin for a dead tile => every store is masked
-      const EpiRow row = epi_row<MODE_SAME, false, false>(cp.pl, b, t, col_lo);
-      const int buf = buf_of(it, cfg.nbA[g]);
-      uint4 resv[2];
-      mbar_wait(tfull_bar(g, buf), phase_of(it, cfg.nbA[g]));
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cfg.acc_col[g] + buf * Ng + col_lo);
-      epi_store<MODE_SAME, false, false>(row, s_bias + bias_off + col_lo, taddr, wcols, slope, resv);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(mapa_u32(tempty_bar(g, buf), 0));
-    };
-    const int boff1 = cp.N[0], boff2 = cp.N[0] + cp.N[1];
-    for (int slot = 0; slot < n_local + NG - 1; ++slot) {
-      if (NG == 2) {
-        if (slot < n_local) epi_mid(0, slot, 0);
-        if (slot >= 1) epi_last(slot - 1, boff1);
-      } else {
-        if (slot >= 2) epi_last(slot - 2, boff2);
-        if (slot >= 1 && slot - 1 < n_local) epi_mid(1, slot - 1, boff1);
-        if (slot < n_local) epi_mid(0, slot, 0);
+    } else {
+      // accumulator of the last GEMM -> the usual fused epilogue to HBM
+      PairIter pit(pair0, pair_step, ppi);
+      for (int it = 0; it < n_local; ++it, pit.next()) {
+        const int tl_in_item = pit.pi * 2 + (int)rank;
+        const int t = tl_in_item * TILE_M + q * 32 + lane;     // >= Tin for a dead tile => every store is masked
+        const EpiRow row = epi_row<MODE_SAME, false, false>(cp.pl, pit.b, t, col_lo);
+        const int buf = buf_of(it, nbA);
+        uint4 resv[2];
+        mbar_wait(tfull_bar(g, buf), phase_of(it, nbA));
+        tc_fence_after();
+        if (tracer) trace_ev(cp.trace, it, 6);
+        if (active) epi_store<MODE_SAME, false, false>(row, bw, taddr0 + (uint32_t)(buf * Ng), wcols, slope, resv);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(tempty0_leader + 8u * buf);
+        if (tracer) trace_ev(cp.trace, it, 7);
       }
     }
   }
@@ -378,12 +415,14 @@ static bool pick_chain_cfg(const ChainParams& cp, ChainCfg& c) {
   }
   c.stage_off = off;
   const int room = CH_SMEM_BUDGET - CH_BAR_BYTES - CH_BIAS_BYTES - off;
+  // Every stage costs the issuer a barrier round trip (~200 cycles) and the tensor pipe's queue is only ~6 MMAs deep, so
+  // stages are as large as still leaves >= 4 of them; the L2 prefetch (not the ring) covers HBM latency.
   for (int kbs = 4; kbs >= 1; kbs >>= 1) {
     if (p.Cin % (16 * kbs)) continue;
     c.kbs = kbs;
     c.stage_bytes = kbs * 2 * c.R * 16;
     int stages = room / c.stage_bytes;
-    if (stages > 8) stages = 8;
+    if (stages > CH_MAX_STAGES) stages = CH_MAX_STAGES;
     if (stages >= 4 || (kbs == 1 && stages >= 2)) {
       c.stages = stages;
       c.nks = p.Cin / (16 * kbs);
@@ -410,7 +449,7 @@ int launch_conv_chain(const ChainParams& cp, cudaStream_t stream) {
     nb += cp.N[g];
   }
   AR_CHECK(nb * 4 <= CH_BIAS_BYTES, AR_ERR_INVALID, "conv_chain: too many bias entries");
-  AR_CHECK(cp.pl.res == nullptr || false, AR_ERR_INVALID, "conv_chain: no residual epilogue");
+  AR_CHECK(cp.pl.res == nullptr && cp.pl.pool == nullptr, AR_ERR_INVALID, "conv_chain: no residual / pool epilogue");
   ChainCfg cfg;
   AR_CHECK(pick_chain_cfg(cp, cfg), AR_ERR_INVALID, "conv_chain: no configuration fits shared memory / TMEM");
   using Kernel = void (*)(ChainParams, ChainCfg, int);
@@ -432,7 +471,7 @@ int launch_conv_chain(const ChainParams& cp, cudaStream_t stream) {
   int groups = sm_count() / 2;
   if (groups > num_pairs) groups = num_pairs;
   if (groups < 1) groups = 1;
-  kernel<<<groups * 2, CH_THREADS, cfg.smem_bytes, stream>>>(cp, cfg, num_pairs);
+  kernel<<<groups * 2, ch_threads(NG), cfg.smem_bytes, stream>>>(cp, cfg, num_pairs);
   AR_CUDA_OK(cudaGetLastError());
   return AR_OK;
 }

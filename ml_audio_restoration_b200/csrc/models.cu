@@ -25,6 +25,9 @@ int set_engine(int e) {
   return AR_OK;
 }
 // Layer fusion (conv_chain.cu) for subsequently created models; AR_FUSE=0 in the environment turns it off too.
+static long long* g_chain_trace = nullptr;   // debug: device buffer the fused-chain kernels trace their pipeline into
+static int g_chain_trace_slot = 0;           // launch k after ar_debug_chain_trace() writes slot k % 4 of [4][64*16]
+int set_chain_trace(long long* dev_buf) { g_chain_trace = dev_buf; g_chain_trace_slot = 0; return AR_OK; }
 static int g_fuse = -1;
 int set_fusion(int on) {
   g_fuse = on ? 1 : 0;
@@ -518,6 +521,7 @@ static int run_chain(Ctx& c, std::initializer_list<const char*> names, const Act
   cp.pl.out = out.h(); cp.pl.out_bs = out.bs; cp.pl.out_Tp = out.Tp; cp.pl.out_coff8 = o.out_coff8;
   cp.pl.Tout = o.Tout >= 0 ? o.Tout : out.T;
   cp.pl.out_tblock = o.out_tblock;
+  cp.trace = g_chain_trace ? g_chain_trace + (size_t)(g_chain_trace_slot++ % 4) * 1024 : nullptr;
   ProfScope ps(CAT_CONV, c.stream, 2.0 * macs * (double)c.B * (double)in.T);
   return launch_conv_chain(cp, c.stream);
 }

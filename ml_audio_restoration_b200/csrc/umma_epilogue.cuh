@@ -73,46 +73,80 @@ __device__ __forceinline__ void epi_prefetch_res(const EpiRow& r, bool active, u
   }
 }
 
+// ---- the per-element math, written for issue slots (the epilogue warps are instruction-latency bound):
+//   bias add and the first LeakyReLU product as packed 2-wide fp32 ops (FADD2 / FMUL2), LeakyReLU as
+//   ca*v + cb*|v| with ca = (1+slope)/2, cb = (1-slope)/2 (two FMA-pipe ops instead of FMUL + FMNMX on the half-rate ALU
+//   pipe; slope = 1 gives exactly v), and ONE saturating convert for the round-to-fp16 + clamp-to-+-65504
+//   (F2FP.SATFINITE.F16.F32.PACK_AB).  2.5 instructions per column instead of 5.75.
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint32_t cvt_half2_sat(float lo, float hi) {   // round to nearest, saturate to the finite fp16 range
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// (acc + bias) -> LeakyReLU for two neighbouring columns
+__device__ __forceinline__ void bias_act2(uint32_t a0, uint32_t a1, float b0, float b1, float ca, float cb, float& y0, float& y1) {
+  unsigned long long v = f2_pack(__uint_as_float(a0), __uint_as_float(a1)), t;
+  const unsigned long long bb = f2_pack(b0, b1), cc = f2_pack(ca, ca);
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(v) : "l"(v), "l"(bb));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(v), "l"(cc));
+  float v0, v1, t0, t1;
+  f2_unpack(v, v0, v1);
+  f2_unpack(t, t0, t1);
+  y0 = fmaf(fabsf(v0), cb, t0);
+  y1 = fmaf(fabsf(v1), cb, t1);
+}
+// eight accumulator columns + bias -> activation -> (residual) -> packed fp16 row piece
+template <bool RES>
+__device__ __forceinline__ uint4 epi_chunk8(const uint32_t* a, const float* bias8, float ca, float cb, uint4 resv) {
+  const float4 b0 = *reinterpret_cast<const float4*>(bias8);
+  const float4 b1 = *reinterpret_cast<const float4*>(bias8 + 4);
+  float v[8];
+  bias_act2(a[0], a[1], b0.x, b0.y, ca, cb, v[0], v[1]);
+  bias_act2(a[2], a[3], b0.z, b0.w, ca, cb, v[2], v[3]);
+  bias_act2(a[4], a[5], b1.x, b1.y, ca, cb, v[4], v[5]);
+  bias_act2(a[6], a[7], b1.z, b1.w, ca, cb, v[6], v[7]);
+  if (RES) {
+    float rr[8];
+    unpack_half8(resv, rr);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += rr[i];
+  }
+  return make_uint4(cvt_half2_sat(v[0], v[1]), cvt_half2_sat(v[2], v[3]), cvt_half2_sat(v[4], v[5]), cvt_half2_sat(v[6], v[7]));
+}
+
 template <int MODE, bool POOL, bool RES>
 __device__ __forceinline__ void epi_store(const EpiRow& r, const float* s_bias_w /* bias of this warp's first column */, uint32_t taddr,
                                           int wcols, float slope, const uint4 (&resv)[2]) {
-  for (int cb = 0; cb < wcols; cb += 32) {
+  const float ca = 0.5f * (1.0f + slope), cb = 0.5f * (1.0f - slope);
+  for (int cb0 = 0; cb0 < wcols; cb0 += 32) {
     uint32_t a[32];
-    const int ncol = wcols - cb < 32 ? 16 : 32;     // wcols is 16 or a multiple of 32
-    if (ncol == 32) tmem_ld32_nowait(taddr + cb, a);
-    else tmem_ld16_nowait(taddr + cb, a);
+    const int ncol = wcols - cb0 < 32 ? 16 : 32;     // wcols is 16 or a multiple of 32
+    if (ncol == 32) tmem_ld32_nowait(taddr + cb0, a);
+    else tmem_ld16_nowait(taddr + cb0, a);
     tmem_wait_ld();
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       if (8 * c < ncol) {
-        const float4 b0 = *reinterpret_cast<const float4*>(s_bias_w + cb + 8 * c);
-        const float4 b1 = *reinterpret_cast<const float4*>(s_bias_w + cb + 8 * c + 4);
-        float v[8] = {__uint_as_float(a[8 * c]) + b0.x,     __uint_as_float(a[8 * c + 1]) + b0.y,
-                      __uint_as_float(a[8 * c + 2]) + b0.z, __uint_as_float(a[8 * c + 3]) + b0.w,
-                      __uint_as_float(a[8 * c + 4]) + b1.x, __uint_as_float(a[8 * c + 5]) + b1.y,
-                      __uint_as_float(a[8 * c + 6]) + b1.z, __uint_as_float(a[8 * c + 7]) + b1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], slope * v[i]);
-        if (RES) {
-          float rr[8];
-          unpack_half8(resv[c & 1], rr);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] += rr[i];
+        const uint4 packed = epi_chunk8<RES>(a + 8 * c, s_bias_w + cb0 + 8 * c, ca, cb, resv[c & 1]);
+        const int ch = (cb0 >> 3) + c;               // 8-column chunk index within this warp's range
+        if (r.ok0) *reinterpret_cast<uint4*>(r.o0 + (long long)ch * r.ostride) = packed;
+        if (MODE == MODE_INTERLEAVE2) {
+          if (r.ok1) *reinterpret_cast<uint4*>(r.o1 + (long long)ch * r.ostride) = make_uint4(0u, 0u, 0u, 0u);
         }
-        const int ch = (cb >> 3) + c;               // 8-column chunk index within this warp's range
-        {
-          const uint4 packed = pack_half8(v);
-          if (r.ok0) *reinterpret_cast<uint4*>(r.o0 + (long long)ch * r.ostride) = packed;
-          if (MODE == MODE_INTERLEAVE2) {
-            if (r.ok1) *reinterpret_cast<uint4*>(r.o1 + (long long)ch * r.ostride) = make_uint4(0u, 0u, 0u, 0u);
-          }
-          if (POOL) {  // MaxPool1d(2,2), floor: rows (t, t+1) live in neighbouring lanes; max of rounded == rounded max
-            float q[8], m[8];
-            unpack_half8(packed, q);
+        if (POOL) {  // MaxPool1d(2,2), floor: rows (t, t+1) live in neighbouring lanes; max of rounded == rounded max
+          float q[8], m[8];
+          unpack_half8(packed, q);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) m[i] = fmaxf(q[i], __shfl_down_sync(0xffffffffu, q[i], 1));
-            if (r.pok) *reinterpret_cast<uint4*>(r.prow + (long long)ch * r.pstride) = pack_half8(m);
-          }
+          for (int i = 0; i < 8; ++i) m[i] = fmaxf(q[i], __shfl_down_sync(0xffffffffu, q[i], 1));
+          if (r.pok) *reinterpret_cast<uint4*>(r.prow + (long long)ch * r.pstride) = pack_half8(m);
         }
       }
     }

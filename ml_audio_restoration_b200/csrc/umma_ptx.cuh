@@ -44,6 +44,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// Fire-and-forget HBM -> L2 prefetch of a contiguous run (multiple of 16 bytes).  The shared-memory ring of a CTA
+// holds ~100 KB, which covers only ~2/3 of the bytes that must be in flight per SM to saturate HBM at its loaded
+// latency; prefetching a few tiles ahead into the 126 MB L2 makes the ring cover L2 latency instead.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 // One elected lane of a fully converged warp; ptxas maps this to ELECT and keeps the guarded region on
 // the uniform datapath, so tcgen05.mma / cp.async.bulk operands need no per-instruction broadcast loop.
 __device__ __forceinline__ bool elect_one() {
