@@ -61,23 +61,6 @@ __device__ __forceinline__ void trace_ev(long long* tr, int it, int ev) {
 __device__ __forceinline__ int buf_of(int it, int nb) { return it & (nb - 1); }
 __device__ __forceinline__ uint32_t phase_of(int it, int nb) { return (uint32_t)(it >> (nb - 1)) & 1u; }
 
-// walks the tile pairs of one cluster (pair0, pair0 + step, ...) without divisions in the loop
-struct PairIter {
-  int b, pi;            // batch item, pair index inside the item
-  int step_b, step_p, ppi;
-  __device__ PairIter(int pair0, int pair_step, int ppi_) : ppi(ppi_) {
-    b = pair0 / ppi_;
-    pi = pair0 - b * ppi_;
-    step_b = pair_step / ppi_;
-    step_p = pair_step - step_b * ppi_;
-  }
-  __device__ __forceinline__ void next() {
-    b += step_b;
-    pi += step_p;
-    if (pi >= ppi) { pi -= ppi; ++b; }
-  }
-};
-
 template <int TAPS, int NG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ch_threads(NG), 1)
 conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant__ ChainCfg cfg, int num_pairs) {

@@ -25,6 +25,7 @@ constexpr int UMMA2_THREADS = 64 + 32 * EPI2_WARPS;
 constexpr int SMEM2_BUDGET = 227 * 1024;
 constexpr int BAR2_BYTES = 512;
 constexpr int BIAS2_BYTES = 1024;
+constexpr int UMMA2_PREFETCH = 4;   // tile pairs the L2 prefetch runs ahead of the shared-memory ring
 
 struct Umma2Cfg {
   int kbs, stages, R;
@@ -45,7 +46,6 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
   const uint32_t bar_base = smem_base + cfg.stages * cfg.stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (cfg.stages + s); };
-  auto peer_bar = [&](int s) { return bar_base + 8u * (2 * cfg.stages + s); };   // used in the leader only
   auto tfull_bar = [&](int i) { return bar_base + 8u * (3 * cfg.stages + i); };
   auto tempty_bar = [&](int i) { return bar_base + 8u * (3 * cfg.stages + 8 + i); };  // used in the leader only
   const uint32_t w_bar = bar_base + 8u * (3 * cfg.stages + 16);
@@ -60,9 +60,10 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < cfg.stages; ++s) {
-      mbar_init(full_bar(s), 1);
+      // the leader's "stage full" also collects the peer's "my rows have landed" arrive: ONE barrier round trip per
+      // stage for the issuing thread (a pipeline trace showed ~200 cycles per wait, more than the stage's MMAs cost to issue)
+      mbar_init(full_bar(s), leader ? 2 : 1);
       mbar_init(empty_bar(s), 1);
-      mbar_init(peer_bar(s), 1);
     }
     for (int i = 0; i < cfg.nbuf; ++i) {
       mbar_init(tfull_bar(i), 1);
@@ -89,6 +90,7 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
   const int R = cfg.R;
   const int pair0 = cid / nsl;
   const int pair_step = (gridDim.x >> 1) / nsl;
+  const int n_local = pair0 < num_pairs ? (num_pairs - pair0 + pair_step - 1) / pair_step : 0;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer (own rows, own weight half)
@@ -104,12 +106,23 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
       const uint32_t row_bytes = (uint32_t)(R * 16);
       const long long chunk_stride = (long long)p.in_Tp * 8;             // halves between 8-channel chunks
       const int chunks_per_stage = cfg.kbs * 2;
-      for (int pr = pair0; pr < num_pairs; pr += pair_step) {
-        const int b = pr / ppi;
-        int tl_in_item = (pr - b * ppi) * 2 + (int)rank;
+      PairIter pit(pair0, pair_step, ppi), pre(pair0, pair_step, ppi);
+      auto tile_src = [&](const PairIter& pi_) {
+        int tl_in_item = pi_.pi * 2 + (int)rank;
         if (tl_in_item > tpi - 1) tl_in_item = tpi - 1;   // odd tile count: the idle half re-reads a valid tile (all its rows get zeroed)
-        const int t0 = tl_in_item * TILE_M;
-        const __half* src = p.in + act_off(p.in_bs, p.in_Tp, b, p.in_coff8, t0 - p.pad_left);
+        return p.in + act_off(p.in_bs, p.in_Tp, pi_.b, p.in_coff8, tl_in_item * TILE_M - p.pad_left);
+      };
+      // HBM -> L2 prefetch runs UMMA2_PREFETCH tile pairs ahead of the shared-memory ring (which then only has to cover L2 latency)
+      const int n_chunks = p.Cin >> 3;
+      for (int d = 0; d < UMMA2_PREFETCH && d < n_local; ++d, pre.next()) {
+        const __half* ps = tile_src(pre);
+        for (int c = 0; c < n_chunks; ++c, ps += chunk_stride) bulk_prefetch_l2(ps, row_bytes);
+      }
+      for (int it = 0; it < n_local; ++it, pit.next()) {
+        const __half* src = tile_src(pit);
+        const bool do_pre = it + UMMA2_PREFETCH < n_local;
+        const __half* ps = do_pre ? tile_src(pre) : nullptr;
+        if (do_pre) pre.next();
         for (int ks = 0; ks < cfg.nks; ++ks) {
           const uint32_t fb = full_bar(s);
           mbar_wait(empty_bar(s), ph ^ 1u);
@@ -117,6 +130,7 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
           uint32_t dst = smem_base + s * cfg.stage_bytes;
           for (int c = 0; c < chunks_per_stage; ++c) {
             bulk_g2s(dst, src, row_bytes, fb);
+            if (do_pre) { bulk_prefetch_l2(ps, row_bytes); ps += chunk_stride; }
             dst += row_bytes;
             src += chunk_stride;
           }
@@ -136,15 +150,14 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
     const uint32_t a_step = (uint32_t)(2 * R);
     const uint32_t w_addr0 = w_base >> 4;
     const uint32_t dil_u = (uint32_t)p.dil;
-    for (int pr = pair0; pr < num_pairs; pr += pair_step) {
-      const int b = pr / ppi;
-      const int tl_in_item = (pr - b * ppi) * 2 + (int)rank;
-      const int t_true = tl_in_item * TILE_M;                          // true first output row of this CTA's tile
+    const uint32_t full0_leader = mapa_u32(full_bar(0), 0);
+    PairIter pit(pair0, pair_step, ppi);
+    for (int it = 0; it < n_local; ++it, pit.next()) {
+      const int tl_in_item = pit.pi * 2 + (int)rank;
       const int t0 = (tl_in_item > tpi - 1 ? tpi - 1 : tl_in_item) * TILE_M;  // tile that was actually loaded
       const int tfirst = t0 - p.pad_left;
       const bool dead = tl_in_item > tpi - 1;                          // no such tile: contribute zeros
       const bool edge = dead || (tfirst < 0) || (tfirst + R > p.Tin);
-      (void)t_true;
       if (leader) {
         mbar_wait(tempty_bar(buf), aph ^ 1u);                          // both epilogues drained this accumulator
         tc_fence_after();
@@ -168,12 +181,11 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
         if (!leader) {
           // my half of this stage (rows + resident weights) is in place: tell the leader
           if (elect_one()) {
-            if (edge) mbar_arrive_remote_release(mapa_u32(peer_bar(s), 0));   // zero-padding writes must be visible
-            else mbar_arrive_remote(mapa_u32(peer_bar(s), 0));
+            if (edge) mbar_arrive_remote_release(full0_leader + 8u * s);   // zero-padding writes must be visible
+            else mbar_arrive_remote(full0_leader + 8u * s);
           }
           __syncwarp();
         } else {
-          mbar_wait(peer_bar(s), ph);
           tc_fence_after();
           if (elect_one()) {
             uint32_t a_addr = (smem_base + s * cfg.stage_bytes) >> 4;
@@ -207,11 +219,11 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
     const uint32_t tempty_leader0 = mapa_u32(tempty_bar(0), 0);   // barriers are 8 bytes apart in the leader too
     int buf = 0;
     uint32_t aph = 0;
-    for (int pr = pair0; pr < num_pairs; pr += pair_step) {
-      const int b = pr / ppi;
-      const int tl_in_item = (pr - b * ppi) * 2 + (int)rank;
+    PairIter pit(pair0, pair_step, ppi);
+    for (int it = 0; it < n_local; ++it, pit.next()) {
+      const int tl_in_item = pit.pi * 2 + (int)rank;
       const int t = tl_in_item * TILE_M + q * 32 + lane;   // >= Tin for a dead tile => every store is masked
-      const EpiRow row = epi_row<MODE, POOL, RES>(p, b, t, gcol0);
+      const EpiRow row = epi_row<MODE, POOL, RES>(p, pit.b, t, gcol0);
       uint4 resv[2];
       epi_prefetch_res<RES>(row, active, resv);
       mbar_wait(tfull_bar(buf), aph);

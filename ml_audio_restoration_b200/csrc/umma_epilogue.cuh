@@ -10,6 +10,23 @@
 
 namespace ar {
 
+// walks the tile pairs of one cluster (pair0, pair0 + step, ...) without divisions in the loop
+struct PairIter {
+  int b, pi;            // batch item, pair index inside the item
+  int step_b, step_p, ppi;
+  __device__ PairIter(int pair0, int pair_step, int ppi_) : ppi(ppi_) {
+    b = pair0 / ppi_;
+    pi = pair0 - b * ppi_;
+    step_b = pair_step / ppi_;
+    step_p = pair_step - step_b * ppi_;
+  }
+  __device__ __forceinline__ void next() {
+    b += step_b;
+    pi += step_p;
+    if (pi >= ppi) { pi -= ppi; ++b; }
+  }
+};
+
 struct EpiRow {
   char* o0;            // output row of this thread, first chunk of this warp's column range
   char* o1;            // interleave mode: the right zero-pad row (written when ok1)
