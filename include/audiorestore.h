@@ -66,6 +66,13 @@ int ar_set_conv_engine(int engine);
  * compute the same fp16-rounded intermediates. */
 int ar_set_fusion(int on);
 
+/* Shared memory one conv CTA may use, in KB (64..227, default 227 = the whole SM).  AR_CORESIDENT_SMEM_KB leaves room
+ * for one CTA of the LSTM recurrence on every SM: when chunk batches are pipelined on two streams the latency-bound
+ * scan of one batch (stereo_separator.py:106) then runs UNDER the convs of the other instead of after them.
+ * Takes effect for subsequent forwards (process-wide, like ar_set_conv_engine). */
+#define AR_CORESIDENT_SMEM_KB 172
+int ar_set_conv_smem_kb(int kb);
+
 /* Replaces: model construction + torch.load + load_state_dict(strict) + .to(device) + .eval()
  * (inference.py:51-55, 66-70, 85-89).  Folds eval-mode BatchNorm into the conv weights,
  * rounds tensor-core operands to fp16 (the 11-bit significand TF32 would keep), packs into the kernels' layouts, uploads.  */

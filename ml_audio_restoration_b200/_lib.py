@@ -11,12 +11,14 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaudiorestore_sm100.so")
+# AR_LIB_PATH: load another build of the same library (A/B measurements of kernel variants on one GPU box)
+LIB_PATH = os.environ.get("AR_LIB_PATH") or os.path.join(_HERE, "libaudiorestore_sm100.so")
 
 AR_OK, AR_ERR_INVALID, AR_ERR_WEIGHTS, AR_ERR_CUDA, AR_ERR_WORKSPACE = 0, 1, 2, 3, 4
 MODEL_DENOISER, MODEL_SUPER_RES, MODEL_STEREO = 0, 1, 2
 ENGINE_UMMA, ENGINE_SIMT = 0, 1
 NORMALIZE_SCRATCH_BYTES = 16384
+CORESIDENT_SMEM_KB, FULL_SMEM_KB = 172, 227
 PROFILE_CATEGORIES = ("conv", "lstm", "stem", "tail", "normalize", "chunk")
 
 
@@ -29,6 +31,7 @@ _SIGNATURES = {
     "ar_version": (C.c_int, []),
     "ar_set_conv_engine": (C.c_int, [C.c_int]),
     "ar_set_fusion": (C.c_int, [C.c_int]),
+    "ar_set_conv_smem_kb": (C.c_int, [C.c_int]),
     "ar_model_create": (C.c_int, [C.c_int, C.POINTER(ArTensor), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "ar_model_destroy": (None, [C.c_void_p]),
     "ar_model_kind": (C.c_int, [C.c_void_p]),

@@ -14,6 +14,7 @@ const char* last_error();
 int set_engine(int e);
 int set_fusion(int on);
 int set_chain_trace(long long* dev_buf);
+int set_conv_smem_kb(int kb);
 int model_create(int kind, const ar_tensor_t* tensors, int n, int device, Model** out);
 int model_workspace_bytes(const Model* m, int B, int T, size_t* bytes);
 int model_forward(const Model* m, const float* x, float* y, int B, int T, const float* st_in, float* st_out, void* ws,
@@ -40,6 +41,7 @@ const char* ar_last_error(void) { return ar::last_error(); }
 int ar_version(void) { return 100; }
 int ar_set_conv_engine(int engine) { return ar::set_engine(engine); }
 int ar_set_fusion(int on) { return ar::set_fusion(on); }
+int ar_set_conv_smem_kb(int kb) { return ar::set_conv_smem_kb(kb); }
 int ar_debug_chain_trace(long long* dev_buf) { return ar::set_chain_trace(dev_buf); }
 
 int ar_model_create(int kind, const ar_tensor_t* tensors, int n_tensors, int device, ar_model_t* out) {

@@ -187,10 +187,14 @@ struct ChainParams {
 };
 
 // ----------------------------------------------------------------------------- launchers
+bool conv_chain_fits(int Cin, int taps, int dil, const int* N, int n_gemms);   // shared memory / TMEM check for a chain
 int launch_conv_chain(const ChainParams& cp, cudaStream_t stream);  // fused k-tap conv -> pointwise conv(s), 2-CTA engine
 int launch_conv_umma(const ConvParams& p, cudaStream_t stream);
 int launch_conv_umma2(const ConvParams& p, cudaStream_t stream);   // cta_group::2 engine (needs p.cta2)
 int launch_conv_simt(const ConvParams& p, cudaStream_t stream);
 int sm_count();
+// Shared memory a conv CTA may take (bytes).  227 KB by default (one CTA owns the SM); AR_CONV_SMEM_KB lowers it so that a
+// CTA of the latency-bound LSTM recurrence can be co-resident on the same SM while chunk batches are pipelined on two streams.
+int conv_smem_budget();
 
 }  // namespace ar

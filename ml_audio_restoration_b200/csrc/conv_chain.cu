@@ -39,6 +39,7 @@ constexpr int CH_PREFETCH = 4;           // tile pairs the L2 prefetch runs ahea
 // epilogue warps per stage
 __host__ __device__ constexpr int ch_group_warps(int NG, int g) { return NG == 2 ? 8 : (g == 2 ? 8 : 4); }
 __host__ __device__ constexpr int ch_threads(int NG) { return 32 * (1 + NG) + 32 * 16; }
+__host__ __device__ constexpr int ch_maxreg(int NG) { return NG == 2 ? 104 : 96; }
 
 struct ChainCfg {
   int kbs, stages, R, nks, stage_bytes;  // activation ring of the first GEMM
@@ -57,12 +58,16 @@ __device__ __forceinline__ void trace_ev(long long* tr, int it, int ev) {
   if (tr != nullptr && blockIdx.x == 0 && it < CH_TRACE_TILES && (threadIdx.x & 31) == 0) tr[it * 16 + ev] = clock64();
 }
 
+__device__ __forceinline__ void trace_ev1(long long* tr, int it, int ev) {   // caller is a single elected thread
+  if (tr != nullptr && blockIdx.x == 0 && it < CH_TRACE_TILES) tr[it * 16 + ev] = clock64();
+}
+
 // buffer index / mbarrier phase of the it-th use of a set of nb (1 or 2) buffers
 __device__ __forceinline__ int buf_of(int it, int nb) { return it & (nb - 1); }
 __device__ __forceinline__ uint32_t phase_of(int it, int nb) { return (uint32_t)(it >> (nb - 1)) & 1u; }
 
 template <int TAPS, int NG>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ch_threads(NG), 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ch_threads(NG), 1) __maxnreg__(ch_maxreg(NG))
 conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant__ ChainCfg cfg, int num_pairs) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const ConvParams& p = cp.p;
@@ -177,62 +182,55 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ issuer of G1: k-tap conv, rows streamed through the ring
-    mbar_wait(w_bar, 0);
-    int s = 0;
-    uint32_t ph = 0;
-    const int N1 = cp.N[0], Nh = N1 >> 1;
-    const uint32_t idesc = make_idesc_f16(256, N1);
-    const uint64_t a_desc_hi = make_desc(0u, (uint32_t)(R * 16), 128u);
-    const uint64_t b_desc_hi = make_desc(0u, (uint32_t)(Nh * 16), 128u);
-    const uint32_t b_step = (uint32_t)(Nh * 2);
-    const uint32_t a_step = (uint32_t)(2 * R);
-    const uint32_t dil_u = (uint32_t)p.dil;
-    const uint32_t w_addr0 = (sbase + cfg.w_off[0]) >> 4;
-    const int nbA = cfg.nbA[0];
-    const uint32_t full0_leader = mapa_u32(full_bar(0), 0);
-    PairIter pit(pair0, pair_step, ppi);
-    for (int it = 0; it < n_local; ++it, pit.next()) {
-      const int tl_in_item = pit.pi * 2 + (int)rank;
-      const int t0 = (tl_in_item > tpi - 1 ? tpi - 1 : tl_in_item) * TILE_M;
-      const int tfirst = t0 - p.pad_left;
-      const bool dead = tl_in_item > tpi - 1;
-      const bool edge = dead || (tfirst < 0) || (tfirst + R > p.Tin);
-      const int buf = buf_of(it, nbA);
-      if (leader) {
-        mbar_wait(tempty_bar(0, buf), phase_of(it, nbA) ^ 1u);
-        tc_fence_after();
-      }
-      trace_ev(cp.trace, it, 0);
-      const uint32_t d_tmem = tmem_base + (uint32_t)(cfg.acc_col[0] + buf * N1);
-      uint32_t b_addr = w_addr0;
-      uint32_t accum = 0u;
-      for (int ks = 0; ks < cfg.nks; ++ks) {
-        mbar_wait(full_bar(s), ph);
-        if (ks == 0) trace_ev(cp.trace, it, 8);
-        if (ks == cfg.nks - 1) trace_ev(cp.trace, it, 14);
-        if (edge) {  // conv zero padding of this CTA's rows
-          uint8_t* a_ptr = stage_ptr + s * cfg.stage_bytes;
-          for (int r = lane; r < R; r += 32) {
-            const int t = tfirst + r;
-            if (dead || t < 0 || t >= p.Tin)
-              for (int c = 0; c < cfg.kbs * 2; ++c)
-                *reinterpret_cast<float4*>(a_ptr + (c * R + r) * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          fence_async_smem();
-          __syncwarp();
+    // ------------------------------------------------------------------ issuer of G1: k-tap conv, rows streamed through the ring.
+    // ONE elected thread walks the loop (waits, rare edge zero-fill, MMA issue, commits).
+    if (elect_one()) {
+      mbar_wait(w_bar, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      const int N1 = cp.N[0], Nh = N1 >> 1;
+      const uint32_t idesc = make_idesc_f16(256, N1);
+      const uint64_t a_desc_hi = make_desc(0u, (uint32_t)(R * 16), 128u);
+      const uint64_t b_desc_hi = make_desc(0u, (uint32_t)(Nh * 16), 128u);
+      const uint32_t b_step = (uint32_t)(Nh * 2);
+      const uint32_t a_step = (uint32_t)(2 * R);
+      const uint32_t dil_u = (uint32_t)p.dil;
+      const uint32_t w_addr0 = (sbase + cfg.w_off[0]) >> 4;
+      const int nbA = cfg.nbA[0];
+      const uint32_t full0_leader = mapa_u32(full_bar(0), 0);
+      PairIter pit(pair0, pair_step, ppi);
+      for (int it = 0; it < n_local; ++it, pit.next()) {
+        const int tl_in_item = pit.pi * 2 + (int)rank;
+        const int t0 = (tl_in_item > tpi - 1 ? tpi - 1 : tl_in_item) * TILE_M;
+        const int tfirst = t0 - p.pad_left;
+        const bool dead = tl_in_item > tpi - 1;
+        const bool edge = dead || (tfirst < 0) || (tfirst + R > p.Tin);
+        const int buf = buf_of(it, nbA);
+        if (leader) {
+          mbar_wait(tempty_bar(0, buf), phase_of(it, nbA) ^ 1u);
+          tc_fence_after();
         }
-        if (!leader) {
-          if (elect_one()) {
+        trace_ev1(cp.trace, it, 0);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(cfg.acc_col[0] + buf * N1);
+        uint32_t b_addr = w_addr0;
+        uint32_t accum = 0u;
+        for (int ks = 0; ks < cfg.nks; ++ks) {
+          mbar_wait(full_bar(s), ph);                          // leader: own rows landed AND the peer's arrive
+          if (ks == 0) trace_ev1(cp.trace, it, 8);
+          if (edge) {  // conv zero padding of this CTA's rows (first / last tiles of an item only)
+            uint8_t* a_ptr = stage_ptr + s * cfg.stage_bytes;
+            for (int r = 0; r < R; ++r) {
+              const int t = tfirst + r;
+              if (dead || t < 0 || t >= p.Tin)
+                for (int c = 0; c < cfg.kbs * 2; ++c)
+                  *reinterpret_cast<float4*>(a_ptr + (c * R + r) * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            fence_async_smem();
+          }
+          if (!leader) {
             if (edge) mbar_arrive_remote_release(full0_leader + 8u * s);   // zero-padding writes must be visible
             else mbar_arrive_remote(full0_leader + 8u * s);
-          }
-          __syncwarp();
-        } else {
-          tc_fence_after();
-          if (ks == 0) trace_ev(cp.trace, it, 9);
-          if (ks == cfg.nks - 1) trace_ev(cp.trace, it, 15);
-          if (elect_one()) {
+          } else {
             uint32_t a_addr = (stage_base + s * cfg.stage_bytes) >> 4;
             for (int kb = 0; kb < cfg.kbs; ++kb) {
 #pragma unroll
@@ -246,12 +244,12 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
             umma_commit2(empty_bar(s));
             if (ks == cfg.nks - 1) umma_commit2(tfull_bar(0, buf));
           }
-          __syncwarp();
+          if (++s == cfg.stages) { s = 0; ph ^= 1u; }
         }
-        if (++s == cfg.stages) { s = 0; ph ^= 1u; }
+        trace_ev1(cp.trace, it, 1);
       }
-      trace_ev(cp.trace, it, 1);
     }
+    __syncwarp();
   } else if (warp <= NG) {
     // ------------------------------------------------------------------ issuer of pointwise GEMM g: A = operand written by epilogue group g-1
     const int g = warp - 1;
@@ -265,15 +263,14 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
     // Only the leader issues.  The operand rows each CTA wrote for itself are published by its epilogue warps
     // (fence.proxy.async, then an arrive on the LEADER's barrier -- same relaxed remote arrive as the per-stage
     // "my half is in place" handshake of G1: the data is read by the writer's own SM, only the trigger is remote).
-    for (int it = 0; leader && it < n_local; ++it) {
-      const int bi = buf_of(it, nbI);
-      mbar_wait(ifull_bar(g - 1, bi), phase_of(it, nbI));   // both CTAs' 128 operand rows are in their shared memory
-      if (NG == 2) trace_ev(cp.trace, it, 10);
-      const int buf = buf_of(it, nbA);
-      mbar_wait(tempty_bar(g, buf), phase_of(it, nbA) ^ 1u);
-      tc_fence_after();
-      trace_ev(cp.trace, it, g == 1 ? 2 : 10);
-      if (elect_one()) {
+    if (leader && elect_one()) {
+      for (int it = 0; it < n_local; ++it) {
+        const int bi = buf_of(it, nbI);
+        mbar_wait(ifull_bar(g - 1, bi), phase_of(it, nbI));   // both CTAs' 128 operand rows are in their shared memory
+        const int buf = buf_of(it, nbA);
+        mbar_wait(tempty_bar(g, buf), phase_of(it, nbA) ^ 1u);
+        tc_fence_after();
+        trace_ev1(cp.trace, it, g == 1 ? 2 : 10);
         const uint32_t d_tmem = tmem_base + (uint32_t)(cfg.acc_col[g] + buf * Ng);
         uint32_t a_addr = (sbase + cfg.i_off[g - 1] + bi * cfg.i_bytes[g - 1]) >> 4;
         uint32_t b_addr = w_addr0;
@@ -284,10 +281,10 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
         }
         umma_commit2(iempty_bar(g - 1, bi));                // both CTAs may overwrite this operand buffer
         umma_commit2(tfull_bar(g, buf));
+        trace_ev1(cp.trace, it, g == 1 ? 3 : 11);
       }
-      __syncwarp();
-      trace_ev(cp.trace, it, g == 1 ? 3 : 11);
     }
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue groups: own 128 rows of one stage's accumulator
     int g = 0, w0 = 1 + NG;
@@ -390,33 +387,47 @@ static bool pick_chain_cfg(const ChainParams& cp, ChainCfg& c) {
   int tc = 32;
   while (tc < cols) tc <<= 1;
   c.tmem_cols = tc;
-  for (int g = 0; g < NG - 1; ++g) {
-    c.nbI[g] = NG == 2 ? 2 : 1;
-    c.i_bytes[g] = (cp.N[g] / 8) * CH_RI * 16;
-    c.i_off[g] = off;
-    off += c.nbI[g] * c.i_bytes[g];
-  }
-  c.stage_off = off;
-  const int room = CH_SMEM_BUDGET - CH_BAR_BYTES - CH_BIAS_BYTES - off;
+  const int w_end = off;
   // Every stage costs the issuer a barrier round trip (~200 cycles) and the tensor pipe's queue is only ~6 MMAs deep, so
-  // stages are as large as still leaves >= 4 of them; the L2 prefetch (not the ring) covers HBM latency.
+  // stages are as large as still leaves >= 4 of them (the L2 prefetch, not the ring, covers HBM latency); the
+  // intermediate operand is double-buffered when that still fits.
   for (int kbs = 4; kbs >= 1; kbs >>= 1) {
     if (p.Cin % (16 * kbs)) continue;
-    c.kbs = kbs;
-    c.stage_bytes = kbs * 2 * c.R * 16;
-    int stages = room / c.stage_bytes;
-    if (stages > CH_MAX_STAGES) stages = CH_MAX_STAGES;
-    if (stages >= 4 || (kbs == 1 && stages >= 2)) {
-      c.stages = stages;
-      c.nks = p.Cin / (16 * kbs);
-      c.bar_off = c.stage_off + stages * c.stage_bytes;
-      c.bar_off = (c.bar_off + 15) / 16 * 16;
-      c.bias_off = c.bar_off + CH_BAR_BYTES;
-      c.smem_bytes = c.bias_off + CH_BIAS_BYTES;
-      return true;
+    for (int nbi = (NG == 2 ? 2 : 1); nbi >= 1; --nbi) {
+      off = w_end;
+      for (int g = 0; g < NG - 1; ++g) {
+        c.nbI[g] = nbi;
+        c.i_bytes[g] = (cp.N[g] / 8) * CH_RI * 16;
+        c.i_off[g] = off;
+        off += c.nbI[g] * c.i_bytes[g];
+      }
+      c.stage_off = off;
+      const int room = conv_smem_budget() - CH_BAR_BYTES - CH_BIAS_BYTES - off;
+      c.kbs = kbs;
+      c.stage_bytes = kbs * 2 * c.R * 16;
+      int stages = room / c.stage_bytes;
+      if (stages > CH_MAX_STAGES) stages = CH_MAX_STAGES;
+      if (stages >= 4 || (kbs == 1 && stages >= 2)) {
+        c.stages = stages;
+        c.nks = p.Cin / (16 * kbs);
+        c.bar_off = c.stage_off + stages * c.stage_bytes;
+        c.bar_off = (c.bar_off + 15) / 16 * 16;
+        c.bias_off = c.bar_off + CH_BAR_BYTES;
+        c.smem_bytes = c.bias_off + CH_BIAS_BYTES;
+        return true;
+      }
     }
   }
   return false;
+}
+
+bool conv_chain_fits(int Cin, int taps, int dil, const int* N, int n_gemms) {
+  ChainParams cp{};
+  cp.p.Cin = Cin; cp.p.taps = taps; cp.p.dil = dil;
+  cp.n_gemms = n_gemms;
+  for (int g = 0; g < n_gemms; ++g) cp.N[g] = N[g];
+  ChainCfg cfg;
+  return pick_chain_cfg(cp, cfg);
 }
 
 int launch_conv_chain(const ChainParams& cp, cudaStream_t stream) {

@@ -23,6 +23,7 @@
 #include "ar_common.cuh"
 #include "umma_ptx.cuh"
 #include "umma_epilogue.cuh"
+#include <cstdlib>
 
 namespace ar {
 
@@ -236,7 +237,7 @@ static bool pick_cfg(const ConvParams& p, UmmaCfg& c) {
   c.ncol = ncol;
   c.tmem_cols = 2 * ncol;
   c.w_bytes = p.Cin * p.taps * Ns * 2;
-  const int room = SMEM_BUDGET - BAR_BYTES - BIAS_BYTES - c.w_bytes;
+  const int room = conv_smem_budget() - BAR_BYTES - BIAS_BYTES - c.w_bytes;
   for (int kbs = 4; kbs >= 1; kbs >>= 1) {
     if (p.Cin % (16 * kbs)) continue;
     c.kbs = kbs;
@@ -251,6 +252,23 @@ static bool pick_cfg(const ConvParams& p, UmmaCfg& c) {
     }
   }
   return false;
+}
+
+static int g_conv_smem = 0;
+int set_conv_smem_kb(int kb) {
+  if (kb < 64 || kb > 227) { set_error("conv shared-memory budget must be within [64, 227] KB"); return AR_ERR_INVALID; }
+  g_conv_smem = kb * 1024;
+  return AR_OK;
+}
+int conv_smem_budget() {
+  if (g_conv_smem == 0) {
+    const char* e = getenv("AR_CONV_SMEM_KB");
+    int kb = e ? atoi(e) : 227;
+    if (kb < 64) kb = 64;
+    if (kb > 227) kb = 227;
+    g_conv_smem = kb * 1024;
+  }
+  return g_conv_smem;
 }
 
 int sm_count() {

@@ -255,7 +255,7 @@ static bool pick_cfg2(const ConvParams& p, Umma2Cfg& c) {
   c.nbuf = 512 / ncol > 8 ? 8 : 512 / ncol;
   c.tmem_cols = c.nbuf * ncol;
   c.w_bytes = p.Cin * p.taps * (Ns / 2) * 2;
-  const int room = SMEM2_BUDGET - BAR2_BYTES - BIAS2_BYTES - c.w_bytes;
+  const int room = conv_smem_budget() - BAR2_BYTES - BIAS2_BYTES - c.w_bytes;
   for (int kbs = 4; kbs >= 1; kbs >>= 1) {
     if (p.Cin % (16 * kbs)) continue;
     c.kbs = kbs;

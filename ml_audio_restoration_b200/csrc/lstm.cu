@@ -397,6 +397,148 @@ lstm_mma_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, const
   }
 }
 
+
+// ---------------------------------------------------------------------------- 4 sequences per CTA, two CTAs per SM
+// The 8-sequence kernel above is latency-bound: every step is one serial chain (h exchange -> MMAs -> gate functions ->
+// barrier) and all 16 warps of the SM walk it in lock step (ncu: 32 % issue utilisation, the special-function unit
+// saturated only in bursts).  This variant gives each SM TWO independent recurrences to interleave: a CTA owns four
+// sequences (the n = 8 MMA columns hold them twice), its 8 warps own 8 hidden units each as two 16-row tiles, (i|f) and
+// (g|o) of those units, so thread (gid, tig) finds all four gates of cell (unit 8w + gid, sequence (tig&1)*2 + (tig>>1))
+// in its own accumulators -- no shuffles -- and carries exactly one cell.  While one CTA sits in its barrier or its
+// gate-function chain the other one issues.
+constexpr int L4_SEQ = 4;
+constexpr int L4_THREADS = 256;
+constexpr int L4_XSTEP = L4_SEQ * LM_XS + 8;       // halves per staged step (+16 B: conflict-free cp.async rows)
+constexpr int L4_XBUF = LSTM_BLK * L4_XSTEP;
+constexpr int L4_HSTEP = L4_SEQ * LM_HST + 4;      // floats per staged step of hidden states
+constexpr int L4_SMEM = 2 * L4_XBUF * 2 + 2 * LSTM_BLK * L4_HSTEP * 4 + 2 * L4_SEQ * LM_HS * 2;
+
+__global__ void __launch_bounds__(L4_THREADS, 3)
+lstm_mma4_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, const float* __restrict__ whh,
+                 __half* __restrict__ hout, long long h_bs, int h_Tp, int B, int T,
+                 const float* __restrict__ state_in, float* __restrict__ state_out) {
+  extern __shared__ __align__(16) float lm_smem[];
+  __half* const xs = reinterpret_cast<__half*>(lm_smem);       // [2][8 steps][4 seq][264] fp16 staged gate pre-activations
+  float* const hstage = lm_smem + L4_XBUF;                     // [2][8 steps][4 seq][68] fp32
+  __half* const hbuf = reinterpret_cast<__half*>(hstage + 2 * LSTM_BLK * L4_HSTEP);   // [2][4 seq][80] fp16
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int unit = warp * 8 + gid;                  // the cell this thread carries: (unit, seq)
+  const int seq = (tig & 1) * 2 + (tig >> 1);
+  const int sel = tig >> 1;                         // accumulator column (0: col 2tig, 1: col 2tig+1) that is `seq`
+  const int seq0 = blockIdx.x * L4_SEQ;
+  const int bq = min(seq0 + seq, B - 1);            // surplus columns replay the last sequence, stores are masked
+
+  // A fragments: tile 0 rows (gid -> i, gid+8 -> f), tile 1 rows (gid -> g, gid+8 -> o) of unit 8w + gid
+  uint32_t wfrag[2][4][4];
+  {
+    auto w2 = [&](int row, int k) {
+      const __half2 h = __floats2half2_rn(whh[row * LSTM_H + k], whh[row * LSTM_H + k + 1]);
+      return *reinterpret_cast<const uint32_t*>(&h);
+    };
+#pragma unroll
+    for (int tl = 0; tl < 2; ++tl) {
+      const int row_lo = (2 * tl) * LSTM_H + unit, row_hi = (2 * tl + 1) * LSTM_H + unit;
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt) {
+        wfrag[tl][kt][0] = w2(row_lo, kt * 16 + 2 * tig);
+        wfrag[tl][kt][1] = w2(row_hi, kt * 16 + 2 * tig);
+        wfrag[tl][kt][2] = w2(row_lo, kt * 16 + 2 * tig + 8);
+        wfrag[tl][kt][3] = w2(row_hi, kt * 16 + 2 * tig + 8);
+      }
+    }
+  }
+  float c = 0.f, hl = 0.f;
+  if (state_in != nullptr) {
+    hl = state_in[(long long)bq * 2 * LSTM_H + unit];
+    c = state_in[(long long)bq * 2 * LSTM_H + LSTM_H + unit];
+  }
+  const int upos = (unit & ~15) + ((((unit & 7) >> 1) * 2 + ((unit >> 3) & 1)) * 2) + (unit & 1);   // see lstm_mma_kernel
+  hbuf[seq * LM_HS + upos] = __float2half_rn(hl);
+
+  const uint32_t xs_u32 = (uint32_t)__cvta_generic_to_shared(xs);
+  auto stage_piece = [&](int blk, int m) {          // piece m (0..3) of this thread's share of block blk
+    const int t0 = blk * LSTM_BLK;
+    const uint32_t dst0 = xs_u32 + (uint32_t)((blk & 1) * L4_XBUF * 2);
+    const int i = tid + L4_THREADS * m;             // 0..1023: [4 seq][32 chunks][8 steps]
+    const int sq = i >> 8, piece = i & 255;
+    const int ch = piece >> 3, k = piece & 7;
+    const int b = min(seq0 + sq, B - 1);
+    cp_async16(dst0 + (uint32_t)((k * L4_XSTEP + sq * LM_XS + ch * 8) * 2), xp + act_off_tb(xp_bs, 32, b, ch, t0 + k));
+  };
+  auto flush_item = [&](int blk) {                  // one 16-byte hidden-state item per thread: [4 seq][8 chunks][8 steps]
+    const float* hst = hstage + (blk & 1) * (LSTM_BLK * L4_HSTEP);
+    const int t0 = blk * LSTM_BLK;
+    const int s = tid >> 6, ch = (tid >> 3) & 7, kk = tid & 7;
+    const int b = seq0 + s;
+    if (b < B && t0 + kk < T) {
+      const float* src = &hst[kk * L4_HSTEP + s * LM_HST + 8 * ch];
+      const float4 v0 = *reinterpret_cast<const float4*>(src);
+      const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
+      const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      *reinterpret_cast<uint4*>(hout + act_off(h_bs, h_Tp, b, ch, t0 + kk)) = pack_half8(v);
+    }
+  };
+#pragma unroll
+  for (int m = 0; m < 4; ++m) stage_piece(0, m);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  int cur = 0;
+  const int nblk = (T + LSTM_BLK - 1) / LSTM_BLK;
+  for (int blk = 0; blk < nblk; ++blk) {
+    const bool more = blk + 1 < nblk;
+    const __half* xb = xs + (blk & 1) * L4_XBUF;
+    float* hst = hstage + (blk & 1) * (LSTM_BLK * L4_HSTEP);
+    const int t0 = blk * LSTM_BLK;
+    const int nst = min(LSTM_BLK, T - t0);
+    if (!more && blk > 0) flush_item(blk - 1);
+#pragma unroll
+    for (int k = 0; k < LSTM_BLK; ++k) {
+      if (k < nst) {  // uniform
+        if (more) {
+          if ((k & 1) == 0) stage_piece(blk + 1, k >> 1);
+          if (k == 6) asm volatile("cp.async.commit_group;" ::: "memory");
+          if (blk > 0 && k == warp) flush_item(blk - 1);      // one warp flushes per step
+        }
+        // pre-activations of this thread's cell: issued before the MMAs so the load hides behind them
+        const uint2 q = *reinterpret_cast<const uint2*>(xb + k * L4_XSTEP + seq * LM_XS + unit * 4);   // [unit][i,f,g,o]
+        float acc[2][4];
+#pragma unroll
+        for (int tl = 0; tl < 2; ++tl)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[tl][i] = 0.f;
+        const uint2* hb = reinterpret_cast<const uint2*>(hbuf + cur * (L4_SEQ * LM_HS) + (gid & 3) * LM_HS) + tig;
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt) {
+          const uint2 bf = hb[kt * 4];
+          mma_f16_16x8x16(acc[0], wfrag[0][kt], bf.x, bf.y);     // two independent chains (tiles), 4 deep
+          mma_f16_16x8x16(acc[1], wfrag[1][kt], bf.x, bf.y);
+        }
+        const float2 x_if = __half22float2(*reinterpret_cast<const __half2*>(&q.x));
+        const float2 x_go = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+        const float pi = (sel ? acc[0][1] : acc[0][0]) + x_if.x;
+        const float pf = (sel ? acc[0][3] : acc[0][2]) + x_if.y;
+        const float pg = (sel ? acc[1][1] : acc[1][0]) + x_go.x;
+        const float po = (sel ? acc[1][3] : acc[1][2]) + x_go.y;
+        lstm_cell(pi, pf, pg, po, c, hl);
+        hbuf[(cur ^ 1) * (L4_SEQ * LM_HS) + seq * LM_HS + upos] = __float2half_rn(hl);
+        hst[k * L4_HSTEP + seq * LM_HST + unit] = hl;
+        if (more && k == LSTM_BLK - 1) asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        cur ^= 1;
+      }
+    }
+  }
+  flush_item(nblk - 1);
+  if (state_out != nullptr && seq0 + seq < B) {
+    state_out[(long long)(seq0 + seq) * 2 * LSTM_H + unit] = hl;
+    state_out[(long long)(seq0 + seq) * 2 * LSTM_H + LSTM_H + unit] = c;
+  }
+}
+
 int launch_lstm(const Act& xp, const float* whh, const Act& h_out, int B, int T, const float* state_in, float* state_out,
                 cudaStream_t stream) {
   AR_CHECK(T >= 1 && B >= 1, AR_ERR_INVALID, "lstm: empty input");
@@ -406,9 +548,10 @@ int launch_lstm(const Act& xp, const float* whh, const Act& h_out, int B, int T,
     const char* e = getenv("AR_LSTM_S");
     forced = e ? atoi(e) : 0;
   }
-  // Heuristic: the CUDA-core kernel (one sequence per CTA, two CTAs per SM) while that covers the batch;
-  // beyond two sequences per SM the tensor-core kernel (eight sequences per CTA) wins.  AR_LSTM_S overrides.
-  if (forced == 8 || (forced == 0 && B > 2 * sm_count())) {
+  // Heuristic: the CUDA-core kernel (one sequence per CTA, two CTAs per SM) while that covers the batch; beyond two
+  // sequences per SM the tensor-core kernels: four sequences per CTA x two CTAs per SM (default), or eight per CTA
+  // (AR_LSTM_S=8).  AR_LSTM_S overrides.
+  if (forced == 8) {
     static bool attr_set = false;
     if (!attr_set) {
       AR_CUDA_OK(cudaFuncSetAttribute(lstm_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_SMEM));
@@ -416,6 +559,17 @@ int launch_lstm(const Act& xp, const float* whh, const Act& h_out, int B, int T,
     }
     lstm_mma_kernel<<<(B + LM_SEQ - 1) / LM_SEQ, LM_THREADS, LM_SMEM, stream>>>(xp.h(), xp.bs, xp.Tp, whh, h_out.h(), h_out.bs, h_out.Tp,
                                                                          B, T, state_in, state_out);
+    AR_CUDA_OK(cudaGetLastError());
+    return AR_OK;
+  }
+  if (forced == 44 || (forced == 0 && B > 2 * sm_count())) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      AR_CUDA_OK(cudaFuncSetAttribute(lstm_mma4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L4_SMEM));
+      attr_set = true;
+    }
+    lstm_mma4_kernel<<<(B + L4_SEQ - 1) / L4_SEQ, L4_THREADS, L4_SMEM, stream>>>(xp.h(), xp.bs, xp.Tp, whh, h_out.h(), h_out.bs, h_out.Tp,
+                                                                          B, T, state_in, state_out);
     AR_CUDA_OK(cudaGetLastError());
     return AR_OK;
   }

@@ -478,17 +478,19 @@ static int run_conv(Ctx& c, const std::string& name, const Act& in, const Act& o
 static bool can_chain(const Ctx& c, std::initializer_list<const char*> names) {
   if (!c.m->fuse || c.m->engine != AR_ENGINE_UMMA) return false;
   bool first = true;
-  int prevN = 0;
+  int prevN = 0, Cin = 0, taps = 0, dil = 0, N[3] = {0, 0, 0}, ng = 0;
   for (const char* n : names) {
     auto it = c.m->conv.find(n);
-    if (it == c.m->conv.end()) return false;
+    if (it == c.m->conv.end() || ng == 3) return false;
     const ConvLayer& L = it->second;
     if (!L.cta2 || L.n_slices != 2) return false;
     if (!first && (L.taps != 1 || L.Cin != prevN)) return false;
+    if (first) { Cin = L.Cin; taps = L.taps; dil = L.dil; }
     prevN = L.N;
+    N[ng++] = L.N;
     first = false;
   }
-  return true;
+  return conv_chain_fits(Cin, taps, dil, N, ng);
 }
 
 static int run_chain(Ctx& c, std::initializer_list<const char*> names, const Act& in, const Act& out, const ConvOpt& o = ConvOpt()) {

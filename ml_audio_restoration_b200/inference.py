@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import argparse
 import ctypes as C
+import os
 import math
 
 import torch
@@ -230,6 +231,12 @@ class RestorationPipeline:
         firsts = list(range(c0, hi, batch_chunks))
         n_streams = max(1, min(streams, len(firsts)))
         main = torch.cuda.current_stream(self.device)
+        # AR_CONV_SMEM_KB (tuning knob): shared memory a conv CTA may take; below ~172 KB one CTA of the LSTM scan fits
+        # next to it on every SM.  Measured on power-capped B200s the overlap buys nothing (the chip is power-limited,
+        # not occupancy-limited), so the default gives every conv CTA the whole SM.
+        smem_kb = os.environ.get("AR_CONV_SMEM_KB")
+        if smem_kb:
+            _lib.check(L.ar_set_conv_smem_kb(int(smem_kb)))
         if n_streams == 1:
             buf = torch.empty((min(batch_chunks, cnt_all), 1, chunk_size), dtype=torch.float32, device=self.device)
             for first in firsts:
