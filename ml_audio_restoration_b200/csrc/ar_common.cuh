@@ -72,11 +72,10 @@ __device__ __forceinline__ long long act_off_tb(long long bs, int C8, int b, int
   return (long long)b * bs + (((long long)(tr >> 3) * C8 + chunk) * 8 + (tr & 7)) * 8;
 }
 
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {  // round to nearest, clamp to the fp16 range
-  a = fminf(fmaxf(a, -HALF_MAX), HALF_MAX);
-  b = fminf(fmaxf(b, -HALF_MAX), HALF_MAX);
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {  // round to nearest, saturate to the finite fp16 range: one F2FP
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
 __device__ __forceinline__ uint4 pack_half8(const float (&v)[8]) {
   return make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));

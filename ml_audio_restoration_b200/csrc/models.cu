@@ -182,33 +182,30 @@ static bool make_conv(const Table& t, Blob& blob, const std::string& conv, const
 }
 
 // ============================================================================ model objects
-struct StemW { size_t w_off, b_off; int taps; };
 
 struct Model {
   int kind = -1, device = 0, engine = AR_ENGINE_UMMA;
   int fuse = 1;   // fused conv chains where the engine has them (tcgen05 engine, 2-CTA packing)
   float* blob = nullptr;
   std::map<std::string, ConvLayer> conv;
-  StemW stem{};
-  // denoiser tail
-  size_t td_w0 = 0, td_b0 = 0, td_w1 = 0, td_b1 = 0, td_w2 = 0, td_wf = 0;
-  float td_b2 = 0.f, td_bf = 0.f;
-  // final k7 convs (sr: 1, stereo: 2)
-  size_t fin_w[2] = {0, 0};
-  float fin_b[2] = {0.f, 0.f};
+  StemP stem{};          // Cin = 1 stem: kernel-parameter weights
+  // CUDA-core tails: weights live on the host and travel as kernel parameters (constant bank)
+  DenTailP den_tail{};   // denoiser: transient detector + final 1x1
+  FinalW fin{};          // final k7 convs (sr: 1 head, stereo: 2)
   size_t whh_off = 0;
   ~Model() { if (blob) cudaFree(blob); }
 };
 
-static bool stem_pack(const Table& t, Blob& blob, const std::string& conv, const std::string& bn, int k, StemW& s) {
+static bool stem_pack(const Table& t, Blob& blob, const std::string& conv, const std::string& bn, int k, StemP& s) {
+  (void)blob;
   const float* W = t.get(conv + ".weight", {32, 1, k});
   Fold f;
   if (!W || !fold_bn(t, conv, bn, 32, f)) return false;
-  std::vector<float> w(32 * k);
-  for (int o = 0; o < 32; ++o)
-    for (int j = 0; j < k; ++j) w[o * k + j] = W[o * k + j] * f.s[o];
-  s.w_off = blob.push(w);
-  s.b_off = blob.push(f.b);
+  std::memset(&s, 0, sizeof(s));
+  for (int o = 0; o < 32; ++o) {
+    for (int j = 0; j < k; ++j) s.w[o][j] = W[o * k + j] * f.s[o];
+    s.b[o] = f.b[o];
+  }
   s.taps = k;
   return true;
 }
@@ -250,21 +247,19 @@ static bool build_denoiser(const Table& t, Blob& blob, Model& m) {
   const float* WF = t.get("final_conv.weight", {1, 32, 1});
   const float* BF = t.get("final_conv.bias", {1});
   if (!W0 || !B0 || !W1 || !B1 || !W2 || !B2 || !WF || !BF) return false;
-  std::vector<float> w0(3 * 8 * 16 * 4), w1(3 * 4 * 8 * 4), w2(24);
-  for (int j = 0; j < 3; ++j)
-    for (int c = 0; c < 8; ++c)
-      for (int o = 0; o < 16; ++o)
-        for (int i = 0; i < 4; ++i) w0[((j * 8 + c) * 16 + o) * 4 + i] = W0[(o * 32 + 4 * c + i) * 3 + j];
-  for (int j = 0; j < 3; ++j)
-    for (int c = 0; c < 4; ++c)
-      for (int o = 0; o < 8; ++o)
-        for (int i = 0; i < 4; ++i) w1[((j * 4 + c) * 8 + o) * 4 + i] = W1[(o * 16 + 4 * c + i) * 3 + j];
-  for (int j = 0; j < 3; ++j)
-    for (int c = 0; c < 8; ++c) w2[j * 8 + c] = W2[c * 3 + j];
-  m.td_w0 = blob.push(w0); m.td_b0 = blob.push(B0, 16);
-  m.td_w1 = blob.push(w1); m.td_b1 = blob.push(B1, 8);
-  m.td_w2 = blob.push(w2); m.td_wf = blob.push(WF, 32);
-  m.td_b2 = B2[0]; m.td_bf = BF[0];
+  DenTailP& P = m.den_tail;
+  for (int j = 0; j < 3; ++j) {
+    for (int c = 0; c < 32; ++c)
+      for (int o = 0; o < 16; ++o) P.w0[j][c][o] = W0[(o * 32 + c) * 3 + j];
+    for (int c = 0; c < 16; ++c)
+      for (int o = 0; o < 8; ++o) P.w1[j][c][o] = W1[(o * 16 + c) * 3 + j];
+    for (int c = 0; c < 8; ++c) P.w2[j][c] = W2[c * 3 + j];
+  }
+  for (int o = 0; o < 16; ++o) P.b0[o] = B0[o];
+  for (int o = 0; o < 8; ++o) P.b1[o] = B1[o];
+  for (int c = 0; c < 32; ++c) P.wf[c] = WF[c];
+  P.b2 = B2[0];
+  P.bf = BF[0];
   return true;
 }
 
@@ -298,8 +293,9 @@ static bool build_sr(const Table& t, Blob& blob, Model& m) {
   const float* WR = t.get("reconstruction.weight", {1, 32, 7});
   const float* BR = t.get("reconstruction.bias", {1});
   if (!WR || !BR) return false;
-  m.fin_w[0] = blob.push(WR, 224);
-  m.fin_b[0] = BR[0];
+  for (int c = 0; c < 32; ++c)
+    for (int j = 0; j < 7; ++j) m.fin.w[0][j][c] = WR[c * 7 + j];
+  m.fin.bias[0] = BR[0];
   return true;
 }
 
@@ -342,8 +338,9 @@ static bool build_stereo(const Table& t, Blob& blob, Model& m) {
     const float* WF = t.get(p + ".9.weight", {1, 32, 7});
     const float* BF = t.get(p + ".9.bias", {1});
     if (!WF || !BF) return false;
-    m.fin_w[s] = blob.push(WF, 224);
-    m.fin_b[s] = BF[0];
+    for (int c = 0; c < 32; ++c)
+      for (int j = 0; j < 7; ++j) m.fin.w[s][j][c] = WF[c * 7 + j];
+    m.fin.bias[s] = BF[0];
   }
   return true;
 }
@@ -537,7 +534,7 @@ static int denoiser_forward(Ctx& c, const float* x, float* y, int T) {
   Act e0a = A.act(B, 32, T), cat0 = A.act(B, 64, T), p0 = A.act(B, 32, T1);
   if (!A.dry) {
     ProfScope ps(CAT_STEM, c.stream, 2.0 * 96 * (double)B * T);
-    AR_TRY(launch_stem(x, B, T, 3, m.blob + m.stem.w_off, m.blob + m.stem.b_off, e0a, 1, c.stream));
+    AR_TRY(launch_stem(x, B, T, m.stem, e0a, 1, c.stream));
   }
   ConvOpt o; o.pool = &p0;
   AR_TRY(run_conv(c, "enc0b", e0a, cat0, o));                 // skip s0 -> cat0[0:32], pooled -> p0
@@ -591,9 +588,8 @@ static int denoiser_forward(Ctx& c, const float* x, float* y, int T) {
   AR_TRY(run_conv(c, "dec2b", d2a, f));
   A.release(d2a);
   if (!A.dry) {
-    DenTailW w{m.blob + m.td_w0, m.blob + m.td_b0, m.blob + m.td_w1, m.blob + m.td_b1, m.blob + m.td_w2, m.blob + m.td_wf, m.td_b2, m.td_bf};
     ProfScope ps(CAT_TAIL, c.stream, 2.0 * 1976 * (double)B * T);
-    AR_TRY(launch_den_tail(f, x, y, B, T, w, c.stream));
+    AR_TRY(launch_den_tail(f, x, y, B, T, m.den_tail, c.stream));
   }
   A.release(f);
   return AR_OK;
@@ -608,7 +604,7 @@ static int sr_forward(Ctx& c, const float* x, float* y, int T) {
   Act f0 = A.act(B, 32, T);
   if (!A.dry) {
     ProfScope ps(CAT_STEM, c.stream, 2.0 * 224 * (double)B * T);
-    AR_TRY(launch_stem(x, B, T, 7, m.blob + m.stem.w_off, m.blob + m.stem.b_off, f0, 1, c.stream));
+    AR_TRY(launch_stem(x, B, T, m.stem, f0, 1, c.stream));
   }
   Act r = f0;
   for (int i = 0; i < 4; ++i) {
@@ -635,9 +631,8 @@ static int sr_forward(Ctx& c, const float* x, float* y, int T) {
   A.release(u);
   if (!A.dry) {
     const int coff[1] = {0};
-    const float* w[1] = {m.blob + m.fin_w[0]};
     ProfScope ps(CAT_TAIL, c.stream, 2.0 * 224 * (double)B * 2 * T);
-    AR_TRY(launch_final_k7(h, coff, w, m.fin_b, 1, y, B, 2 * T, x, c.stream));
+    AR_TRY(launch_final_k7(h, coff, m.fin, 1, y, B, 2 * T, x, c.stream));
   }
   A.release(h);
   return AR_OK;
@@ -652,7 +647,7 @@ static int stereo_forward(Ctx& c, const float* x, float* y, int T, const float* 
   Act cur = A.act(B, 32, T);
   if (!A.dry) {
     ProfScope ps(CAT_STEM, c.stream, 2.0 * 224 * (double)B * T);
-    AR_TRY(launch_stem(x, B, T, 7, m.blob + m.stem.w_off, m.blob + m.stem.b_off, cur, 1, c.stream));
+    AR_TRY(launch_stem(x, B, T, m.stem, cur, 1, c.stream));
   }
   const int widths[4] = {64, 128, 128, 128};
   static const char* const NA[4] = {"enc1a", "enc2a", "enc3a", "enc4a"};
@@ -710,9 +705,8 @@ static int stereo_forward(Ctx& c, const float* x, float* y, int T, const float* 
   A.release(d1);
   if (!A.dry) {
     const int coff[2] = {0, 32 / 8};
-    const float* w[2] = {m.blob + m.fin_w[0], m.blob + m.fin_w[1]};
     ProfScope ps(CAT_TAIL, c.stream, 2.0 * 448 * (double)B * T);
-    AR_TRY(launch_final_k7(d2, coff, w, m.fin_b, 2, y, B, T, nullptr, c.stream));
+    AR_TRY(launch_final_k7(d2, coff, m.fin, 2, y, B, T, nullptr, c.stream));
   }
   A.release(d2);
   return AR_OK;

@@ -11,14 +11,8 @@ namespace ar {
 // x[B][T] plain fp32 -> H8 fp16 out (32 channels): conv(k taps, pad k/2) + folded BN bias + LeakyReLU.
 // denoiser.py:54 (encoder.0.0), super_resolution.py:25 (initial.0), stereo_separator.py:25.
 template <int TAPS>
-__global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ x, int T, const float* __restrict__ w /*[32][TAPS]*/,
-                                                   const float* __restrict__ bias, __half* __restrict__ out,
-                                                   long long out_bs, int out_Tp, int lrelu) {
-  __shared__ float sw[32 * TAPS];
-  __shared__ float sb[32];
-  for (int i = threadIdx.x; i < 32 * TAPS; i += blockDim.x) sw[i] = w[i];
-  if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
+__global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ x, int T, const __grid_constant__ StemP w,
+                                                   __half* __restrict__ out, long long out_bs, int out_Tp, int lrelu) {
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
@@ -29,28 +23,27 @@ __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ x, 
     const int ti = t + j - TAPS / 2;
     xin[j] = (ti >= 0 && ti < T) ? __ldg(xb + ti) : 0.f;
   }
+  const float slope = lrelu ? LRELU_SLOPE : 1.0f;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float a = sb[8 * c + i];
+      float a = w.b[8 * c + i];
 #pragma unroll
-      for (int j = 0; j < TAPS; ++j) a = fmaf(sw[(8 * c + i) * TAPS + j], xin[j], a);
-      if (lrelu) a = a > 0.f ? a : LRELU_SLOPE * a;
-      v[i] = a;
+      for (int j = 0; j < TAPS; ++j) a = fmaf(w.w[8 * c + i][j], xin[j], a);   // weights: constant-bank operands
+      v[i] = fmaxf(a, slope * a);
     }
     *reinterpret_cast<uint4*>(out + act_off(out_bs, out_Tp, b, c, t)) = pack_half8(v);
   }
 }
 
-int launch_stem(const float* x, int B, int T, int taps, const float* w, const float* bias, const Act& out, int lrelu,
-                cudaStream_t stream) {
+int launch_stem(const float* x, int B, int T, const StemP& w, const Act& out, int lrelu, cudaStream_t stream) {
   dim3 grid((T + 127) / 128, B);
-  if (taps == 3)
-    stem_kernel<3><<<grid, 128, 0, stream>>>(x, T, w, bias, out.h(), out.bs, out.Tp, lrelu);
-  else if (taps == 7)
-    stem_kernel<7><<<grid, 128, 0, stream>>>(x, T, w, bias, out.h(), out.bs, out.Tp, lrelu);
+  if (w.taps == 3)
+    stem_kernel<3><<<grid, 128, 0, stream>>>(x, T, w, out.h(), out.bs, out.Tp, lrelu);
+  else if (w.taps == 7)
+    stem_kernel<7><<<grid, 128, 0, stream>>>(x, T, w, out.h(), out.bs, out.Tp, lrelu);
   else {
     set_error("stem: unsupported tap count");
     return AR_ERR_INVALID;
@@ -63,101 +56,116 @@ int launch_stem(const float* x, int B, int T, int taps, const float* w, const fl
 // y[b][och][t] = bias + sum_{c<32, j<7} w[c][j] * in[c][t+j-3]   (+ linear x2 interpolation of x_lr)
 // super_resolution.py:62,96-99 (reconstruction + F.interpolate residual, App. B.3);
 // stereo_separator.py:81 ({left,right}_decoder.9) with blockIdx.z selecting the side.
+// A block stages 256+6 rows of raw fp16 in shared memory once; every thread produces TWO neighbouring outputs from
+// the 8 rows it reads (each row is used by 7 taps x 2 outputs), all 448 FFMAs take their weight as a constant-bank
+// operand.  Rows are stored at index r + (r >> 3) so that the 32-byte lane stride of the reads is conflict-free.
 struct FinalArgs {
   const __half* in;
   long long in_bs;
   int in_Tp;
   int in_coff8[2];
-  const float* w[2];     // [32][7] each (c-major)
-  float bias[2];
   float* y;              // [B][nout][T]
   int nout;
   int T;
   const float* x_lr;     // optional [B][T/2] low-rate input for the interp residual
 };
+constexpr int FK_THREADS = 128;
+constexpr int FK_OUT = 2 * FK_THREADS;               // outputs per block
+constexpr int FK_ROWS = FK_OUT + 6;
+constexpr int FK_PITCH = FK_ROWS + (FK_ROWS >> 3) + 1;
 
-__global__ void __launch_bounds__(128) final_k7_kernel(const FinalArgs a) {
-  __shared__ float sw[7][32];
-  const int o = blockIdx.z;
-  for (int i = threadIdx.x; i < 224; i += blockDim.x) sw[i % 7][i / 7] = a.w[o][i];
-  __syncthreads();
-  const int b = blockIdx.y;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= a.T) return;
-  float acc = a.bias[o];
+template <int O>
+__device__ __forceinline__ void final_k7_rows(const uint4 (*tile)[FK_PITCH], const FinalW& w, int r0, float& acc0, float& acc1) {
 #pragma unroll
-  for (int j = 0; j < 7; ++j) {
-    const int ti = t + j - 3;
-    if (ti < 0 || ti >= a.T) continue;
+  for (int c = 0; c < 4; ++c) {
+    float x[8][8];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float v[8];
-      unpack_half8(*reinterpret_cast<const uint4*>(a.in + act_off(a.in_bs, a.in_Tp, b, a.in_coff8[o] + c, ti)), v);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc = fmaf(v[i], sw[j][8 * c + i], acc);
+    for (int k = 0; k < 8; ++k) {
+      const int r = r0 + k;
+      unpack_half8(tile[c][r + (r >> 3)], x[k]);
     }
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc0 = fmaf(x[j][i], w.w[O][j][8 * c + i], acc0);
+        acc1 = fmaf(x[j + 1][i], w.w[O][j][8 * c + i], acc1);
+      }
   }
-  if (a.x_lr != nullptr) {
+}
+
+__global__ void __launch_bounds__(FK_THREADS) final_k7_kernel(const __grid_constant__ FinalArgs a, const __grid_constant__ FinalW w) {
+  __shared__ uint4 tile[4][FK_PITCH];
+  const int o = blockIdx.z, b = blockIdx.y;
+  const int t0 = blockIdx.x * FK_OUT;
+  for (int i = threadIdx.x; i < 4 * FK_ROWS; i += FK_THREADS) {
+    const int c = i / FK_ROWS, r = i - c * FK_ROWS;
+    const int t = t0 - 3 + r;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);                 // conv zero padding
+    if (t >= 0 && t < a.T) v = *reinterpret_cast<const uint4*>(a.in + act_off(a.in_bs, a.in_Tp, b, a.in_coff8[o] + c, t));
+    tile[c][r + (r >> 3)] = v;
+  }
+  __syncthreads();
+  const int t = t0 + 2 * threadIdx.x;
+  if (t >= a.T) return;
+  float acc0 = w.bias[o], acc1 = acc0;
+  if (o == 0) final_k7_rows<0>(tile, w, 2 * threadIdx.x, acc0, acc1);
+  else final_k7_rows<1>(tile, w, 2 * threadIdx.x, acc0, acc1);
+  if (a.x_lr != nullptr) {   // F.interpolate(scale 2, linear, align_corners=False): t is even
     const int Tl = a.T >> 1;
     const float* xl = a.x_lr + (long long)b * Tl;
     const int s = t >> 1;
     const float x0 = __ldg(xl + s);
-    float up;
-    if (t & 1) {
-      const float x1 = __ldg(xl + (s + 1 < Tl ? s + 1 : Tl - 1));
-      up = 0.75f * x0 + 0.25f * x1;
-    } else {
-      const float xm = __ldg(xl + (s > 0 ? s - 1 : 0));
-      up = 0.25f * xm + 0.75f * x0;
-    }
-    acc += up;
+    const float xm = __ldg(xl + (s > 0 ? s - 1 : 0));
+    const float x1 = __ldg(xl + (s + 1 < Tl ? s + 1 : Tl - 1));
+    acc0 += 0.25f * xm + 0.75f * x0;
+    acc1 += 0.75f * x0 + 0.25f * x1;
   }
-  a.y[((long long)b * a.nout + o) * a.T + t] = acc;
+  float* yo = a.y + ((long long)b * a.nout + o) * a.T + t;
+  if (t + 1 < a.T && (reinterpret_cast<uintptr_t>(yo) & 7) == 0) {
+    *reinterpret_cast<float2*>(yo) = make_float2(acc0, acc1);
+  } else {
+    yo[0] = acc0;
+    if (t + 1 < a.T) yo[1] = acc1;
+  }
 }
 
-int launch_final_k7(const Act& in, const int* in_coff8, const float* const* w, const float* bias, int nout, float* y,
-                    int B, int T, const float* x_lr, cudaStream_t stream) {
+int launch_final_k7(const Act& in, const int* in_coff8, const FinalW& w, int nout, float* y, int B, int T, const float* x_lr,
+                    cudaStream_t stream) {
   FinalArgs a;
   a.in = in.h(); a.in_bs = in.bs; a.in_Tp = in.Tp;
-  for (int i = 0; i < nout; ++i) { a.in_coff8[i] = in_coff8[i]; a.w[i] = w[i]; a.bias[i] = bias[i]; }
+  a.in_coff8[0] = in_coff8[0];
+  a.in_coff8[1] = nout > 1 ? in_coff8[1] : in_coff8[0];
   a.y = y; a.nout = nout; a.T = T; a.x_lr = x_lr;
-  dim3 grid((T + 127) / 128, B, nout);
-  final_k7_kernel<<<grid, 128, 0, stream>>>(a);
+  dim3 grid((T + FK_OUT - 1) / FK_OUT, B, nout);
+  final_k7_kernel<<<grid, FK_THREADS, 0, stream>>>(a, w);
   AR_CUDA_OK(cudaGetLastError());
   return AR_OK;
 }
 
 // ============================================================================ denoiser tail
-// f (C4, 32 ch) and the raw input x -> y:
+// f (H8, 32 ch) and the raw input x -> y:
 //   m_t = sigmoid(conv3(lrelu(conv3(lrelu(conv3(f, 32->16)), 16->8)), 8->1))   denoiser.py:39-46
 //   m_i = clamp(box5((2|d2x| + |dx| + .5|x|)/3.5), 0, 1)                        denoiser.py:62-86
 //   y   = conv1(f, 32->1) * (1 - 0.9*max(m_t, m_i))                              denoiser.py:134-142
 // Every conv zero-pads ITS OWN input at the sequence ends, so intermediate activations are
-// forced to zero outside [0,T).
-constexpr int DT = 128;  // outputs per block
-
+// forced to zero outside [0,T).  Activations are staged in shared memory (fp32); all weights are constant-bank
+// FFMA operands (DenTailP is a kernel parameter), so the 1976 MACs per sample cost 1976 FFMA + ~40 shared loads.
+constexpr int DT = 128;       // threads per block = rows of the first detector layer a block computes
+constexpr int DT_OUT = DT - 4;  // outputs per block: 128 td0 rows -> 126 td1 rows -> 124 outputs, one pass per thread each
 
 __global__ void __launch_bounds__(DT) den_tail_kernel(const __half* __restrict__ fin, long long f_bs, int f_Tp,
                                                       const float* __restrict__ x, float* __restrict__ y, int T,
-                                                      const DenTailW w) {
-  __shared__ float4 sf[8][DT + 6];
-  __shared__ float4 s0[4][DT + 4];
-  __shared__ float4 s1[2][DT + 2];
-  __shared__ float4 sw0[3 * 8 * 16];
-  __shared__ float4 sw1[3 * 4 * 8];
-  __shared__ float sb0[16], sb1[8], sw2[24], swf[32];
+                                                      const __grid_constant__ DenTailP w) {
+  __shared__ float4 sf[8][DT + 2];
+  __shared__ float4 s0[4][DT];
+  __shared__ float4 s1[2][DT - 2];
   const int b = blockIdx.y;
-  const int t0 = blockIdx.x * DT;
+  const int t0 = blockIdx.x * DT_OUT;
   const int tid = threadIdx.x;
-  for (int i = tid; i < 3 * 8 * 16; i += DT) sw0[i] = reinterpret_cast<const float4*>(w.w0)[i];
-  for (int i = tid; i < 3 * 4 * 8; i += DT) sw1[i] = reinterpret_cast<const float4*>(w.w1)[i];
-  if (tid < 16) sb0[tid] = w.b0[tid];
-  if (tid < 8) sb1[tid] = w.b1[tid];
-  if (tid < 24) sw2[tid] = w.w2[tid];
-  if (tid < 32) swf[tid] = w.wf[tid];
-  // f tile: rows t0-3 .. t0+DT+2
-  for (int i = tid; i < 4 * (DT + 6); i += DT) {
-    const int c = i / (DT + 6), r = i % (DT + 6);   // c: 8-channel chunk of the H8 input
+  // f tile: rows t0-3 .. t0+DT-2
+  for (int i = tid; i < 4 * (DT + 2); i += DT) {
+    const int c = i / (DT + 2), r = i % (DT + 2);   // c: 8-channel chunk of the H8 input
     const int t = t0 - 3 + r;
     float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (t >= 0 && t < T) unpack_half8(*reinterpret_cast<const uint4*>(fin + act_off(f_bs, f_Tp, b, c, t)), v);
@@ -165,21 +173,21 @@ __global__ void __launch_bounds__(DT) den_tail_kernel(const __half* __restrict__
     sf[2 * c + 1][r] = make_float4(v[4], v[5], v[6], v[7]);
   }
   __syncthreads();
-  // td0: 32 -> 16 at rows t0-2 .. t0+DT+1 (local r in [0, DT+4)), input rows r..r+2 of sf
-  for (int r = tid; r < DT + 4; r += DT) {
+  // td0: 32 -> 16 at rows t0-2 .. t0+DT-3 (local r in [0, DT)), input rows r..r+2 of sf
+  {
+    const int r = tid;
     const int t = t0 - 2 + r;
     float acc[16];
 #pragma unroll
-    for (int o = 0; o < 16; ++o) acc[o] = sb0[o];
+    for (int o = 0; o < 16; ++o) acc[o] = w.b0[o];
+#pragma unroll
     for (int j = 0; j < 3; ++j)
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const float4 v = sf[c][r + j];
 #pragma unroll
-        for (int o = 0; o < 16; ++o) {
-          const float4 k = sw0[(j * 8 + c) * 16 + o];
-          acc[o] = fmaf(v.x, k.x, fmaf(v.y, k.y, fmaf(v.z, k.z, fmaf(v.w, k.w, acc[o]))));
-        }
+        for (int o = 0; o < 16; ++o)
+          acc[o] = fmaf(v.x, w.w0[j][4 * c][o], fmaf(v.y, w.w0[j][4 * c + 1][o], fmaf(v.z, w.w0[j][4 * c + 2][o], fmaf(v.w, w.w0[j][4 * c + 3][o], acc[o]))));
       }
     const bool ok = (t >= 0 && t < T);
 #pragma unroll
@@ -188,21 +196,21 @@ __global__ void __launch_bounds__(DT) den_tail_kernel(const __half* __restrict__
     for (int c = 0; c < 4; ++c) s0[c][r] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
   }
   __syncthreads();
-  // td1: 16 -> 8 at rows t0-1 .. t0+DT (local r in [0, DT+2))
-  for (int r = tid; r < DT + 2; r += DT) {
+  // td1: 16 -> 8 at rows t0-1 .. t0+DT-4 (local r in [0, DT-2))
+  if (tid < DT - 2) {
+    const int r = tid;
     const int t = t0 - 1 + r;
     float acc[8];
 #pragma unroll
-    for (int o = 0; o < 8; ++o) acc[o] = sb1[o];
+    for (int o = 0; o < 8; ++o) acc[o] = w.b1[o];
+#pragma unroll
     for (int j = 0; j < 3; ++j)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const float4 v = s0[c][r + j];
 #pragma unroll
-        for (int o = 0; o < 8; ++o) {
-          const float4 k = sw1[(j * 4 + c) * 8 + o];
-          acc[o] = fmaf(v.x, k.x, fmaf(v.y, k.y, fmaf(v.z, k.z, fmaf(v.w, k.w, acc[o]))));
-        }
+        for (int o = 0; o < 8; ++o)
+          acc[o] = fmaf(v.x, w.w1[j][4 * c][o], fmaf(v.y, w.w1[j][4 * c + 1][o], fmaf(v.z, w.w1[j][4 * c + 2][o], fmaf(v.w, w.w1[j][4 * c + 3][o], acc[o]))));
       }
     const bool ok = (t >= 0 && t < T);
 #pragma unroll
@@ -212,14 +220,14 @@ __global__ void __launch_bounds__(DT) den_tail_kernel(const __half* __restrict__
   }
   __syncthreads();
   const int t = t0 + tid;
-  if (t >= T) return;
+  if (tid >= DT_OUT || t >= T) return;
   // td2: 8 -> 1, sigmoid
   float m = w.b2;
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     const float4 a0 = s1[0][tid + j], a1 = s1[1][tid + j];
-    const float* k = sw2 + j * 8;
-    m += a0.x * k[0] + a0.y * k[1] + a0.z * k[2] + a0.w * k[3] + a1.x * k[4] + a1.y * k[5] + a1.z * k[6] + a1.w * k[7];
+    m += a0.x * w.w2[j][0] + a0.y * w.w2[j][1] + a0.z * w.w2[j][2] + a0.w * w.w2[j][3] + a1.x * w.w2[j][4] + a1.y * w.w2[j][5] +
+         a1.z * w.w2[j][6] + a1.w * w.w2[j][7];
   }
   const float mt = 1.f / (1.f + expf(-m));
   // final 1x1 conv
@@ -227,7 +235,7 @@ __global__ void __launch_bounds__(DT) den_tail_kernel(const __half* __restrict__
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const float4 v = sf[c][tid + 3];
-    yv += v.x * swf[4 * c] + v.y * swf[4 * c + 1] + v.z * swf[4 * c + 2] + v.w * swf[4 * c + 3];
+    yv += v.x * w.wf[4 * c] + v.y * w.wf[4 * c + 1] + v.z * w.wf[4 * c + 2] + v.w * w.wf[4 * c + 3];
   }
   // analytic impulse mask from the raw input
   const float* xb = x + (long long)b * T;
@@ -251,8 +259,8 @@ __global__ void __launch_bounds__(DT) den_tail_kernel(const __half* __restrict__
   y[(long long)b * T + t] = yv * (1.0f - fmaxf(mt, mi) * 0.9f);
 }
 
-int launch_den_tail(const Act& f, const float* x, float* y, int B, int T, const DenTailW& w, cudaStream_t stream) {
-  dim3 grid((T + DT - 1) / DT, B);
+int launch_den_tail(const Act& f, const float* x, float* y, int B, int T, const DenTailP& w, cudaStream_t stream) {
+  dim3 grid((T + DT_OUT - 1) / DT_OUT, B);
   den_tail_kernel<<<grid, DT, 0, stream>>>(f.h(), f.bs, f.Tp, x, y, T, w);
   AR_CUDA_OK(cudaGetLastError());
   return AR_OK;

@@ -4,21 +4,31 @@
 
 namespace ar {
 
-struct DenTailW {
-  const float* w0;  // [3 taps][8 chunks][16 cout][4 cin]
-  const float* b0;  // [16]
-  const float* w1;  // [3][4][8][4]
-  const float* b1;  // [8]
-  const float* w2;  // [3][8]
-  const float* wf;  // [32]
+// Weights of the CUDA-core tail kernels travel as __grid_constant__ kernel parameters (the parameter space is constant
+// bank 0): every FFMA then takes its weight as a c[0][imm] operand -- no weight loads at all in the inner loops.
+struct DenTailP {        // transient detector 32->16->8->1 (k3) + final 1x1 conv, denoiser.py:39-48
+  float w0[3][32][16];   // [tap][cin][cout]
+  float b0[16];
+  float w1[3][16][8];
+  float b1[8];
+  float w2[3][8];
+  float wf[32];
   float b2, bf;
 };
+struct StemP {           // Cin = 1 first conv (+ folded BN): 32 x taps weights, 32 biases
+  float w[32][7];
+  float b[32];
+  int taps;
+};
+struct FinalW {          // up to two 32 -> 1 k7 heads
+  float w[2][7][32];     // [head][tap][cin]
+  float bias[2];
+};
 
-int launch_stem(const float* x, int B, int T, int taps, const float* w, const float* bias, const Act& out, int lrelu,
-                cudaStream_t stream);
-int launch_final_k7(const Act& in, const int* in_coff8, const float* const* w, const float* bias, int nout, float* y,
-                    int B, int T, const float* x_lr, cudaStream_t stream);
-int launch_den_tail(const Act& f, const float* x, float* y, int B, int T, const DenTailW& w, cudaStream_t stream);
+int launch_stem(const float* x, int B, int T, const StemP& w, const Act& out, int lrelu, cudaStream_t stream);
+int launch_final_k7(const Act& in, const int* in_coff8, const FinalW& w, int nout, float* y, int B, int T, const float* x_lr,
+                    cudaStream_t stream);
+int launch_den_tail(const Act& f, const float* x, float* y, int B, int T, const DenTailP& w, cudaStream_t stream);
 int launch_normalize(float* x, long long n, float target_db, float* scratch, cudaStream_t stream);
 int launch_split(const float* audio, long long n, float* chunks, int first, int count, int chunk_size, int overlap,
                  cudaStream_t stream);
