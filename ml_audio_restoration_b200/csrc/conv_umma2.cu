@@ -17,6 +17,7 @@
 #include "ar_common.cuh"
 #include "umma_ptx.cuh"
 #include "umma_epilogue.cuh"
+#include <cstdlib>
 
 namespace ar {
 
@@ -32,8 +33,27 @@ struct Umma2Cfg {
   int w_bytes;      // resident weights per CTA: Cin*taps*(Ns/2)*2
   int stage_bytes;  // activation stage per CTA
   int ncol, tmem_cols, nks, smem_bytes;
-  int nbuf;         // TMEM accumulator buffers (2..8): how many tile pairs the MMAs may run ahead of the epilogue
+  int nbuf;         // TMEM accumulator buffers (2..8): how many tile groups the MMAs may run ahead of the epilogue
+  int G;            // tiles per CTA per group (1, 2 or 4): each CTA owns G consecutive 128-row tiles of a group, loaded as ONE
+                    // run of rows per channel chunk; the barrier round trips of a stage / an accumulator are paid once per
+                    // group, which is what bounds the layers with few MMAs per tile (Cin <= 64, k <= 3)
+  int RG;           // rows of a group's run: G*128 + (taps-1)*dil
 };
+
+// Rows of CTA `rank`'s run for group `gi` of an item: first row (time index, may be negative), how many rows exist in the
+// buffer from there (the run is clamped to the padded chunk), and whether every tile of the run lies beyond the item
+// (then a valid run is loaded instead and all rows are zeroed).
+struct RunGeom { int t_start, rows, tile0; bool all_dead; };
+__device__ __forceinline__ RunGeom run_geom(const ConvParams& p, const Umma2Cfg& cfg, int gi, int rank) {
+  RunGeom g;
+  g.tile0 = (gi * 2 + rank) * cfg.G;
+  g.all_dead = g.tile0 > p.tiles_per_item - 1;
+  const int tl = g.all_dead ? p.tiles_per_item - 1 : g.tile0;
+  g.t_start = tl * TILE_M - p.pad_left;
+  const int avail = p.in_Tp - (HALO + g.t_start);
+  g.rows = cfg.RG < avail ? cfg.RG : avail;
+  return g;
+}
 
 template <int MODE, bool POOL, bool RES, int TAPS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UMMA2_THREADS, 1)
@@ -86,8 +106,8 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   const int tpi = p.tiles_per_item;
-  const int ppi = (tpi + 1) >> 1;                        // tile pairs per batch item
-  const int R = cfg.R;
+  const int ppi = (tpi + 2 * cfg.G - 1) / (2 * cfg.G);   // tile groups (2G tiles: G per CTA) per batch item
+  const int RG = cfg.RG;
   const int pair0 = cid / nsl;
   const int pair_step = (gridDim.x >> 1) / nsl;
   const int n_local = pair0 < num_pairs ? (num_pairs - pair0 + pair_step - 1) / pair_step : 0;
@@ -103,35 +123,39 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
       }
       int s = 0;
       uint32_t ph = 0;
-      const uint32_t row_bytes = (uint32_t)(R * 16);
       const long long chunk_stride = (long long)p.in_Tp * 8;             // halves between 8-channel chunks
       const int chunks_per_stage = cfg.kbs * 2;
       PairIter pit(pair0, pair_step, ppi), pre(pair0, pair_step, ppi);
-      auto tile_src = [&](const PairIter& pi_) {
-        int tl_in_item = pi_.pi * 2 + (int)rank;
-        if (tl_in_item > tpi - 1) tl_in_item = tpi - 1;   // odd tile count: the idle half re-reads a valid tile (all its rows get zeroed)
-        return p.in + act_off(p.in_bs, p.in_Tp, pi_.b, p.in_coff8, tl_in_item * TILE_M - p.pad_left);
-      };
-      // HBM -> L2 prefetch runs UMMA2_PREFETCH tile pairs ahead of the shared-memory ring (which then only has to cover L2 latency)
+      // HBM -> L2 prefetch runs UMMA2_PREFETCH groups ahead of the shared-memory ring (which then only has to cover L2 latency)
       const int n_chunks = p.Cin >> 3;
-      for (int d = 0; d < UMMA2_PREFETCH && d < n_local; ++d, pre.next()) {
-        const __half* ps = tile_src(pre);
-        for (int c = 0; c < n_chunks; ++c, ps += chunk_stride) bulk_prefetch_l2(ps, row_bytes);
+      const int pre_dist = cfg.G >= 2 ? 2 : UMMA2_PREFETCH;
+      for (int d = 0; d < pre_dist && d < n_local; ++d, pre.next()) {
+        const RunGeom g = run_geom(p, cfg, pre.pi, (int)rank);
+        const __half* ps = p.in + act_off(p.in_bs, p.in_Tp, pre.b, p.in_coff8, g.t_start);
+        for (int c = 0; c < n_chunks; ++c, ps += chunk_stride) bulk_prefetch_l2(ps, (uint32_t)(g.rows * 16));
       }
       for (int it = 0; it < n_local; ++it, pit.next()) {
-        const __half* src = tile_src(pit);
-        const bool do_pre = it + UMMA2_PREFETCH < n_local;
-        const __half* ps = do_pre ? tile_src(pre) : nullptr;
-        if (do_pre) pre.next();
+        const RunGeom g = run_geom(p, cfg, pit.pi, (int)rank);
+        const __half* src = p.in + act_off(p.in_bs, p.in_Tp, pit.b, p.in_coff8, g.t_start);
+        const uint32_t row_bytes = (uint32_t)(g.rows * 16);
+        const bool do_pre = it + pre_dist < n_local;
+        const __half* ps = nullptr;
+        uint32_t pre_bytes = 0;
+        if (do_pre) {
+          const RunGeom gp = run_geom(p, cfg, pre.pi, (int)rank);
+          ps = p.in + act_off(p.in_bs, p.in_Tp, pre.b, p.in_coff8, gp.t_start);
+          pre_bytes = (uint32_t)(gp.rows * 16);
+          pre.next();
+        }
         for (int ks = 0; ks < cfg.nks; ++ks) {
           const uint32_t fb = full_bar(s);
           mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_expect_tx(fb, (uint32_t)cfg.stage_bytes);
+          mbar_expect_tx(fb, (uint32_t)chunks_per_stage * row_bytes);
           uint32_t dst = smem_base + s * cfg.stage_bytes;
           for (int c = 0; c < chunks_per_stage; ++c) {
             bulk_g2s(dst, src, row_bytes, fb);
-            if (do_pre) { bulk_prefetch_l2(ps, row_bytes); ps += chunk_stride; }
-            dst += row_bytes;
+            if (do_pre) { bulk_prefetch_l2(ps, pre_bytes); ps += chunk_stride; }
+            dst += (uint32_t)(RG * 16);
             src += chunk_stride;
           }
           if (++s == cfg.stages) { s = 0; ph ^= 1u; }
@@ -141,39 +165,39 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA warp
     const uint32_t idesc = make_idesc_f16(256, Ns);          // M = 256: both CTAs' 128 rows
-    const uint64_t a_desc_hi = make_desc(0u, (uint32_t)(R * 16), 128u);
+    const uint64_t a_desc_hi = make_desc(0u, (uint32_t)(RG * 16), 128u);
     const uint64_t b_desc_hi = make_desc(0u, (uint32_t)(Nh * 16), 128u);
     mbar_wait(w_bar, 0);
     int s = 0, buf = 0;
     uint32_t ph = 0, aph = 0;
     const uint32_t b_step = (uint32_t)(Nh * 2);
-    const uint32_t a_step = (uint32_t)(2 * R);
+    const uint32_t a_step = (uint32_t)(2 * RG);
     const uint32_t w_addr0 = w_base >> 4;
     const uint32_t dil_u = (uint32_t)p.dil;
     const uint32_t full0_leader = mapa_u32(full_bar(0), 0);
+    const int G = cfg.G;
     PairIter pit(pair0, pair_step, ppi);
     for (int it = 0; it < n_local; ++it, pit.next()) {
-      const int tl_in_item = pit.pi * 2 + (int)rank;
-      const int t0 = (tl_in_item > tpi - 1 ? tpi - 1 : tl_in_item) * TILE_M;  // tile that was actually loaded
-      const int tfirst = t0 - p.pad_left;
-      const bool dead = tl_in_item > tpi - 1;                          // no such tile: contribute zeros
-      const bool edge = dead || (tfirst < 0) || (tfirst + R > p.Tin);
+      const RunGeom g = run_geom(p, cfg, pit.pi, (int)rank);
+      const int tfirst = g.t_start;
+      const bool dead = g.all_dead;                                    // no such tiles: contribute zeros
+      const bool edge = dead || (tfirst < 0) || (tfirst + RG > p.Tin);
       if (leader) {
         mbar_wait(tempty_bar(buf), aph ^ 1u);                          // both epilogues drained this accumulator
         tc_fence_after();
       }
-      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * cfg.ncol);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * G * cfg.ncol);
       uint32_t b_addr = w_addr0;
       uint32_t accum = 0u;
       for (int ks = 0; ks < cfg.nks; ++ks) {
         mbar_wait(full_bar(s), ph);
-        if (edge) {  // conv zero padding of this CTA's rows
+        if (edge) {  // conv zero padding of this CTA's rows (and the rows of the run that were never loaded)
           uint8_t* a_ptr = stage_ptr + s * cfg.stage_bytes;
-          for (int r = lane; r < R; r += 32) {
+          for (int r = lane; r < RG; r += 32) {
             const int t = tfirst + r;
             if (dead || t < 0 || t >= p.Tin)
               for (int c = 0; c < cfg.kbs * 2; ++c)
-                *reinterpret_cast<float4*>(a_ptr + (c * R + r) * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(a_ptr + (c * RG + r) * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
           }
           fence_async_smem();
           __syncwarp();
@@ -190,10 +214,14 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
           if (elect_one()) {
             uint32_t a_addr = (smem_base + s * cfg.stage_bytes) >> 4;
             for (int kb = 0; kb < cfg.kbs; ++kb) {
+              for (int gg = 0; gg < G; ++gg) {
+                const uint32_t a_g = a_addr + (uint32_t)(gg * TILE_M);          // 128 rows x 16 B further down the run
+                const uint32_t d_g = d_tmem + (uint32_t)(gg * cfg.ncol);
 #pragma unroll
-              for (int j = 0; j < TAPS; ++j)
-                umma2_f16(d_tmem, a_desc_hi | (uint64_t)(a_addr + (uint32_t)j * dil_u),
-                           b_desc_hi | (uint64_t)(b_addr + (uint32_t)j * b_step), idesc, (j == 0) ? accum : 1u);
+                for (int j = 0; j < TAPS; ++j)
+                  umma2_f16(d_g, a_desc_hi | (uint64_t)(a_g + (uint32_t)j * dil_u),
+                            b_desc_hi | (uint64_t)(b_addr + (uint32_t)j * b_step), idesc, (j == 0) ? accum : 1u);
+              }
               accum = 1u;
               b_addr += (uint32_t)TAPS * b_step;
               a_addr += a_step;
@@ -208,7 +236,7 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
       if (++buf == cfg.nbuf) { buf = 0; aph ^= 1u; }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..9), own 128 rows
+    // ------------------------------------------------------------------ epilogue (warps 2..9), own G x 128 rows
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int wcols = Ns >= 32 ? Ns / 2 : Ns;
@@ -217,20 +245,27 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
     const float slope = p.lrelu ? LRELU_SLOPE : 1.0f;
     const int gcol0 = slice * Ns + col_lo;
     const uint32_t tempty_leader0 = mapa_u32(tempty_bar(0), 0);   // barriers are 8 bytes apart in the leader too
+    const int G = cfg.G;
     int buf = 0;
     uint32_t aph = 0;
     PairIter pit(pair0, pair_step, ppi);
     for (int it = 0; it < n_local; ++it, pit.next()) {
-      const int tl_in_item = pit.pi * 2 + (int)rank;
-      const int t = tl_in_item * TILE_M + q * 32 + lane;   // >= Tin for a dead tile => every store is masked
-      const EpiRow row = epi_row<MODE, POOL, RES>(p, pit.b, t, gcol0);
-      uint4 resv[2];
-      epi_prefetch_res<RES>(row, active, resv);
-      mbar_wait(tfull_bar(buf), aph);
-      tc_fence_after();
-      if (active) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * cfg.ncol + col_lo);
-        epi_store<MODE, POOL, RES>(row, s_bias + col_lo, taddr, wcols, slope, resv);
+      const int tile0 = (pit.pi * 2 + (int)rank) * G;
+      bool waited = false;
+      for (int gg = 0; gg < G; ++gg) {
+        const int t = (tile0 + gg) * TILE_M + q * 32 + lane;   // >= Tin for a dead tile => every store is masked
+        const EpiRow row = epi_row<MODE, POOL, RES>(p, pit.b, t, gcol0);
+        uint4 resv[2];
+        epi_prefetch_res<RES>(row, active, resv);
+        if (!waited) {
+          mbar_wait(tfull_bar(buf), aph);
+          tc_fence_after();
+          waited = true;
+        }
+        if (active) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * G + gg) * cfg.ncol + col_lo);
+          epi_store<MODE, POOL, RES>(row, s_bias + col_lo, taddr, wcols, slope, resv);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -252,21 +287,34 @@ static bool pick_cfg2(const ConvParams& p, Umma2Cfg& c) {
   int ncol = 32;
   while (ncol < Ns) ncol <<= 1;
   c.ncol = ncol;
-  c.nbuf = 512 / ncol > 8 ? 8 : 512 / ncol;
-  c.tmem_cols = c.nbuf * ncol;
   c.w_bytes = p.Cin * p.taps * (Ns / 2) * 2;
   const int room = conv_smem_budget() - BAR2_BYTES - BIAS2_BYTES - c.w_bytes;
+  static int g_max = -1;          // AR_TILE_GROUP=1|2|4 caps the group size (tuning / cross-check knob)
+  if (g_max < 0) {
+    const char* e = getenv("AR_TILE_GROUP");
+    g_max = e ? atoi(e) : 4;
+    if (g_max != 1 && g_max != 2) g_max = 4;
+  }
   for (int kbs = 4; kbs >= 1; kbs >>= 1) {
     if (p.Cin % (16 * kbs)) continue;
-    c.kbs = kbs;
-    c.stage_bytes = kbs * 2 * c.R * 16;
-    int stages = room / c.stage_bytes;
-    if (stages > 8) stages = 8;
-    if (stages >= 4 || (kbs == 1 && stages >= 2)) {
-      c.stages = stages;
-      c.nks = p.Cin / (16 * kbs);
-      c.smem_bytes = c.w_bytes + stages * c.stage_bytes + BAR2_BYTES + BIAS2_BYTES;
-      return true;
+    // group size: enough tiles per barrier round that a stage carries >= ~24 MMAs, within TMEM (two buffers) and the ring
+    int G = 1;
+    while (G < g_max && kbs * p.taps * G < 24 && 2 * (2 * G) * ncol <= 512) G *= 2;
+    for (; G >= 1; G >>= 1) {
+      c.RG = G * TILE_M + (p.taps - 1) * p.dil;
+      c.stage_bytes = kbs * 2 * c.RG * 16;
+      int stages = room / c.stage_bytes;
+      if (stages > 8) stages = 8;
+      if (stages >= 4 || (kbs == 1 && G == 1 && stages >= 2)) {
+        c.kbs = kbs;
+        c.G = G;
+        c.stages = stages;
+        c.nks = p.Cin / (16 * kbs);
+        c.nbuf = 512 / (G * ncol) > 8 ? 8 : 512 / (G * ncol);
+        c.tmem_cols = c.nbuf * G * ncol;
+        c.smem_bytes = c.w_bytes + stages * c.stage_bytes + BAR2_BYTES + BIAS2_BYTES;
+        return true;
+      }
     }
   }
   return false;
@@ -303,7 +351,7 @@ int launch_conv_umma2(const ConvParams& p, cudaStream_t stream) {
   for (const Entry& e : table)
     if (e.variant == variant && e.taps == p.taps) kernel = e.k;
   AR_CHECK(kernel != nullptr, AR_ERR_INVALID, "conv_umma2: no kernel instantiated for this (epilogue, taps) combination");
-  const int ppi = (p.tiles_per_item + 1) / 2;
+  const int ppi = (p.tiles_per_item + 2 * cfg.G - 1) / (2 * cfg.G);   // tile groups per item
   const int num_pairs = p.B * ppi;
   int groups = (sm_count() / 2) / nsl;                   // clusters per pair-slice
   if (groups > num_pairs) groups = num_pairs;
