@@ -38,6 +38,7 @@ struct Umma2Cfg {
                     // run of rows per channel chunk; the barrier round trips of a stage / an accumulator are paid once per
                     // group, which is what bounds the layers with few MMAs per tile (Cin <= 64, k <= 3)
   int RG;           // rows of a group's run: G*128 + (taps-1)*dil
+  int res_off, res_bytes;   // residual epilogue: two-deep shared-memory ring of the group's residual rows (bulk-copied by the producer)
 };
 
 // Rows of CTA `rank`'s run for group `gi` of an item: first row (time index, may be negative), how many rows exist in the
@@ -66,6 +67,8 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
   const uint32_t bar_base = smem_base + cfg.stages * cfg.stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (cfg.stages + s); };
+  auto rfull_bar = [&](int i) { return bar_base + 8u * (2 * cfg.stages + i); };        // residual ring (RES kernels)
+  auto rempty_bar = [&](int i) { return bar_base + 8u * (2 * cfg.stages + 2 + i); };
   auto tfull_bar = [&](int i) { return bar_base + 8u * (3 * cfg.stages + i); };
   auto tempty_bar = [&](int i) { return bar_base + 8u * (3 * cfg.stages + 8 + i); };  // used in the leader only
   const uint32_t w_bar = bar_base + 8u * (3 * cfg.stages + 16);
@@ -88,6 +91,10 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
     for (int i = 0; i < cfg.nbuf; ++i) {
       mbar_init(tfull_bar(i), 1);
       mbar_init(tempty_bar(i), 2 * EPI2_WARPS);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(rfull_bar(i), 1);
+      mbar_init(rempty_bar(i), EPI2_WARPS);
     }
     mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -159,6 +166,30 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
             src += chunk_stride;
           }
           if (++s == cfg.stages) { s = 0; ph ^= 1u; }
+        }
+        if (RES) {
+          // The residual operand of the group's epilogue: rows [tile0*128, +G*128) of Ns/8 chunks, bulk-copied into a
+          // two-deep ring (a per-thread global load in the epilogue keeps only ~8 KB in flight per SM, far too little
+          // to cover the memory latency -- measured 2.5x the time of the same layer without residual).
+          const int rb = it & 1;
+          const uint32_t rph = (uint32_t)(it >> 1) & 1u;
+          mbar_wait(rempty_bar(rb), rph ^ 1u);
+          const int t_res = g.tile0 * TILE_M;
+          int rows_res = p.res_Tp - (HALO + t_res);
+          if (rows_res > cfg.G * TILE_M) rows_res = cfg.G * TILE_M;
+          if (g.all_dead || rows_res <= 0) {
+            mbar_arrive(rfull_bar(rb));                              // nothing to fetch: every store of the group is masked
+          } else {
+            const int nch = Ns >> 3;
+            mbar_expect_tx(rfull_bar(rb), (uint32_t)(nch * rows_res * 16));
+            const __half* pr = p.res + act_off(p.res_bs, p.res_Tp, pit.b, p.res_coff8 + ((slice * Ns) >> 3), t_res);
+            uint32_t dst = w_base + cfg.res_off + rb * cfg.res_bytes;
+            for (int c = 0; c < nch; ++c) {
+              bulk_g2s(dst, pr, (uint32_t)(rows_res * 16), rfull_bar(rb));
+              dst += (uint32_t)(cfg.G * TILE_M * 16);
+              pr += (long long)p.res_Tp * 8;
+            }
+          }
         }
       }
     }
@@ -251,21 +282,29 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
     PairIter pit(pair0, pair_step, ppi);
     for (int it = 0; it < n_local; ++it, pit.next()) {
       const int tile0 = (pit.pi * 2 + (int)rank) * G;
-      bool waited = false;
+      mbar_wait(tfull_bar(buf), aph);
+      tc_fence_after();
+      const uint4* res_s = nullptr;
+      if (RES) {   // this group's residual rows, staged by the producer: [chunk][G*128 rows] x 16 B
+        mbar_wait(rfull_bar(it & 1), (uint32_t)(it >> 1) & 1u);
+        res_s = reinterpret_cast<const uint4*>(smem + cfg.res_off + (it & 1) * cfg.res_bytes) + (col_lo >> 3) * (G * TILE_M) + q * 32 + lane;
+      }
       for (int gg = 0; gg < G; ++gg) {
         const int t = (tile0 + gg) * TILE_M + q * 32 + lane;   // >= Tin for a dead tile => every store is masked
         const EpiRow row = epi_row<MODE, POOL, RES>(p, pit.b, t, gcol0);
         uint4 resv[2];
-        epi_prefetch_res<RES>(row, active, resv);
-        if (!waited) {
-          mbar_wait(tfull_bar(buf), aph);
-          tc_fence_after();
-          waited = true;
+        if (RES) {
+          resv[0] = res_s[gg * TILE_M];
+          resv[1] = res_s[G * TILE_M + gg * TILE_M];
         }
         if (active) {
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * G + gg) * cfg.ncol + col_lo);
           epi_store<MODE, POOL, RES>(row, s_bias + col_lo, taddr, wcols, slope, resv);
         }
+      }
+      if (RES) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(rempty_bar(it & 1));
       }
       tc_fence_before();
       __syncwarp();
@@ -288,7 +327,7 @@ static bool pick_cfg2(const ConvParams& p, Umma2Cfg& c) {
   while (ncol < Ns) ncol <<= 1;
   c.ncol = ncol;
   c.w_bytes = p.Cin * p.taps * (Ns / 2) * 2;
-  const int room = conv_smem_budget() - BAR2_BYTES - BIAS2_BYTES - c.w_bytes;
+  const int room0 = conv_smem_budget() - BAR2_BYTES - BIAS2_BYTES - c.w_bytes;
   static int g_max = -1;          // AR_TILE_GROUP=1|2|4 caps the group size (tuning / cross-check knob)
   if (g_max < 0) {
     const char* e = getenv("AR_TILE_GROUP");
@@ -303,6 +342,8 @@ static bool pick_cfg2(const ConvParams& p, Umma2Cfg& c) {
     for (; G >= 1; G >>= 1) {
       c.RG = G * TILE_M + (p.taps - 1) * p.dil;
       c.stage_bytes = kbs * 2 * c.RG * 16;
+      c.res_bytes = p.res != nullptr ? G * TILE_M * (Ns / 8) * 16 : 0;
+      const int room = room0 - 2 * c.res_bytes;
       int stages = room / c.stage_bytes;
       if (stages > 8) stages = 8;
       if (stages >= 4 || (kbs == 1 && G == 1 && stages >= 2)) {
@@ -312,7 +353,8 @@ static bool pick_cfg2(const ConvParams& p, Umma2Cfg& c) {
         c.nks = p.Cin / (16 * kbs);
         c.nbuf = 512 / (G * ncol) > 8 ? 8 : 512 / (G * ncol);
         c.tmem_cols = c.nbuf * G * ncol;
-        c.smem_bytes = c.w_bytes + stages * c.stage_bytes + BAR2_BYTES + BIAS2_BYTES;
+        c.res_off = c.w_bytes + stages * c.stage_bytes + BAR2_BYTES + BIAS2_BYTES;
+        c.smem_bytes = c.res_off + 2 * c.res_bytes;
         return true;
       }
     }
