@@ -36,21 +36,23 @@ METRIC = "restored audio-sec/sec (full chain)"
 
 def conv_algorithmic_bytes_per_audio_s():
     """fp16 activation bytes (inputs read + outputs written, incl. pooled copies and residual operands) that the
-    conv engine's 41 layer launches must move per source audio-second when layers are not fused."""
+    conv engine's 36 launches per chunk batch must move per source audio-second: entries are
+    (bytes per row, rows per audio-second) per tensor stream of a launch; the stereo encoder entries are the FUSED
+    chains (dilated block, and the last block + LSTM input projection), whose intermediates never reach HBM."""
     r = SR                                   # denoiser / SR input rate; stereo runs at 2r
     den = [(160, r), (192, r // 2), (320, r // 2), (384, r // 4), (640, r // 4), (768, r // 8), (1024, r // 8),
            (512, r // 8), (256, r // 4), (768, r // 4), (512, r // 4), (256, r // 4), (128, r // 2), (384, r // 2),
            (256, r // 2), (128, r // 2), (64, r), (192, r), (128, r)]
     sr = [(128, r)] * 4 + [(192, r)] * 5 + [(64, r), (64, 2 * r), (128, 2 * r)]
-    st = [(192, 2 * r), (256, 2 * r), (384, 2 * r), (512, 2 * r)] + [(512, 2 * r)] * 4 + [(768, 2 * r), (640, 2 * r),
-          (384, 2 * r), (384, 2 * r), (192, 2 * r), (192, 2 * r)]
+    st = [(192, 2 * r), (384, 2 * r), (512, 2 * r), (768, 2 * r),                     # fused enc1, enc2, enc3, enc4 + xproj
+          (640, 2 * r), (384, 2 * r), (384, 2 * r), (192, 2 * r), (192, 2 * r)]       # dec0 (L+R), dec1 L/R, dec2 L/R
     return float(sum(b * n for b, n in den + sr + st))
 
 
 def load_conv_traffic(args):
     """Measured DRAM bytes per conv launch from the committed ncu capture, if it was taken at this configuration."""
     try:
-        with open(os.path.join(ROOT, "profiles", "conv_traffic_r01.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "conv_traffic_r01_final.json")) as f:
             t = json.load(f)
         c = t["config"]
         if c["chunks_per_step_per_gpu"] == args.chunks_per_step and c["batch_chunks"] == args.batch_chunks:
@@ -279,14 +281,15 @@ def run_b200(args, rank, world, local_rank):
     conv_bytes = conv_algorithmic_bytes_per_audio_s() * audio_s * args.steps      # algorithmic, this rank
     hbm_gbs = (conv_bytes / 1e9) / (conv["ms"] / 1e3) if conv["ms"] > 0 else 0.0
     roofline = {
-        "kernel": "conv_umma2_kernel (2-CTA tcgen05 implicit-GEMM Conv1d: all conv / convT / LSTM-input layers)",
+        "kernel": "tcgen05 conv engine: conv_umma2_kernel (2-CTA implicit-GEMM Conv1d / ConvT) + conv_chain_kernel "
+                  "(fused dilated blocks + LSTM input projection), all template variants",
         "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
         "frac": achieved / peaks["tflops"], "peak_source": f"{peaks['src']} bf16 dense sustained (fp16 operands run at the same rate)",
         "avg_launch_ms": conv["ms"] / max(1, conv["launches"]), "launches": conv["launches"],
         "share_of_step": conv["ms"] / (1e3 * t_s), "traffic": load_conv_traffic(args),
         "algorithmic_bytes_per_launch": conv_bytes / max(1, conv["launches"]),
         "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_gbs / peaks["hbm_gbs"],
-                "note": "same launches against the HBM roofline (unfused layers: algorithmic activation bytes)"},
+                "note": "same launches against the HBM roofline (algorithmic fp16 activation bytes of the 36 launches)"},
         "per_category_ms_per_step": {k: v["ms"] / args.steps for k, v in cats.items()},
     }
     line = {

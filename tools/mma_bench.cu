@@ -15,7 +15,7 @@ __device__ __forceinline__ uint64_t desc_of(uint32_t saddr, uint32_t lbo, uint32
 
 // mode: 0 = same A/B every MMA; 1 = A advances like a 3-tap conv stage (tap shift 16 B, K block shift); nacc = accumulators cycled
 template <int CTA2>
-__global__ void __launch_bounds__(128, 1) mma_bench(int N, int nmma, int layout, int nacc, int a_rows, long long* out) {
+__global__ void __launch_bounds__(128, 1) mma_bench(int N, int nmma, int layout, int nacc, int a_rows, int a_shift_rows, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) unsigned long long bar;
   __shared__ uint32_t tmem_slot;
@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(128, 1) mma_bench(int N, int nmma, int layout,
       for (int i = 0; i < nmma; ++i) {
         const uint32_t d = tmem_base + (uint32_t)((i % nacc) * N);
         // walk A through a few K blocks like the real kernels do (keeps addresses inside the 96 KB region)
-        const uint64_t adi = ad + (uint64_t)((i % 8) * ((layout == 0 ? 2 * a_rows * 16 : 32) >> 4));
+        // a_shift_rows != 0: start the A operand a_shift_rows*(i%7) rows (16 B each) into the run, like tap j of a conv
+        const uint64_t adi = ad + (uint64_t)((i % 8) * ((layout == 0 ? 2 * a_rows * 16 : 32) >> 4)) + (uint64_t)((i % 7) * a_shift_rows);
         const uint64_t bdi = bd + (uint64_t)((i % 8) * ((layout == 0 ? 2 * Nh * 16 : 32) >> 4));
         if (CTA2) umma2_f16(d, adi, bdi, idesc, i >= nacc ? 1u : 0u);
         else umma_f16(d, adi, bdi, idesc, i >= nacc ? 1u : 0u);
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(128, 1) mma_bench(int N, int nmma, int layout,
 }
 
 template <int CTA2>
-static void run(int N, int layout, int nacc, int grid) {
+static void run(int N, int layout, int nacc, int grid, int a_shift_rows = 0) {
   long long* d;
   cudaMalloc(&d, 16);
   const int nmma = 512, smem = 160 * 1024;
@@ -97,7 +98,7 @@ static void run(int N, int layout, int nacc, int grid) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   for (int rep = 0; rep < 2; ++rep) {
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k, N, nmma, layout, nacc, 136, d);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k, N, nmma, layout, nacc, 136, a_shift_rows, d);
     if (e != cudaSuccess) { printf("launch: %s\n", cudaGetErrorString(e)); return; }
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("run: %s\n", cudaGetErrorString(e)); return; }
@@ -105,8 +106,8 @@ static void run(int N, int layout, int nacc, int grid) {
   long long h[2];
   cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
   const double ideal = (CTA2 ? 256.0 : 128.0) * N / (256.0 * (CTA2 ? 2 : 1));
-  printf("cta_group::%d M=%3d N=%3d layout=%s nacc=%d grid=%3d: issue %.1f cyc/mma, complete %.1f cyc/mma (math floor %.0f)\n", CTA2 ? 2 : 1,
-         CTA2 ? 256 : 128, N, layout ? "swz128" : "none  ", nacc, grid, (double)h[0] / nmma, (double)h[1] / nmma, ideal);
+  printf("shift=%d cta_group::%d M=%3d N=%3d layout=%s nacc=%d grid=%3d: issue %.1f cyc/mma, complete %.1f cyc/mma (math floor %.0f)\n",
+         a_shift_rows, CTA2 ? 2 : 1, CTA2 ? 256 : 128, N, layout ? "swz128" : "none  ", nacc, grid, (double)h[0] / nmma, (double)h[1] / nmma, ideal);
   cudaFree(d);
 }
 
@@ -117,9 +118,10 @@ int main() {
       run<0>(N, layout, 1, 148);
       run<1>(N, layout, 1, 148);
     }
-  run<1>(128, 0, 2, 148);
-  run<1>(128, 0, 1, 2);
-  run<1>(64, 0, 1, 2);
-  run<1>(256, 0, 1, 2);
+  for (int sh : {1, 2, 4, 8}) {   // tap-shifted A start (rows of 16 B): is an unaligned operand start more expensive?
+    run<1>(64, 0, 1, 148, sh);
+    run<1>(128, 0, 1, 148, sh);
+    run<1>(256, 0, 1, 148, sh);
+  }
   return 0;
 }
