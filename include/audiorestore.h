@@ -111,6 +111,17 @@ int ar_chain_forward(ar_chain_t c, const float* x, float* y, int B, int T,
 #define AR_NORMALIZE_SCRATCH_BYTES 16384
 int ar_normalize(float* audio, int64_t n, float target_db, void* scratch, void* stream);
 
+/* Front end of load_audio (audio_processing.py:10-42) on the device:
+ *   ar_pcm16_to_float : interleaved PCM16 frames [n][channels] -> planar fp32 [channels][n] (x / 32768, as
+ *                       soundfile's float32 read at :24)
+ *   ar_resample_mono  : planar fp32 [channels][n] -> mono fp32 [n_out]: torch.mean(dim=0) (:33) fused with
+ *                       torchaudio.transforms.Resample(orig_sr, new_sr) (:38; sinc_interp_hann, lowpass_filter_width 6,
+ *                       rolloff 0.99 polyphase FIR).  n_out must be ar_resample_length() = ceil(new * n / orig)
+ *                       (== n when the rates match: then only the mono mix is applied). */
+int ar_resample_length(int64_t n, int orig_sr, int new_sr, int64_t* n_out);
+int ar_resample_mono(const float* x, int channels, int64_t n, int orig_sr, int new_sr, float* y, int64_t n_out, void* stream);
+int ar_pcm16_to_float(const int16_t* pcm, int channels, int64_t n, float* y, void* stream);
+
 /* Chunk / stitch (vocabulary of chunk_audio, audio_processing.py:229-253; tail zero-pad of
  * trainer.py:656-665).  hop = chunk_size - overlap, overlap <= chunk_size/2.
  *   ar_num_chunks     : chunks needed for n samples

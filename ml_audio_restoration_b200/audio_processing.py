@@ -60,9 +60,12 @@ def _read_wav(path: str):
         return torch.from_numpy(np.ascontiguousarray(data.T)), sr
     except ImportError:
         pass
-    with wave.open(path, "rb") as w:
-        sr, nch, width, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
-        raw = w.readframes(n)
+    try:
+        with wave.open(path, "rb") as w:
+            sr, nch, width, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
+            raw = w.readframes(n)
+    except wave.Error:
+        return _read_float_wav(path)
     if width == 2:
         a = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
     elif width == 4:
@@ -79,8 +82,29 @@ def _read_wav(path: str):
     return torch.from_numpy(np.ascontiguousarray(a.reshape(-1, nch).T)), sr
 
 
+def _read_float_wav(path: str):
+    """32-bit IEEE-float WAV (format tag 3), which the stdlib `wave` module rejects."""
+    import struct
+    with open(path, "rb") as f:
+        blob = f.read()
+    if blob[:4] != b"RIFF" or blob[8:12] != b"WAVE":
+        raise RuntimeError(f"{path}: not a RIFF/WAVE file")
+    pos, fmt, data = 12, None, None
+    while pos + 8 <= len(blob):
+        cid, size = struct.unpack_from("<4sI", blob, pos)
+        if cid == b"fmt ":
+            fmt = struct.unpack_from("<HHIIHH", blob, pos + 8)
+        elif cid == b"data":
+            data = blob[pos + 8:pos + 8 + size]
+        pos += 8 + size + (size & 1)
+    if fmt is None or data is None or fmt[0] != 3 or fmt[5] != 32:
+        raise RuntimeError(f"{path}: unsupported WAV encoding")
+    a = np.frombuffer(data, dtype="<f4").reshape(-1, fmt[1])
+    return torch.from_numpy(np.ascontiguousarray(a.T)), fmt[2]
+
+
 def load_audio(file_path: str, sample_rate: int = 22050, mono: bool = True):
-    """(audio [C,N] float32, sample_rate) -- audio_processing.py:10-42."""
+    """(audio [C,N] float32, sample_rate) -- audio_processing.py:10-42 (host tensors, as the reference returns)."""
     audio, sr = _read_wav(file_path)
     if mono and audio.shape[0] > 1:
         audio = audio.mean(dim=0, keepdim=True)
@@ -90,14 +114,65 @@ def load_audio(file_path: str, sample_rate: int = 22050, mono: bool = True):
     return audio, sample_rate
 
 
-def save_audio(file_path: str, audio: torch.Tensor, sample_rate: int = 22050) -> None:
-    """Write `[C,N]` float audio as 16-bit PCM WAV (audio_processing.py:45-55)."""
-    a = audio.detach().to("cpu", torch.float32).clamp(-1.0, 1.0).numpy()
+def resample_mono_cuda(audio: torch.Tensor, sr: int, sample_rate: int = 22050) -> torch.Tensor:
+    """`[C,N]` float32 CUDA -> `[1, ceil(sample_rate*N/sr)]`: the mono mix (`torch.mean(dim=0)`, audio_processing.py:33)
+    fused with `torchaudio.transforms.Resample(sr, sample_rate)` (:38) in one kernel (`ar_resample_mono`)."""
+    if not audio.is_cuda or audio.dim() != 2:
+        raise RuntimeError("resample_mono_cuda: expected a [C,N] CUDA tensor -- this build has no CPU fallback")
+    x = audio.to(torch.float32).contiguous()
+    L = _lib.lib()
+    n_out = C.c_int64()
+    _lib.check(L.ar_resample_length(x.shape[1], int(sr), int(sample_rate), C.byref(n_out)))
+    y = torch.empty((1, n_out.value), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(L.ar_resample_mono(x.data_ptr(), x.shape[0], x.shape[1], int(sr), int(sample_rate), y.data_ptr(),
+                                      n_out.value, torch.cuda.current_stream(x.device).cuda_stream))
+    return y
+
+
+def load_audio_cuda(file_path: str, sample_rate: int = 22050, device="cuda"):
+    """`load_audio(..., mono=True)` with the arithmetic on the GPU: 16-bit PCM files are uploaded as raw
+    int16 frames (half the H2D bytes of float32) from pinned memory, decoded, mixed to mono and resampled on the device.
+    Returns (audio [1,N] float32 CUDA, sample_rate)."""
+    dev = torch.device(device)
+    with wave.open(file_path, "rb") as w:
+        sr, nch, width, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
+        raw = w.readframes(n) if width == 2 else None
+    if raw is None:                                    # other encodings: host decode, device mix + resample
+        audio, sr = _read_wav(file_path)
+        return resample_mono_cuda(audio.to(dev), sr, sample_rate), sample_rate
+    pcm = torch.frombuffer(bytearray(raw), dtype=torch.int16).pin_memory().to(dev, non_blocking=True)
+    planar = torch.empty((nch, n), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().ar_pcm16_to_float(pcm.data_ptr(), nch, n, planar.data_ptr(),
+                                                torch.cuda.current_stream(dev).cuda_stream))
+    return resample_mono_cuda(planar, sr, sample_rate), sample_rate
+
+
+def save_audio(file_path: str, audio: torch.Tensor, sample_rate: int = 22050, encoding: str = "float32") -> None:
+    """Write `[C,N]` float audio as WAV (audio_processing.py:45-55).  The reference's `torchaudio.save` of a float
+    tensor writes 32-bit IEEE-float samples; `encoding="pcm16"` writes 16-bit PCM instead."""
+    import os
+    import struct
+    a = audio.detach().to("cpu", torch.float32).numpy()
     if a.ndim == 1:
         a = a[None]
-    pcm = np.round(a.T * 32767.0).astype("<i2")
-    with wave.open(file_path, "wb") as w:
-        w.setnchannels(a.shape[0])
-        w.setsampwidth(2)
-        w.setframerate(int(sample_rate))
-        w.writeframes(pcm.tobytes())
+    parent = os.path.dirname(os.path.abspath(file_path))
+    os.makedirs(parent, exist_ok=True)
+    if encoding == "pcm16":
+        pcm = np.round(np.clip(a, -1.0, 1.0).T * 32767.0).astype("<i2")
+        with wave.open(file_path, "wb") as w:
+            w.setnchannels(a.shape[0])
+            w.setsampwidth(2)
+            w.setframerate(int(sample_rate))
+            w.writeframes(pcm.tobytes())
+        return
+    if encoding != "float32":
+        raise ValueError(f"unknown WAV encoding {encoding!r}")
+    data = np.ascontiguousarray(a.T).astype("<f4").tobytes()
+    nch, sr = a.shape[0], int(sample_rate)
+    fmt = struct.pack("<4sIHHIIHH", b"fmt ", 16, 3, nch, sr, sr * nch * 4, nch * 4, 32)      # format tag 3 = IEEE float
+    fact = struct.pack("<4sII", b"fact", 4, a.shape[1])
+    body = b"WAVE" + fmt + fact + struct.pack("<4sI", b"data", len(data)) + data
+    with open(file_path, "wb") as f:
+        f.write(struct.pack("<4sI", b"RIFF", len(body)) + body)

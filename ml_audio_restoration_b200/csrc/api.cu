@@ -15,6 +15,10 @@ int set_engine(int e);
 int set_fusion(int on);
 int set_chain_trace(long long* dev_buf);
 int set_conv_smem_kb(int kb);
+long long resample_length(long long n, int orig_sr, int new_sr);
+int launch_resample_mono(const float* x, int channels, long long n, int orig_sr, int new_sr, float* y, long long n_out,
+                         cudaStream_t stream);
+int launch_pcm16(const short* pcm, int channels, long long n, float* y, cudaStream_t stream);
 int model_create(int kind, const ar_tensor_t* tensors, int n, int device, Model** out);
 int model_workspace_bytes(const Model* m, int B, int T, size_t* bytes);
 int model_forward(const Model* m, const float* x, float* y, int B, int T, const float* st_in, float* st_out, void* ws,
@@ -42,6 +46,17 @@ int ar_version(void) { return 100; }
 int ar_set_conv_engine(int engine) { return ar::set_engine(engine); }
 int ar_set_fusion(int on) { return ar::set_fusion(on); }
 int ar_set_conv_smem_kb(int kb) { return ar::set_conv_smem_kb(kb); }
+int ar_resample_length(int64_t n, int orig_sr, int new_sr, int64_t* n_out) {
+  if (!n_out || n < 0 || orig_sr < 1 || new_sr < 1) { ar::set_error("resample_length: bad argument"); return AR_ERR_INVALID; }
+  *n_out = ar::resample_length(n, orig_sr, new_sr);
+  return AR_OK;
+}
+int ar_resample_mono(const float* x, int channels, int64_t n, int orig_sr, int new_sr, float* y, int64_t n_out, void* stream) {
+  return ar::launch_resample_mono(x, channels, n, orig_sr, new_sr, y, n_out, reinterpret_cast<cudaStream_t>(stream));
+}
+int ar_pcm16_to_float(const int16_t* pcm, int channels, int64_t n, float* y, void* stream) {
+  return ar::launch_pcm16(pcm, channels, n, y, reinterpret_cast<cudaStream_t>(stream));
+}
 int ar_debug_chain_trace(long long* dev_buf) { return ar::set_chain_trace(dev_buf); }
 
 int ar_model_create(int kind, const ar_tensor_t* tensors, int n_tensors, int device, ar_model_t* out) {

@@ -22,7 +22,7 @@ import math
 import torch
 
 from . import _lib
-from .audio_processing import load_audio, save_audio
+from .audio_processing import load_audio, load_audio_cuda, save_audio
 from .models import AudioDenoiser, AudioSuperResolution, StereoSeparator
 
 DEFAULT_CHUNK = 44100     # 2.0 s at 22.05 kHz (trainer.py:652)
@@ -299,7 +299,11 @@ def restore_audio(
     print(f"Processing: {input_path}")
     print(f"Device: {device}")
     print("Loading audio...")
-    audio, _ = load_audio(input_path, sample_rate=sample_rate, mono=True)
+    if input_path.lower().endswith(".wav"):
+        audio, _ = load_audio_cuda(input_path, sample_rate=sample_rate, device=device)   # decode / mono mix / resample on the GPU
+    else:
+        audio, _ = load_audio(input_path, sample_rate=sample_rate, mono=True)
+        audio = audio.pin_memory()
     print("Loading denoiser model...")
     den = _load_checkpoint(AudioDenoiser(), denoiser_checkpoint, device)
     sr = None
@@ -313,7 +317,7 @@ def restore_audio(
     if enable_super_resolution:
         print("Applying bandwidth extension (22.05kHz -> 44.1kHz)...")
     print("Applying stereo separation...")
-    stereo = pipe.restore(audio.pin_memory(), mode=mode, chunk_size=chunk_size, overlap=overlap)
+    stereo = pipe.restore(audio, mode=mode, chunk_size=chunk_size, overlap=overlap)
     out_rate = sample_rate * pipe.rate
     print(f"Saving to: {output_path}")
     save_audio(output_path, stereo, out_rate)

@@ -12,6 +12,9 @@ Parity status
   * model forwards, normalize_audio: PINNED -- checked against the reference modules
     imported from /root/reference (tests/golden/make_golden.py) and the committed
     golden vectors under tests/golden/.
+  * load_audio front end (PCM16 decode, mono mix, torchaudio sinc resampler -- oracle/audio_io.py): PINNED against
+    golden vectors generated from the installed torchaudio 2.11 (tests/golden/make_golden_io.py); the dependency is
+    not vendored in the reference (requirements.txt: torchaudio>=2.0.0), its published algorithm is restated.
   * chunk -> batch -> overlap-add stitching: PARITY UNPINNED by the reference (it has no
     such function); the oracle restates THIS repo's scheme from the
     oracle model forwards.  With overlap=0 it reduces to the reference's
