@@ -100,7 +100,7 @@ def _read_float_wav(path: str):
     if fmt is None or data is None or fmt[0] != 3 or fmt[5] != 32:
         raise RuntimeError(f"{path}: unsupported WAV encoding")
     a = np.frombuffer(data, dtype="<f4").reshape(-1, fmt[1])
-    return torch.from_numpy(np.ascontiguousarray(a.T)), fmt[2]
+    return torch.from_numpy(np.array(a.T, dtype=np.float32, order="C")), fmt[2]
 
 
 def load_audio(file_path: str, sample_rate: int = 22050, mono: bool = True):

@@ -277,6 +277,76 @@ class RestorationPipeline:
         return out[:, begin:end].contiguous()
 
 
+def chunked_model_eval(model, waveform: torch.Tensor, chunk_size: int = 2 * 22050) -> torch.Tensor:
+    """The tensor part of `Trainer.generate_test_output` (src/training/trainer.py:652-681) for ONE model: cut `[1,N]`
+    into `chunk_size` pieces, zero-pad the last one, run the model per chunk (LSTM state reset per chunk), strip the
+    padding and concatenate along time -> `[C_out, N_out]`.  The reference loops with batch 1 and a `.cpu()` per chunk;
+    chunks are independent, so here they form ONE batch (`ar_split_chunks` with overlap 0 + one batched forward).
+    As in the reference, exactly `padding` samples are stripped from the last chunk's output (`restored_chunk[:, :-padding]`,
+    :674-675) whatever the model's rate, so a x2 model keeps `padding` samples computed from the zero-padded tail."""
+    if waveform.dim() != 2 or waveform.shape[0] != 1 or not waveform.is_cuda:
+        raise RuntimeError("chunked_model_eval: expected a mono [1,N] CUDA tensor -- this build has no CPU fallback")
+    N = waveform.shape[1]
+    n = (N + chunk_size - 1) // chunk_size
+    a = waveform.to(torch.float32).contiguous()
+    chunks = torch.empty((n, 1, chunk_size), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.lib().ar_split_chunks(a.data_ptr(), N, chunks.data_ptr(), 0, n, chunk_size, 0,
+                                              torch.cuda.current_stream(a.device).cuda_stream))
+    with torch.no_grad():
+        y = model(chunks)                                   # [n, C, L]
+    C_out, L = y.shape[1], y.shape[2]
+    out = y.permute(1, 0, 2).reshape(C_out, n * L)
+    padding = n * chunk_size - N
+    return out[:, :n * L - padding].contiguous() if padding else out.contiguous()
+
+
+def generate_test_output(model, test_audio_dir: str, test_output_dir: str, suffix: str, device: str = "cuda",
+                         max_seconds: int = 30) -> list:
+    """Drop-in for `Trainer.generate_test_output` (src/training/trainer.py:582-721) as a free function: for every
+    `*.wav` in `test_audio_dir` (root only) take the first `max_seconds` of the mono 22.05 kHz signal, restore it in 2 s
+    chunks with `model`, and write `<stem>_original.wav` (once), `<stem>_degraded_<suffix>.wav` and
+    `<stem>_restored_<suffix>.wav`; for `epoch_<k>` suffixes older epoch files of the same stem are deleted.
+    Returns the restored file paths.  (mp3/flac/ogg inputs of the reference need soundfile, which this image lacks.)"""
+    import glob
+    import os
+    os.makedirs(test_output_dir, exist_ok=True)
+    written = []
+    model.eval()
+    for path in sorted(glob.glob(os.path.join(test_audio_dir, "*.wav"))):
+        stem = os.path.splitext(os.path.basename(path))[0]
+        original = os.path.join(test_output_dir, f"{stem}_original.wav")
+        if not os.path.exists(original):
+            host, sr_file = _read_original(path)
+            save_audio(original, host[:, :sr_file * max_seconds], sr_file)
+        wave_dev, sr = load_audio_cuda(path, sample_rate=22050, device=device)
+        wave_dev = wave_dev[:, :22050 * max_seconds].contiguous()
+        restored = chunked_model_eval(model, wave_dev)
+        save_audio(os.path.join(test_output_dir, f"{stem}_degraded_{suffix}.wav"), wave_dev, sr)
+        out_path = os.path.join(test_output_dir, f"{stem}_restored_{suffix}.wav")
+        save_audio(out_path, restored, sr)
+        written.append(out_path)
+        if suffix.startswith("epoch_"):
+            cur = int(suffix.split("_")[1])
+            for pat in (f"{stem}_restored_epoch_*.wav", f"{stem}_degraded_epoch_*.wav"):
+                for f in glob.glob(os.path.join(test_output_dir, pat)):
+                    try:
+                        if int(os.path.splitext(os.path.basename(f))[0].split("_epoch_")[1]) != cur:
+                            os.remove(f)
+                    except (ValueError, IndexError):
+                        pass
+    return written
+
+
+def _read_original(path: str):
+    """(mono [1,N] host float32 at the file's own rate, rate) -- the `_original.wav` copy of trainer.py:612-628."""
+    from .audio_processing import _read_wav
+    a, sr = _read_wav(path)
+    if a.shape[0] > 1:
+        a = a.mean(dim=0, keepdim=True)
+    return a, sr
+
+
 def restore_audio(
     input_path: str,
     output_path: str,

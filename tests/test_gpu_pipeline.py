@@ -107,3 +107,41 @@ def test_split_and_overlap_add_identities(pipe):
     assert torch.equal(ref_chunks, chunks.cpu())
     with pytest.raises(ValueError):
         _lib.check(L.ar_num_chunks(100, 10, 6, C.byref(C.c_int())))
+
+
+@pytest.mark.parametrize("name,N", [("denoiser", 5 * 44100 + 1234), ("stereo", 2 * 44100), ("super_resolution", 44100 + 17)])
+def test_chunked_model_eval_matches_trainer_loop(state_dicts, name, N):
+    """Drop-in of the reference's only chunked inference, Trainer.generate_test_output (trainer.py:652-681): 2 s chunks,
+    zero-padded tail, per-chunk forward, `[:, :-padding]` strip, concat -- here as one batched forward."""
+    from ml_audio_restoration_b200 import chunked_model_eval
+    from gpu_util import make_model, assert_close
+    fwd = {"denoiser": oracle.denoiser_forward, "super_resolution": oracle.super_resolution_forward, "stereo": oracle.stereo_forward}[name]
+    x = make_input(1, N, seed=N % 101)[0]                      # [1, N]
+    pieces = []
+    for i in range(0, N, 44100):                                # the reference loop, on the oracle forward
+        chunk = x[:, i:i + 44100]
+        padding = 44100 - chunk.shape[1]
+        if padding:
+            chunk = torch.nn.functional.pad(chunk, (0, padding))
+        y = fwd(state_dicts[name], chunk.unsqueeze(0)).squeeze(0)
+        pieces.append(y[:, :-padding] if padding else y)
+    ref = torch.cat(pieces, dim=1)
+    got = chunked_model_eval(make_model(name, state_dicts[name]), x.cuda())
+    assert_close(ref, got, f"chunked_model_eval {name} N={N}")
+
+
+def test_generate_test_output_files(state_dicts, tmp_path):
+    from ml_audio_restoration_b200 import generate_test_output, save_audio
+    from ml_audio_restoration_b200.audio_processing import _read_wav
+    from gpu_util import make_model
+    src, dst = tmp_path / "in", tmp_path / "out"
+    src.mkdir()
+    save_audio(str(src / "side_a.wav"), make_input(1, 3 * 44100 + 5, seed=3)[0], 44100, encoding="pcm16")   # 44.1 kHz: resampled on the GPU
+    model = make_model("stereo", state_dicts["stereo"])
+    generate_test_output(model, str(src), str(dst), "epoch_1")
+    out = generate_test_output(model, str(src), str(dst), "epoch_2")
+    names = sorted(p.name for p in dst.iterdir())
+    assert names == ["side_a_degraded_epoch_2.wav", "side_a_original.wav", "side_a_restored_epoch_2.wav"]   # epoch_1 cleaned up
+    y, sr = _read_wav(out[0])
+    d, _ = _read_wav(str(dst / "side_a_degraded_epoch_2.wav"))
+    assert sr == 22050 and y.shape[0] == 2 and y.shape[1] == d.shape[1] == (3 * 44100 + 5 + 1) // 2
