@@ -11,6 +11,7 @@
 // h that feeds the decoder convs is rounded to TF32.
 #include "ar_common.cuh"
 #include "pointwise.cuh"
+#include <cstdio>
 #include <cstdlib>
 
 namespace ar {
@@ -30,26 +31,33 @@ __device__ __forceinline__ float rcp_f(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// One LSTM cell update with 5 ex2 + 2 rcp (the special-function unit, 16 lanes/clk/SM, is the throughput limit of
-// the tensor-core recurrence kernel): the three gate functions of the cell state share ONE reciprocal,
+// Gate pre-activations arrive PRE-SCALED (models.cu scales the rows of W_ih, W_hh and the biases at pack time):
+//   p_i, p_f, p_o = log2(e) * (gate pre-activation),   p_g = 2 log2(e) * (cell-candidate pre-activation),
+// so every gate function is an ex2 of the negated input with no multiply in front of it.
+// One LSTM cell update with 5 ex2 + 2 rcp (the special-function unit, 16 lanes/clk/SM, and the issue slots are the
+// throughput limits of the tensor-core recurrence kernels): the three gate functions of the cell state share ONE
+// reciprocal,
 //   s(f) c + s(i) tanh(g) = [ c (1+b)(1+d) + (1-d)(1+a) ] / [ (1+a)(1+b)(1+d) ],  a=e^-f, b=e^-i, d=e^-2g,
-// and so do s(o) tanh(c').  Pre-activations are clamped to +-20 (changes a gate by < 3e-9) so the product of
-// three exponentials stays finite.
+// and so do s(o) tanh(c').  Only the lower side needs a clamp (e^-x overflows for very negative x; for large x it
+// underflows to 0, which is exact enough): -20 natural units changes a gate by < 3e-9 and keeps the product of three
+// exponentials finite.
+constexpr float LSTM_L2E = 1.4426950408889634f;
 __device__ __forceinline__ void lstm_cell(float pi, float pf, float pg, float po, float& c, float& h) {
-  const float L2E = 1.4426950408889634f;
-  pi = fminf(fmaxf(pi, -20.f), 20.f);
-  pf = fminf(fmaxf(pf, -20.f), 20.f);
-  pg = fminf(fmaxf(pg, -20.f), 20.f);
-  po = fminf(fmaxf(po, -20.f), 20.f);
-  const float a = ex2_f(-L2E * pf), b = ex2_f(-L2E * pi), d = ex2_f(-2.f * L2E * pg);
+  pi = fmaxf(pi, -20.f * LSTM_L2E);
+  pf = fmaxf(pf, -20.f * LSTM_L2E);
+  pg = fmaxf(pg, -40.f * LSTM_L2E);
+  po = fmaxf(po, -20.f * LSTM_L2E);
+  const float a = ex2_f(-pf), b = ex2_f(-pi), d = ex2_f(-pg);
   const float bd = (1.f + b) * (1.f + d);
   const float num = fmaf(c, bd, (1.f - d) * (1.f + a));
   c = num * rcp_f((1.f + a) * bd);
-  const float cc = fminf(fmaxf(c, -20.f), 20.f);
-  const float q = ex2_f(-L2E * po), e = ex2_f(-2.f * L2E * cc);
+  const float cc = fmaxf(c, -20.f);
+  const float q = ex2_f(-po), e = ex2_f(-2.f * LSTM_L2E * cc);
   h = (1.f - e) * rcp_f((1.f + q) * (1.f + e));
 }
-__device__ __forceinline__ float sigmoid_f(float x) { return rcp_f(1.0f + ex2_f(-1.4426950408889634f * x)); }
+// pre-scaled variants for the CUDA-core kernel (x already multiplied by log2(e), resp. 2 log2(e))
+__device__ __forceinline__ float sigmoid_s(float x) { return rcp_f(1.0f + ex2_f(-x)); }
+__device__ __forceinline__ float tanh_s(float x) { return 1.0f - 2.0f * rcp_f(ex2_f(x) + 1.0f); }
 __device__ __forceinline__ float tanh_f(float x) { return 1.0f - 2.0f * rcp_f(ex2_f(2.8853900817779268f * x) + 1.0f); }
 
 // Packed 2-wide fp32 FMA (Blackwell FFMA2): halves the FMA issue slots of the 64-term dot product.
@@ -162,7 +170,7 @@ lstm_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, const flo
           unpack2(acc[s][2], a4, a5);
           unpack2(acc[s][3], a6, a7);
           const float pre = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
-          const float a = (gate == 2) ? tanh_f(pre) : sigmoid_f(pre);
+          const float a = (gate == 2) ? tanh_s(pre) : sigmoid_s(pre);
           const float af = __shfl_sync(0xffffffffu, a, (lane & 7) + 8);
           const float ag = __shfl_sync(0xffffffffu, a, (lane & 7) + 16);
           const float ao = __shfl_sync(0xffffffffu, a, (lane & 7) + 24);
@@ -403,8 +411,9 @@ lstm_mma_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, const
 // barrier) and all 16 warps of the SM walk it in lock step (ncu: 32 % issue utilisation, the special-function unit
 // saturated only in bursts).  This variant gives each SM TWO independent recurrences to interleave: a CTA owns four
 // sequences (the n = 8 MMA columns hold them twice), its 8 warps own 8 hidden units each as two 16-row tiles, (i|f) and
-// (g|o) of those units, so thread (gid, tig) finds all four gates of cell (unit 8w + gid, sequence (tig&1)*2 + (tig>>1))
-// in its own accumulators -- no shuffles -- and carries exactly one cell.  While one CTA sits in its barrier or its
+// (g|o) of those units, and the eight MMA columns hold the sequences as (s0 s0 s1 s1 s2 s2 s3 s3), so thread (gid, tig)
+// finds all four gates of cell (unit 8w + gid, sequence tig) in fixed accumulator registers -- no shuffles, no
+// selects -- and carries exactly one cell.  While one CTA sits in its barrier or its
 // gate-function chain the other one issues.
 constexpr int L4_SEQ = 4;
 constexpr int L4_THREADS = 256;
@@ -425,8 +434,8 @@ lstm_mma4_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, cons
   const int warp = tid >> 5, lane = tid & 31;
   const int gid = lane >> 2, tig = lane & 3;
   const int unit = warp * 8 + gid;                  // the cell this thread carries: (unit, seq)
-  const int seq = (tig & 1) * 2 + (tig >> 1);
-  const int sel = tig >> 1;                         // accumulator column (0: col 2tig, 1: col 2tig+1) that is `seq`
+  const int seq = tig;                              // MMA columns hold the sequences as (s0 s0 s1 s1 s2 s2 s3 s3): the thread's
+                                                    // own columns 2tig, 2tig+1 are both sequence tig -> it reads c0 / c2, no select
   const int seq0 = blockIdx.x * L4_SEQ;
   const int bq = min(seq0 + seq, B - 1);            // surplus columns replay the last sequence, stores are masked
 
@@ -510,7 +519,7 @@ lstm_mma4_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, cons
         for (int tl = 0; tl < 2; ++tl)
 #pragma unroll
           for (int i = 0; i < 4; ++i) acc[tl][i] = 0.f;
-        const uint2* hb = reinterpret_cast<const uint2*>(hbuf + cur * (L4_SEQ * LM_HS) + (gid & 3) * LM_HS) + tig;
+        const uint2* hb = reinterpret_cast<const uint2*>(hbuf + cur * (L4_SEQ * LM_HS) + (gid >> 1) * LM_HS) + tig;   // B column gid = sequence gid/2
 #pragma unroll
         for (int kt = 0; kt < 4; ++kt) {
           const uint2 bf = hb[kt * 4];
@@ -519,10 +528,10 @@ lstm_mma4_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, cons
         }
         const float2 x_if = __half22float2(*reinterpret_cast<const __half2*>(&q.x));
         const float2 x_go = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
-        const float pi = (sel ? acc[0][1] : acc[0][0]) + x_if.x;
-        const float pf = (sel ? acc[0][3] : acc[0][2]) + x_if.y;
-        const float pg = (sel ? acc[1][1] : acc[1][0]) + x_go.x;
-        const float po = (sel ? acc[1][3] : acc[1][2]) + x_go.y;
+        const float pi = acc[0][0] + x_if.x;
+        const float pf = acc[0][2] + x_if.y;
+        const float pg = acc[1][0] + x_go.x;
+        const float po = acc[1][2] + x_go.y;
         lstm_cell(pi, pf, pg, po, c, hl);
         hbuf[(cur ^ 1) * (L4_SEQ * LM_HS) + seq * LM_HS + upos] = __float2half_rn(hl);
         hst[k * L4_HSTEP + seq * LM_HST + unit] = hl;
@@ -566,6 +575,14 @@ int launch_lstm(const Act& xp, const float* whh, const Act& h_out, int B, int T,
     static bool attr_set = false;
     if (!attr_set) {
       AR_CUDA_OK(cudaFuncSetAttribute(lstm_mma4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L4_SMEM));
+      // two (three) CTAs of 53 KB must fit: ask for the largest shared-memory carve-out, the driver's default
+      // heuristic sizes it for ONE CTA and the second recurrence of the SM would run after the first instead of under it
+      AR_CUDA_OK(cudaFuncSetAttribute(lstm_mma4_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      if (getenv("AR_DEBUG_OCCUPANCY")) {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lstm_mma4_kernel, L4_THREADS, L4_SMEM);
+        fprintf(stderr, "lstm_mma4_kernel: %d CTAs per SM\n", nb);
+      }
       attr_set = true;
     }
     lstm_mma4_kernel<<<(B + L4_SEQ - 1) / L4_SEQ, L4_THREADS, L4_SMEM, stream>>>(xp.h(), xp.bs, xp.Tp, whh, h_out.h(), h_out.bs, h_out.Tp,

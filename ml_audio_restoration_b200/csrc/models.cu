@@ -315,15 +315,25 @@ static bool build_stereo(const Table& t, Blob& blob, Model& m) {
   if (!Wih || !Whh || !bih || !bhh) return false;
   // Output channels are permuted to [unit][gate] (gate order i,f,g,o) so that the four gate pre-activations a
   // recurrence thread needs are 8 contiguous bytes of the H8 tensor.
+  // Rows are pre-scaled so that the recurrence kernels' gate functions are bare ex2's (lstm.cu, lstm_cell): log2(e) for the
+  // i, f, o gates, 2 log2(e) for the cell candidate g -- applied to W_ih, both biases and W_hh alike.
+  const float L2E = 1.4426950408889634f;
+  const float gate_scale[4] = {L2E, L2E, 2.0f * L2E, L2E};
   Gemm g;
   g.init(128, 256, 1, 1, 0);
   for (int o = 0; o < 256; ++o) {
     const int op = (o % 64) * 4 + o / 64;
-    for (int c = 0; c < 128; ++c) g.at(0, c, op) = Wih[o * 128 + c];
-    g.bias[op] = bih[o] + bhh[o];
+    const float sc = gate_scale[o / 64];
+    for (int c = 0; c < 128; ++c) g.at(0, c, op) = Wih[o * 128 + c] * sc;
+    g.bias[op] = (bih[o] + bhh[o]) * sc;
   }
   m.conv["xproj"] = blob.push_gemm(g);
-  m.whh_off = blob.push(Whh, 256 * 64);
+  {
+    std::vector<float> whh_s(256 * 64);
+    for (int o = 0; o < 256; ++o)
+      for (int k = 0; k < 64; ++k) whh_s[o * 64 + k] = Whh[o * 64 + k] * gate_scale[o / 64];
+    m.whh_off = blob.push(whh_s);
+  }
   // decoders: first layers of L and R share their input -> one GEMM with N = 256
   Gemm d0;
   d0.init(64, 256, 7, 1, 3);
