@@ -145,3 +145,45 @@ def test_generate_test_output_files(state_dicts, tmp_path):
     y, sr = _read_wav(out[0])
     d, _ = _read_wav(str(dst / "side_a_degraded_epoch_2.wav"))
     assert sr == 22050 and y.shape[0] == 2 and y.shape[1] == d.shape[1] == (3 * 44100 + 5 + 1) // 2
+
+
+def test_config4_three_minute_side_properties_and_sampled_parity(pipe, state_dicts):
+    """BASELINE config 4 at full size: a synthetic 3-minute 22.05 kHz side (95 chunks of 44100 / overlap 2052).
+    Size-independent properties: the result does not depend on how the chunks are batched (one batch of 95 = tile
+    groups + fused chains over many items, vs. batches of 40 with a ragged last one); sampled parity: the first two
+    chunks against the oracle (normalisation off so a prefix of the file is comparable)."""
+    sr, hop, chunk = 22050, 42048, 44100
+    N = 180 * sr
+    t = torch.arange(N, dtype=torch.float32) / sr
+    g = torch.Generator().manual_seed(4)
+    audio = (0.08 * torch.sin(2 * torch.pi * 220.0 * t) + 0.05 * torch.sin(2 * torch.pi * 554.4 * t + 0.3)
+             + 0.02 * torch.randn(N, generator=g))
+    audio[::7919] += 0.6                                   # pops
+    audio = audio[None]
+    dev = audio.cuda()
+    y_all = pipe.restore(dev, mode="chunked", normalize=False)                       # one batch of 95 chunks
+    y_b40 = pipe.restore(dev, mode="chunked", normalize=False, batch_chunks=40)      # 40 + 40 + 15
+    assert y_all.shape == (2, 2 * N) and torch.isfinite(y_all).all()
+    assert torch.equal(y_all, y_b40), "chunk results depend on the batch they were computed in"
+    y_norm = pipe.restore(dev, mode="chunked")                                       # with input/output normalize_audio
+    rms = float(y_norm.double().pow(2).mean().sqrt())
+    assert abs(20 * np.log10(rms) + 20.0) < 0.05 or float(y_norm.abs().max()) <= 1.0 + 1e-6
+    n_pre = hop + chunk                                                              # two chunks
+    ref = opipe.restore_chunked(state_dicts, audio[:, :n_pre], normalize=False, batch=2)
+    keep = 2 * hop                                                                   # output samples the 3rd chunk does not touch
+    assert_close(ref[:, :keep], y_all[:, :keep], "config 4: first two chunks vs oracle")
+
+
+def test_lstm_kernels_agree_at_full_length(state_dicts):
+    """The tensor-core recurrence (batch > 2 sequences per SM) against the CUDA-core one (small batch) on full-length
+    2 s chunks at the stereo stage's rate (88 200 steps): same chunks, different batch composition."""
+    from gpu_util import make_model, assert_close as close
+    m = make_model("stereo", state_dicts["stereo"])
+    B = 2 * torch.cuda.get_device_properties(0).multi_processor_count + 8
+    x = make_input(8, 88200, seed=21).cuda()
+    xb = x.repeat((B + 7) // 8, 1, 1)[:B].contiguous()
+    with torch.no_grad():
+        y_small = m(x)                      # CUDA-core LSTM kernel
+        y_big = m(xb)                       # tensor-core LSTM kernel
+    assert torch.equal(y_big[:8], y_big[8:16]), "identical sequences in one batch must give identical outputs"
+    close(y_small, y_big[:8], "stereo T=88200: tensor-core vs CUDA-core recurrence", max_abs=1e-3, min_snr=60.0)
