@@ -192,6 +192,8 @@ struct Model {
   // CUDA-core tails: weights live on the host and travel as kernel parameters (constant bank)
   DenTailP den_tail{};   // denoiser: transient detector + final 1x1
   FinalW fin{};          // final k7 convs (sr: 1 head, stereo: 2)
+  size_t fin_umma_off = 0;   // the same heads packed as a tap-along-N tensor-core operand (final_umma.cu)
+  int fin_heads = 0;
   size_t whh_off = 0;
   ~Model() { if (blob) cudaFree(blob); }
 };
@@ -296,6 +298,14 @@ static bool build_sr(const Table& t, Blob& blob, Model& m) {
   for (int c = 0; c < 32; ++c)
     for (int j = 0; j < 7; ++j) m.fin.w[0][j][c] = WR[c * 7 + j];
   m.fin.bias[0] = BR[0];
+  m.fin_heads = 1;
+  {
+    std::vector<uint16_t> pk;
+    pack_final_umma(m.fin, 1, pk);
+    std::vector<float> raw((pk.size() + 1) / 2);
+    std::memcpy(raw.data(), pk.data(), pk.size() * 2);
+    m.fin_umma_off = blob.push(raw);
+  }
   return true;
 }
 
@@ -351,6 +361,14 @@ static bool build_stereo(const Table& t, Blob& blob, Model& m) {
     for (int c = 0; c < 32; ++c)
       for (int j = 0; j < 7; ++j) m.fin.w[s][j][c] = WF[c * 7 + j];
     m.fin.bias[s] = BF[0];
+  }
+  m.fin_heads = 2;
+  {
+    std::vector<uint16_t> pk;
+    pack_final_umma(m.fin, 2, pk);
+    std::vector<float> raw((pk.size() + 1) / 2);
+    std::memcpy(raw.data(), pk.data(), pk.size() * 2);
+    m.fin_umma_off = blob.push(raw);
   }
   return true;
 }
@@ -535,6 +553,17 @@ static int run_chain(Ctx& c, std::initializer_list<const char*> names, const Act
   return launch_conv_chain(cp, c.stream);
 }
 
+// the k7 output heads run on the tensor core (final_umma.cu) with the tcgen05 engine; AR_FINAL_SIMT=1 or the
+// CUDA-core cross-check engine select the CUDA-core kernel
+static bool use_final_umma(const Model& m) {
+  static int simt = -1;
+  if (simt < 0) {
+    const char* e = getenv("AR_FINAL_SIMT");
+    simt = e ? atoi(e) : 0;
+  }
+  return m.engine == AR_ENGINE_UMMA && simt <= 0;
+}
+
 // ---------------------------------------------------------------------------- denoiser.py:88-144
 static int denoiser_forward(Ctx& c, const float* x, float* y, int T) {
   AR_CHECK(T >= 8, AR_ERR_INVALID, "max_pool1d(): Invalid computed output size: 0 (denoiser needs at least 8 samples)");
@@ -642,7 +671,12 @@ static int sr_forward(Ctx& c, const float* x, float* y, int T) {
   if (!A.dry) {
     const int coff[1] = {0};
     ProfScope ps(CAT_TAIL, c.stream, 2.0 * 224 * (double)B * 2 * T);
-    AR_TRY(launch_final_k7(h, coff, m.fin, 1, y, B, 2 * T, x, c.stream));
+    // one head = 8 KB of activations per tile: the tensor-core kernel is latency-bound there (3.0 ms per 1184-chunk
+    // step against 2.5 ms of the CUDA-core kernel); AR_FINAL_SIMT=-1 forces it for measurements
+    if (use_final_umma(m) && getenv("AR_FINAL_SIMT") && atoi(getenv("AR_FINAL_SIMT")) < 0)
+      AR_TRY(launch_final_umma(h, 0, reinterpret_cast<const __half*>(m.blob + m.fin_umma_off), m.fin, 1, y, B, 2 * T, x, c.stream));
+    else
+      AR_TRY(launch_final_k7(h, coff, m.fin, 1, y, B, 2 * T, x, c.stream));
   }
   A.release(h);
   return AR_OK;
@@ -716,7 +750,10 @@ static int stereo_forward(Ctx& c, const float* x, float* y, int T, const float* 
   if (!A.dry) {
     const int coff[2] = {0, 32 / 8};
     ProfScope ps(CAT_TAIL, c.stream, 2.0 * 448 * (double)B * T);
-    AR_TRY(launch_final_k7(d2, coff, m.fin, 2, y, B, T, nullptr, c.stream));
+    if (use_final_umma(m))
+      AR_TRY(launch_final_umma(d2, 0, reinterpret_cast<const __half*>(m.blob + m.fin_umma_off), m.fin, 2, y, B, T, nullptr, c.stream));
+    else
+      AR_TRY(launch_final_k7(d2, coff, m.fin, 2, y, B, T, nullptr, c.stream));
   }
   A.release(d2);
   return AR_OK;

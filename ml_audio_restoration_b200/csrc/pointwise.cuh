@@ -1,5 +1,7 @@
 // Launchers of the CUDA-core kernels (pointwise.cu, lstm.cu).
 #pragma once
+#include <vector>
+
 #include "ar_common.cuh"
 
 namespace ar {
@@ -28,6 +30,10 @@ struct FinalW {          // up to two 32 -> 1 k7 heads
 int launch_stem(const float* x, int B, int T, const StemP& w, const Act& out, int lrelu, cudaStream_t stream);
 int launch_final_k7(const Act& in, const int* in_coff8, const FinalW& w, int nout, float* y, int B, int T, const float* x_lr,
                     cudaStream_t stream);
+// tensor-core version of the k7 heads (final_umma.cu): taps along N, shifted sum in the epilogue
+void pack_final_umma(const FinalW& w, int nheads, std::vector<uint16_t>& out);
+int launch_final_umma(const Act& in, int in_coff8, const __half* w_packed, const FinalW& w, int nheads, float* y, int B, int T,
+                      const float* x_lr, cudaStream_t stream);
 int launch_den_tail(const Act& f, const float* x, float* y, int B, int T, const DenTailP& w, cudaStream_t stream);
 int launch_normalize(float* x, long long n, float target_db, float* scratch, cudaStream_t stream);
 int launch_split(const float* audio, long long n, float* chunks, int first, int count, int chunk_size, int overlap,

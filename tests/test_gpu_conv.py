@@ -55,3 +55,19 @@ def test_engines_agree_bitwise_close():
     a = debug_conv(x, w, b, dilation=2, engine=_lib.ENGINE_SIMT)
     c = debug_conv(x, w, b, dilation=2, engine=_lib.ENGINE_UMMA)
     assert_close(a, c, "simt vs umma", max_abs=1e-2, min_snr=66.0)   # both outputs are fp16-rounded
+
+
+def test_k7_heads_tensor_core_vs_cuda_core(state_dicts):
+    """The two stereo output heads run as a tap-along-N tcgen05 GEMM with a shifted-sum epilogue (final_umma.cu); the
+    CUDA-core cross-check engine keeps the scalar kernel.  Same model, both paths, ragged lengths around the 122-output
+    tile stride."""
+    import torch
+    from oracle.weights import make_input
+    from gpu_util import make_model, assert_close
+    from ml_audio_restoration_b200 import _lib
+    mt = make_model("stereo", state_dicts["stereo"])
+    ms = make_model("stereo", state_dicts["stereo"], engine=_lib.ENGINE_SIMT)
+    for T in (121, 122, 123, 244, 245, 1000):
+        x = make_input(3, T, seed=T).cuda()
+        with torch.no_grad():
+            assert_close(ms(x), mt(x), f"stereo heads T={T}: tensor-core vs CUDA-core engine")
