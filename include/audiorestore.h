@@ -122,6 +122,37 @@ int ar_resample_length(int64_t n, int orig_sr, int new_sr, int64_t* n_out);
 int ar_resample_mono(const float* x, int channels, int64_t n, int orig_sr, int new_sr, float* y, int64_t n_out, void* stream);
 int ar_pcm16_to_float(const int16_t* pcm, int channels, int64_t n, float* y, void* stream);
 
+/* Synthetic 78 rpm degradation generator (simulate_vinyl_artifacts, audio_processing.py:122-226).
+ * The random draws (np.random levels / pop plan, torch.randn noise tensors) stay with the caller; these entry points
+ * are the deterministic arithmetic, rows = channels (or any batch of equal-length rows), all device fp32 [rows][n]:
+ *   ar_butter       : scipy.signal.butter(order, wn, 'low' | 'high') as used at :196,208,220 -- HOST function,
+ *                     b / a receive order+1 float64 coefficients, order <= 4
+ *   ar_vinyl_mix    : y = audio + surface_noise * surface_level (:152-153), then every pop of `pops` (DEVICE array,
+ *                     draw order) added to all rows (:157-188): float64 `amp_signed * exp(-k / tau)` plus, when
+ *                     has_resonance, `0.3 * sin(omega * k / sample_rate) * decay * amp * 0.2`, rounded to float32
+ *   ar_filtfilt     : y = float32(scipy.signal.filtfilt(b, a, row)) of row = scale * x (+ add1) (+ add2) (float32 sums;
+ *                     add1 / add2 may be NULL): odd extension by 3*(order+1) samples, lfilter_zi initial state, forward
+ *                     and backward float64 passes (:197-199, 209-211, 221-223).  n <= 3*(order+1) -> AR_ERR_INVALID
+ *                     (scipy: ValueError).  y may alias x / add1 / add2.
+ *   ar_vinyl_sum    : y = x0 (+ x1) (+ x2), float32 left to right (the `+ crackle`, `+ rumble` of :200,213 when no
+ *                     roll-off filter follows) */
+typedef struct {
+  int64_t loc;           /* first sample                                                    */
+  int32_t length;        /* min(int(sample_rate * decay_time), n - loc)                     */
+  int32_t has_resonance; /* length > 10                                                     */
+  double amp_signed;     /* amp * polarity                                                  */
+  double amp;
+  double tau;            /* sample_rate * decay_time * 0.3                                  */
+  double omega;          /* 2 * pi * resonance_freq                                         */
+} ar_pop_t;
+int ar_butter(int order, double wn, int highpass, double* b, double* a);
+int ar_vinyl_mix(const float* audio, const float* surface_noise, float surface_level, const ar_pop_t* pops, int n_pops,
+                 int sample_rate, float* y, int rows, int64_t n, void* stream);
+int ar_vinyl_sum(const float* x0, const float* x1, const float* x2, float* y, int64_t count, void* stream);
+int ar_filtfilt_workspace_bytes(int rows, int64_t n, int order, size_t* bytes);
+int ar_filtfilt(const float* x, float scale, const float* add1, const float* add2, float* y, int rows, int64_t n,
+                const double* b, const double* a, int order, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Chunk / stitch (vocabulary of chunk_audio, audio_processing.py:229-253; tail zero-pad of
  * trainer.py:656-665).  hop = chunk_size - overlap, overlap <= chunk_size/2.
  *   ar_num_chunks     : chunks needed for n samples

@@ -47,6 +47,13 @@ _SIGNATURES = {
     "ar_resample_length": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64)]),
     "ar_resample_mono": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "ar_pcm16_to_float": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ar_butter": (C.c_int, [C.c_int, C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "ar_vinyl_mix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int64,
+                               C.c_void_p]),
+    "ar_vinyl_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ar_filtfilt_workspace_bytes": (C.c_int, [C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_size_t)]),
+    "ar_filtfilt": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
+                              C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ar_num_chunks": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "ar_split_chunks": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ar_overlap_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -87,6 +94,6 @@ def check(rc: int) -> None:
     if rc == AR_OK:
         return
     msg = (lib().ar_last_error() or b"").decode("utf-8", "replace")
-    if rc == AR_ERR_INVALID and ("overlap" in msg or "empty audio" in msg):
+    if rc == AR_ERR_INVALID and ("overlap" in msg or "empty audio" in msg or "padlen" in msg or "0 < Wn < 1" in msg):
         raise ValueError(msg)
     raise RuntimeError(msg or f"libaudiorestore error {rc}")

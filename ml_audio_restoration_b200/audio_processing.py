@@ -1,8 +1,9 @@
 """Audio helpers on the restoration path (reference: src/utils/audio_processing.py).
 
-Only what inference needs: `normalize_audio` (device kernel, no host syncs), `chunk_audio`
-(the reference's chunk vocabulary), and small WAV load/save helpers so `restore_audio` works
-without `soundfile` (not installed in this image).
+What inference needs -- `normalize_audio` (device kernel, no host syncs), `chunk_audio` (the reference's chunk
+vocabulary), small WAV load/save helpers so `restore_audio` works without `soundfile` (not installed in this image) --
+plus the synthetic degradation generator `simulate_vinyl_artifacts` that produces the path's
+78 rpm-like inputs, with its pops and zero-phase Butterworth filters on the GPU.
 """
 from __future__ import annotations
 
@@ -50,6 +51,142 @@ def chunk_audio(audio: torch.Tensor, chunk_size: int, overlap: int = 0) -> list:
     if n % stride != 0:
         pieces.append(audio[..., -chunk_size:])
     return pieces
+
+
+# ----------------------------------------------------------------------------- synthetic 78 rpm degradation
+POP_DTYPE = np.dtype([("loc", "<i8"), ("length", "<i4"), ("has_resonance", "<i4"), ("amp_signed", "<f8"), ("amp", "<f8"),
+                      ("tau", "<f8"), ("omega", "<f8")])      # == ar_pop_t (include/audiorestore.h)
+
+
+def butter(order: int, wn: float, btype: str = "low"):
+    """(b, a) float64 arrays -- `scipy.signal.butter(order, wn, btype)` for 'low' / 'high' (host design, `ar_butter`)."""
+    if btype not in ("low", "high"):
+        raise ValueError(f"butter: unsupported btype {btype!r}")
+    b = (C.c_double * (order + 1))()
+    a = (C.c_double * (order + 1))()
+    _lib.check(_lib.lib().ar_butter(int(order), float(wn), int(btype == "high"), b, a))
+    return np.array(b[:]), np.array(a[:])
+
+
+def filtfilt(b, a, x: torch.Tensor, scale: float = 1.0, add1: torch.Tensor = None, add2: torch.Tensor = None) -> torch.Tensor:
+    """float32 `scipy.signal.filtfilt(b, a, row)` of every row of `scale * x (+ add1) (+ add2)` ([rows, n] CUDA float32):
+    the zero-phase forward/backward float64 IIR the reference runs per channel on the CPU (audio_processing.py:197-199,
+    209-211, 221-223), as six block-parallel launches (`ar_filtfilt`).  Raises ValueError when n <= 3 * len(b) like scipy."""
+    if not x.is_cuda or x.dim() != 2 or x.dtype != torch.float32:
+        raise RuntimeError("filtfilt: expected a [rows, n] float32 CUDA tensor -- this build has no CPU fallback")
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if b.ndim != 1 or b.shape != a.shape or not 2 <= len(b) <= 5:
+        raise ValueError("filtfilt: b and a must be 1-D, of equal length 2..5 (filter order 1..4)")
+    x = x.contiguous()
+    adds = []
+    for t in (add1, add2):
+        if t is not None:
+            if t.shape != x.shape or t.dtype != torch.float32 or t.device != x.device:
+                raise RuntimeError("filtfilt: addends must match x in shape, dtype and device")
+            t = t.contiguous()
+        adds.append(t)
+    rows, n = x.shape
+    L = _lib.lib()
+    need = C.c_size_t()
+    _lib.check(L.ar_filtfilt_workspace_bytes(rows, n, len(b) - 1, C.byref(need)))
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        ws = torch.empty(need.value, dtype=torch.uint8, device=x.device)
+        _lib.check(L.ar_filtfilt(x.data_ptr(), float(scale), adds[0].data_ptr() if adds[0] is not None else None,
+                                 adds[1].data_ptr() if adds[1] is not None else None, y.data_ptr(), rows, n,
+                                 b.ctypes.data_as(C.POINTER(C.c_double)), a.ctypes.data_as(C.POINTER(C.c_double)),
+                                 len(b) - 1, ws.data_ptr(), need.value, torch.cuda.current_stream(x.device).cuda_stream))
+    return y
+
+
+def plan_vinyl_artifacts(num_samples: int, sample_rate: int, impulse_rate: float = 10.0, impulse_amplitude=(0.1, 0.5),
+                         surface_noise_level=(0.015, 0.03), crackle_level=(0.01, 0.02), add_rumble: bool = True,
+                         add_rolloff: bool = True) -> dict:
+    """Host half of `simulate_vinyl_artifacts`: draws every scalar the reference draws from the global `np.random`
+    generator, in the reference's order (audio_processing.py:152, 158, 161-165, 171, 182, 191, 204, 219), so that
+    `np.random.seed(s)` reproduces the reference's levels, pops and roll-off frequency.  Returns
+    {surface_level, crackle_level, rumble_level | None, rolloff_hz | None, pops: structured array of POP_DTYPE}."""
+    duration = num_samples / sample_rate
+    surface = np.random.uniform(*surface_noise_level)
+    num_pops = np.random.poisson(int(duration * impulse_rate))
+    pops = np.zeros(num_pops, dtype=POP_DTYPE)
+    kept = 0
+    if num_pops > 0:
+        locs = np.random.randint(0, num_samples, num_pops)
+        amps = np.random.uniform(*impulse_amplitude, num_pops)
+        pols = np.random.choice([-1, 1], num_pops, p=[0.45, 0.55])
+        for loc, amp, pol in zip(locs, amps, pols):
+            decay_time = np.random.uniform(0.001, 0.003) * (1 + amp)
+            length = min(int(sample_rate * decay_time), num_samples - loc)
+            if length <= 0:
+                continue
+            resonant = length > 10
+            omega = 2 * np.pi * np.random.uniform(3000, 8000) if resonant else 0.0
+            pops[kept] = (loc, length, int(resonant), amp * pol, amp, sample_rate * decay_time * 0.3, omega)
+            kept += 1
+    crackle = np.random.uniform(*crackle_level)
+    rumble = np.random.uniform(0.005, 0.015) if add_rumble else None
+    rolloff = np.random.uniform(6000, 8000) if add_rolloff else None
+    return {"surface_level": surface, "crackle_level": crackle, "rumble_level": rumble, "rolloff_hz": rolloff,
+            "pops": pops[:kept]}
+
+
+def apply_vinyl_artifacts(audio: torch.Tensor, sample_rate: int, plan: dict, surface: torch.Tensor, crackle: torch.Tensor,
+                          rumble: torch.Tensor = None) -> torch.Tensor:
+    """Device half: `audio` [..., n] float32 CUDA, unit-variance noise tensors of the same shape and a plan ->
+    degraded audio.  Launches: 1 mix (surface noise + pops), 6 per Butterworth filtfilt (crackle high-pass 2.5 kHz,
+    rumble low-pass 100 Hz, roll-off low-pass) with the noise scaling and the `+ crackle + rumble` sums fused into the
+    filters' loads."""
+    if not audio.is_cuda:
+        raise RuntimeError("simulate_vinyl_artifacts: input must be a CUDA tensor -- this build has no CPU fallback")
+    shape = audio.shape
+    n = shape[-1]
+    x = audio.to(torch.float32).reshape(-1, n).contiguous()
+    rows = x.shape[0]
+
+    def flat(t):
+        if t.shape != shape or not t.is_cuda:
+            raise RuntimeError("simulate_vinyl_artifacts: noise tensors must match the audio tensor")
+        return t.to(torch.float32).reshape(rows, n).contiguous()
+
+    L = _lib.lib()
+    pops = np.ascontiguousarray(plan["pops"], dtype=POP_DTYPE)
+    mixed = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        pops_dev = None
+        if len(pops):
+            pops_dev = torch.from_numpy(pops.view(np.uint8).copy()).to(x.device)
+        _lib.check(L.ar_vinyl_mix(x.data_ptr(), flat(surface).data_ptr(), float(plan["surface_level"]),
+                                  pops_dev.data_ptr() if pops_dev is not None else None, len(pops), int(sample_rate),
+                                  mixed.data_ptr(), rows, n, stream))
+        nyquist = sample_rate / 2
+        crk = filtfilt(*butter(4, 2500 / nyquist, "high"), flat(crackle), scale=float(plan["crackle_level"]))
+        rmb = None
+        if plan["rumble_level"] is not None:
+            rmb = filtfilt(*butter(4, 100 / nyquist, "low"), flat(rumble), scale=float(plan["rumble_level"]))
+        if plan["rolloff_hz"] is not None:
+            out = filtfilt(*butter(3, plan["rolloff_hz"] / nyquist, "low"), mixed, add1=crk, add2=rmb)
+        else:
+            out = torch.empty_like(x)
+            _lib.check(L.ar_vinyl_sum(mixed.data_ptr(), crk.data_ptr(), rmb.data_ptr() if rmb is not None else None,
+                                      out.data_ptr(), out.numel(), stream))
+    return out.reshape(shape)
+
+
+def simulate_vinyl_artifacts(audio: torch.Tensor, sample_rate: int, impulse_rate: float = 10.0,
+                             impulse_amplitude=(0.1, 0.5), surface_noise_level=(0.015, 0.03),
+                             crackle_level=(0.01, 0.02), add_rumble: bool = True, add_rolloff: bool = True) -> torch.Tensor:
+    """Shellac-record artifacts for a clean `(channels, samples)` CUDA tensor -- same signature, same defaults and the
+    same use of the two global generators as the reference (audio_processing.py:122-226): three `torch.randn_like`
+    draws on the audio's device (surface, crackle, rumble) and the `np.random` plan of `plan_vinyl_artifacts`."""
+    surface = torch.randn_like(audio)
+    crackle = torch.randn_like(audio)
+    rumble = torch.randn_like(audio) if add_rumble else None
+    plan = plan_vinyl_artifacts(audio.shape[-1], sample_rate, impulse_rate, impulse_amplitude, surface_noise_level,
+                                crackle_level, add_rumble, add_rolloff)
+    return apply_vinyl_artifacts(audio, sample_rate, plan, surface, crackle, rumble)
 
 
 # ----------------------------------------------------------------------------- minimal WAV I/O

@@ -19,6 +19,13 @@ long long resample_length(long long n, int orig_sr, int new_sr);
 int launch_resample_mono(const float* x, int channels, long long n, int orig_sr, int new_sr, float* y, long long n_out,
                          cudaStream_t stream);
 int launch_pcm16(const short* pcm, int channels, long long n, float* y, cudaStream_t stream);
+int butter(int order, double wn, int highpass, double* b, double* a);
+int launch_vinyl_mix(const float* audio, const float* noise, float level, const void* pops, int n_pops, int sample_rate,
+                     float* y, int rows, long long n, cudaStream_t stream);
+int launch_vinyl_sum(const float* x0, const float* x1, const float* x2, float* y, long long count, cudaStream_t stream);
+int filtfilt_workspace_bytes(int rows, long long n, int order, size_t* bytes);
+int launch_filtfilt(const float* x, float scale, const float* add1, const float* add2, float* y, int rows, long long n,
+                    const double* b, const double* a, int order, void* ws, size_t ws_bytes, cudaStream_t stream);
 int model_create(int kind, const ar_tensor_t* tensors, int n, int device, Model** out);
 int model_workspace_bytes(const Model* m, int B, int T, size_t* bytes);
 int model_forward(const Model* m, const float* x, float* y, int B, int T, const float* st_in, float* st_out, void* ws,
@@ -56,6 +63,24 @@ int ar_resample_mono(const float* x, int channels, int64_t n, int orig_sr, int n
 }
 int ar_pcm16_to_float(const int16_t* pcm, int channels, int64_t n, float* y, void* stream) {
   return ar::launch_pcm16(pcm, channels, n, y, reinterpret_cast<cudaStream_t>(stream));
+}
+int ar_butter(int order, double wn, int highpass, double* b, double* a) { return ar::butter(order, wn, highpass, b, a); }
+int ar_vinyl_mix(const float* audio, const float* surface_noise, float surface_level, const ar_pop_t* pops, int n_pops,
+                 int sample_rate, float* y, int rows, int64_t n, void* stream) {
+  static_assert(sizeof(ar_pop_t) == 48, "ar_pop_t layout");
+  return ar::launch_vinyl_mix(audio, surface_noise, surface_level, pops, n_pops, sample_rate, y, rows, n,
+                              reinterpret_cast<cudaStream_t>(stream));
+}
+int ar_vinyl_sum(const float* x0, const float* x1, const float* x2, float* y, int64_t count, void* stream) {
+  return ar::launch_vinyl_sum(x0, x1, x2, y, count, reinterpret_cast<cudaStream_t>(stream));
+}
+int ar_filtfilt_workspace_bytes(int rows, int64_t n, int order, size_t* bytes) {
+  return ar::filtfilt_workspace_bytes(rows, n, order, bytes);
+}
+int ar_filtfilt(const float* x, float scale, const float* add1, const float* add2, float* y, int rows, int64_t n,
+                const double* b, const double* a, int order, void* workspace, size_t workspace_bytes, void* stream) {
+  return ar::launch_filtfilt(x, scale, add1, add2, y, rows, n, b, a, order, workspace, workspace_bytes,
+                             reinterpret_cast<cudaStream_t>(stream));
 }
 int ar_debug_chain_trace(long long* dev_buf) { return ar::set_chain_trace(dev_buf); }
 

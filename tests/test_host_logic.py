@@ -6,6 +6,7 @@ import re
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 import torch
 
@@ -198,3 +199,54 @@ def test_bench_algorithmic_constants():
     assert bench.CHAIN_GFLOP_PER_AUDIO_S == pytest.approx(2e-9 * (148504 * 22050 + 42656 * 22050 + 490144 * 44100), rel=1e-4)
     # 354.2 MB per audio-second layer by layer; the fused stereo chains (enc k3 -> k1 [-> xproj]) remove 101.6 MB of it
     assert bench.conv_algorithmic_bytes_per_audio_s() == pytest.approx(252.6e6, rel=1e-3)
+
+
+def test_butter_design_matches_scipy():
+    """`ar_butter` (host function of the C-ABI) against scipy.signal.butter at the three designs the reference uses
+    (audio_processing.py:196, 208, 220) and a few others."""
+    from scipy import signal
+    from ml_audio_restoration_b200 import audio_processing as ap
+    for order, wn, btype in [(4, 2500 / 11025, "high"), (4, 100 / 11025, "low"), (3, 6000 / 11025, "low"),
+                             (3, 8000 / 11025, "low"), (4, 2500 / 22050, "high"), (1, 0.3, "high"), (2, 0.5, "low")]:
+        b, a = ap.butter(order, wn, btype)
+        bs, as_ = signal.butter(order, wn, btype=btype)
+        np.testing.assert_allclose(b, bs, rtol=1e-12, atol=0)
+        np.testing.assert_allclose(a, as_, rtol=1e-12, atol=0)
+    with pytest.raises(ValueError):
+        ap.butter(4, 1.0, "low")           # scipy: "Digital filter critical frequencies must be 0 < Wn < 1"
+    with pytest.raises(ValueError):
+        ap.butter(4, 0.2, "band")
+
+
+def test_vinyl_plan_consumes_numpy_generator_like_the_oracle():
+    """The host half of simulate_vinyl_artifacts draws from np.random in the reference's order: with the same seed it
+    yields the plan the (reference-pinned) oracle draws, and leaves the generator in the same state."""
+    from oracle import degrade
+    from ml_audio_restoration_b200 import audio_processing as ap
+    for seed, n, sr, kw in [(3, 500, 22050, {"impulse_rate": 300.0}), (4, 44100, 22050, {}),
+                            (5, 3000, 44100, {"add_rumble": False}), (6, 2205, 22050, {"add_rolloff": False}),
+                            (7, 16, 22050, {"impulse_rate": 5000.0})]:
+        np.random.seed(seed)
+        mine = ap.plan_vinyl_artifacts(n, sr, **kw)
+        after_mine = np.random.uniform()
+        np.random.seed(seed)
+        ref = degrade.draw_plan(n, sr, **kw)
+        assert after_mine == np.random.uniform()
+        for key in ("surface_level", "crackle_level", "rumble_level", "rolloff_hz"):
+            assert mine[key] == ref[key]
+        assert len(mine["pops"]) == len(ref["pops"])
+        for p, q in zip(mine["pops"], ref["pops"]):
+            assert (p["loc"], p["length"], bool(p["has_resonance"])) == (q["loc"], q["length"], q["resonance_freq"] is not None)
+            assert p["amp_signed"] == q["amp"] * q["polarity"] and p["amp"] == q["amp"]
+            assert p["tau"] == sr * q["decay_time"] * 0.3
+            if q["resonance_freq"] is not None:
+                assert p["omega"] == 2 * np.pi * q["resonance_freq"]
+    assert ap.POP_DTYPE.itemsize == 48
+
+
+def test_vinyl_artifacts_fail_loudly_on_cpu_tensors():
+    from ml_audio_restoration_b200 import audio_processing as ap
+    with pytest.raises(RuntimeError):
+        ap.simulate_vinyl_artifacts(torch.zeros(1, 100), 22050)
+    with pytest.raises(RuntimeError):
+        ap.filtfilt([1.0, 0.0], [1.0, 0.0], torch.zeros(1, 100))
