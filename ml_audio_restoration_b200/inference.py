@@ -15,6 +15,7 @@ Two ways through the same three native models:
 from __future__ import annotations
 
 import argparse
+import collections
 import ctypes as C
 import os
 import math
@@ -71,6 +72,7 @@ class RestorationPipeline:
         self._ws = None
         self._streams = None
         self._host_out = None
+        self._io_streams = None
         self._scratch = torch.empty(_lib.NORMALIZE_SCRATCH_BYTES, dtype=torch.uint8, device=self.device)
 
     @classmethod
@@ -207,6 +209,74 @@ class RestorationPipeline:
                 torch.cuda.current_stream(self.device).synchronize()
                 return host
         return y
+
+    def restore_stream(self, audios, depth: int = 2, **restore_kwargs):
+        """Serving loop over an iterable of mono host tensors (one per file): yields the restored stereo `[2, rate*N]`
+        of each, in order, as a view of a pinned host buffer that stays valid until the next item is requested.
+
+        The copies are double-buffered on their own streams: while file i is in the chain, file i+1 is
+        uploaded from pinned memory and file i-1 is downloaded, so `inference.py:47`'s H2D and `:102`'s D2H leave the
+        critical path.  Inputs that are not pinned are staged through `pin_memory()` first.  `restore_kwargs` are those
+        of `restore` (mode, chunk_size, overlap, batch_chunks, normalize, streams)."""
+        if depth < 2:
+            raise ValueError("restore_stream: depth must be >= 2")
+        for key in ("return_device", "reuse_output", "chunk_range"):
+            if key in restore_kwargs:
+                raise ValueError(f"restore_stream does not take {key}")
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        if self._io_streams is None:
+            self._io_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        s_in, s_out = self._io_streams
+        dev_in, in_free, host_out = [None] * depth, [None] * depth, [None] * depth
+        pending = collections.deque()               # (device result kept alive, host view, D2H-done event)
+        for i, audio in enumerate(audios):
+            k = i % depth
+            if audio.dim() == 1:
+                audio = audio.unsqueeze(0)
+            if audio.dim() != 2 or audio.shape[0] != 1:
+                raise RuntimeError(f"expected mono audio [1, N], got {tuple(audio.shape)}")
+            n = audio.shape[1]
+            if n == 0:
+                raise ValueError("empty audio")
+            if audio.is_cuda:
+                a = audio
+            else:
+                src = audio.to(torch.float32)
+                if not src.is_pinned():
+                    src = src.pin_memory()
+                if dev_in[k] is None or dev_in[k].numel() < n:
+                    dev_in[k] = torch.empty(n, dtype=torch.float32, device=dev)
+                    s_in.wait_stream(main)          # a fresh block may still be read by kernels queued on `main`
+                elif in_free[k] is not None:
+                    s_in.wait_event(in_free[k])     # the chain call that read this slot `depth` files ago is done
+                a = dev_in[k][:n].view(1, n)
+                with torch.cuda.stream(s_in):
+                    a.copy_(src, non_blocking=True)
+                    uploaded = torch.cuda.Event()
+                    uploaded.record(s_in)
+                main.wait_event(uploaded)
+            y = self.restore(a, return_device=True, **restore_kwargs)
+            computed = torch.cuda.Event()
+            computed.record(main)
+            in_free[k] = computed
+            if host_out[k] is None or host_out[k].numel() < y.numel():
+                host_out[k] = torch.empty(y.numel(), dtype=torch.float32).pin_memory()
+            host = host_out[k][:y.numel()].view(y.shape)
+            s_out.wait_event(computed)
+            with torch.cuda.stream(s_out):
+                host.copy_(y, non_blocking=True)
+                downloaded = torch.cuda.Event()
+                downloaded.record(s_out)
+            pending.append((y, host, downloaded, src if not audio.is_cuda else None))
+            if len(pending) >= depth:
+                _, h, ev, _ = pending.popleft()
+                ev.synchronize()
+                yield h
+        while pending:
+            _, h, ev, _ = pending.popleft()
+            ev.synchronize()
+            yield h
 
     def _restore_chunked(self, a, N, chunk_size, overlap, batch_chunks, chunk_range, streams=1):
         L = _lib.lib()

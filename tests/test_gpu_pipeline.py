@@ -187,3 +187,24 @@ def test_lstm_kernels_agree_at_full_length(state_dicts):
         y_big = m(xb)                       # tensor-core LSTM kernel
     assert torch.equal(y_big[:8], y_big[8:16]), "identical sequences in one batch must give identical outputs"
     close(y_small, y_big[:8], "stereo T=88200: tensor-core vs CUDA-core recurrence", max_abs=1e-3, min_snr=60.0)
+
+
+def test_restore_stream_matches_per_file_restore(pipe):
+    """The double-buffered serving loop (uploads / downloads of neighbouring files overlap the chain on their own
+    streams) returns, file by file, exactly what a synchronous `restore` of each file returns -- ragged lengths, pinned
+    and pageable inputs, buffers reused across files."""
+    lengths = [30000, 9000, 47111, 2048, 30000, 64]
+    files = [make_input(1, n, 40 + i, scale=0.2)[0] for i, n in enumerate(lengths)]
+    files[2] = files[2].pin_memory()
+    kw = dict(mode="chunked", chunk_size=4096, overlap=256, batch_chunks=3)
+    want = [pipe.restore(f, **kw) for f in files]
+    got = []
+    for out in pipe.restore_stream(iter(files), **kw):
+        assert not out.is_cuda and out.is_pinned()
+        got.append(out.clone())             # a yielded view is only valid until the next item is requested
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g.shape == w.shape and torch.equal(g, w)
+    assert list(pipe.restore_stream(iter([]))) == []
+    with pytest.raises(ValueError):
+        list(pipe.restore_stream(iter(files), return_device=True))
