@@ -548,6 +548,166 @@ lstm_mma4_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, cons
   }
 }
 
+// ---------------------------------------------------------------------------- warp-specialised variant of the above
+// lstm_mma4_kernel's 8 warps also stage the next block's pre-activations (cp.async) and flush the previous block's hidden
+// states (one warp per step: two LDS.128, four packs, 64-bit address math, one STG): ~40 extra instructions in front of
+// that warp's MMAs, and since every step ends in a CTA barrier ALL warps wait for the one that flushed.  Here two extra
+// warps do nothing but that data movement; the eight recurrence warps run the bare step (5 LDS, 8 HMMA, the gate
+// functions, 2 STS) and meet at a named barrier of their own 256 threads.  The two groups meet once per 8-step block
+// (named barrier 1, all 320 threads): by then the movers have long finished (16 cp.async + 4 flush items per thread per
+// block).  The ping-pong index of the h exchange buffer is the step's parity inside the block -- a compile-time
+// constant in the unrolled loop -- and full blocks run without the `step < T` tests.
+constexpr int L4W_THREADS = L4_THREADS + 64;
+
+__global__ void __launch_bounds__(L4W_THREADS, 2)
+lstm_mma4w_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, const float* __restrict__ whh,
+                  __half* __restrict__ hout, long long h_bs, int h_Tp, int B, int T,
+                  const float* __restrict__ state_in, float* __restrict__ state_out) {
+  extern __shared__ __align__(16) float lm_smem[];
+  __half* const xs = reinterpret_cast<__half*>(lm_smem);       // [2][8 steps][4 seq][264] fp16 staged gate pre-activations
+  float* const hstage = lm_smem + L4_XBUF;                     // [2][8 steps][4 seq][68] fp32
+  __half* const hbuf = reinterpret_cast<__half*>(hstage + 2 * LSTM_BLK * L4_HSTEP);   // [2][4 seq][80] fp16
+  const int tid = threadIdx.x;
+  const int seq0 = blockIdx.x * L4_SEQ;
+  const int nblk = (T + LSTM_BLK - 1) / LSTM_BLK;
+  const int nfull = T / LSTM_BLK;
+
+  if (tid >= L4_THREADS) {
+    // ------------------------------------------------------------------ movers (warps 8, 9)
+    const int ht = tid - L4_THREADS;
+    const uint32_t xs_u32 = (uint32_t)__cvta_generic_to_shared(xs);
+    auto stage_block = [&](int blk) {               // [4 seq][32 chunks][8 steps] 16-byte pieces, 16 per thread
+      const int t0 = blk * LSTM_BLK;
+      const uint32_t dst0 = xs_u32 + (uint32_t)((blk & 1) * L4_XBUF * 2);
+#pragma unroll 4
+      for (int m = 0; m < 16; ++m) {
+        const int i = ht + 64 * m;
+        const int sq = i >> 8, piece = i & 255;
+        const int ch = piece >> 3, k = piece & 7;
+        const int b = min(seq0 + sq, B - 1);
+        cp_async16(dst0 + (uint32_t)((k * L4_XSTEP + sq * LM_XS + ch * 8) * 2), xp + act_off_tb(xp_bs, 32, b, ch, t0 + k));
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto flush_block = [&](int blk) {               // [4 seq][8 chunks][8 steps] 16-byte items, 4 per thread
+      const float* hst = hstage + (blk & 1) * (LSTM_BLK * L4_HSTEP);
+      const int t0 = blk * LSTM_BLK;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int i = ht + 64 * m;
+        const int s = i >> 6, ch = (i >> 3) & 7, kk = i & 7;
+        const int b = seq0 + s;
+        if (b < B && t0 + kk < T) {
+          const float* src = &hst[kk * L4_HSTEP + s * LM_HST + 8 * ch];
+          const float4 v0 = *reinterpret_cast<const float4*>(src);
+          const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
+          const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+          *reinterpret_cast<uint4*>(hout + act_off(h_bs, h_Tp, b, ch, t0 + kk)) = pack_half8(v);
+        }
+      }
+    };
+    stage_block(0);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(L4W_THREADS) : "memory");
+    for (int blk = 0; blk < nblk; ++blk) {
+      if (blk + 1 < nblk) stage_block(blk + 1);
+      if (blk > 0) flush_block(blk - 1);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(L4W_THREADS) : "memory");     // block blk is done, block blk + 1 has landed
+    }
+    flush_block(nblk - 1);
+    return;
+  }
+
+  // -------------------------------------------------------------------- recurrence (warps 0..7), as in lstm_mma4_kernel
+  const int warp = tid >> 5, lane = tid & 31;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int unit = warp * 8 + gid;
+  const int seq = tig;
+  const int bq = min(seq0 + seq, B - 1);
+  uint32_t wfrag[2][4][4];
+  {
+    auto w2 = [&](int row, int k) {
+      const __half2 h = __floats2half2_rn(whh[row * LSTM_H + k], whh[row * LSTM_H + k + 1]);
+      return *reinterpret_cast<const uint32_t*>(&h);
+    };
+#pragma unroll
+    for (int tl = 0; tl < 2; ++tl) {
+      const int row_lo = (2 * tl) * LSTM_H + unit, row_hi = (2 * tl + 1) * LSTM_H + unit;
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt) {
+        wfrag[tl][kt][0] = w2(row_lo, kt * 16 + 2 * tig);
+        wfrag[tl][kt][1] = w2(row_hi, kt * 16 + 2 * tig);
+        wfrag[tl][kt][2] = w2(row_lo, kt * 16 + 2 * tig + 8);
+        wfrag[tl][kt][3] = w2(row_hi, kt * 16 + 2 * tig + 8);
+      }
+    }
+  }
+  float c = 0.f, hl = 0.f;
+  if (state_in != nullptr) {
+    hl = state_in[(long long)bq * 2 * LSTM_H + unit];
+    c = state_in[(long long)bq * 2 * LSTM_H + LSTM_H + unit];
+  }
+  const int upos = (unit & ~15) + ((((unit & 7) >> 1) * 2 + ((unit >> 3) & 1)) * 2) + (unit & 1);   // see lstm_mma_kernel
+  hbuf[seq * LM_HS + upos] = __float2half_rn(hl);
+  const uint2* const hb_rd = reinterpret_cast<const uint2*>(hbuf + (gid >> 1) * LM_HS) + tig;   // B column gid = sequence gid/2
+  __half* const hb_wr = hbuf + seq * LM_HS + upos;
+  const int xoff = seq * LM_XS + unit * 4;          // [unit][i,f,g,o] of this thread's cell inside a staged step
+  const int hoff = seq * LM_HST + unit;
+  asm volatile("bar.sync 1, %0;" ::"n"(L4W_THREADS) : "memory");
+
+  // one step; `cur` (which half of hbuf holds h_{t-1}) is the step's parity inside the block: static when unrolled
+  auto step = [&](const __half* xb, float* hst, int k) {
+    const int cur = k & 1;
+    const uint2 q = *reinterpret_cast<const uint2*>(xb + k * L4_XSTEP + xoff);
+    float acc[2][4];
+#pragma unroll
+    for (int tl = 0; tl < 2; ++tl)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[tl][i] = 0.f;
+    const uint2* hb = hb_rd + cur * (L4_SEQ * LM_HS / 4);
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+      const uint2 bf = hb[kt * 4];
+      mma_f16_16x8x16(acc[0], wfrag[0][kt], bf.x, bf.y);
+      mma_f16_16x8x16(acc[1], wfrag[1][kt], bf.x, bf.y);
+    }
+    const float2 x_if = __half22float2(*reinterpret_cast<const __half2*>(&q.x));
+    const float2 x_go = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+    lstm_cell(acc[0][0] + x_if.x, acc[0][2] + x_if.y, acc[1][0] + x_go.x, acc[1][2] + x_go.y, c, hl);
+    hb_wr[(cur ^ 1) * (L4_SEQ * LM_HS)] = __float2half_rn(hl);
+    hst[k * L4_HSTEP + hoff] = hl;
+  };
+  for (int blk = 0; blk < nfull; ++blk) {
+    const __half* xb = xs + (blk & 1) * L4_XBUF;
+    float* hst = hstage + (blk & 1) * (LSTM_BLK * L4_HSTEP);
+#pragma unroll
+    for (int k = 0; k < LSTM_BLK; ++k) {
+      step(xb, hst, k);
+      if (k < LSTM_BLK - 1) asm volatile("bar.sync 2, %0;" ::"n"(L4_THREADS) : "memory");
+      else asm volatile("bar.sync 1, %0;" ::"n"(L4W_THREADS) : "memory");
+    }
+  }
+  if (nfull < nblk) {                                // ragged last block
+    const __half* xb = xs + (nfull & 1) * L4_XBUF;
+    float* hst = hstage + (nfull & 1) * (LSTM_BLK * L4_HSTEP);
+    const int nst = T - nfull * LSTM_BLK;
+#pragma unroll
+    for (int k = 0; k < LSTM_BLK - 1; ++k) {
+      if (k < nst) {   // uniform
+        step(xb, hst, k);
+        asm volatile("bar.sync 2, %0;" ::"n"(L4_THREADS) : "memory");
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(L4W_THREADS) : "memory");
+  }
+  if (state_out != nullptr && seq0 + seq < B) {
+    state_out[(long long)(seq0 + seq) * 2 * LSTM_H + unit] = hl;
+    state_out[(long long)(seq0 + seq) * 2 * LSTM_H + LSTM_H + unit] = c;
+  }
+}
+
+
 int launch_lstm(const Act& xp, const float* whh, const Act& h_out, int B, int T, const float* state_in, float* state_out,
                 cudaStream_t stream) {
   AR_CHECK(T >= 1 && B >= 1, AR_ERR_INVALID, "lstm: empty input");
@@ -571,22 +731,30 @@ int launch_lstm(const Act& xp, const float* whh, const Act& h_out, int B, int T,
     AR_CUDA_OK(cudaGetLastError());
     return AR_OK;
   }
-  if (forced == 44 || (forced == 0 && B > 2 * sm_count())) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      AR_CUDA_OK(cudaFuncSetAttribute(lstm_mma4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L4_SMEM));
+  if (forced == 44 || forced == 45 || (forced == 0 && B > 2 * sm_count())) {
+    // default: the warp-specialised kernel (two mover warps + eight recurrence warps); AR_LSTM_S=44 keeps all data
+    // movement in the recurrence warps (lstm_mma4_kernel, A/B measurements)
+    const bool movers = forced != 44;
+    const void* fn = movers ? (const void*)lstm_mma4w_kernel : (const void*)lstm_mma4_kernel;
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[movers]) {
+      AR_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, L4_SMEM));
       // two (three) CTAs of 53 KB must fit: ask for the largest shared-memory carve-out, the driver's default
       // heuristic sizes it for ONE CTA and the second recurrence of the SM would run after the first instead of under it
-      AR_CUDA_OK(cudaFuncSetAttribute(lstm_mma4_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      AR_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       if (getenv("AR_DEBUG_OCCUPANCY")) {
         int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lstm_mma4_kernel, L4_THREADS, L4_SMEM);
-        fprintf(stderr, "lstm_mma4_kernel: %d CTAs per SM\n", nb);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, movers ? L4W_THREADS : L4_THREADS, L4_SMEM);
+        fprintf(stderr, "lstm_mma4%s_kernel: %d CTAs per SM\n", movers ? "w" : "", nb);
       }
-      attr_set = true;
+      attr_set[movers] = true;
     }
-    lstm_mma4_kernel<<<(B + L4_SEQ - 1) / L4_SEQ, L4_THREADS, L4_SMEM, stream>>>(xp.h(), xp.bs, xp.Tp, whh, h_out.h(), h_out.bs, h_out.Tp,
-                                                                          B, T, state_in, state_out);
+    if (movers)
+      lstm_mma4w_kernel<<<(B + L4_SEQ - 1) / L4_SEQ, L4W_THREADS, L4_SMEM, stream>>>(xp.h(), xp.bs, xp.Tp, whh, h_out.h(), h_out.bs,
+                                                                              h_out.Tp, B, T, state_in, state_out);
+    else
+      lstm_mma4_kernel<<<(B + L4_SEQ - 1) / L4_SEQ, L4_THREADS, L4_SMEM, stream>>>(xp.h(), xp.bs, xp.Tp, whh, h_out.h(), h_out.bs,
+                                                                            h_out.Tp, B, T, state_in, state_out);
     AR_CUDA_OK(cudaGetLastError());
     return AR_OK;
   }
