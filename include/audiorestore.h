@@ -66,6 +66,13 @@ int ar_set_conv_engine(int engine);
  * compute the same fp16-rounded intermediates. */
 int ar_set_fusion(int on);
 
+/* Enable / disable (default) the tap-grouped form of the k7 decoder layers (stereo_separator.py:72-79: 128 -> 64 and
+ * 64 -> 32) for subsequently created models: two resp. four taps side by side along the GEMM's N, recombined by a shifted
+ * sum in the epilogue -- 32 resp. 8 tensor-core instructions per tile pair instead of 56 resp. 28.  Measured slower on
+ * power-capped B200s (profiles/README_r01.md), hence off by default; both settings compute the same convolution (fp32
+ * sums in a different order) and the parity tests exercise both. */
+int ar_set_tap_groups(int on);
+
 /* Shared memory one conv CTA may use, in KB (64..227, default 227 = the whole SM).  AR_CORESIDENT_SMEM_KB leaves room
  * for one CTA of the LSTM recurrence on every SM: when chunk batches are pipelined on two streams the latency-bound
  * scan of one batch (stereo_separator.py:106) then runs UNDER the convs of the other instead of after them.

@@ -31,6 +31,7 @@ _SIGNATURES = {
     "ar_version": (C.c_int, []),
     "ar_set_conv_engine": (C.c_int, [C.c_int]),
     "ar_set_fusion": (C.c_int, [C.c_int]),
+    "ar_set_tap_groups": (C.c_int, [C.c_int]),
     "ar_set_conv_smem_kb": (C.c_int, [C.c_int]),
     "ar_model_create": (C.c_int, [C.c_int, C.POINTER(ArTensor), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "ar_model_destroy": (None, [C.c_void_p]),

@@ -13,6 +13,7 @@ struct Model;
 const char* last_error();
 int set_engine(int e);
 int set_fusion(int on);
+int set_tap_groups(int on);
 int set_chain_trace(long long* dev_buf);
 int set_conv_smem_kb(int kb);
 long long resample_length(long long n, int orig_sr, int new_sr);
@@ -52,6 +53,7 @@ const char* ar_last_error(void) { return ar::last_error(); }
 int ar_version(void) { return 100; }
 int ar_set_conv_engine(int engine) { return ar::set_engine(engine); }
 int ar_set_fusion(int on) { return ar::set_fusion(on); }
+int ar_set_tap_groups(int on) { return ar::set_tap_groups(on); }
 int ar_set_conv_smem_kb(int kb) { return ar::set_conv_smem_kb(kb); }
 int ar_resample_length(int64_t n, int orig_sr, int new_sr, int64_t* n_out) {
   if (!n_out || n < 0 || orig_sr < 1 || new_sr < 1) { ar::set_error("resample_length: bad argument"); return AR_ERR_INVALID; }

@@ -128,8 +128,20 @@ struct ConvParams {
   int res_Tp, res_coff8;
   int lrelu;             // LeakyReLU(0.2) after bias
   int B;
-  int tiles_per_item;    // ceil(Tin / TILE_M)
+  int tiles_per_item;    // ceil(Tin / tile stride): TILE_M, or TILE_M - (tg-1)*dil/tg for a tap-grouped layer
+  // Tap-grouped layers (2-CTA engine only; 0 / 1 = off).  A k-tap conv with few output channels is bound by the fixed
+  // cost of a tcgen05.mma (~70 cycles for every N <= 128), i.e. by the NUMBER of MMAs, k * Cin/16 per tile.  With
+  // tg taps side by side along N -- column block i of group g holds tap g*tg + i -- the layer looks to the producer
+  // and the MMA warp like a conv with `taps` = ceil(k/tg) taps, dilation `dil` = tg*d and N = tg*Cout columns, and
+  // needs tg times fewer MMAs.  Accumulator row t, block i then holds  sum_g x[t + g*tg*d - pad] W_{g*tg+i},  so the
+  // output is the SHIFTED sum  y[u] = sum_i D[u + i*d][block i]  -- done in the epilogue with warp shuffles (rows are
+  // TMEM lanes) plus a small shared-memory exchange at the warp boundaries; a 128-row tile yields
+  // TILE_M - (tg-1)*d outputs (the tile stride).
+  int tg;
 };
+__host__ __device__ inline int conv_tile_stride(const ConvParams& p) {
+  return p.tg > 1 ? TILE_M - (p.tg - 1) * (p.dil / p.tg) : TILE_M;
+}
 
 // Fused epilogue for 8 consecutive GEMM columns [n0, n0+8) of GEMM row t (batch item b), shared by the
 // CUDA-core cross-check engine.  Must be called by all 32 lanes of a warp whose lanes hold consecutive rows

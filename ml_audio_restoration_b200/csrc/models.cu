@@ -41,6 +41,24 @@ static int fusion_default() {
   return g_fuse;
 }
 
+// Tap-grouped k7 decoder layers (ConvParams::tg) for subsequently created models.  OFF by default (ar_set_tap_groups(1) or
+// AR_TAPGROUP=1 turns them on): measured on B200 the grouped 128 -> 64 layer needs 32 instead of 56 MMAs per tile pair but
+// runs 11.8 vs 11.0 ms per 1184-chunk step, the grouped 64 -> 32 layer 6.5 vs 5.3 ms -- the chip is power-limited (the
+// denser instruction stream runs at a lower SM clock and the zero eighth tap adds 14 % FLOPs), and with 8 MMAs per tile the
+// per-tile barrier round trips of the MMA warp dominate (tensor pipe 24 % active, epilogue waiting on the accumulator).
+static int g_tap_groups = -1;
+int set_tap_groups(int on) {
+  g_tap_groups = on ? 1 : 0;
+  return AR_OK;
+}
+static bool want_tap_groups() {
+  if (g_tap_groups < 0) {
+    const char* e = getenv("AR_TAPGROUP");
+    g_tap_groups = e ? (atoi(e) != 0) : 0;
+  }
+  return g_tap_groups != 0;
+}
+
 // ============================================================================ weight folding / packing
 static uint16_t half_bits_host(float x) {  // fp32 -> fp16, round to nearest even, clamped to the finite range
   if (x > 65504.f) x = 65504.f;
@@ -83,6 +101,7 @@ struct ConvLayer {  // device-resident packed layer
   double macs_per_row;  // algorithmic MACs of the reference op per input time step (structural zeros excluded)
   int n_slices;         // column slices (each slice's weights stay resident in one CTA's shared memory)
   int cta2;             // slices come in (2i, 2i+1) pairs: the two halves of a 2-CTA pair-slice
+  int tg = 1;           // taps side by side along N (ConvParams::tg); N, taps, dil describe the grouped GEMM
 };
 
 // Resident-weight budget per CTA (fp16 weights): leaves >= ~96 KB of the 227 KB for the activation ring.
@@ -181,6 +200,16 @@ static bool make_conv(const Table& t, Blob& blob, const std::string& conv, const
   return true;
 }
 
+// The tap-grouped form of a conv GEMM (ConvParams::tg): tap j = g*tg + i moves to column block i of group g.
+static Gemm tap_grouped(const Gemm& g, int tg) {
+  Gemm r;
+  r.init(g.Cin, g.N * tg, (g.taps + tg - 1) / tg, g.dil * tg, g.pad_left);
+  for (int j = 0; j < g.taps; ++j)
+    for (int c = 0; c < g.Cin; ++c)
+      for (int n = 0; n < g.N; ++n) r.at(j / tg, c, (j % tg) * g.N + n) = g.G[((size_t)j * g.Cin + c) * g.N + n];
+  for (int n = 0; n < g.N; ++n) r.bias[n] = g.bias[n];   // the epilogue adds the bias of block 0's columns only
+  return r;
+}
 // ============================================================================ model objects
 
 struct Model {
@@ -355,6 +384,21 @@ static bool build_stereo(const Table& t, Blob& blob, Model& m) {
     const std::string p = sides[s], tag = s ? "R" : "L";
     if (!make_conv(t, blob, p + ".3", p + ".4", 128, 64, 7, 1, m.conv["dec1" + tag])) return false;
     if (!make_conv(t, blob, p + ".6", p + ".7", 64, 32, 7, 1, m.conv["dec2" + tag])) return false;
+    // the same two layers tap-grouped for the 2-CTA engine: 128 -> 64 k7 as 4 groups of 2 taps (N = 128, 32 MMAs per
+    // tile pair instead of 56), 64 -> 32 k7 as 2 groups of 4 taps (N = 128, 8 MMAs instead of 28)
+    if (want_tap_groups() && want_cta2(128)) {
+      const int cin[2] = {128, 64}, cout[2] = {64, 32}, tgs[2] = {2, 4};
+      const char* idx[2][2] = {{".3", ".4"}, {".6", ".7"}};
+      for (int l = 0; l < 2; ++l) {
+        Gemm g;
+        g.init(cin[l], cout[l], 7, 1, 3);
+        if (!add_conv(t, p + idx[l][0], p + idx[l][1], cin[l], cout[l], 7, g)) return false;
+        Gemm gt = tap_grouped(g, tgs[l]);
+        ConvLayer L = blob.push_gemm(gt);
+        L.tg = tgs[l];
+        m.conv[std::string(l ? "dec2" : "dec1") + tag + ".tg"] = L;
+      }
+    }
     const float* WF = t.get(p + ".9.weight", {1, 32, 7});
     const float* BF = t.get(p + ".9.bias", {1});
     if (!WF || !BF) return false;
@@ -477,9 +521,14 @@ static int run_conv(Ctx& c, const std::string& name, const Act& in, const Act& o
   if (c.ar.dry) return AR_OK;
   auto it = c.m->conv.find(name);
   AR_CHECK(it != c.m->conv.end(), AR_ERR_INVALID, "internal: unknown conv layer " + name);
+  if (c.m->engine == AR_ENGINE_UMMA && o.mode == MODE_SAME && !o.pool && !o.res && !o.out_tblock) {
+    auto tw = c.m->conv.find(name + ".tg");          // tap-grouped twin of this layer (2-CTA engine only)
+    if (tw != c.m->conv.end() && tw->second.cta2) it = tw;
+  }
   const ConvLayer& L = it->second;
   ConvParams p;
   std::memset(&p, 0, sizeof(p));
+  p.tg = L.tg;
   p.in = in.h(); p.in_bs = in.bs; p.in_Tp = in.Tp; p.in_coff8 = o.in_coff8;
   p.Tin = in.T; p.Cin = L.Cin; p.taps = L.taps; p.dil = L.dil; p.pad_left = L.pad_left;
   p.w = reinterpret_cast<const __half*>(c.m->blob + L.w_off); p.bias = c.m->blob + L.b_off; p.N = L.N; p.n_slices = L.n_slices; p.cta2 = L.cta2;
@@ -491,7 +540,8 @@ static int run_conv(Ctx& c, const std::string& name, const Act& in, const Act& o
   p.lrelu = o.lrelu;
   p.out_tblock = o.out_tblock;
   p.B = c.B;
-  p.tiles_per_item = (in.T + TILE_M - 1) / TILE_M;
+  const int stride = conv_tile_stride(p);
+  p.tiles_per_item = (in.T + stride - 1) / stride;
   ProfScope ps(CAT_CONV, c.stream, 2.0 * L.macs_per_row * (double)c.B * (double)in.T);
   if (c.m->engine == AR_ENGINE_SIMT) return launch_conv_simt(p, c.stream);
   return p.cta2 ? launch_conv_umma2(p, c.stream) : launch_conv_umma(p, c.stream);
@@ -811,6 +861,14 @@ int debug_conv(const float* x, const float* w_host, const float* bias_host, floa
   }
   Blob blob;
   ConvLayer L = blob.push_gemm(g);
+  // the k7 decoder shapes go through the tap-grouped path of the 2-CTA engine when it is enabled (ar_set_tap_groups)
+  int tg = 1;
+  if (engine == AR_ENGINE_UMMA && want_tap_groups() && want_cta2(128) && k == 7 && dil == 1 && (Cout == 64 || Cout == 32)) {
+    tg = Cout == 64 ? 2 : 4;
+    Gemm gt = tap_grouped(g, tg);
+    L = blob.push_gemm(gt);
+    L.tg = tg;
+  }
   Arena A;
   A.dry = true;
   Act in = A.act(B, Cin, T), out = A.act(B, Cout, T);
@@ -825,10 +883,11 @@ int debug_conv(const float* x, const float* w_host, const float* bias_host, floa
   if (rc == AR_OK) {
     ConvParams p;
     std::memset(&p, 0, sizeof(p));
-    p.in = in.h(); p.in_bs = in.bs; p.in_Tp = in.Tp; p.Tin = T; p.Cin = Cin; p.taps = k; p.dil = dil; p.pad_left = g.pad_left;
-    p.w = reinterpret_cast<const __half*>(dblob + L.w_off); p.bias = dblob + L.b_off; p.N = Cout; p.n_slices = L.n_slices; p.cta2 = L.cta2; p.mode = MODE_SAME;
+    p.tg = L.tg;
+    p.in = in.h(); p.in_bs = in.bs; p.in_Tp = in.Tp; p.Tin = T; p.Cin = Cin; p.taps = L.taps; p.dil = L.dil; p.pad_left = g.pad_left;
+    p.w = reinterpret_cast<const __half*>(dblob + L.w_off); p.bias = dblob + L.b_off; p.N = L.N; p.n_slices = L.n_slices; p.cta2 = L.cta2; p.mode = MODE_SAME;
     p.out = out.h(); p.out_bs = out.bs; p.out_Tp = out.Tp; p.Tout = T; p.lrelu = lrelu;
-    p.B = B; p.tiles_per_item = (T + TILE_M - 1) / TILE_M;
+    p.B = B; p.tiles_per_item = (T + conv_tile_stride(p) - 1) / conv_tile_stride(p);
     rc = engine == AR_ENGINE_SIMT ? launch_conv_simt(p, stream) : (p.cta2 ? launch_conv_umma2(p, stream) : launch_conv_umma(p, stream));
   }
   if (rc == AR_OK) rc = launch_c4_to_plain(out, B, Cout, T, y, stream);
