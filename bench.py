@@ -36,13 +36,14 @@ METRIC = "restored audio-sec/sec (full chain)"
 
 def conv_algorithmic_bytes_per_audio_s():
     """fp16 activation bytes (inputs read + outputs written, incl. pooled copies and residual operands) that the
-    conv engine's 36 launches per chunk batch must move per source audio-second: entries are
+    conv engine's 37 launches per chunk batch must move per source audio-second: entries are
     (bytes per row, rows per audio-second) per tensor stream of a launch; the stereo encoder entries are the FUSED
     chains (dilated block, and the last block + LSTM input projection), whose intermediates never reach HBM."""
     r = SR                                   # denoiser / SR input rate; stereo runs at 2r
     den = [(160, r), (192, r // 2), (320, r // 2), (384, r // 4), (640, r // 4), (768, r // 8), (1024, r // 8),
            (512, r // 8), (256, r // 4), (768, r // 4), (512, r // 4), (256, r // 4), (128, r // 2), (384, r // 2),
-           (256, r // 2), (128, r // 2), (64, r), (192, r), (128, r)]
+           (256, r // 2), (128, r // 2), (64, r), (192, r), (128, r),
+           (128, r)]                         # first transient-detector layer (32 -> 16 padded to 32 columns)
     sr = [(128, r)] * 4 + [(192, r)] * 5 + [(64, r), (64, 2 * r), (128, 2 * r)]
     st = [(192, 2 * r), (384, 2 * r), (512, 2 * r), (768, 2 * r),                     # fused enc1, enc2, enc3, enc4 + xproj
           (640, 2 * r), (384, 2 * r), (384, 2 * r), (192, 2 * r), (192, 2 * r)]       # dec0 (L+R), dec1 L/R, dec2 L/R
@@ -293,7 +294,7 @@ def run_b200(args, rank, world, local_rank):
         "share_of_step": conv["ms"] / (1e3 * t_s), "traffic": load_conv_traffic(args),
         "algorithmic_bytes_per_launch": conv_bytes / max(1, conv["launches"]),
         "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_gbs / peaks["hbm_gbs"],
-                "note": "same launches against the HBM roofline (algorithmic fp16 activation bytes of the 36 launches)"},
+                "note": "same launches against the HBM roofline (algorithmic fp16 activation bytes of the 37 launches)"},
         "per_category_ms_per_step": {k: v["ms"] / args.steps for k, v in cats.items()},
     }
     line = {

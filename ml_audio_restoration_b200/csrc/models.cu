@@ -291,6 +291,12 @@ static bool build_denoiser(const Table& t, Blob& blob, Model& m) {
   for (int c = 0; c < 32; ++c) P.wf[c] = WF[c];
   P.b2 = B2[0];
   P.bf = BF[0];
+  // the first detector layer (32 -> 16 k3 + LeakyReLU, denoiser.py:40-41) as a conv-engine layer: padded to 32 output
+  // columns (zero weights / bias) so that it runs in the 2-CTA engine with tile groups like the other 32-channel layers
+  Gemm g;
+  g.init(32, 32, 3, 1, 1);
+  if (!add_conv(t, "transient_detector.0", "", 32, 16, 3, g, 0)) return false;
+  m.conv["td0"] = blob.push_gemm(g);
   return true;
 }
 
@@ -676,9 +682,23 @@ static int denoiser_forward(Ctx& c, const float* x, float* y, int T) {
   Act f = A.act(B, 32, T);
   AR_TRY(run_conv(c, "dec2b", d2a, f));
   A.release(d2a);
-  if (!A.dry) {
+  // AR_DEN_TAIL_SIMT=1 (or the cross-check engine) keeps the whole transient detector on CUDA cores
+  static int tail_simt = -1;
+  if (tail_simt < 0) {
+    const char* e = getenv("AR_DEN_TAIL_SIMT");
+    tail_simt = e ? atoi(e) : 0;
+  }
+  if (c.m->engine == AR_ENGINE_UMMA && !tail_simt) {
+    Act h1 = A.act(B, 32, T);
+    AR_TRY(run_conv(c, "td0", f, h1));
+    if (!A.dry) {
+      ProfScope ps(CAT_TAIL, c.stream, 2.0 * 440 * (double)B * T);
+      AR_TRY(launch_den_tail(f, &h1, x, y, B, T, m.den_tail, c.stream));
+    }
+    A.release(h1);
+  } else if (!A.dry) {
     ProfScope ps(CAT_TAIL, c.stream, 2.0 * 1976 * (double)B * T);
-    AR_TRY(launch_den_tail(f, x, y, B, T, m.den_tail, c.stream));
+    AR_TRY(launch_den_tail(f, nullptr, x, y, B, T, m.den_tail, c.stream));
   }
   A.release(f);
   return AR_OK;

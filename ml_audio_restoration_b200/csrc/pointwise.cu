@@ -150,20 +150,43 @@ int launch_final_k7(const Act& in, const int* in_coff8, const FinalW& w, int nou
 //   y   = conv1(f, 32->1) * (1 - 0.9*max(m_t, m_i))                              denoiser.py:134-142
 // Every conv zero-pads ITS OWN input at the sequence ends, so intermediate activations are
 // forced to zero outside [0,T).  Activations are staged in shared memory (fp32); all weights are constant-bank
-// FFMA operands (DenTailP is a kernel parameter), so the 1976 MACs per sample cost 1976 FFMA + ~40 shared loads.
+// FFMA operands (DenTailP is a kernel parameter).
+// PRE = true (product path): the first detector layer (32 -> 16, 1536 of the 1976 MACs per sample) has already run on
+// the tensor core as an ordinary conv-engine layer ("td0", padded to 32 columns) and arrives as `h1` (H8, channels
+// 0..15); this kernel then costs 440 FFMA per sample instead of 1976 (it was FMA-issue bound: 5.9 ms per 1184-chunk step).
+// PRE = false: everything on CUDA cores from f (cross-check engine, AR_DEN_TAIL_SIMT=1).
 constexpr int DT = 128;       // threads per block = rows of the first detector layer a block computes
 constexpr int DT_OUT = DT - 4;  // outputs per block: 128 td0 rows -> 126 td1 rows -> 124 outputs, one pass per thread each
 
+template <bool PRE>
 __global__ void __launch_bounds__(DT) den_tail_kernel(const __half* __restrict__ fin, long long f_bs, int f_Tp,
+                                                      const __half* __restrict__ h1, long long h_bs, int h_Tp,
                                                       const float* __restrict__ x, float* __restrict__ y, int T,
                                                       const __grid_constant__ DenTailP w) {
-  __shared__ float4 sf[8][DT + 2];
+  __shared__ float4 sf[PRE ? 1 : 8][DT + 2];
   __shared__ float4 s0[4][DT];
   __shared__ float4 s1[2][DT - 2];
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * DT_OUT;
   const int tid = threadIdx.x;
+  if (PRE) {
+    // td0 output rows t0-2 .. t0+DT-3 from the conv engine (already LeakyReLU'd; zero outside [0,T))
+    const int t = t0 - 2 + tid;
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    if (t >= 0 && t < T) {
+      float lo[8], hi[8];
+      unpack_half8(*reinterpret_cast<const uint4*>(h1 + act_off(h_bs, h_Tp, b, 0, t)), lo);
+      unpack_half8(*reinterpret_cast<const uint4*>(h1 + act_off(h_bs, h_Tp, b, 1, t)), hi);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { v[i] = lo[i]; v[8 + i] = hi[i]; }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) s0[c][tid] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+  }
   // f tile: rows t0-3 .. t0+DT-2
+  if (!PRE)
   for (int i = tid; i < 4 * (DT + 2); i += DT) {
     const int c = i / (DT + 2), r = i % (DT + 2);   // c: 8-channel chunk of the H8 input
     const int t = t0 - 3 + r;
@@ -174,7 +197,7 @@ __global__ void __launch_bounds__(DT) den_tail_kernel(const __half* __restrict__
   }
   __syncthreads();
   // td0: 32 -> 16 at rows t0-2 .. t0+DT-3 (local r in [0, DT)), input rows r..r+2 of sf
-  {
+  if (!PRE) {
     const int r = tid;
     const int t = t0 - 2 + r;
     float acc[16];
@@ -232,10 +255,20 @@ __global__ void __launch_bounds__(DT) den_tail_kernel(const __half* __restrict__
   const float mt = 1.f / (1.f + expf(-m));
   // final 1x1 conv
   float yv = w.bf;
+  if (PRE) {   // this thread's own row of f, straight from global memory
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const float4 v = sf[c][tid + 3];
-    yv += v.x * w.wf[4 * c] + v.y * w.wf[4 * c + 1] + v.z * w.wf[4 * c + 2] + v.w * w.wf[4 * c + 3];
+    for (int c = 0; c < 4; ++c) {
+      float v[8];
+      unpack_half8(*reinterpret_cast<const uint4*>(fin + act_off(f_bs, f_Tp, b, c, t)), v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) yv += v[i] * w.wf[8 * c + i];
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float4 v = sf[c][tid + 3];
+      yv += v.x * w.wf[4 * c] + v.y * w.wf[4 * c + 1] + v.z * w.wf[4 * c + 2] + v.w * w.wf[4 * c + 3];
+    }
   }
   // analytic impulse mask from the raw input
   const float* xb = x + (long long)b * T;
@@ -259,9 +292,12 @@ __global__ void __launch_bounds__(DT) den_tail_kernel(const __half* __restrict__
   y[(long long)b * T + t] = yv * (1.0f - fmaxf(mt, mi) * 0.9f);
 }
 
-int launch_den_tail(const Act& f, const float* x, float* y, int B, int T, const DenTailP& w, cudaStream_t stream) {
+int launch_den_tail(const Act& f, const Act* h1, const float* x, float* y, int B, int T, const DenTailP& w, cudaStream_t stream) {
   dim3 grid((T + DT_OUT - 1) / DT_OUT, B);
-  den_tail_kernel<<<grid, DT, 0, stream>>>(f.h(), f.bs, f.Tp, x, y, T, w);
+  if (h1 != nullptr)
+    den_tail_kernel<true><<<grid, DT, 0, stream>>>(f.h(), f.bs, f.Tp, h1->h(), h1->bs, h1->Tp, x, y, T, w);
+  else
+    den_tail_kernel<false><<<grid, DT, 0, stream>>>(f.h(), f.bs, f.Tp, nullptr, 0, 0, x, y, T, w);
   AR_CUDA_OK(cudaGetLastError());
   return AR_OK;
 }

@@ -34,7 +34,8 @@ int launch_final_k7(const Act& in, const int* in_coff8, const FinalW& w, int nou
 void pack_final_umma(const FinalW& w, int nheads, std::vector<uint16_t>& out);
 int launch_final_umma(const Act& in, int in_coff8, const __half* w_packed, const FinalW& w, int nheads, float* y, int B, int T,
                       const float* x_lr, cudaStream_t stream);
-int launch_den_tail(const Act& f, const float* x, float* y, int B, int T, const DenTailP& w, cudaStream_t stream);
+// h1 != nullptr: the first detector layer already ran in the conv engine (H8, channels 0..15 of *h1)
+int launch_den_tail(const Act& f, const Act* h1, const float* x, float* y, int B, int T, const DenTailP& w, cudaStream_t stream);
 int launch_normalize(float* x, long long n, float target_db, float* scratch, cudaStream_t stream);
 int launch_split(const float* audio, long long n, float* chunks, int first, int count, int chunk_size, int overlap,
                  cudaStream_t stream);
