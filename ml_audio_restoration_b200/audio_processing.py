@@ -175,6 +175,19 @@ def apply_vinyl_artifacts(audio: torch.Tensor, sample_rate: int, plan: dict, sur
     return out.reshape(shape)
 
 
+def add_noise(audio: torch.Tensor, noise_level: float = 0.01) -> torch.Tensor:
+    """`audio + randn_like(audio) * noise_level` (audio_processing.py:107-119) -- the pop-free case of `ar_vinyl_mix`."""
+    if not audio.is_cuda:
+        raise RuntimeError("add_noise: input must be a CUDA tensor -- this build has no CPU fallback")
+    x = audio.to(torch.float32).contiguous()
+    noise = torch.randn_like(x)
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().ar_vinyl_mix(x.data_ptr(), noise.data_ptr(), float(noise_level), None, 0, 1, y.data_ptr(), 1,
+                                           x.numel(), torch.cuda.current_stream(x.device).cuda_stream))
+    return y
+
+
 def simulate_vinyl_artifacts(audio: torch.Tensor, sample_rate: int, impulse_rate: float = 10.0,
                              impulse_amplitude=(0.1, 0.5), surface_noise_level=(0.015, 0.03),
                              crackle_level=(0.01, 0.02), add_rumble: bool = True, add_rolloff: bool = True) -> torch.Tensor:

@@ -125,3 +125,37 @@ def test_drop_in_signature_draws_on_device():
     assert outs[0].shape == x.shape and outs[0].dtype == torch.float32 and outs[0].is_cuda
     assert torch.equal(outs[0], outs[1])
     assert 0.01 < (outs[0] - x).std().item() < 0.2
+
+
+def test_add_noise_matches_reference_formula():
+    x = (0.1 * torch.randn(2, 5000)).cuda()
+    torch.manual_seed(3)
+    y = ap.add_noise(x, 0.02)
+    torch.manual_seed(3)
+    ref = x + torch.randn_like(x) * 0.02           # audio_processing.py:118-119 on the same (CUDA) generator
+    assert torch.equal(y, ref)
+
+
+def test_generated_side_through_the_chain(state_dicts):
+    """BASELINE config 4 recipe end to end on the GPU: a clean music proxy -> `simulate_vinyl_artifacts` -> the chunked
+    restoration chain; the degraded input equals the oracle's degradation of the same draws and the restored output equals
+    the oracle chain on that input."""
+    from oracle import pipeline as opipe
+    from ml_audio_restoration_b200 import RestorationPipeline
+    sr, n = 22050, 3 * 4096 + 777
+    t = torch.arange(n) / sr
+    clean = (0.1 * torch.sin(2 * torch.pi * 220 * t) + 0.05 * torch.sin(2 * torch.pi * 554.4 * t))[None]
+    surface, crackle, rumble = cpu_noise(31, clean.shape)
+    np.random.seed(31)
+    plan = ap.plan_vinyl_artifacts(n, sr, impulse_rate=40.0)
+    worn = ap.apply_vinyl_artifacts(clean.cuda(), sr, plan, surface.cuda(), crackle.cuda(), rumble.cuda())
+    np.random.seed(31)
+    torch.manual_seed(31)
+    worn_ref = degrade.simulate_vinyl_artifacts(clean, sr, impulse_rate=40.0)
+    assert (worn.cpu() - worn_ref).abs().max().item() <= TOL
+    pipe = RestorationPipeline.from_state_dicts(state_dicts["denoiser"], state_dicts["super_resolution"], state_dicts["stereo"], "cuda")
+    out = pipe.restore(worn, mode="chunked", chunk_size=4096, overlap=256, return_device=True)
+    ref = opipe.restore_chunked(state_dicts, worn_ref, chunk_size=4096, overlap=256)
+    assert out.shape == ref.shape == (2, 2 * n)
+    err = (out.cpu() - ref).abs().max().item()
+    assert err <= 1e-3, err
