@@ -427,7 +427,7 @@ int filtfilt_workspace_bytes(int rows, long long n, int order, size_t* bytes) {
 
 int launch_filtfilt(const float* x, float scale, const float* add1, const float* add2, float* y, int rows, long long n,
                     const double* b, const double* a, int order, void* ws, size_t ws_bytes, cudaStream_t stream) {
-  AR_CHECK(x && y && b && a && rows >= 1 && rows <= 65535 && order >= 1 && order <= 4, AR_ERR_INVALID, "filtfilt: bad argument");
+  AR_CHECK(x && y && b && a && rows >= 1 && order >= 1 && order <= 4, AR_ERR_INVALID, "filtfilt: bad argument");
   AR_CHECK(a[0] != 0.0, AR_ERR_INVALID, "filtfilt: a[0] must be non-zero");
   const int pad = 3 * (order + 1);
   if (n <= pad) {
@@ -473,17 +473,24 @@ int launch_filtfilt(const float* x, float scale, const float* add1, const float*
   mat4_pow(A, (long long)IIR_L * P.S, P.AS);
 
   const uintptr_t base = (reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255;
-  double* yfwd = reinterpret_cast<double*>(base);
-  double* st = yfwd + (size_t)rows * P.m;
-  const IirIn in = {x, add1, add2, scale};
-  const dim3 grid((unsigned)((P.m + IIR_TILE - 1) / IIR_TILE), (unsigned)rows);
-  iir_block_kernel<false, false><<<grid, IIR_THREADS, 0, stream>>>(P, in, nullptr, nullptr, nullptr, st);
-  iir_scan_kernel<<<rows, SCAN_THREADS, 0, stream>>>(P, 0, in, nullptr, st);
-  iir_block_kernel<false, true><<<grid, IIR_THREADS, 0, stream>>>(P, in, nullptr, yfwd, nullptr, st);
-  iir_block_kernel<true, false><<<grid, IIR_THREADS, 0, stream>>>(P, in, yfwd, nullptr, nullptr, st);
-  iir_scan_kernel<<<rows, SCAN_THREADS, 0, stream>>>(P, 1, in, yfwd, st);
-  iir_block_kernel<true, true><<<grid, IIR_THREADS, 0, stream>>>(P, in, yfwd, nullptr, y, st);
-  prof_count_launch(6);
+  double* const yfwd_all = reinterpret_cast<double*>(base);
+  double* const st_all = yfwd_all + (size_t)rows * P.m;
+  // rows ride on gridDim.y (<= 65535): larger batches go in slabs
+  for (int r0 = 0; r0 < rows; r0 += 65535) {
+    const int nr = rows - r0 < 65535 ? rows - r0 : 65535;
+    double* yfwd = yfwd_all + (size_t)r0 * P.m;
+    double* st = st_all + (size_t)r0 * P.nsub * 4;
+    const IirIn in = {x + (size_t)r0 * n, add1 ? add1 + (size_t)r0 * n : nullptr, add2 ? add2 + (size_t)r0 * n : nullptr, scale};
+    float* yr = y + (size_t)r0 * n;
+    const dim3 grid((unsigned)((P.m + IIR_TILE - 1) / IIR_TILE), (unsigned)nr);
+    iir_block_kernel<false, false><<<grid, IIR_THREADS, 0, stream>>>(P, in, nullptr, nullptr, nullptr, st);
+    iir_scan_kernel<<<nr, SCAN_THREADS, 0, stream>>>(P, 0, in, nullptr, st);
+    iir_block_kernel<false, true><<<grid, IIR_THREADS, 0, stream>>>(P, in, nullptr, yfwd, nullptr, st);
+    iir_block_kernel<true, false><<<grid, IIR_THREADS, 0, stream>>>(P, in, yfwd, nullptr, nullptr, st);
+    iir_scan_kernel<<<nr, SCAN_THREADS, 0, stream>>>(P, 1, in, yfwd, st);
+    iir_block_kernel<true, true><<<grid, IIR_THREADS, 0, stream>>>(P, in, yfwd, nullptr, yr, st);
+    prof_count_launch(6);
+  }
   AR_CUDA_OK(cudaGetLastError());
   return AR_OK;
 }

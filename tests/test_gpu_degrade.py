@@ -74,6 +74,16 @@ def test_filtfilt_fused_inputs_and_errors():
         ap.filtfilt(b, a, x.cuda(), add1=u.cuda()[:, :100])
 
 
+def test_filtfilt_many_short_rows():
+    """More rows than one grid dimension holds (the launcher walks them in slabs of 65 535)."""
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((70000, 40)).astype(np.float32)
+    b, a = signal.butter(4, 2500 / 11025, btype="high")
+    y = ap.filtfilt(b, a, torch.from_numpy(x).cuda()).cpu().numpy()
+    for r in (0, 1, 65534, 65535, 65536, 69999):
+        assert np.abs(y[r] - signal.filtfilt(b, a, x[r])).max() <= TOL
+
+
 def test_filtfilt_is_linear_and_zero_phase_at_full_size():
     """Size-independent properties on a 3-minute side (3 969 000 samples): linearity, DC gain 1 for the low-pass, and
     time-reversal symmetry filtfilt(rev(x)) == rev(filtfilt(x)) (zero phase) away from the two ends, where the
