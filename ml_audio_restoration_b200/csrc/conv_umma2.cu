@@ -421,9 +421,17 @@ static bool pick_cfg2(const ConvParams& p, Umma2Cfg& c) {
   }
   for (int kbs = 4; kbs >= 1; kbs >>= 1) {
     if (p.Cin % (16 * kbs)) continue;
-    // group size: enough tiles per barrier round that a stage carries >= ~24 MMAs, within TMEM (two buffers) and the ring
+    // group size: enough tiles per barrier round that a stage carries >= ~64 MMAs, within TMEM (two buffers) and the ring
     int G = 1;
-    while (tg == 1 && G < g_max && kbs * p.taps * G < 24 && 2 * (2 * G) * ncol <= 512) G *= 2;   // tap-grouped layers: G = 1
+    // AR_GROUP_MMAS: MMAs per stage below which tiles are grouped.  64 by default: also the k7 decoders (28 MMAs per
+    // stage) take G = 2 (128 -> 64) / G = 4 (64 -> 32) -- fewer barrier round trips per tile and 4-8 KB instead of 2 KB
+    // runs per bulk copy: 10.8 -> 10.2 ms and 5.3 -> 4.3 ms per launch at 1184 chunks (with 24 only k <= 3 layers group)
+    static int g_mma_target = -1;
+    if (g_mma_target < 0) {
+      const char* e = getenv("AR_GROUP_MMAS");
+      g_mma_target = e ? atoi(e) : 64;
+    }
+    while (tg == 1 && G < g_max && kbs * p.taps * G < g_mma_target && 2 * (2 * G) * ncol <= 512) G *= 2;   // tap-grouped layers: G = 1
     for (; G >= 1; G >>= 1) {
       c.RG = G * TILE_M + (p.taps - 1) * p.dil;
       c.stage_bytes = kbs * 2 * c.RG * 16;
