@@ -71,3 +71,38 @@ def test_plan_consumes_numpy_generator_like_the_reference():
     assert all(0 < p["length"] <= 500 - p["loc"] for p in plan["pops"])
     assert any(p["resonance_freq"] is None for p in plan["pops"]) or all(p["length"] > 10 for p in plan["pops"])
     assert 0.015 <= plan["surface_level"] <= 0.03 and 6000 <= plan["rolloff_hz"] <= 8000
+
+
+def test_lfilter_delegation_matches_a_plain_python_recurrence():
+    """The oracle delegates the serial direct-form-II-transposed recurrence to scipy.signal.lfilter; a pure-Python loop of
+    the same recurrence (small case) pins that delegation, state hand-over included."""
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal(60)
+    for order, wn, btype in [(4, 100 / 11025, "low"), (3, 7000 / 11025, "low"), (4, 2500 / 11025, "high")]:
+        b, a = degrade.butter(order, wn, btype)
+        zi = degrade.lfilter_zi(b, a) * x[0]
+        y_ref, z_ref = signal.lfilter(b, a, x, zi=zi)
+        z = list(zi)
+        y = []
+        for xn in x:
+            yn = z[0] + b[0] * xn
+            for i in range(order - 1):
+                z[i] = z[i + 1] + xn * b[i + 1] - yn * a[i + 1]
+            z[order - 1] = xn * b[order] - yn * a[order]
+            y.append(yn)
+        np.testing.assert_allclose(np.array(y), y_ref, rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(np.array(z), z_ref, rtol=1e-9, atol=1e-15)
+
+
+def test_pop_impulse_shape():
+    """One pop: exponential decay from amp*polarity with the 0.3*tau time constant, ringing only beyond 10 samples
+    (audio_processing.py:171-186)."""
+    pop = {"loc": 0, "amp": 0.4, "polarity": -1, "decay_time": 0.002, "length": 44, "resonance_freq": None}
+    imp = degrade.pop_impulse(pop, 22050)
+    assert imp[0] == pytest.approx(-0.4) and np.all(np.diff(imp) > 0) and len(imp) == 44
+    assert imp[10] == pytest.approx(-0.4 * np.exp(-10 / (22050 * 0.002 * 0.3)))
+    pop["resonance_freq"] = 5000.0
+    ring = degrade.pop_impulse(pop, 22050) - imp
+    k = np.arange(44)
+    np.testing.assert_allclose(ring, 0.3 * np.sin(2 * np.pi * 5000.0 * k / 22050) * np.exp(-k / (22050 * 0.002 * 0.3)) * 0.4 * 0.2,
+                               rtol=1e-12, atol=1e-18)
