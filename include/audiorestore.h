@@ -12,8 +12,10 @@
  *   - all pointers named x/y/audio/chunks/out/workspace are DEVICE pointers unless the
  *     function name ends in _host; the caller owns them.  Handles own the packed weights.
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no entry point
- *     synchronises the device except ar_restore_host (which must, to hand back host data)
- *     and the *_create functions (weight upload).
+ *     synchronises the device except the *_create functions (weight upload), the diagnostic
+ *     ar_model_audit_* pair and ar_debug_conv1d.
+ *   - a process may drive several GPUs: handles belong to the device they were created on, calls
+ *     are made with that device current (the Python shim does), kernel attributes are set per device.
  *   - tensors are fp32, contiguous, in the reference's layout: audio batches are
  *     [B,1,T], stereo outputs [B,2,T] (denoiser.py:93, super_resolution.py:69,
  *     stereo_separator.py:88).
@@ -66,23 +68,20 @@ int ar_set_conv_engine(int engine);
  * compute the same fp16-rounded intermediates. */
 int ar_set_fusion(int on);
 
-/* Enable / disable (default) the tap-grouped form of the k7 decoder layers (stereo_separator.py:72-79: 128 -> 64 and
- * 64 -> 32) for subsequently created models: two resp. four taps side by side along the GEMM's N, recombined by a shifted
- * sum in the epilogue -- 32 resp. 8 tensor-core instructions per tile pair instead of 56 resp. 28.  Measured slower on
- * power-capped B200s (profiles/README_r01.md), hence off by default; both settings compute the same convolution (fp32
- * sums in a different order) and the parity tests exercise both. */
-int ar_set_tap_groups(int on);
-
 /* Shared memory one conv CTA may use, in KB (64..227, default 227 = the whole SM).  AR_CORESIDENT_SMEM_KB leaves room
  * for one CTA of the LSTM recurrence on every SM: when chunk batches are pipelined on two streams the latency-bound
- * scan of one batch (stereo_separator.py:106) then runs UNDER the convs of the other instead of after them.
+ * scan of one batch (stereo_separator.py:106) then runs UNDER the convs of the other instead of after them (measured:
+ * no gain on power-capped B200s, profiles/README_r01.md; kept as a tuning hook).
  * Takes effect for subsequent forwards (process-wide, like ar_set_conv_engine). */
 #define AR_CORESIDENT_SMEM_KB 172
 int ar_set_conv_smem_kb(int kb);
 
 /* Replaces: model construction + torch.load + load_state_dict(strict) + .to(device) + .eval()
  * (inference.py:51-55, 66-70, 85-89).  Folds eval-mode BatchNorm into the conv weights,
- * rounds tensor-core operands to fp16 (the 11-bit significand TF32 would keep), packs into the kernels' layouts, uploads.  */
+ * rounds tensor-core operands to fp16 (the 11-bit significand TF32 would keep), packs into the kernels' layouts, uploads.
+ * An optional entry "<bn>.eps" (shape [1]) overrides nn.BatchNorm1d's default eps = 1e-5 for that layer.
+ * AR_ERR_WEIGHTS: missing / mis-shaped entry, or a BatchNorm-folded weight outside the fp16 operand range
+ * (|w| > 65504, not finite, or a whole layer below 6.1e-5) -- refused, never clamped silently. */
 int ar_model_create(int kind, const ar_tensor_t* tensors, int n_tensors, int device, ar_model_t* out);
 void ar_model_destroy(ar_model_t m);
 int ar_model_kind(ar_model_t m);
@@ -97,11 +96,32 @@ int ar_model_workspace_bytes(ar_model_t m, int B, int T, size_t* bytes);
 int ar_model_forward(ar_model_t m, const float* x, float* y, int B, int T,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* Dynamic-range audit of a checkpoint (diagnostic; INTEGRATION.md "dynamic range").  Activations between layers are
+ * stored in fp16 and SATURATE at +-65504; random-init and BatchNorm-calibrated checkpoints stay orders of magnitude below,
+ * but nothing in the state_dict ABI guarantees it.  While the audit is on, forwards of this model run layer by layer
+ * (fused launches off) and record max |activation| of every fp16 tensor they write; ar_model_audit_read synchronises the
+ * device and returns them in launch order (n_layers <= AR_AUDIT_MAX_LAYERS; names via ar_model_audit_name).  A maximum
+ * of 65504 means that layer clipped.  Not re-entrant: one audited forward at a time per model. */
+#define AR_AUDIT_MAX_LAYERS 64
+int ar_model_audit_enable(ar_model_t m, int on);
+int ar_model_audit_read(ar_model_t m, float* max_abs, int cap, int* n_layers);
+const char* ar_model_audit_name(ar_model_t m, int i);
+
 /* Stereo forward with explicit LSTM carry (whole-file-exact mode):
  * state_in/state_out are [B,2,64] (h then c) device buffers; either may be NULL. */
 int ar_stereo_forward_state(ar_model_t m, const float* x, float* y, int B, int T,
                             const float* state_in, float* state_out,
                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stereo forward on a WINDOW of a longer signal (whole-file-exact chunked mode): x[B,1,T] is a segment that carries conv
+ * halos on both sides.  The encoder and the decoders run over all T samples; the LSTM scan covers steps [lstm_start, T)
+ * only, starting from state_in (NULL = zeros; hidden states of earlier steps are zero), and state_out receives (h, c)
+ * after step state_pos - 1 (lstm_start < state_pos <= T) -- the state the NEXT segment's scan starts from, taken where
+ * this segment's LSTM inputs are still exact.  lstm_start and state_pos are multiples of 8 (state_pos may equal T).
+ * Chaining segments this way reproduces the single scan of stereo_separator.py:106-107 over the whole file. */
+int ar_stereo_forward_window(ar_model_t m, const float* x, float* y, int B, int T, int lstm_start, int state_pos,
+                             const float* state_in, float* state_out,
+                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* denoise -> (super-res) -> stereo on a batch of equal-length chunks
  * (the three model applications of inference.py:59-61,73-75,93-95).  sr may be NULL

@@ -19,6 +19,8 @@ MODEL_DENOISER, MODEL_SUPER_RES, MODEL_STEREO = 0, 1, 2
 ENGINE_UMMA, ENGINE_SIMT = 0, 1
 NORMALIZE_SCRATCH_BYTES = 16384
 CORESIDENT_SMEM_KB, FULL_SMEM_KB = 172, 227
+AUDIT_MAX_LAYERS = 64
+HALF_MAX = 65504.0
 PROFILE_CATEGORIES = ("conv", "lstm", "stem", "tail", "normalize", "chunk")
 
 
@@ -31,15 +33,19 @@ _SIGNATURES = {
     "ar_version": (C.c_int, []),
     "ar_set_conv_engine": (C.c_int, [C.c_int]),
     "ar_set_fusion": (C.c_int, [C.c_int]),
-    "ar_set_tap_groups": (C.c_int, [C.c_int]),
     "ar_set_conv_smem_kb": (C.c_int, [C.c_int]),
     "ar_model_create": (C.c_int, [C.c_int, C.POINTER(ArTensor), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "ar_model_destroy": (None, [C.c_void_p]),
     "ar_model_kind": (C.c_int, [C.c_void_p]),
+    "ar_model_audit_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "ar_model_audit_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]),
+    "ar_model_audit_name": (C.c_char_p, [C.c_void_p, C.c_int]),
     "ar_model_workspace_bytes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "ar_model_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ar_stereo_forward_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ar_stereo_forward_window": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ar_chain_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "ar_chain_destroy": (None, [C.c_void_p]),
     "ar_chain_workspace_bytes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),

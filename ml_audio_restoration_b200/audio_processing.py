@@ -285,9 +285,15 @@ def load_audio_cuda(file_path: str, sample_rate: int = 22050, device="cuda"):
     int16 frames (half the H2D bytes of float32) from pinned memory, decoded, mixed to mono and resampled on the device.
     Returns (audio [1,N] float32 CUDA, sample_rate)."""
     dev = torch.device(device)
-    with wave.open(file_path, "rb") as w:
-        sr, nch, width, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
-        raw = w.readframes(n) if width == 2 else None
+    raw = None
+    try:
+        with wave.open(file_path, "rb") as w:
+            sr, nch, width, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
+            raw = w.readframes(n) if width == 2 else None
+    except wave.Error:
+        # IEEE-float WAV (format tag 3) -- what `save_audio` / the reference's `torchaudio.save` write by default and the
+        # stdlib `wave` module rejects ("unknown format: 3"): `_read_wav` decodes it on the host
+        raw = None
     if raw is None:                                    # other encodings: host decode, device mix + resample
         audio, sr = _read_wav(file_path)
         return resample_mono_cuda(audio.to(dev), sr, sample_rate), sample_rate

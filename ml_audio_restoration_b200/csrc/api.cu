@@ -13,9 +13,7 @@ struct Model;
 const char* last_error();
 int set_engine(int e);
 int set_fusion(int on);
-int set_tap_groups(int on);
 int set_chain_trace(long long* dev_buf);
-int set_conv_smem_kb(int kb);
 long long resample_length(long long n, int orig_sr, int new_sr);
 int launch_resample_mono(const float* x, int channels, long long n, int orig_sr, int new_sr, float* y, long long n_out,
                          cudaStream_t stream);
@@ -30,9 +28,12 @@ int launch_filtfilt(const float* x, float scale, const float* add1, const float*
 int model_create(int kind, const ar_tensor_t* tensors, int n, int device, Model** out);
 int model_workspace_bytes(const Model* m, int B, int T, size_t* bytes);
 int model_forward(const Model* m, const float* x, float* y, int B, int T, const float* st_in, float* st_out, void* ws,
-                  size_t ws_bytes, cudaStream_t stream);
+                  size_t ws_bytes, cudaStream_t stream, int lstm_start = 0, int state_pos = -1);
 void model_destroy(Model* m);
 int model_kind(const Model* m);
+int model_audit_enable(Model* m, int on);
+int model_audit_read(Model* m, float* max_abs, int cap, int* n_layers);
+const char* model_audit_name(const Model* m, int i);
 struct ConvLayerPublic;
 int debug_conv(const float* x, const float* w_host, const float* bias_host, float* y, int B, int Cin, int Cout, int T, int k,
                int dil, int lrelu, int engine, cudaStream_t stream);
@@ -53,7 +54,6 @@ const char* ar_last_error(void) { return ar::last_error(); }
 int ar_version(void) { return 100; }
 int ar_set_conv_engine(int engine) { return ar::set_engine(engine); }
 int ar_set_fusion(int on) { return ar::set_fusion(on); }
-int ar_set_tap_groups(int on) { return ar::set_tap_groups(on); }
 int ar_set_conv_smem_kb(int kb) { return ar::set_conv_smem_kb(kb); }
 int ar_resample_length(int64_t n, int orig_sr, int new_sr, int64_t* n_out) {
   if (!n_out || n < 0 || orig_sr < 1 || new_sr < 1) { ar::set_error("resample_length: bad argument"); return AR_ERR_INVALID; }
@@ -95,6 +95,12 @@ int ar_model_create(int kind, const ar_tensor_t* tensors, int n_tensors, int dev
 void ar_model_destroy(ar_model_t m) { ar::model_destroy(reinterpret_cast<ar::Model*>(m)); }
 int ar_model_kind(ar_model_t m) { return m ? ar::model_kind(reinterpret_cast<ar::Model*>(m)) : -1; }
 
+int ar_model_audit_enable(ar_model_t m, int on) { return ar::model_audit_enable(reinterpret_cast<ar::Model*>(m), on); }
+int ar_model_audit_read(ar_model_t m, float* max_abs, int cap, int* n_layers) {
+  return ar::model_audit_read(reinterpret_cast<ar::Model*>(m), max_abs, cap, n_layers);
+}
+const char* ar_model_audit_name(ar_model_t m, int i) { return ar::model_audit_name(reinterpret_cast<ar::Model*>(m), i); }
+
 int ar_model_workspace_bytes(ar_model_t m, int B, int T, size_t* bytes) {
   return ar::model_workspace_bytes(reinterpret_cast<ar::Model*>(m), B, T, bytes);
 }
@@ -110,6 +116,14 @@ int ar_stereo_forward_state(ar_model_t m, const float* x, float* y, int B, int T
            "ar_stereo_forward_state: not a stereo model");
   return ar::model_forward(reinterpret_cast<ar::Model*>(m), x, y, B, T, state_in, state_out, workspace, workspace_bytes,
                            reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ar_stereo_forward_window(ar_model_t m, const float* x, float* y, int B, int T, int lstm_start, int state_pos,
+                             const float* state_in, float* state_out, void* workspace, size_t workspace_bytes, void* stream) {
+  AR_CHECK(m && ar::model_kind(reinterpret_cast<ar::Model*>(m)) == AR_MODEL_STEREO, AR_ERR_INVALID,
+           "ar_stereo_forward_window: not a stereo model");
+  return ar::model_forward(reinterpret_cast<ar::Model*>(m), x, y, B, T, state_in, state_out, workspace, workspace_bytes,
+                           reinterpret_cast<cudaStream_t>(stream), lstm_start, state_pos);
 }
 
 int ar_chain_create(ar_model_t denoiser, ar_model_t sr, ar_model_t stereo, ar_chain_t* out) {

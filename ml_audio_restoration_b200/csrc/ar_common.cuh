@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include <string>
 
 #include "../../include/audiorestore.h"
@@ -128,21 +129,8 @@ struct ConvParams {
   int res_Tp, res_coff8;
   int lrelu;             // LeakyReLU(0.2) after bias
   int B;
-  int tiles_per_item;    // ceil(Tin / tile stride): TILE_M, or TILE_M - (tg-1)*dil/tg for a tap-grouped layer
-  // Tap-grouped layers (2-CTA engine only; 0 / 1 = off).  A k-tap conv with few output channels is bound by the fixed
-  // cost of a tcgen05.mma (~70 cycles for every N <= 128), i.e. by the NUMBER of MMAs, k * Cin/16 per tile.  With
-  // tg taps side by side along N -- column block i of group g holds tap g*tg + i -- the layer looks to the producer
-  // and the MMA warp like a conv with `taps` = ceil(k/tg) taps, dilation `dil` = tg*d and N = tg*Cout columns, and
-  // needs tg times fewer MMAs.  Accumulator row t, block i then holds  sum_g x[t + g*tg*d - pad] W_{g*tg+i},  so the
-  // output is the SHIFTED sum  y[u] = sum_i D[u + i*d][block i]  -- done in the epilogue with warp shuffles (rows are
-  // TMEM lanes) plus a small shared-memory exchange at the warp boundaries; a 128-row tile yields
-  // TILE_M - (tg-1)*d outputs (the tile stride).
-  int tg;
+  int tiles_per_item;    // ceil(Tin / TILE_M)
 };
-__host__ __device__ inline int conv_tile_stride(const ConvParams& p) {
-  return p.tg > 1 ? TILE_M - (p.tg - 1) * (p.dil / p.tg) : TILE_M;
-}
-
 // Fused epilogue for 8 consecutive GEMM columns [n0, n0+8) of GEMM row t (batch item b), shared by the
 // CUDA-core cross-check engine.  Must be called by all 32 lanes of a warp whose lanes hold consecutive rows
 // (the pool path exchanges neighbours with shuffles); `acc` = raw accumulators, `resv` = residual operand.
@@ -200,12 +188,24 @@ struct ChainParams {
 // ----------------------------------------------------------------------------- launchers
 bool conv_chain_fits(int Cin, int taps, int dil, const int* N, int n_gemms);   // shared memory / TMEM check for a chain
 int launch_conv_chain(const ChainParams& cp, cudaStream_t stream);  // fused k-tap conv -> pointwise conv(s), 2-CTA engine
-int launch_conv_umma(const ConvParams& p, cudaStream_t stream);
-int launch_conv_umma2(const ConvParams& p, cudaStream_t stream);   // cta_group::2 engine (needs p.cta2)
-int launch_conv_simt(const ConvParams& p, cudaStream_t stream);
-int sm_count();
-// Shared memory a conv CTA may take (bytes).  227 KB by default (one CTA owns the SM); AR_CONV_SMEM_KB lowers it so that a
-// CTA of the latency-bound LSTM recurrence can be co-resident on the same SM while chunk batches are pipelined on two streams.
+int launch_conv_umma2(const ConvParams& p, cudaStream_t stream);   // the tcgen05 engine (cta_group::2; needs p.cta2)
+int launch_conv_simt(const ConvParams& p, cudaStream_t stream);    // CUDA-core cross-check engine
+
+// ----------------------------------------------------------------------------- per-device host state (device.cu)
+int current_device();
+int sm_count();            // of the CURRENT device
+// "Done once" flag kept per device: kernel attributes (opt-in dynamic shared memory, carve-out) are per device / context,
+// so a process that drives cuda:0 and cuda:1 must set them on both.
+//   static DeviceOnce once;  if (once.pending()) { cudaFuncSetAttribute(...); once.done(); }
+struct DeviceOnce {
+  static constexpr int MAX_DEVICES = 64;
+  std::atomic<unsigned long long> bits{0};
+  bool pending() const;
+  void done();
+};
+// Shared memory a conv CTA may take (bytes): 227 KB by default (one CTA owns the SM); ar_set_conv_smem_kb lowers it so
+// that a CTA of the latency-bound LSTM recurrence can be co-resident on the same SM.
 int conv_smem_budget();
+int set_conv_smem_kb(int kb);
 
 }  // namespace ar

@@ -25,7 +25,6 @@
 #include "ar_common.cuh"
 #include "umma_ptx.cuh"
 #include "umma_epilogue.cuh"
-#include <cstdlib>
 
 namespace ar {
 
@@ -451,10 +450,10 @@ int launch_conv_chain(const ChainParams& cp, cudaStream_t stream) {
   static const Entry table[] = {
       {3, 2, conv_chain_kernel<3, 2>}, {3, 3, conv_chain_kernel<3, 3>}, {1, 2, conv_chain_kernel<1, 2>},
   };
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attrs;
+  if (attrs.pending()) {
     for (const Entry& e : table) AR_CUDA_OK(cudaFuncSetAttribute(e.k, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_BUDGET));
-    attr_set = true;
+    attrs.done();
   }
   Kernel kernel = nullptr;
   for (const Entry& e : table)

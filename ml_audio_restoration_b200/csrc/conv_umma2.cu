@@ -17,7 +17,6 @@
 #include "ar_common.cuh"
 #include "umma_ptx.cuh"
 #include "umma_epilogue.cuh"
-#include <cstdlib>
 
 namespace ar {
 
@@ -39,8 +38,6 @@ struct Umma2Cfg {
                     // group, which is what bounds the layers with few MMAs per tile (Cin <= 64, k <= 3)
   int RG;           // rows of a group's run: G*128 + (taps-1)*dil
   int res_off, res_bytes;   // residual epilogue: two-deep shared-memory ring of the group's residual rows (bulk-copied by the producer)
-  int S;                    // tile stride in rows: TILE_M, or TILE_M - (tg-1)*d for a tap-grouped layer (ConvParams::tg)
-  int xch_off;              // tap-grouped epilogue: warp-boundary exchange [2 buffers][2 halves][4 quarters][tg-1][(tg-1)*d rows][nch] floats
 };
 
 // Rows of CTA `rank`'s run for group `gi` of an item: first row (time index, may be negative), how many rows exist in the
@@ -52,13 +49,13 @@ __device__ __forceinline__ RunGeom run_geom(const ConvParams& p, const Umma2Cfg&
   g.tile0 = (gi * 2 + rank) * cfg.G;
   g.all_dead = g.tile0 > p.tiles_per_item - 1;
   const int tl = g.all_dead ? p.tiles_per_item - 1 : g.tile0;
-  g.t_start = tl * cfg.S - p.pad_left;
+  g.t_start = tl * TILE_M - p.pad_left;
   const int avail = p.in_Tp - (HALO + g.t_start);
   g.rows = cfg.RG < avail ? cfg.RG : avail;
   return g;
 }
 
-template <int MODE, bool POOL, bool RES, int TAPS, int TG = 1>
+template <int MODE, bool POOL, bool RES, int TAPS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UMMA2_THREADS, 1)
 conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ Umma2Cfg cfg, int num_pairs) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -248,7 +245,7 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
             uint32_t a_addr = (smem_base + s * cfg.stage_bytes) >> 4;
             for (int kb = 0; kb < cfg.kbs; ++kb) {
               for (int gg = 0; gg < G; ++gg) {
-                const uint32_t a_g = a_addr + (uint32_t)(gg * cfg.S);           // one tile stride (x 16 B) further down the run
+                const uint32_t a_g = a_addr + (uint32_t)(gg * TILE_M);          // one tile (128 rows x 16 B) further down the run
                 const uint32_t d_g = d_tmem + (uint32_t)(gg * cfg.ncol);
 #pragma unroll
                 for (int j = 0; j < TAPS; ++j)
@@ -282,87 +279,6 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
     int buf = 0;
     uint32_t aph = 0;
     PairIter pit(pair0, pair_step, ppi);
-    if (TG > 1) {
-      // ---- tap-grouped layer: y[u] = bias + sum_i D[u + i*d][block i] (ConvParams::tg).  Rows are TMEM lanes = threads of
-      // this warp: block i comes from the lane i*d further up (shuffle); the last i*d lanes of a quarter need the first
-      // rows of the NEXT quarter, which that warp parks in shared memory (double-buffered; one 128-thread named barrier
-      // per tile among the four warps that share a column half).  The last (TG-1)*d rows of the tile have no output:
-      // the tile stride is cfg.S.
-      constexpr int NCH = TG == 2 ? 32 : 16;          // output channels per warp: Cout = 64 (two taps per group) or 32 (four)
-      constexpr int Cout = 2 * NCH;
-      const int ch_lo = half * NCH;
-      const int d = p.dil / TG;
-      const int XR = (TG - 1) * d;                    // rows a quarter parks for its predecessor (per block: i*d of them)
-      float* const xch = reinterpret_cast<float*>(smem + cfg.xch_off);
-      const float ca = 0.5f * (1.0f + slope), cb = 0.5f * (1.0f - slope);
-      const int r = q * 32 + lane;
-      for (int it = 0; it < n_local; ++it, pit.next()) {
-        const int tile0 = pit.pi * 2 + (int)rank;     // G == 1
-        const int t = tile0 * cfg.S + r;
-        EpiRow row = epi_row<MODE_SAME, false, false>(p, pit.b, t, ch_lo);
-        row.ok0 = row.ok0 && r < cfg.S;
-        float* const xw = xch + ((((it & 1) * 2 + half) * 4 + q) * (TG - 1)) * XR * NCH;          // my quarter's slots
-        const float* const xr = xch + ((((it & 1) * 2 + half) * 4 + (q + 1)) * (TG - 1)) * XR * NCH;   // the next quarter's
-        mbar_wait(tfull_bar(buf), aph);
-        tc_fence_after();
-        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * cfg.ncol + ch_lo);
-        uint32_t v[TG][NCH];
-#pragma unroll
-        for (int i = 0; i < TG; ++i) {
-          if (NCH == 32) tmem_ld32_nowait(tbase + (uint32_t)(i * Cout), reinterpret_cast<uint32_t(&)[32]>(v[i]));
-          else tmem_ld16_nowait(tbase + (uint32_t)(i * Cout), v[i]);
-        }
-        tmem_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_remote(tempty_leader0 + 8u * buf);   // accumulator drained: the leader may reuse it
-        float acc[NCH];
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) acc[c] = __uint_as_float(v[0][c]);
-#pragma unroll
-        for (int i = 1; i < TG; ++i) {
-          const int sh = i * d;
-          if (lane < sh) {                            // rows the previous quarter needs from me
-            float4* dst = reinterpret_cast<float4*>(xw + ((i - 1) * XR + lane) * NCH);
-#pragma unroll
-            for (int c = 0; c < NCH / 4; ++c)
-              dst[c] = make_float4(__uint_as_float(v[i][4 * c]), __uint_as_float(v[i][4 * c + 1]), __uint_as_float(v[i][4 * c + 2]),
-                                   __uint_as_float(v[i][4 * c + 3]));
-          }
-          const bool mine = lane < 32 - sh;
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            const float sv = __shfl_down_sync(0xffffffffu, __uint_as_float(v[i][c]), (unsigned)sh);
-            acc[c] += mine ? sv : 0.f;
-          }
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");   // the four quarters of this column half have parked
-        if (q < 3) {
-#pragma unroll
-          for (int i = 1; i < TG; ++i) {
-            const int sh = i * d;
-            if (lane >= 32 - sh) {
-              const float4* src = reinterpret_cast<const float4*>(xr + ((i - 1) * XR + (lane - (32 - sh))) * NCH);
-#pragma unroll
-              for (int c = 0; c < NCH / 4; ++c) {
-                const float4 f = src[c];
-                acc[4 * c] += f.x; acc[4 * c + 1] += f.y; acc[4 * c + 2] += f.z; acc[4 * c + 3] += f.w;
-              }
-            }
-          }
-        }
-        const uint4 nores = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-        for (int c8 = 0; c8 < NCH / 8; ++c8) {
-          uint32_t bits[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) bits[e] = __float_as_uint(acc[8 * c8 + e]);
-          const uint4 packed = epi_chunk8<false>(bits, s_bias + ch_lo + 8 * c8, ca, cb, nores);
-          if (row.ok0) *reinterpret_cast<uint4*>(row.o0 + (long long)c8 * row.ostride) = packed;
-        }
-        if (++buf == cfg.nbuf) { buf = 0; aph ^= 1u; }
-      }
-    } else
     for (int it = 0; it < n_local; ++it, pit.next()) {
       const int tile0 = (pit.pi * 2 + (int)rank) * G;
       mbar_wait(tfull_bar(buf), aph);
@@ -405,39 +321,26 @@ conv_umma2_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
 // ----------------------------------------------------------------------------- host side
 static bool pick_cfg2(const ConvParams& p, Umma2Cfg& c) {
   const int Ns = p.N / (p.n_slices / 2);
-  const int tg = p.tg > 1 ? p.tg : 1;
-  c.S = conv_tile_stride(p);
   c.R = TILE_M + (p.taps - 1) * p.dil;
   int ncol = 32;
   while (ncol < Ns) ncol <<= 1;
   c.ncol = ncol;
   c.w_bytes = p.Cin * p.taps * (Ns / 2) * 2;
   const int room0 = conv_smem_budget() - BAR2_BYTES - BIAS2_BYTES - c.w_bytes;
-  static int g_max = -1;          // AR_TILE_GROUP=1|2|4 caps the group size (tuning / cross-check knob)
-  if (g_max < 0) {
-    const char* e = getenv("AR_TILE_GROUP");
-    g_max = e ? atoi(e) : 4;
-    if (g_max != 1 && g_max != 2) g_max = 4;
-  }
   for (int kbs = 4; kbs >= 1; kbs >>= 1) {
     if (p.Cin % (16 * kbs)) continue;
     // group size: enough tiles per barrier round that a stage carries >= ~64 MMAs, within TMEM (two buffers) and the ring
     int G = 1;
-    // AR_GROUP_MMAS: MMAs per stage below which tiles are grouped.  64 by default: also the k7 decoders (28 MMAs per
-    // stage) take G = 2 (128 -> 64) / G = 4 (64 -> 32) -- fewer barrier round trips per tile and 4-8 KB instead of 2 KB
-    // runs per bulk copy: 10.8 -> 10.2 ms and 5.3 -> 4.3 ms per launch at 1184 chunks (with 24 only k <= 3 layers group)
-    static int g_mma_target = -1;
-    if (g_mma_target < 0) {
-      const char* e = getenv("AR_GROUP_MMAS");
-      g_mma_target = e ? atoi(e) : 64;
-    }
-    while (tg == 1 && G < g_max && kbs * p.taps * G < g_mma_target && 2 * (2 * G) * ncol <= 512) G *= 2;   // tap-grouped layers: G = 1
+    // Below 64 MMAs per stage tiles are grouped: also the k7 decoders (28 MMAs per stage) take G = 2 (128 -> 64) / G = 4
+    // (64 -> 32) -- fewer barrier round trips per tile and 4-8 KB instead of 2 KB runs per bulk copy (10.8 -> 10.2 ms and
+    // 5.3 -> 4.3 ms per launch at 1184 chunks)
+    constexpr int kGroupMmas = 64, kMaxGroup = 4;
+    while (G < kMaxGroup && kbs * p.taps * G < kGroupMmas && 2 * (2 * G) * ncol <= 512) G *= 2;
     for (; G >= 1; G >>= 1) {
       c.RG = G * TILE_M + (p.taps - 1) * p.dil;
       c.stage_bytes = kbs * 2 * c.RG * 16;
       c.res_bytes = p.res != nullptr ? G * TILE_M * (Ns / 8) * 16 : 0;
-      const int xch_bytes = tg > 1 ? 16 * (tg - 1) * ((tg - 1) * (p.dil / tg)) * (Ns / tg / 2) * 4 : 0;
-      const int room = room0 - 2 * c.res_bytes - xch_bytes;
+      const int room = room0 - 2 * c.res_bytes;
       int stages = room / c.stage_bytes;
       if (stages > 8) stages = 8;
       if (stages >= 4 || (kbs == 1 && G == 1 && stages >= 2)) {
@@ -448,8 +351,7 @@ static bool pick_cfg2(const ConvParams& p, Umma2Cfg& c) {
         c.nbuf = 512 / (G * ncol) > 8 ? 8 : 512 / (G * ncol);
         c.tmem_cols = c.nbuf * G * ncol;
         c.res_off = c.w_bytes + stages * c.stage_bytes + BAR2_BYTES + BIAS2_BYTES;
-        c.xch_off = c.res_off + 2 * c.res_bytes;
-        c.smem_bytes = c.xch_off + xch_bytes;
+        c.smem_bytes = c.res_off + 2 * c.res_bytes;
         return true;
       }
     }
@@ -467,35 +369,26 @@ int launch_conv_umma2(const ConvParams& p, cudaStream_t stream) {
   AR_CHECK(p.mode == MODE_SAME || (p.pool == nullptr && p.res == nullptr), AR_ERR_INVALID, "conv_umma2: interleave mode has no pool/residual epilogue");
   AR_CHECK(p.mode == MODE_SAME || (p.N / 2) % (Ns / 2) == 0, AR_ERR_INVALID, "conv_umma2: interleave phases must align with the epilogue column split");
   AR_CHECK(!(p.pool && p.res), AR_ERR_INVALID, "conv_umma2: pool and residual epilogues are exclusive");
-  const int tg = p.tg > 1 ? p.tg : 1;
-  if (tg > 1) {
-    AR_CHECK(p.mode == MODE_SAME && !p.pool && !p.res && !p.out_tblock && nsl == 1, AR_ERR_INVALID,
-             "conv_umma2: a tap-grouped layer is a plain same-length conv in one pair-slice");
-    AR_CHECK(p.dil % tg == 0 && ((tg == 2 && p.N == 128) || (tg == 4 && p.N == 128)) && (tg - 1) * (p.dil / tg) <= 8,
-             AR_ERR_INVALID, "conv_umma2: unsupported tap-group geometry (two taps x 64 channels or four taps x 32 channels)");
-  }
   Umma2Cfg cfg;
   AR_CHECK(pick_cfg2(p, cfg), AR_ERR_INVALID, "conv_umma2: no pipeline configuration fits shared memory");
   using Kernel = void (*)(ConvParams, Umma2Cfg, int);
-  struct Entry { int variant, taps, tg; Kernel k; };
+  struct Entry { int variant, taps; Kernel k; };
   static const Entry table[] = {
-      {EV_PLAIN, 1, 1, conv_umma2_kernel<MODE_SAME, false, false, 1>}, {EV_PLAIN, 3, 1, conv_umma2_kernel<MODE_SAME, false, false, 3>},
-      {EV_PLAIN, 5, 1, conv_umma2_kernel<MODE_SAME, false, false, 5>}, {EV_PLAIN, 7, 1, conv_umma2_kernel<MODE_SAME, false, false, 7>},
-      {EV_POOL, 3, 1, conv_umma2_kernel<MODE_SAME, true, false, 3>},   {EV_RES, 3, 1, conv_umma2_kernel<MODE_SAME, false, true, 3>},
-      {EV_INTERLEAVE, 1, 1, conv_umma2_kernel<MODE_INTERLEAVE2, false, false, 1>},
-      {EV_INTERLEAVE, 3, 1, conv_umma2_kernel<MODE_INTERLEAVE2, false, false, 3>},
-      // tap-grouped k7 layers: 4 groups of 2 taps, 2 groups of 4 taps (the kernel's TAPS counts groups)
-      {EV_PLAIN, 4, 2, conv_umma2_kernel<MODE_SAME, false, false, 4, 2>}, {EV_PLAIN, 2, 4, conv_umma2_kernel<MODE_SAME, false, false, 2, 4>},
+      {EV_PLAIN, 1, conv_umma2_kernel<MODE_SAME, false, false, 1>}, {EV_PLAIN, 3, conv_umma2_kernel<MODE_SAME, false, false, 3>},
+      {EV_PLAIN, 5, conv_umma2_kernel<MODE_SAME, false, false, 5>}, {EV_PLAIN, 7, conv_umma2_kernel<MODE_SAME, false, false, 7>},
+      {EV_POOL, 3, conv_umma2_kernel<MODE_SAME, true, false, 3>},   {EV_RES, 3, conv_umma2_kernel<MODE_SAME, false, true, 3>},
+      {EV_INTERLEAVE, 1, conv_umma2_kernel<MODE_INTERLEAVE2, false, false, 1>},
+      {EV_INTERLEAVE, 3, conv_umma2_kernel<MODE_INTERLEAVE2, false, false, 3>},
   };
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attrs;   // per device: function attributes belong to the device's context
+  if (attrs.pending()) {
     for (const Entry& e : table) AR_CUDA_OK(cudaFuncSetAttribute(e.k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BUDGET));
-    attr_set = true;
+    attrs.done();
   }
   const int variant = epi_variant(p);
   Kernel kernel = nullptr;
   for (const Entry& e : table)
-    if (e.variant == variant && e.taps == p.taps && e.tg == tg) kernel = e.k;
+    if (e.variant == variant && e.taps == p.taps) kernel = e.k;
   AR_CHECK(kernel != nullptr, AR_ERR_INVALID, "conv_umma2: no kernel instantiated for this (epilogue, taps) combination");
   const int ppi = (p.tiles_per_item + 2 * cfg.G - 1) / (2 * cfg.G);   // tile groups per item
   const int num_pairs = p.B * ppi;

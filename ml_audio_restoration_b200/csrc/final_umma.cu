@@ -244,10 +244,10 @@ int launch_final_umma(const Act& in, int in_coff8, const __half* w_packed, const
   const int num_tiles = B * a.tiles_per_item;
   const int stage_bytes = nheads * 4 * TILE_M * 16;
   const int smem = 2048 + FU_STAGES * stage_bytes + 2 * TILE_M * FU_SROW * 4 + FU_RING_BYTES + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attrs;
+  if (attrs.pending()) {
     AR_CUDA_OK(cudaFuncSetAttribute(final_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
+    attrs.done();
   }
   int grid = sm_count();
   if (grid > num_tiles) grid = num_tiles;

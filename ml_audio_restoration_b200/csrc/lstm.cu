@@ -11,8 +11,6 @@
 // h that feeds the decoder convs is rounded to TF32.
 #include "ar_common.cuh"
 #include "pointwise.cuh"
-#include <cstdio>
-#include <cstdlib>
 
 namespace ar {
 
@@ -222,17 +220,31 @@ lstm_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, const flo
 }
 
 // ============================================================================ tensor-core recurrence
-// Eight sequences per CTA: the recurrent mat-vec of a step becomes a [256 x 64] x [64 x 8] product run on
-// warp-level tensor-core MMAs (mma.sync m16n8k16, fp16 operands, fp32 accumulate).  W_hh is rounded to fp16
-// like every other weight of the model and h is rounded to fp16 before it is fed back -- it is the same
-// rounded value the decoder convs consume -- while the cell state c, the gate pre-activations and all gate
-// math stay fp32 (measured on the oracle: output SNR > 100 dB vs the all-fp32 recurrence, tests/ check it).
-// Warp w owns hidden units [8w, 8w+8): its two 16-row MMA tiles hold rows (i,f) and (g,o) of those units, so
-// in the accumulator layout one thread ends up with all four gates of ONE unit for TWO sequences and the
-// cell update needs no cross-thread exchange.  h goes through shared memory ([seq][unit] fp16, stride 72
-// halves: conflict-free B-fragment loads); one block barrier per step.
-constexpr int LM_SEQ = 8;       // sequences per CTA
+// Used when the batch exceeds two sequences per SM (the bench: 8 per SM).  The recurrent mat-vec of a step becomes a
+// [256 x 64] x [64 x 8] product on warp-level tensor-core MMAs (mma.sync m16n8k16, fp16 operands, fp32 accumulate).
+// W_hh is rounded to fp16 like every other weight of the model and h is rounded to fp16 before it is fed back -- it is
+// the same rounded value the decoder convs consume -- while the cell state c, the gate pre-activations and all gate math
+// stay fp32 (tests: direct comparison with the fp32 oracle at 88 200 steps).
+//
+// A CTA owns FOUR sequences and an SM holds two such CTAs, i.e. two independent recurrences to interleave: every step is
+// one serial chain (h exchange -> MMAs -> gate functions -> barrier), and while one CTA sits in its barrier or its
+// gate-function chain the other one issues.  The 8 recurrence warps own 8 hidden units each as two 16-row tiles, (i|f)
+// and (g|o) of those units; the eight MMA columns hold the sequences as (s0 s0 s1 s1 s2 s2 s3 s3), so thread (gid, tig)
+// finds all four gates of cell (unit 8w + gid, sequence tig) in fixed accumulator registers -- no shuffles, no selects --
+// and carries exactly one cell.  h goes through shared memory ([seq][unit] fp16, padded stride: conflict-free 8-byte
+// B-fragment loads).
+//
+// Warp specialisation: two extra "mover" warps do nothing but data movement -- they stage the next 8-step block of
+// gate pre-activations (cp.async) and flush the previous block's hidden states -- so the eight recurrence warps run the
+// bare step (5 LDS, 8 HMMA, the gate functions, 2 STS) and meet at a named barrier of their own 256 threads.  (With the
+// flush inside the recurrence warps, the warp whose turn it was arrived ~40 instructions late at every step's barrier:
+// 49.8 -> 43.4 ms per 1184-chunk step.)  The two groups meet once per 8-step block (named barrier 1, all 320 threads):
+// by then the movers have long finished (16 cp.async + 4 flush items per thread per block).  The ping-pong index of the
+// h exchange buffer is the step's parity inside the block -- a compile-time constant in the unrolled loop -- and full
+// blocks run without the `step < T` tests.
 constexpr int LM_HS = 80;       // padded row stride of the h exchange buffer (halves): conflict-free 8-byte fragment loads
+constexpr int LM_XS = 264;      // padded per-sequence stride of a staged pre-activation row (halves)
+constexpr int LM_HST = 68;      // padded [seq] row stride of the hidden-state staging buffer (floats): conflict-free stores
 
 __device__ __forceinline__ void mma_f16_16x8x16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -240,324 +252,17 @@ __device__ __forceinline__ void mma_f16_16x8x16(float (&d)[4], const uint32_t (&
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-
-constexpr int LM_XS = 264;                        // padded per-sequence stride of a staged pre-activation row (halves)
-constexpr int LM_XSTEP = LM_SEQ * LM_XS + 8;      // halves per staged step; +16 bytes so the 8 steps that consecutive lanes stage
-                                                  // with one cp.async land in 8 different bank groups (a multiple of 128 B would be 8-way conflicted)
-constexpr int LM_XBUF = LSTM_BLK * LM_XSTEP;      // halves per 8-step buffer
-constexpr int LM_HST = 68;      // padded [seq] row stride of the hidden-state staging buffer (floats): conflict-free stores
-constexpr int LM_HSTEP = LM_SEQ * LM_HST + 4;     // floats per staged step of hidden states; +16 bytes: the flush reads 8 steps with consecutive lanes
-constexpr int LM_SMEM = 2 * LM_XBUF * 2 + 2 * LM_SEQ * LM_HS * 2 + 2 * LSTM_BLK * LM_HSTEP * 4;
-
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
-// 16 warps: warp w owns hidden units [4w, 4w+4) = ONE 16-row MMA tile ordered (i | g | f | o) x 4 units.  In
-// the accumulator layout lane (gid, tig) then holds gates (i,f) [gid < 4] or (g,o) [gid >= 4] of unit 4w+(gid&3)
-// for sequences 2tig and 2tig+1; one shuffle pair with lane^16 gives every thread all four gates of ONE
-// (unit, sequence), so the 512 threads each carry one cell.  The per-step dependent chain per warp is short
-// (4 MMAs, 5 gate functions) and four warps per scheduler interleave -- the kernel is latency-bound.
-constexpr int LM_THREADS = 512;
-
-__global__ void __launch_bounds__(LM_THREADS, 1)
-lstm_mma_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, const float* __restrict__ whh,
-                __half* __restrict__ hout, long long h_bs, int h_Tp, int B, int T,
-                const float* __restrict__ state_in, float* __restrict__ state_out) {
-  extern __shared__ __align__(16) float lm_smem[];
-  __half* const xs = reinterpret_cast<__half*>(lm_smem);       // [2][8 steps][8 seq][264] fp16: staged gate pre-activations
-  float* const hstage = lm_smem + LM_XBUF;                     // [2][8 steps][8 seq][64] fp32 (2*LM_XBUF halves == LM_XBUF floats)
-  __half* const hbuf = reinterpret_cast<__half*>(hstage + 2 * LSTM_BLK * LM_HSTEP);   // [2][8 seq][80] fp16
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  const int gid = lane >> 2, tig = lane & 3;        // mma fragment coordinates
-  const bool lowhalf = gid < 4;                     // holds (i,f); the partner lane^16 holds (g,o)
-  const int unit = warp * 4 + (gid & 3);            // the cell this thread carries: (unit, seq)
-  const int seq = 2 * tig + (lowhalf ? 0 : 1);
-  const int seq0 = blockIdx.x * LM_SEQ;
-  const int bq = min(seq0 + seq, B - 1);            // surplus columns replay the last sequence, stores are masked
-
-  // A fragment rows of this lane: gid -> (gate i or g), gid+8 -> (gate f or o) of unit 4w + (gid & 3)
-  uint32_t wfrag[4][4];
-  {
-    const int u = warp * 4 + (gid & 3);
-    const int row_lo = (lowhalf ? 0 : 2) * LSTM_H + u;     // i or g
-    const int row_hi = (lowhalf ? 1 : 3) * LSTM_H + u;     // f or o
-    auto w2 = [&](int row, int k) {
-      const __half2 h = __floats2half2_rn(whh[row * LSTM_H + k], whh[row * LSTM_H + k + 1]);
-      return *reinterpret_cast<const uint32_t*>(&h);
-    };
-#pragma unroll
-    for (int kt = 0; kt < 4; ++kt) {
-      wfrag[kt][0] = w2(row_lo, kt * 16 + 2 * tig);
-      wfrag[kt][1] = w2(row_hi, kt * 16 + 2 * tig);
-      wfrag[kt][2] = w2(row_lo, kt * 16 + 2 * tig + 8);
-      wfrag[kt][3] = w2(row_hi, kt * 16 + 2 * tig + 8);
-    }
-  }
-
-  float c = 0.f, hl = 0.f;
-  if (state_in != nullptr) {
-    hl = state_in[(long long)bq * 2 * LSTM_H + unit];
-    c = state_in[(long long)bq * 2 * LSTM_H + LSTM_H + unit];
-  }
-  // position of hidden unit `unit` inside its sequence row: within each 16-unit k-tile the pairs (2j, 2j+1) and
-  // (2j+8, 2j+9) that form one thread's B fragment (b0, b1) are made adjacent => one 8-byte load per k-tile
-  const int upos = (unit & ~15) + ((((unit & 7) >> 1) * 2 + ((unit >> 3) & 1)) * 2) + (unit & 1);
-  hbuf[seq * LM_HS + upos] = __float2half_rn(hl);
-
-  // Staging of the gate pre-activations: 8 steps x 8 sequences x 32 chunks of 16 bytes per block, copied with
-  // cp.async (4 pieces per thread, consecutive threads = consecutive steps of one (sequence, chunk) run =>
-  // 128-byte coalesced reads), one block ahead of its use.
-  const uint32_t xs_u32 = (uint32_t)__cvta_generic_to_shared(xs);
-  auto stage_piece = [&](int blk, int m) {          // piece m (0..3) of this thread's share of block blk
-    const int t0 = blk * LSTM_BLK;
-    const uint32_t dst0 = xs_u32 + (uint32_t)((blk & 1) * LM_XBUF * 2);
-    // 8 steps x 32 chunks of one sequence are ONE contiguous 4 KB run (HALO == 8 keeps blocks aligned):
-    // consecutive threads take consecutive 16-byte pieces of it
-    const int i = tid + LM_THREADS * m;           // 0..2047
-    const int sq = i >> 8, piece = i & 255;       // piece = chunk*8 + step
-    const int ch = piece >> 3, k = piece & 7;
-    const int b = min(seq0 + sq, B - 1);
-    cp_async16(dst0 + (uint32_t)((k * LM_XSTEP + sq * LM_XS + ch * 8) * 2), xp + act_off_tb(xp_bs, 32, b, ch, t0 + k));
-  };
-  // one hidden-state item per thread per block: [8 seq][8 chunks][8 steps] x 16 bytes, coalesced along time
-  auto flush_item = [&](int blk) {
-    const float* hst = hstage + (blk & 1) * (LSTM_BLK * LM_HSTEP);
-    const int t0 = blk * LSTM_BLK;
-    const int s = tid / (8 * LSTM_BLK);              // LM_SEQ * 8 * LSTM_BLK == 512 == LM_THREADS
-    const int ch = (tid / LSTM_BLK) % 8;
-    const int kk = tid % LSTM_BLK;
-    const int b = seq0 + s;
-    if (b < B && t0 + kk < T) {
-      const float* src = &hst[kk * LM_HSTEP + s * LM_HST + 8 * ch];
-      const float4 v0 = *reinterpret_cast<const float4*>(src);
-      const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
-      const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-      *reinterpret_cast<uint4*>(hout + act_off(h_bs, h_Tp, b, ch, t0 + kk)) = pack_half8(v);
-    }
-  };
-#pragma unroll
-  for (int m = 0; m < 4; ++m) stage_piece(0, m);
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-
-  // The staging of block blk+1 and the write-back of block blk-1 are spread over the steps of block blk (one
-  // cp.async every other step, one warp-pair flushing per step) instead of bursting at the block boundary,
-  // where all 16 warps would queue on the memory pipe at once.
-  int cur = 0;
-  const int nblk = (T + LSTM_BLK - 1) / LSTM_BLK;
-  const int my_flush_step = warp & 7;
-  for (int blk = 0; blk < nblk; ++blk) {
-    const bool more = blk + 1 < nblk;
-    const __half* xb = xs + (blk & 1) * LM_XBUF;
-    float* hst = hstage + (blk & 1) * (LSTM_BLK * LM_HSTEP);
-    const int t0 = blk * LSTM_BLK;
-    const int nst = min(LSTM_BLK, T - t0);
-    if (!more && blk > 0) flush_item(blk - 1);       // last (possibly short) block: write the previous one up front
-#pragma unroll
-    for (int k = 0; k < LSTM_BLK; ++k) {
-      if (k < nst) {  // uniform
-        if (more) {
-          if ((k & 1) == 0) stage_piece(blk + 1, k >> 1);
-          if (k == 6) asm volatile("cp.async.commit_group;" ::: "memory");
-          if (blk > 0 && k == my_flush_step) flush_item(blk - 1);
-        }
-        float acc[2][4];
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) acc[h][i] = 0.f;
-        const uint2* hb = reinterpret_cast<const uint2*>(hbuf + cur * (LM_SEQ * LM_HS) + gid * LM_HS) + tig;
-#pragma unroll
-        for (int kt = 0; kt < 4; ++kt) {
-          const uint2 bf = hb[kt * 4];           // .x = h[16kt + 2tig, +1], .y = h[16kt + 2tig + 8, +9] of sequence gid
-          mma_f16_16x8x16(acc[kt & 1], wfrag[kt], bf.x, bf.y);
-        }
-        // [0]=(row gid, seq 2tig) [1]=(gid, 2tig+1) [2]=(gid+8, 2tig) [3]=(gid+8, 2tig+1)
-        const float v0 = acc[0][0] + acc[1][0], v1 = acc[0][1] + acc[1][1];
-        const float v2 = acc[0][2] + acc[1][2], v3 = acc[0][3] + acc[1][3];
-        // lowhalf keeps sequence 2tig (needs g,o of it), the partner keeps 2tig+1 (needs i,f of it)
-        const float r0 = __shfl_xor_sync(0xffffffffu, lowhalf ? v1 : v0, 16);
-        const float r1 = __shfl_xor_sync(0xffffffffu, lowhalf ? v3 : v2, 16);
-        const uint2 q = *reinterpret_cast<const uint2*>(xb + k * LM_XSTEP + seq * LM_XS + unit * 4);   // [unit][i,f,g,o]
-        const float2 x_if = __half22float2(*reinterpret_cast<const __half2*>(&q.x));
-        const float2 x_go = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
-        const float pi = (lowhalf ? v0 : r0) + x_if.x;
-        const float pf = (lowhalf ? v2 : r1) + x_if.y;
-        const float pg = (lowhalf ? r0 : v1) + x_go.x;
-        const float po = (lowhalf ? r1 : v3) + x_go.y;
-        lstm_cell(pi, pf, pg, po, c, hl);
-        // fed-back h == the fp16-rounded value the decoder convs will read
-        hbuf[(cur ^ 1) * (LM_SEQ * LM_HS) + seq * LM_HS + upos] = __float2half_rn(hl);
-        hst[k * LM_HSTEP + seq * LM_HST + unit] = hl;     // rounded to fp16 (the same value) when flushed
-        if (more && k == LSTM_BLK - 1) asm volatile("cp.async.wait_group 0;" ::: "memory");   // next block's staging has landed
-        __syncthreads();
-        cur ^= 1;
-      }
-    }
-  }
-  flush_item(nblk - 1);
-  if (state_out != nullptr && seq0 + seq < B) {
-    state_out[(long long)(seq0 + seq) * 2 * LSTM_H + unit] = hl;
-    state_out[(long long)(seq0 + seq) * 2 * LSTM_H + LSTM_H + unit] = c;
-  }
-}
-
-
-// ---------------------------------------------------------------------------- 4 sequences per CTA, two CTAs per SM
-// The 8-sequence kernel above is latency-bound: every step is one serial chain (h exchange -> MMAs -> gate functions ->
-// barrier) and all 16 warps of the SM walk it in lock step (ncu: 32 % issue utilisation, the special-function unit
-// saturated only in bursts).  This variant gives each SM TWO independent recurrences to interleave: a CTA owns four
-// sequences (the n = 8 MMA columns hold them twice), its 8 warps own 8 hidden units each as two 16-row tiles, (i|f) and
-// (g|o) of those units, and the eight MMA columns hold the sequences as (s0 s0 s1 s1 s2 s2 s3 s3), so thread (gid, tig)
-// finds all four gates of cell (unit 8w + gid, sequence tig) in fixed accumulator registers -- no shuffles, no
-// selects -- and carries exactly one cell.  While one CTA sits in its barrier or its
-// gate-function chain the other one issues.
 constexpr int L4_SEQ = 4;
-constexpr int L4_THREADS = 256;
-constexpr int L4_XSTEP = L4_SEQ * LM_XS + 8;       // halves per staged step (+16 B: conflict-free cp.async rows)
+constexpr int L4_THREADS = 256;                    // recurrence warps
+constexpr int L4W_THREADS = L4_THREADS + 64;       // + two mover warps
+constexpr int L4_XSTEP = L4_SEQ * LM_XS + 8;       // halves per staged step (+16 B: the 8 steps that consecutive lanes stage land in 8 bank groups)
 constexpr int L4_XBUF = LSTM_BLK * L4_XSTEP;
 constexpr int L4_HSTEP = L4_SEQ * LM_HST + 4;      // floats per staged step of hidden states
 constexpr int L4_SMEM = 2 * L4_XBUF * 2 + 2 * LSTM_BLK * L4_HSTEP * 4 + 2 * L4_SEQ * LM_HS * 2;
-
-__global__ void __launch_bounds__(L4_THREADS, 3)
-lstm_mma4_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, const float* __restrict__ whh,
-                 __half* __restrict__ hout, long long h_bs, int h_Tp, int B, int T,
-                 const float* __restrict__ state_in, float* __restrict__ state_out) {
-  extern __shared__ __align__(16) float lm_smem[];
-  __half* const xs = reinterpret_cast<__half*>(lm_smem);       // [2][8 steps][4 seq][264] fp16 staged gate pre-activations
-  float* const hstage = lm_smem + L4_XBUF;                     // [2][8 steps][4 seq][68] fp32
-  __half* const hbuf = reinterpret_cast<__half*>(hstage + 2 * LSTM_BLK * L4_HSTEP);   // [2][4 seq][80] fp16
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  const int gid = lane >> 2, tig = lane & 3;
-  const int unit = warp * 8 + gid;                  // the cell this thread carries: (unit, seq)
-  const int seq = tig;                              // MMA columns hold the sequences as (s0 s0 s1 s1 s2 s2 s3 s3): the thread's
-                                                    // own columns 2tig, 2tig+1 are both sequence tig -> it reads c0 / c2, no select
-  const int seq0 = blockIdx.x * L4_SEQ;
-  const int bq = min(seq0 + seq, B - 1);            // surplus columns replay the last sequence, stores are masked
-
-  // A fragments: tile 0 rows (gid -> i, gid+8 -> f), tile 1 rows (gid -> g, gid+8 -> o) of unit 8w + gid
-  uint32_t wfrag[2][4][4];
-  {
-    auto w2 = [&](int row, int k) {
-      const __half2 h = __floats2half2_rn(whh[row * LSTM_H + k], whh[row * LSTM_H + k + 1]);
-      return *reinterpret_cast<const uint32_t*>(&h);
-    };
-#pragma unroll
-    for (int tl = 0; tl < 2; ++tl) {
-      const int row_lo = (2 * tl) * LSTM_H + unit, row_hi = (2 * tl + 1) * LSTM_H + unit;
-#pragma unroll
-      for (int kt = 0; kt < 4; ++kt) {
-        wfrag[tl][kt][0] = w2(row_lo, kt * 16 + 2 * tig);
-        wfrag[tl][kt][1] = w2(row_hi, kt * 16 + 2 * tig);
-        wfrag[tl][kt][2] = w2(row_lo, kt * 16 + 2 * tig + 8);
-        wfrag[tl][kt][3] = w2(row_hi, kt * 16 + 2 * tig + 8);
-      }
-    }
-  }
-  float c = 0.f, hl = 0.f;
-  if (state_in != nullptr) {
-    hl = state_in[(long long)bq * 2 * LSTM_H + unit];
-    c = state_in[(long long)bq * 2 * LSTM_H + LSTM_H + unit];
-  }
-  const int upos = (unit & ~15) + ((((unit & 7) >> 1) * 2 + ((unit >> 3) & 1)) * 2) + (unit & 1);   // see lstm_mma_kernel
-  hbuf[seq * LM_HS + upos] = __float2half_rn(hl);
-
-  const uint32_t xs_u32 = (uint32_t)__cvta_generic_to_shared(xs);
-  auto stage_piece = [&](int blk, int m) {          // piece m (0..3) of this thread's share of block blk
-    const int t0 = blk * LSTM_BLK;
-    const uint32_t dst0 = xs_u32 + (uint32_t)((blk & 1) * L4_XBUF * 2);
-    const int i = tid + L4_THREADS * m;             // 0..1023: [4 seq][32 chunks][8 steps]
-    const int sq = i >> 8, piece = i & 255;
-    const int ch = piece >> 3, k = piece & 7;
-    const int b = min(seq0 + sq, B - 1);
-    cp_async16(dst0 + (uint32_t)((k * L4_XSTEP + sq * LM_XS + ch * 8) * 2), xp + act_off_tb(xp_bs, 32, b, ch, t0 + k));
-  };
-  auto flush_item = [&](int blk) {                  // one 16-byte hidden-state item per thread: [4 seq][8 chunks][8 steps]
-    const float* hst = hstage + (blk & 1) * (LSTM_BLK * L4_HSTEP);
-    const int t0 = blk * LSTM_BLK;
-    const int s = tid >> 6, ch = (tid >> 3) & 7, kk = tid & 7;
-    const int b = seq0 + s;
-    if (b < B && t0 + kk < T) {
-      const float* src = &hst[kk * L4_HSTEP + s * LM_HST + 8 * ch];
-      const float4 v0 = *reinterpret_cast<const float4*>(src);
-      const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
-      const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-      *reinterpret_cast<uint4*>(hout + act_off(h_bs, h_Tp, b, ch, t0 + kk)) = pack_half8(v);
-    }
-  };
-#pragma unroll
-  for (int m = 0; m < 4; ++m) stage_piece(0, m);
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-
-  int cur = 0;
-  const int nblk = (T + LSTM_BLK - 1) / LSTM_BLK;
-  for (int blk = 0; blk < nblk; ++blk) {
-    const bool more = blk + 1 < nblk;
-    const __half* xb = xs + (blk & 1) * L4_XBUF;
-    float* hst = hstage + (blk & 1) * (LSTM_BLK * L4_HSTEP);
-    const int t0 = blk * LSTM_BLK;
-    const int nst = min(LSTM_BLK, T - t0);
-    if (!more && blk > 0) flush_item(blk - 1);
-#pragma unroll
-    for (int k = 0; k < LSTM_BLK; ++k) {
-      if (k < nst) {  // uniform
-        if (more) {
-          if ((k & 1) == 0) stage_piece(blk + 1, k >> 1);
-          if (k == 6) asm volatile("cp.async.commit_group;" ::: "memory");
-          if (blk > 0 && k == warp) flush_item(blk - 1);      // one warp flushes per step
-        }
-        // pre-activations of this thread's cell: issued before the MMAs so the load hides behind them
-        const uint2 q = *reinterpret_cast<const uint2*>(xb + k * L4_XSTEP + seq * LM_XS + unit * 4);   // [unit][i,f,g,o]
-        float acc[2][4];
-#pragma unroll
-        for (int tl = 0; tl < 2; ++tl)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) acc[tl][i] = 0.f;
-        const uint2* hb = reinterpret_cast<const uint2*>(hbuf + cur * (L4_SEQ * LM_HS) + (gid >> 1) * LM_HS) + tig;   // B column gid = sequence gid/2
-#pragma unroll
-        for (int kt = 0; kt < 4; ++kt) {
-          const uint2 bf = hb[kt * 4];
-          mma_f16_16x8x16(acc[0], wfrag[0][kt], bf.x, bf.y);     // two independent chains (tiles), 4 deep
-          mma_f16_16x8x16(acc[1], wfrag[1][kt], bf.x, bf.y);
-        }
-        const float2 x_if = __half22float2(*reinterpret_cast<const __half2*>(&q.x));
-        const float2 x_go = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
-        const float pi = acc[0][0] + x_if.x;
-        const float pf = acc[0][2] + x_if.y;
-        const float pg = acc[1][0] + x_go.x;
-        const float po = acc[1][2] + x_go.y;
-        lstm_cell(pi, pf, pg, po, c, hl);
-        hbuf[(cur ^ 1) * (L4_SEQ * LM_HS) + seq * LM_HS + upos] = __float2half_rn(hl);
-        hst[k * L4_HSTEP + seq * LM_HST + unit] = hl;
-        if (more && k == LSTM_BLK - 1) asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
-        cur ^= 1;
-      }
-    }
-  }
-  flush_item(nblk - 1);
-  if (state_out != nullptr && seq0 + seq < B) {
-    state_out[(long long)(seq0 + seq) * 2 * LSTM_H + unit] = hl;
-    state_out[(long long)(seq0 + seq) * 2 * LSTM_H + LSTM_H + unit] = c;
-  }
-}
-
-// ---------------------------------------------------------------------------- warp-specialised variant of the above
-// lstm_mma4_kernel's 8 warps also stage the next block's pre-activations (cp.async) and flush the previous block's hidden
-// states (one warp per step: two LDS.128, four packs, 64-bit address math, one STG): ~40 extra instructions in front of
-// that warp's MMAs, and since every step ends in a CTA barrier ALL warps wait for the one that flushed.  Here two extra
-// warps do nothing but that data movement; the eight recurrence warps run the bare step (5 LDS, 8 HMMA, the gate
-// functions, 2 STS) and meet at a named barrier of their own 256 threads.  The two groups meet once per 8-step block
-// (named barrier 1, all 320 threads): by then the movers have long finished (16 cp.async + 4 flush items per thread per
-// block).  The ping-pong index of the h exchange buffer is the step's parity inside the block -- a compile-time
-// constant in the unrolled loop -- and full blocks run without the `step < T` tests.
-constexpr int L4W_THREADS = L4_THREADS + 64;
 
 __global__ void __launch_bounds__(L4W_THREADS, 2)
 lstm_mma4w_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, const float* __restrict__ whh,
@@ -619,7 +324,7 @@ lstm_mma4w_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, con
     return;
   }
 
-  // -------------------------------------------------------------------- recurrence (warps 0..7), as in lstm_mma4_kernel
+  // -------------------------------------------------------------------- recurrence (warps 0..7)
   const int warp = tid >> 5, lane = tid & 31;
   const int gid = lane >> 2, tig = lane & 3;
   const int unit = warp * 8 + gid;
@@ -648,7 +353,9 @@ lstm_mma4w_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, con
     hl = state_in[(long long)bq * 2 * LSTM_H + unit];
     c = state_in[(long long)bq * 2 * LSTM_H + LSTM_H + unit];
   }
-  const int upos = (unit & ~15) + ((((unit & 7) >> 1) * 2 + ((unit >> 3) & 1)) * 2) + (unit & 1);   // see lstm_mma_kernel
+  // position of hidden unit `unit` inside its sequence row: within each 16-unit k-tile the pairs (2j, 2j+1) and
+  // (2j+8, 2j+9) that form one thread's B fragment (b0, b1) are made adjacent => one 8-byte load per k-tile
+  const int upos = (unit & ~15) + ((((unit & 7) >> 1) * 2 + ((unit >> 3) & 1)) * 2) + (unit & 1);
   hbuf[seq * LM_HS + upos] = __float2half_rn(hl);
   const uint2* const hb_rd = reinterpret_cast<const uint2*>(hbuf + (gid >> 1) * LM_HS) + tig;   // B column gid = sequence gid/2
   __half* const hb_wr = hbuf + seq * LM_HS + upos;
@@ -711,61 +418,22 @@ lstm_mma4w_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, con
 int launch_lstm(const Act& xp, const float* whh, const Act& h_out, int B, int T, const float* state_in, float* state_out,
                 cudaStream_t stream) {
   AR_CHECK(T >= 1 && B >= 1, AR_ERR_INVALID, "lstm: empty input");
-  // AR_LSTM_S=1|2|4 selects the CUDA-core kernel with S sequences per CTA (cross-check / tuning knob).
-  static int forced = -1;
-  if (forced < 0) {
-    const char* e = getenv("AR_LSTM_S");
-    forced = e ? atoi(e) : 0;
-  }
-  // Heuristic: the CUDA-core kernel (one sequence per CTA, two CTAs per SM) while that covers the batch; beyond two
-  // sequences per SM the tensor-core kernels: four sequences per CTA x two CTAs per SM (default), or eight per CTA
-  // (AR_LSTM_S=8).  AR_LSTM_S overrides.
-  if (forced == 8) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      AR_CUDA_OK(cudaFuncSetAttribute(lstm_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_SMEM));
-      attr_set = true;
+  // One sequence per CTA on CUDA cores (two CTAs per SM) while that covers the batch; beyond two sequences per SM the
+  // tensor-core kernel: four sequences per CTA x two CTAs per SM.
+  if (B > 2 * sm_count()) {
+    static DeviceOnce attrs;
+    if (attrs.pending()) {
+      AR_CUDA_OK(cudaFuncSetAttribute(lstm_mma4w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L4_SMEM));
+      // two CTAs of 53 KB must fit: ask for the largest shared-memory carve-out, the driver's default heuristic sizes it
+      // for ONE CTA and the second recurrence of the SM would run after the first instead of under it
+      AR_CUDA_OK(cudaFuncSetAttribute(lstm_mma4w_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      attrs.done();
     }
-    lstm_mma_kernel<<<(B + LM_SEQ - 1) / LM_SEQ, LM_THREADS, LM_SMEM, stream>>>(xp.h(), xp.bs, xp.Tp, whh, h_out.h(), h_out.bs, h_out.Tp,
-                                                                         B, T, state_in, state_out);
-    AR_CUDA_OK(cudaGetLastError());
-    return AR_OK;
-  }
-  if (forced == 44 || forced == 45 || (forced == 0 && B > 2 * sm_count())) {
-    // default: the warp-specialised kernel (two mover warps + eight recurrence warps); AR_LSTM_S=44 keeps all data
-    // movement in the recurrence warps (lstm_mma4_kernel, A/B measurements)
-    const bool movers = forced != 44;
-    const void* fn = movers ? (const void*)lstm_mma4w_kernel : (const void*)lstm_mma4_kernel;
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[movers]) {
-      AR_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, L4_SMEM));
-      // two (three) CTAs of 53 KB must fit: ask for the largest shared-memory carve-out, the driver's default
-      // heuristic sizes it for ONE CTA and the second recurrence of the SM would run after the first instead of under it
-      AR_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-      if (getenv("AR_DEBUG_OCCUPANCY")) {
-        int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, movers ? L4W_THREADS : L4_THREADS, L4_SMEM);
-        fprintf(stderr, "lstm_mma4%s_kernel: %d CTAs per SM\n", movers ? "w" : "", nb);
-      }
-      attr_set[movers] = true;
-    }
-    if (movers)
-      lstm_mma4w_kernel<<<(B + L4_SEQ - 1) / L4_SEQ, L4W_THREADS, L4_SMEM, stream>>>(xp.h(), xp.bs, xp.Tp, whh, h_out.h(), h_out.bs,
-                                                                              h_out.Tp, B, T, state_in, state_out);
-    else
-      lstm_mma4_kernel<<<(B + L4_SEQ - 1) / L4_SEQ, L4_THREADS, L4_SMEM, stream>>>(xp.h(), xp.bs, xp.Tp, whh, h_out.h(), h_out.bs,
+    lstm_mma4w_kernel<<<(B + L4_SEQ - 1) / L4_SEQ, L4W_THREADS, L4_SMEM, stream>>>(xp.h(), xp.bs, xp.Tp, whh, h_out.h(), h_out.bs,
                                                                             h_out.Tp, B, T, state_in, state_out);
-    AR_CUDA_OK(cudaGetLastError());
-    return AR_OK;
+  } else {
+    lstm_kernel<1, 8><<<B, 256, 0, stream>>>(xp.h(), xp.bs, xp.Tp, whh, h_out.h(), h_out.bs, h_out.Tp, B, T, state_in, state_out);
   }
-  int S = forced ? forced : 1;
-#define AR_LSTM_LAUNCH(SS, PF)                                                                                 \
-  lstm_kernel<SS, PF><<<(B + SS - 1) / SS, 256, 0, stream>>>(xp.h(), xp.bs, xp.Tp, whh, h_out.h(), h_out.bs, h_out.Tp, B, \
-                                                             T, state_in, state_out)
-  if (S == 4) AR_LSTM_LAUNCH(4, 4);
-  else if (S == 2) AR_LSTM_LAUNCH(2, 4);
-  else AR_LSTM_LAUNCH(1, 8);
-#undef AR_LSTM_LAUNCH
   AR_CUDA_OK(cudaGetLastError());
   return AR_OK;
 }

@@ -1,5 +1,6 @@
 // Host side of libaudiorestore_sm100: state_dict -> folded / packed device weights, the
 // workspace planner, and the three model forwards + the chain expressed as kernel sequences.
+#include <atomic>
 #include <cmath>
 #include <cuda_fp16.h>
 #include <cstdlib>
@@ -18,46 +19,21 @@ namespace ar {
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 const char* last_error() { return g_err.c_str(); }
-static int g_engine = AR_ENGINE_UMMA;
+// Process-wide knobs read when a model is created (cross-check / tuning hooks of the C-ABI, no environment variables).
+static std::atomic<int> g_engine{AR_ENGINE_UMMA};
 int set_engine(int e) {
   if (e != AR_ENGINE_UMMA && e != AR_ENGINE_SIMT) { set_error("unknown conv engine"); return AR_ERR_INVALID; }
-  g_engine = e;
+  g_engine.store(e);
   return AR_OK;
 }
-// Layer fusion (conv_chain.cu) for subsequently created models; AR_FUSE=0 in the environment turns it off too.
-static long long* g_chain_trace = nullptr;   // debug: device buffer the fused-chain kernels trace their pipeline into
-static int g_chain_trace_slot = 0;           // launch k after ar_debug_chain_trace() writes slot k % 4 of [4][64*16]
-int set_chain_trace(long long* dev_buf) { g_chain_trace = dev_buf; g_chain_trace_slot = 0; return AR_OK; }
-static int g_fuse = -1;
+static std::atomic<int> g_fuse{1};   // fused multi-layer launches (conv_chain.cu, sr_trunk.cu) for subsequently created models
 int set_fusion(int on) {
-  g_fuse = on ? 1 : 0;
+  g_fuse.store(on ? 1 : 0);
   return AR_OK;
 }
-static int fusion_default() {
-  if (g_fuse < 0) {
-    const char* e = getenv("AR_FUSE");
-    g_fuse = e ? (atoi(e) != 0) : 1;
-  }
-  return g_fuse;
-}
-
-// Tap-grouped k7 decoder layers (ConvParams::tg) for subsequently created models.  OFF by default (ar_set_tap_groups(1) or
-// AR_TAPGROUP=1 turns them on): measured on B200 the grouped 128 -> 64 layer needs 32 instead of 56 MMAs per tile pair but
-// runs 11.8 vs 11.0 ms per 1184-chunk step, the grouped 64 -> 32 layer 6.5 vs 5.3 ms -- the chip is power-limited (the
-// denser instruction stream runs at a lower SM clock and the zero eighth tap adds 14 % FLOPs), and with 8 MMAs per tile the
-// per-tile barrier round trips of the MMA warp dominate (tensor pipe 24 % active, epilogue waiting on the accumulator).
-static int g_tap_groups = -1;
-int set_tap_groups(int on) {
-  g_tap_groups = on ? 1 : 0;
-  return AR_OK;
-}
-static bool want_tap_groups() {
-  if (g_tap_groups < 0) {
-    const char* e = getenv("AR_TAPGROUP");
-    g_tap_groups = e ? (atoi(e) != 0) : 0;
-  }
-  return g_tap_groups != 0;
-}
+static std::atomic<long long*> g_chain_trace{nullptr};   // debug: device buffer the fused-chain kernels trace their pipeline into
+static std::atomic<int> g_chain_trace_slot{0};           // launch k after ar_debug_chain_trace() writes slot k % 4 of [4][64*16]
+int set_chain_trace(long long* dev_buf) { g_chain_trace.store(dev_buf); g_chain_trace_slot.store(0); return AR_OK; }
 
 // ============================================================================ weight folding / packing
 static uint16_t half_bits_host(float x) {  // fp32 -> fp16, round to nearest even, clamped to the finite range
@@ -101,7 +77,6 @@ struct ConvLayer {  // device-resident packed layer
   double macs_per_row;  // algorithmic MACs of the reference op per input time step (structural zeros excluded)
   int n_slices;         // column slices (each slice's weights stay resident in one CTA's shared memory)
   int cta2;             // slices come in (2i, 2i+1) pairs: the two halves of a 2-CTA pair-slice
-  int tg = 1;           // taps side by side along N (ConvParams::tg); N, taps, dil describe the grouped GEMM
 };
 
 // Resident-weight budget per CTA (fp16 weights): leaves >= ~96 KB of the 227 KB for the activation ring.
@@ -112,19 +87,14 @@ static int pick_slices(int Cin, int taps, int N) {
   while ((size_t)Cin * taps * (N / s) * 2 > W_SLICE_BUDGET && (N / (2 * s)) % 16 == 0) s *= 2;
   return s;
 }
-// 2-CTA engine: every layer with N >= 32 is packed as pair-slices of two halves (one per CTA of the pair);
-// AR_CTA2=0 (read at model creation) packs for the 1-CTA engine instead.
-static bool want_cta2(int N) {
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("AR_CTA2");
-    on = e ? atoi(e) : 1;
-  }
-  return on && N >= 32 && N % 32 == 0;
-}
+// Every layer with N a multiple of 32 is packed as pair-slices of two halves (one per CTA of the 2-CTA engine).
+static bool want_cta2(int N) { return N >= 32 && N % 32 == 0; }
 
 struct Blob {
   std::vector<float> host;
+  // Largest |folded weight| seen and the smallest per-layer maximum: operands are stored in fp16 (finite range 65504,
+  // normal range down to 6.1e-5), so a BN fold with a tiny running_var can push a layer outside it.
+  float w_max = 0.f, w_min_layer_max = 1e30f;
   size_t push(const float* p, size_t n) {
     size_t off = (host.size() + 63) / 64 * 64;  // 256-byte aligned
     host.resize(off + n);
@@ -148,7 +118,14 @@ struct Blob {
                 w[(((((size_t)sl * KB + kb) * g.taps + t) * 2 + h) * Ns + n) * 8 + j] =
                     half_bits_host(g.at(t, kb * 16 + h * 8 + j, sl * Ns + n));
     ConvLayer L{g.Cin, g.N, g.taps, g.dil, g.pad_left, 0, 0, 0.0, ns, cta2 ? 1 : 0};
-    for (float v : g.G) L.macs_per_row += (v != 0.f) ? 1.0 : 0.0;  // == Cin*N*taps except the 2-phase ConvT
+    float lmax = 0.f;
+    for (float v : g.G) {
+      L.macs_per_row += (v != 0.f) ? 1.0 : 0.0;  // == Cin*N*taps except the 2-phase ConvT
+      const float av = std::fabs(v);
+      if (!(av <= lmax)) lmax = av;               // also catches NaN
+    }
+    if (!(lmax <= w_max)) w_max = lmax;
+    if (lmax < w_min_layer_max) w_min_layer_max = lmax;
     std::vector<float> raw((w.size() + 1) / 2);
     std::memcpy(raw.data(), w.data(), w.size() * 2);
     L.w_off = push(raw);
@@ -170,8 +147,11 @@ static bool fold_bn(const Table& t, const std::string& conv, const std::string& 
   const float* mu = t.get(bn + ".running_mean", {cout});
   const float* var = t.get(bn + ".running_var", {cout});
   if (!g || !be || !mu || !var) return false;
+  float eps = 1e-5f;                                   // nn.BatchNorm1d default; "<bn>.eps" ([1]) overrides it
+  auto it = t.m.find(bn + ".eps");
+  if (it != t.m.end() && it->second->data != nullptr) eps = it->second->data[0];
   for (int o = 0; o < cout; ++o) {
-    const float s = g[o] / std::sqrt(var[o] + 1e-5f);
+    const float s = g[o] / std::sqrt(var[o] + eps);
     f.s[o] = s;
     f.b[o] = (b[o] - mu[o]) * s + be[o];
   }
@@ -200,16 +180,6 @@ static bool make_conv(const Table& t, Blob& blob, const std::string& conv, const
   return true;
 }
 
-// The tap-grouped form of a conv GEMM (ConvParams::tg): tap j = g*tg + i moves to column block i of group g.
-static Gemm tap_grouped(const Gemm& g, int tg) {
-  Gemm r;
-  r.init(g.Cin, g.N * tg, (g.taps + tg - 1) / tg, g.dil * tg, g.pad_left);
-  for (int j = 0; j < g.taps; ++j)
-    for (int c = 0; c < g.Cin; ++c)
-      for (int n = 0; n < g.N; ++n) r.at(j / tg, c, (j % tg) * g.N + n) = g.G[((size_t)j * g.Cin + c) * g.N + n];
-  for (int n = 0; n < g.N; ++n) r.bias[n] = g.bias[n];   // the epilogue adds the bias of block 0's columns only
-  return r;
-}
 // ============================================================================ model objects
 
 struct Model {
@@ -224,8 +194,14 @@ struct Model {
   size_t fin_umma_off = 0;   // the same heads packed as a tap-along-N tensor-core operand (final_umma.cu)
   int fin_heads = 0;
   size_t whh_off = 0;
-  ~Model() { if (blob) cudaFree(blob); }
+  // dynamic-range audit (ar_model_audit_*): while on, forwards run layer by layer and fold max |activation| of every
+  // fp16 tensor they write into audit_dev[slot]; names are recorded in launch order.  Not re-entrant.
+  bool audit = false;
+  unsigned int* audit_dev = nullptr;
+  std::vector<std::string> audit_names;
+  ~Model() { if (blob) cudaFree(blob); if (audit_dev) cudaFree(audit_dev); }
 };
+constexpr int AUDIT_SLOTS = AR_AUDIT_MAX_LAYERS;
 
 static bool stem_pack(const Table& t, Blob& blob, const std::string& conv, const std::string& bn, int k, StemP& s) {
   (void)blob;
@@ -390,21 +366,6 @@ static bool build_stereo(const Table& t, Blob& blob, Model& m) {
     const std::string p = sides[s], tag = s ? "R" : "L";
     if (!make_conv(t, blob, p + ".3", p + ".4", 128, 64, 7, 1, m.conv["dec1" + tag])) return false;
     if (!make_conv(t, blob, p + ".6", p + ".7", 64, 32, 7, 1, m.conv["dec2" + tag])) return false;
-    // the same two layers tap-grouped for the 2-CTA engine: 128 -> 64 k7 as 4 groups of 2 taps (N = 128, 32 MMAs per
-    // tile pair instead of 56), 64 -> 32 k7 as 2 groups of 4 taps (N = 128, 8 MMAs instead of 28)
-    if (want_tap_groups() && want_cta2(128)) {
-      const int cin[2] = {128, 64}, cout[2] = {64, 32}, tgs[2] = {2, 4};
-      const char* idx[2][2] = {{".3", ".4"}, {".6", ".7"}};
-      for (int l = 0; l < 2; ++l) {
-        Gemm g;
-        g.init(cin[l], cout[l], 7, 1, 3);
-        if (!add_conv(t, p + idx[l][0], p + idx[l][1], cin[l], cout[l], 7, g)) return false;
-        Gemm gt = tap_grouped(g, tgs[l]);
-        ConvLayer L = blob.push_gemm(gt);
-        L.tg = tgs[l];
-        m.conv[std::string(l ? "dec2" : "dec1") + tag + ".tg"] = L;
-      }
-    }
     const float* WF = t.get(p + ".9.weight", {1, 32, 7});
     const float* BF = t.get(p + ".9.bias", {1});
     if (!WF || !BF) return false;
@@ -436,8 +397,8 @@ int model_create(int kind, const ar_tensor_t* tensors, int n, int device, Model*
   std::unique_ptr<Model> m(new Model);
   m->kind = kind;
   m->device = device;
-  m->engine = g_engine;
-  m->fuse = fusion_default() && g_engine == AR_ENGINE_UMMA;
+  m->engine = g_engine.load();
+  m->fuse = g_fuse.load() && m->engine == AR_ENGINE_UMMA;
   Blob blob;
   bool ok = false;
   if (kind == AR_MODEL_DENOISER) ok = build_denoiser(t, blob, *m);
@@ -445,6 +406,19 @@ int model_create(int kind, const ar_tensor_t* tensors, int n, int device, Model*
   else if (kind == AR_MODEL_STEREO) ok = build_stereo(t, blob, *m);
   else { set_error("model_create: unknown model kind"); return AR_ERR_INVALID; }
   if (!ok) return AR_ERR_WEIGHTS;
+  // Dynamic-range envelope of the fp16 operand storage: refuse a checkpoint whose BN-folded weights do
+  // not fit instead of silently clamping them.
+  if (!(blob.w_max <= HALF_MAX)) {
+    set_error("model_create: a BatchNorm-folded conv weight is " + std::to_string(blob.w_max) +
+              " (or not finite): outside the fp16 operand range of the tensor-core path (|w| <= 65504); "
+              "check running_var / weight of the checkpoint's BatchNorm layers");
+    return AR_ERR_WEIGHTS;
+  }
+  if (blob.w_min_layer_max > 0.f && blob.w_min_layer_max < 6.2e-5f) {
+    set_error("model_create: every BatchNorm-folded weight of one conv layer is below the fp16 normal range (max " +
+              std::to_string(blob.w_min_layer_max) + "): the tensor-core path would lose its precision");
+    return AR_ERR_WEIGHTS;
+  }
   AR_CUDA_OK(cudaSetDevice(device));
   AR_CUDA_OK(cudaMalloc(&m->blob, blob.host.size() * sizeof(float)));
   AR_CUDA_OK(cudaMemcpy(m->blob, blob.host.data(), blob.host.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -523,18 +497,26 @@ struct ConvOpt {
   int Tout = -1;
 };
 
+// Dynamic-range audit hook: fold max |value| of the channel window a layer just wrote into the model's audit slot `name`.
+static int audit_act(Ctx& c, const std::string& name, const Act& a, int coff8, int nch8, int T, int tblock = 0) {
+  if (c.ar.dry || !c.m->audit) return AR_OK;
+  Model* m = const_cast<Model*>(c.m);
+  size_t slot = 0;
+  while (slot < m->audit_names.size() && m->audit_names[slot] != name) ++slot;
+  if (slot == m->audit_names.size()) {
+    AR_CHECK(slot < (size_t)AUDIT_SLOTS, AR_ERR_INVALID, "internal: too many audited layers");
+    m->audit_names.push_back(name);
+  }
+  return launch_audit(a, c.B, coff8, nch8, T, tblock, m->audit_dev + slot, c.stream);
+}
+
 static int run_conv(Ctx& c, const std::string& name, const Act& in, const Act& out, const ConvOpt& o = ConvOpt()) {
   if (c.ar.dry) return AR_OK;
   auto it = c.m->conv.find(name);
   AR_CHECK(it != c.m->conv.end(), AR_ERR_INVALID, "internal: unknown conv layer " + name);
-  if (c.m->engine == AR_ENGINE_UMMA && o.mode == MODE_SAME && !o.pool && !o.res && !o.out_tblock) {
-    auto tw = c.m->conv.find(name + ".tg");          // tap-grouped twin of this layer (2-CTA engine only)
-    if (tw != c.m->conv.end() && tw->second.cta2) it = tw;
-  }
   const ConvLayer& L = it->second;
   ConvParams p;
   std::memset(&p, 0, sizeof(p));
-  p.tg = L.tg;
   p.in = in.h(); p.in_bs = in.bs; p.in_Tp = in.Tp; p.in_coff8 = o.in_coff8;
   p.Tin = in.T; p.Cin = L.Cin; p.taps = L.taps; p.dil = L.dil; p.pad_left = L.pad_left;
   p.w = reinterpret_cast<const __half*>(c.m->blob + L.w_off); p.bias = c.m->blob + L.b_off; p.N = L.N; p.n_slices = L.n_slices; p.cta2 = L.cta2;
@@ -546,18 +528,24 @@ static int run_conv(Ctx& c, const std::string& name, const Act& in, const Act& o
   p.lrelu = o.lrelu;
   p.out_tblock = o.out_tblock;
   p.B = c.B;
-  const int stride = conv_tile_stride(p);
-  p.tiles_per_item = (in.T + stride - 1) / stride;
-  ProfScope ps(CAT_CONV, c.stream, 2.0 * L.macs_per_row * (double)c.B * (double)in.T);
-  if (c.m->engine == AR_ENGINE_SIMT) return launch_conv_simt(p, c.stream);
-  return p.cta2 ? launch_conv_umma2(p, c.stream) : launch_conv_umma(p, c.stream);
+  p.tiles_per_item = (in.T + TILE_M - 1) / TILE_M;
+  {
+    ProfScope ps(CAT_CONV, c.stream, 2.0 * L.macs_per_row * (double)c.B * (double)in.T);
+    AR_TRY(c.m->engine == AR_ENGINE_SIMT ? launch_conv_simt(p, c.stream) : launch_conv_umma2(p, c.stream));
+  }
+  if (c.m->audit) {
+    const int ncols = o.mode == MODE_INTERLEAVE2 ? L.N / 2 : L.N;
+    AR_TRY(audit_act(c, name, out, o.out_coff8, ncols / 8, p.Tout, o.out_tblock));
+    if (o.pool) AR_TRY(audit_act(c, name + ".pool", *o.pool, 0, ncols / 8, in.T / 2));
+  }
+  return AR_OK;
 }
 
 // A k-tap conv followed by one or two pointwise convs as ONE fused launch (conv_chain.cu).  `o` describes the
 // LAST stage's output (lrelu, time-blocked layout); intermediate stages apply LeakyReLU (they are
 // `_dilated_block` halves, stereo_separator.py:49-64).
 static bool can_chain(const Ctx& c, std::initializer_list<const char*> names) {
-  if (!c.m->fuse || c.m->engine != AR_ENGINE_UMMA) return false;
+  if (!c.m->fuse || c.m->audit || c.m->engine != AR_ENGINE_UMMA) return false;   // the audit looks at every intermediate
   bool first = true;
   int prevN = 0, Cin = 0, taps = 0, dil = 0, N[3] = {0, 0, 0}, ng = 0;
   for (const char* n : names) {
@@ -604,21 +592,14 @@ static int run_chain(Ctx& c, std::initializer_list<const char*> names, const Act
   cp.pl.out = out.h(); cp.pl.out_bs = out.bs; cp.pl.out_Tp = out.Tp; cp.pl.out_coff8 = o.out_coff8;
   cp.pl.Tout = o.Tout >= 0 ? o.Tout : out.T;
   cp.pl.out_tblock = o.out_tblock;
-  cp.trace = g_chain_trace ? g_chain_trace + (size_t)(g_chain_trace_slot++ % 4) * 1024 : nullptr;
+  long long* const trace = g_chain_trace.load();
+  cp.trace = trace ? trace + (size_t)(g_chain_trace_slot.fetch_add(1) % 4) * 1024 : nullptr;
   ProfScope ps(CAT_CONV, c.stream, 2.0 * macs * (double)c.B * (double)in.T);
   return launch_conv_chain(cp, c.stream);
 }
 
-// the k7 output heads run on the tensor core (final_umma.cu) with the tcgen05 engine; AR_FINAL_SIMT=1 or the
-// CUDA-core cross-check engine select the CUDA-core kernel
-static bool use_final_umma(const Model& m) {
-  static int simt = -1;
-  if (simt < 0) {
-    const char* e = getenv("AR_FINAL_SIMT");
-    simt = e ? atoi(e) : 0;
-  }
-  return m.engine == AR_ENGINE_UMMA && simt <= 0;
-}
+// the stereo k7 output heads run on the tensor core (final_umma.cu) with the tcgen05 engine, on CUDA cores with the cross-check engine
+static bool use_final_umma(const Model& m) { return m.engine == AR_ENGINE_UMMA; }
 
 // ---------------------------------------------------------------------------- denoiser.py:88-144
 static int denoiser_forward(Ctx& c, const float* x, float* y, int T) {
@@ -631,6 +612,7 @@ static int denoiser_forward(Ctx& c, const float* x, float* y, int T) {
     ProfScope ps(CAT_STEM, c.stream, 2.0 * 96 * (double)B * T);
     AR_TRY(launch_stem(x, B, T, m.stem, e0a, 1, c.stream));
   }
+  AR_TRY(audit_act(c, "stem", e0a, 0, 4, T));
   ConvOpt o; o.pool = &p0;
   AR_TRY(run_conv(c, "enc0b", e0a, cat0, o));                 // skip s0 -> cat0[0:32], pooled -> p0
   A.release(e0a);
@@ -682,13 +664,8 @@ static int denoiser_forward(Ctx& c, const float* x, float* y, int T) {
   Act f = A.act(B, 32, T);
   AR_TRY(run_conv(c, "dec2b", d2a, f));
   A.release(d2a);
-  // AR_DEN_TAIL_SIMT=1 (or the cross-check engine) keeps the whole transient detector on CUDA cores
-  static int tail_simt = -1;
-  if (tail_simt < 0) {
-    const char* e = getenv("AR_DEN_TAIL_SIMT");
-    tail_simt = e ? atoi(e) : 0;
-  }
-  if (c.m->engine == AR_ENGINE_UMMA && !tail_simt) {
+  // the cross-check engine keeps the whole transient detector on CUDA cores
+  if (c.m->engine == AR_ENGINE_UMMA) {
     Act h1 = A.act(B, 32, T);
     AR_TRY(run_conv(c, "td0", f, h1));
     if (!A.dry) {
@@ -715,6 +692,7 @@ static int sr_forward(Ctx& c, const float* x, float* y, int T) {
     ProfScope ps(CAT_STEM, c.stream, 2.0 * 224 * (double)B * T);
     AR_TRY(launch_stem(x, B, T, m.stem, f0, 1, c.stream));
   }
+  AR_TRY(audit_act(c, "stem", f0, 0, 4, T));
   Act r = f0;
   for (int i = 0; i < 4; ++i) {
     Act o1 = A.act(B, 32, T);
@@ -741,20 +719,27 @@ static int sr_forward(Ctx& c, const float* x, float* y, int T) {
   if (!A.dry) {
     const int coff[1] = {0};
     ProfScope ps(CAT_TAIL, c.stream, 2.0 * 224 * (double)B * 2 * T);
-    // one head = 8 KB of activations per tile: the tensor-core kernel is latency-bound there (3.0 ms per 1184-chunk
-    // step against 2.5 ms of the CUDA-core kernel); AR_FINAL_SIMT=-1 forces it for measurements
-    if (use_final_umma(m) && getenv("AR_FINAL_SIMT") && atoi(getenv("AR_FINAL_SIMT")) < 0)
-      AR_TRY(launch_final_umma(h, 0, reinterpret_cast<const __half*>(m.blob + m.fin_umma_off), m.fin, 1, y, B, 2 * T, x, c.stream));
-    else
-      AR_TRY(launch_final_k7(h, coff, m.fin, 1, y, B, 2 * T, x, c.stream));
+    // one head = 8 KB of activations per tile: the tensor-core head kernel is latency-bound there (measured 3.0 ms per
+    // 1184-chunk step against 2.5 ms of this CUDA-core kernel)
+    AR_TRY(launch_final_k7(h, coff, m.fin, 1, y, B, 2 * T, x, c.stream));
   }
   A.release(h);
   return AR_OK;
 }
 
 // ---------------------------------------------------------------------------- stereo_separator.py:85-122
-static int stereo_forward(Ctx& c, const float* x, float* y, int T, const float* state_in, float* state_out) {
+// The LSTM scan covers steps [w.lstm_start, T) (hidden states before it are zero) starting from `state_in`, and
+// `state_out` receives (h, c) after step w.state_pos - 1: the window parameters of the whole-file-exact chunked mode
+// (ar_stereo_forward_window), where a segment carries conv halos on both sides of the range whose state it hands on.
+struct LstmWindow { int lstm_start = 0, state_pos = -1; };
+
+static int stereo_forward(Ctx& c, const float* x, float* y, int T, const float* state_in, float* state_out,
+                          LstmWindow w = LstmWindow()) {
   AR_CHECK(T >= 1, AR_ERR_INVALID, "stereo: empty input");
+  if (w.state_pos < 0) w.state_pos = T;
+  AR_CHECK(w.lstm_start >= 0 && w.lstm_start < w.state_pos && w.state_pos <= T && w.lstm_start % 8 == 0 &&
+               (w.state_pos % 8 == 0 || w.state_pos == T),
+           AR_ERR_INVALID, "stereo: LSTM window must satisfy 0 <= lstm_start < state_pos <= T, both multiples of 8 (state_pos may be T)");
   const Model& m = *c.m;
   const int B = c.B;
   Arena& A = c.ar;
@@ -763,6 +748,7 @@ static int stereo_forward(Ctx& c, const float* x, float* y, int T, const float* 
     ProfScope ps(CAT_STEM, c.stream, 2.0 * 224 * (double)B * T);
     AR_TRY(launch_stem(x, B, T, m.stem, cur, 1, c.stream));
   }
+  AR_TRY(audit_act(c, "stem", cur, 0, 4, T));
   const int widths[4] = {64, 128, 128, 128};
   static const char* const NA[4] = {"enc1a", "enc2a", "enc3a", "enc4a"};
   static const char* const NB[4] = {"enc1b", "enc2b", "enc3b", "enc4b"};
@@ -798,8 +784,25 @@ static int stereo_forward(Ctx& c, const float* x, float* y, int T, const float* 
   }
   Act h = A.act(B, 64, T);
   if (!A.dry) {
-    ProfScope ps(CAT_LSTM, c.stream, 2.0 * 16384 * (double)B * T);
-    AR_TRY(launch_lstm(xp, m.blob + m.whh_off, h, B, T, state_in, state_out, c.stream));
+    ProfScope ps(CAT_LSTM, c.stream, 2.0 * 16384 * (double)B * (T - w.lstm_start), w.state_pos < T ? 2 : 1);
+    // a scan over steps [t0, t1) is the same kernel on base pointers advanced by t0 rows (t0 % 8 == 0 keeps the 8-step
+    // blocks of the time-blocked pre-activations aligned)
+    auto scan = [&](int t0, int t1, const float* st_in, float* st_out) {
+      Act xs = xp, hs = h;
+      xs.base = xp.h() + (long long)(t0 / 8) * 32 * 64;
+      hs.base = h.h() + (long long)t0 * 8;
+      xs.T = hs.T = t1 - t0;
+      return launch_lstm(xs, m.blob + m.whh_off, hs, B, t1 - t0, st_in, st_out, c.stream);
+    };
+    if (w.lstm_start > 0)   // rows [0, lstm_start) of all 8 chunks of every item: zero hidden states
+      AR_CUDA_OK(cudaMemset2DAsync(h.h() + (long long)HALO * 8, (size_t)h.Tp * 16, 0, (size_t)w.lstm_start * 16, (size_t)B * 8, c.stream));
+    if (w.state_pos < T) {
+      AR_CHECK(state_out != nullptr, AR_ERR_INVALID, "stereo: an interior state_pos needs state_out");
+      AR_TRY(scan(w.lstm_start, w.state_pos, state_in, state_out));
+      AR_TRY(scan(w.state_pos, T, state_out, nullptr));
+    } else {
+      AR_TRY(scan(w.lstm_start, T, state_in, state_out));
+    }
   }
   A.release(xp);
   Act d0 = A.act(B, 256, T);
@@ -829,11 +832,11 @@ static int stereo_forward(Ctx& c, const float* x, float* y, int T, const float* 
   return AR_OK;
 }
 
-static int dispatch(Ctx& c, const float* x, float* y, int T, const float* st_in, float* st_out) {
+static int dispatch(Ctx& c, const float* x, float* y, int T, const float* st_in, float* st_out, LstmWindow w = LstmWindow()) {
   switch (c.m->kind) {
     case AR_MODEL_DENOISER: return denoiser_forward(c, x, y, T);
     case AR_MODEL_SUPER_RES: return sr_forward(c, x, y, T);
-    case AR_MODEL_STEREO: return stereo_forward(c, x, y, T, st_in, st_out);
+    case AR_MODEL_STEREO: return stereo_forward(c, x, y, T, st_in, st_out, w);
   }
   set_error("internal: bad model kind");
   return AR_ERR_INVALID;
@@ -849,7 +852,7 @@ int model_workspace_bytes(const Model* m, int B, int T, size_t* bytes) {
 }
 
 int model_forward(const Model* m, const float* x, float* y, int B, int T, const float* st_in, float* st_out, void* ws,
-                  size_t ws_bytes, cudaStream_t stream) {
+                  size_t ws_bytes, cudaStream_t stream, int lstm_start, int state_pos) {
   AR_CHECK(m && x && y && B >= 1 && T >= 1, AR_ERR_INVALID, "forward: bad argument");
   size_t need = 0;
   AR_TRY(model_workspace_bytes(m, B, T, &need));
@@ -860,7 +863,43 @@ int model_forward(const Model* m, const float* x, float* y, int B, int T, const 
   uintptr_t a = (reinterpret_cast<uintptr_t>(ws) + 255) / 256 * 256;
   c.ar.base = reinterpret_cast<char*>(a);
   c.ar.cap = ws_bytes;
-  return dispatch(c, x, y, T, st_in, st_out);
+  LstmWindow w;
+  w.lstm_start = lstm_start;
+  w.state_pos = state_pos;
+  return dispatch(c, x, y, T, st_in, st_out, w);
+}
+
+// ---------------------------------------------------------------------------- dynamic-range audit (ar_model_audit_*)
+int model_audit_enable(Model* m, int on) {
+  AR_CHECK(m != nullptr, AR_ERR_INVALID, "audit: null model");
+  if (on && m->audit_dev == nullptr) {
+    AR_CUDA_OK(cudaSetDevice(m->device));
+    AR_CUDA_OK(cudaMalloc(&m->audit_dev, AUDIT_SLOTS * sizeof(unsigned int)));
+  }
+  if (on) {
+    AR_CUDA_OK(cudaSetDevice(m->device));
+    AR_CUDA_OK(cudaMemset(m->audit_dev, 0, AUDIT_SLOTS * sizeof(unsigned int)));
+    AR_CUDA_OK(cudaDeviceSynchronize());   // diagnostic path: the clear is complete before launches on any stream
+    m->audit_names.clear();
+  }
+  m->audit = on != 0;
+  return AR_OK;
+}
+// Synchronises the device; max_abs[i] / name(i) describe the i-th audited tensor since the audit was enabled.
+int model_audit_read(Model* m, float* max_abs, int cap, int* n_layers) {
+  AR_CHECK(m && max_abs && n_layers && cap >= 1, AR_ERR_INVALID, "audit: bad argument");
+  AR_CHECK(m->audit_dev != nullptr, AR_ERR_INVALID, "audit: not enabled for this model");
+  AR_CUDA_OK(cudaSetDevice(m->device));
+  AR_CUDA_OK(cudaDeviceSynchronize());
+  unsigned int bits[AUDIT_SLOTS];
+  AR_CUDA_OK(cudaMemcpy(bits, m->audit_dev, sizeof(bits), cudaMemcpyDeviceToHost));
+  const int n = (int)m->audit_names.size();
+  *n_layers = n;
+  for (int i = 0; i < n && i < cap; ++i) std::memcpy(&max_abs[i], &bits[i], 4);
+  return AR_OK;
+}
+const char* model_audit_name(const Model* m, int i) {
+  return (m && i >= 0 && i < (int)m->audit_names.size()) ? m->audit_names[i].c_str() : nullptr;
 }
 
 void model_destroy(Model* m) { delete m; }
@@ -872,6 +911,7 @@ int debug_conv(const float* x, const float* w_host, const float* bias_host, floa
   AR_CHECK(x && w_host && bias_host && y && B >= 1 && T >= 1, AR_ERR_INVALID, "debug_conv: bad argument");
   AR_CHECK(Cin % 16 == 0 && Cout % 16 == 0 && Cout <= 256 && (k & 1) == 1 && dil * (k - 1) / 2 <= HALO, AR_ERR_INVALID,
            "debug_conv: unsupported shape");
+  AR_CHECK(engine == AR_ENGINE_SIMT || Cout % 32 == 0, AR_ERR_INVALID, "debug_conv: the tcgen05 engine needs Cout % 32 == 0");
   Gemm g;
   g.init(Cin, Cout, k, dil, dil * (k - 1) / 2);
   for (int o = 0; o < Cout; ++o) {
@@ -881,14 +921,6 @@ int debug_conv(const float* x, const float* w_host, const float* bias_host, floa
   }
   Blob blob;
   ConvLayer L = blob.push_gemm(g);
-  // the k7 decoder shapes go through the tap-grouped path of the 2-CTA engine when it is enabled (ar_set_tap_groups)
-  int tg = 1;
-  if (engine == AR_ENGINE_UMMA && want_tap_groups() && want_cta2(128) && k == 7 && dil == 1 && (Cout == 64 || Cout == 32)) {
-    tg = Cout == 64 ? 2 : 4;
-    Gemm gt = tap_grouped(g, tg);
-    L = blob.push_gemm(gt);
-    L.tg = tg;
-  }
   Arena A;
   A.dry = true;
   Act in = A.act(B, Cin, T), out = A.act(B, Cout, T);
@@ -903,12 +935,11 @@ int debug_conv(const float* x, const float* w_host, const float* bias_host, floa
   if (rc == AR_OK) {
     ConvParams p;
     std::memset(&p, 0, sizeof(p));
-    p.tg = L.tg;
-    p.in = in.h(); p.in_bs = in.bs; p.in_Tp = in.Tp; p.Tin = T; p.Cin = Cin; p.taps = L.taps; p.dil = L.dil; p.pad_left = g.pad_left;
+      p.in = in.h(); p.in_bs = in.bs; p.in_Tp = in.Tp; p.Tin = T; p.Cin = Cin; p.taps = L.taps; p.dil = L.dil; p.pad_left = g.pad_left;
     p.w = reinterpret_cast<const __half*>(dblob + L.w_off); p.bias = dblob + L.b_off; p.N = L.N; p.n_slices = L.n_slices; p.cta2 = L.cta2; p.mode = MODE_SAME;
     p.out = out.h(); p.out_bs = out.bs; p.out_Tp = out.Tp; p.Tout = T; p.lrelu = lrelu;
-    p.B = B; p.tiles_per_item = (T + conv_tile_stride(p) - 1) / conv_tile_stride(p);
-    rc = engine == AR_ENGINE_SIMT ? launch_conv_simt(p, stream) : (p.cta2 ? launch_conv_umma2(p, stream) : launch_conv_umma(p, stream));
+    p.B = B; p.tiles_per_item = (T + TILE_M - 1) / TILE_M;
+    rc = engine == AR_ENGINE_SIMT ? launch_conv_simt(p, stream) : launch_conv_umma2(p, stream);
   }
   if (rc == AR_OK) rc = launch_c4_to_plain(out, B, Cout, T, y, stream);
   cudaError_t e = cudaStreamSynchronize(stream);

@@ -472,4 +472,32 @@ int launch_c4_to_plain(const Act& in, int B, int C, int T, float* y, cudaStream_
   return AR_OK;
 }
 
+// ----------------------------------------------------------------------------- dynamic-range audit
+// max |value| over the valid rows [0,T) of an H8 (or time-blocked H8) activation tensor, folded into *slot with an
+// atomic max on the float's bit pattern (non-negative floats order like unsigned integers).  fp16 storage saturates at
+// +-65504: a layer whose maximum reaches that value has clipped (ar_model_audit_*).
+__global__ void __launch_bounds__(256) audit_kernel(const __half* a, long long bs, int Tp, int C8, int coff8, int T, int tblock, unsigned int* slot) {
+  const int b = blockIdx.z, ch = coff8 + blockIdx.y;
+  float m = 0.f;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+    const long long off = tblock ? act_off_tb(bs, C8, b, ch, t) : act_off(bs, Tp, b, ch, t);
+    float v[8];
+    unpack_half8(*reinterpret_cast<const uint4*>(a + off), v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m = fmaxf(m, fabsf(v[i]));   // fmaxf drops a NaN operand: NaNs are caught by the finite check of the output
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(slot, __float_as_uint(m));
+}
+
+int launch_audit(const Act& a, int B, int coff8, int nch8, int T, int tblock, unsigned int* slot, cudaStream_t stream) {
+  int gx = (T + 255) / 256;
+  if (gx > 64) gx = 64;
+  dim3 grid(gx, nch8, B);
+  audit_kernel<<<grid, 256, 0, stream>>>(a.h(), a.bs, a.Tp, a.C / 8, coff8, T, tblock, slot);
+  AR_CUDA_OK(cudaGetLastError());
+  return AR_OK;
+}
+
 }  // namespace ar

@@ -11,6 +11,10 @@ Two ways through the same three native models:
   run denoise -> super-res -> stereo on batches of chunks with the LSTM state reset per chunk
   (trainer.py:671), cross-fade overlap-add, normalise.  Chunks are independent, so batches
   shard across GPUs with no collective.
+* exact (`mode="exact"`): chunked, but equal to the whole-file result: chunk starts are multiples of 8
+  (the U-Net's three pools), every chunk carries conv halos that are computed and discarded, and the stereo LSTM's
+  (h, c) is carried from segment to segment of the file, so the scan is the reference's single scan
+  (stereo_separator.py:106-107).  Bounded memory for files of any length; the scan of one file is serial.
 """
 from __future__ import annotations
 
@@ -28,6 +32,13 @@ from .models import AudioDenoiser, AudioSuperResolution, StereoSeparator
 
 DEFAULT_CHUNK = 44100     # 2.0 s at 22.05 kHz (trainer.py:652)
 DEFAULT_OVERLAP = 2052    # hop 42048 = 0 (mod 8): chunk starts stay aligned to the U-Net's three pools
+# mode="exact" (receptive fields: SURVEY.md App. E)
+EXACT_HALO = 96           # input samples computed and discarded on each interior chunk edge of denoise -> super-res:
+                          # denoiser reach 54 + super-res reach 15 = 69, rounded up to a multiple of 8 with margin
+EXACT_STEREO_HALO = 40    # stereo stage, in ITS samples: encoder reach 18 (k7 stem 3 + dilated k3 1+2+4+8) on the side the
+                          # scan enters, decoder reach 12 (four k7) on both
+EXACT_LSTM_LEAD = 16      # a segment's scan starts (and its predecessor's state is taken) this many samples before the
+                          # segment's kept range: >= decoder reach 12, and 40 - 16 = 24 >= encoder reach 18; multiples of 8
 
 
 def plan_chunks(num_samples: int, chunk_size: int = DEFAULT_CHUNK, overlap: int = DEFAULT_OVERLAP):
@@ -194,6 +205,10 @@ class RestorationPipeline:
                 y = self.forward_chunks(a.view(1, 1, N))[0]
             elif mode == "chunked":
                 y = self._restore_chunked(a, N, chunk_size, overlap, batch_chunks, chunk_range, streams)
+            elif mode == "exact":
+                if chunk_range is not None:
+                    raise ValueError("mode='exact' carries the LSTM state through the file: it cannot be sharded by chunk range")
+                y = self._restore_exact(a, N, chunk_size, batch_chunks)
             else:
                 raise ValueError(f"unknown mode {mode!r}")
             if normalize:
@@ -278,6 +293,104 @@ class RestorationPipeline:
             ev.synchronize()
             yield h
 
+    def _restore_exact(self, a, N, chunk_size, batch_chunks):
+        """Whole-file-exact chunked restoration of a normalised mono `[1,N]` device signal -> `[2, rate*N]`.
+
+        Stage 1, denoise (-> super-res): chunk i covers input samples `[i*hop, i*hop + L)` with `L = chunk_size` rounded
+        down to a multiple of 8 and `hop = L - 2*EXACT_HALO`; all full chunks run as batches, a ragged tail chunk runs
+        alone at its true length (zero-padding it would move the file end), and only the samples further than
+        EXACT_HALO from an interior chunk edge are kept.  Chunk starts are multiples of 8, so every chunk sees the
+        pooling grid of the whole file.
+        Stage 2, stereo: segments of the stage-1 signal with EXACT_STEREO_HALO samples of context on both sides go
+        through `forward_window` one after the other; the scan of segment j starts EXACT_LSTM_LEAD samples before the
+        segment's kept range from the (h, c) its predecessor recorded at exactly that sample."""
+        r, H = self.rate, EXACT_HALO
+        L = chunk_size - chunk_size % 8
+        if L < 4 * H:
+            raise ValueError(f"mode='exact' needs chunk_size >= {4 * H} (conv halos of {H} samples per chunk edge)")
+        hop = L - 2 * H
+        lib = _lib.lib()
+        n = 1 if N <= L else -(-(N - 2 * H) // hop)
+        n_full = n if (n - 1) * hop + L <= N else n - 1
+        sig = torch.empty((1, r * N), dtype=torch.float32, device=self.device)
+
+        def stage1(x):                                  # [B,1,T] -> [B,1,r*T]
+            y = self.denoiser(x)
+            return self.super_res(y) if self.super_res is not None else y
+
+        def keep(i):                                    # kept input range of chunk i
+            lo = 0 if i == 0 else i * hop + H
+            hi = N if i == n - 1 else (i + 1) * hop + H
+            return lo, hi
+
+        if batch_chunks <= 0:
+            free, _ = torch.cuda.mem_get_info(self.device)
+            sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+            batch_chunks = max(1, min(n_full, 8 * sms, self.max_batch(L, int(free * 0.5))))
+        for first in range(0, n_full, batch_chunks):
+            cnt = min(batch_chunks, n_full - first)
+            buf = torch.empty((cnt, 1, L), dtype=torch.float32, device=self.device)
+            _lib.check(lib.ar_split_chunks(a.data_ptr(), N, buf.data_ptr(), first, cnt, L, 2 * H, self._stream()))
+            z = stage1(buf)
+            for i in range(first, first + cnt):
+                if i == 0 or i == n - 1:                # file edges keep their outer side
+                    lo, hi = keep(i)
+                    sig[:, r * lo:r * hi] = z[i - first, :, r * (lo - i * hop):r * (hi - i * hop)]
+            i0, i1 = max(first, 1), min(first + cnt, n - 1)     # interior chunks: one strided copy
+            if i1 > i0:
+                lo = i0 * hop + H
+                sig[0, r * lo:r * (lo + (i1 - i0) * hop)].view(i1 - i0, r * hop).copy_(z[i0 - first:i1 - first, 0, r * H:r * (H + hop)])
+        if n_full < n:                                  # ragged tail chunk at its true length
+            lo, hi = keep(n - 1)
+            start = (n - 1) * hop
+            z = stage1(a[:, start:N].reshape(1, 1, N - start).contiguous())
+            sig[:, r * lo:r * hi] = z[0, :, r * (lo - start):r * (hi - start)]
+
+        M, E, P = r * N, EXACT_STEREO_HALO, EXACT_LSTM_LEAD
+        S2 = (r * L - 2 * E) // 16 * 16                 # kept samples per stereo segment
+        out = torch.empty((2, M), dtype=torch.float32, device=self.device)
+        state = None
+        n_seg = -(-M // S2)
+        for j in range(n_seg):
+            a0, a1 = j * S2, min(M, (j + 1) * S2)
+            e0, e1 = max(0, a0 - E), min(M, a1 + E)
+            last = j == n_seg - 1
+            y, state = self.stereo.forward_window(sig[:, e0:e1].reshape(1, 1, e1 - e0).contiguous(), state,
+                                                  lstm_start=0 if j == 0 else a0 - P - e0,
+                                                  state_pos=None if last else a1 - P - e0)
+            out[:, a0:a1] = y[0, :, a0 - e0:a1 - e0]
+        return out
+
+    def check_dynamic_range(self, audio: torch.Tensor, chunk_size: int = DEFAULT_CHUNK, max_chunks: int = 8) -> dict:
+        """Dynamic-range audit of this checkpoint set on `audio` (`[1,N]`, any device; normalised here like `restore`
+        does): runs the three models layer by layer on up to `max_chunks` chunks -- evenly spread over the file plus the
+        one holding the global peak -- and returns `{"<model>.<layer>": max |activation|}`.  Inter-layer activations
+        are stored in fp16 and saturate at +-65504; raises RuntimeError naming the layer if one clipped
+        (INTEGRATION.md, "dynamic range")."""
+        if audio.dim() == 1:
+            audio = audio.unsqueeze(0)
+        N = audio.shape[1]
+        with torch.cuda.device(self.device), torch.no_grad():
+            a = audio.to(self.device, torch.float32).contiguous().clone()
+            self._normalize_(a)
+            T = min(chunk_size, N)
+            n = max(1, N // T)
+            picks = sorted(set([int(k * (n - 1) / max(1, max_chunks - 2)) for k in range(max_chunks - 1)] if n > 1 else [0])
+                           | {min(n - 1, int(a.abs().argmax()) // T)})
+            x = torch.stack([a[:, i * T:(i + 1) * T] for i in picks])          # [B,1,T]
+            report = {}
+            report.update({"denoiser." + k: v for k, v in self.denoiser.audit(x).items()})
+            y = self.denoiser(x)
+            if self.super_res is not None:
+                report.update({"super_resolution." + k: v for k, v in self.super_res.audit(y).items()})
+                y = self.super_res(y)
+            report.update({"stereo." + k: v for k, v in self.stereo.audit(y).items()})
+        clipped = [k for k, v in report.items() if not v < _lib.HALF_MAX]
+        if clipped:
+            raise RuntimeError("fp16 activation storage clipped (|x| >= 65504) in " + ", ".join(clipped) +
+                               ": this checkpoint exceeds the dynamic-range envelope of the tensor-core path")
+        return report
+
     def _restore_chunked(self, a, N, chunk_size, overlap, batch_chunks, chunk_range, streams=1):
         L = _lib.lib()
         n_chunks = C.c_int()
@@ -301,12 +414,6 @@ class RestorationPipeline:
         firsts = list(range(c0, hi, batch_chunks))
         n_streams = max(1, min(streams, len(firsts)))
         main = torch.cuda.current_stream(self.device)
-        # AR_CONV_SMEM_KB (tuning knob): shared memory a conv CTA may take; below ~172 KB one CTA of the LSTM scan fits
-        # next to it on every SM.  Measured on power-capped B200s the overlap buys nothing (the chip is power-limited,
-        # not occupancy-limited), so the default gives every conv CTA the whole SM.
-        smem_kb = os.environ.get("AR_CONV_SMEM_KB")
-        if smem_kb:
-            _lib.check(L.ar_set_conv_smem_kb(int(smem_kb)))
         if n_streams == 1:
             buf = torch.empty((min(batch_chunks, cnt_all), 1, chunk_size), dtype=torch.float32, device=self.device)
             for first in firsts:
@@ -432,7 +539,9 @@ def restore_audio(
 ):
     """Drop-in for the reference `restore_audio` (inference.py:17-108): same positional/keyword
     arguments and progress prints; `mode`, `chunk_size`, `overlap` are additions (default
-    `mode='whole'` keeps the reference's whole-file semantics; `'chunked'` is the fast path).
+    `mode='whole'` keeps the reference's whole-file semantics; `'chunked'` is the fast path, `'exact'` the
+    bounded-memory chunked form of `'whole'`).  Before restoring, the checkpoints' dynamic range is audited on a few
+    chunks of the file (`RestorationPipeline.check_dynamic_range`).
     """
     if torch.device(device).type != 'cuda':
         raise RuntimeError("restore_audio: device must be a CUDA device -- this build has no CPU fallback")
@@ -453,6 +562,7 @@ def restore_audio(
     print("Loading stereo separator model...")
     st = _load_checkpoint(StereoSeparator(), stereo_checkpoint, device)
     pipe = RestorationPipeline(den, sr, st, device)
+    pipe.check_dynamic_range(audio, chunk_size)      # raises if this checkpoint clips the fp16 activation storage
     print("Applying denoising...")
     if enable_super_resolution:
         print("Applying bandwidth extension (22.05kHz -> 44.1kHz)...")
@@ -479,8 +589,9 @@ def main(argv=None):
     ap.add_argument('--no-super-res', action='store_true', help='Disable bandwidth extension (super-resolution)')
     ap.add_argument('--device', type=str, default='cuda' if torch.cuda.is_available() else 'cpu',
                     help='Device to use (cuda or cpu)')
-    ap.add_argument('--mode', choices=('whole', 'chunked'), default='whole',
-                    help="'whole' = reference semantics; 'chunked' = batched 2 s chunks with overlap-add")
+    ap.add_argument('--mode', choices=('whole', 'chunked', 'exact'), default='whole',
+                    help="'whole' = reference semantics; 'chunked' = batched 2 s chunks with overlap-add (fast path); "
+                         "'exact' = chunked with conv halos and LSTM state carry, equal to 'whole' in bounded memory")
     ap.add_argument('--chunk-size', type=int, default=DEFAULT_CHUNK)
     ap.add_argument('--overlap', type=int, default=DEFAULT_OVERLAP)
     a = ap.parse_args(argv)

@@ -8,6 +8,7 @@ keys so `load_state_dict(ckpt['model_state_dict'])` works unc
 from __future__ import annotations
 
 import ctypes as C
+import threading
 
 import torch
 import torch.nn as nn
@@ -16,18 +17,34 @@ from .. import _lib
 
 
 class _Workspace:
-    """Grow-only device scratch shared by all native modules on one device."""
+    """Grow-only device scratch, one buffer per (device, CUDA stream).
+
+    Work on one stream is ordered, so forwards issued on the same stream can share scratch; forwards on different streams
+    (or threads using their own streams) get different buffers and never overwrite each other's activations -- the
+    reference `nn.Module`s are stream-safe and so are these.  A buffer that is replaced by a larger one is handed back
+    to the caching allocator with `record_stream`, so its memory is not reused before the kernels still reading it end."""
     _bufs: dict = {}
+    _lock = threading.Lock()
 
     @classmethod
     def get(cls, device: torch.device, nbytes: int) -> torch.Tensor:
-        key = (device.type, device.index)
-        buf = cls._bufs.get(key)
-        if buf is None or buf.numel() < nbytes:
-            cls._bufs[key] = None
-            buf = torch.empty(int(nbytes * 1.05) + 4096, dtype=torch.uint8, device=device)
-            cls._bufs[key] = buf
-        return buf
+        stream = torch.cuda.current_stream(device)
+        key = (device.index, stream.cuda_stream)
+        with cls._lock:
+            buf = cls._bufs.get(key)
+            if buf is None or buf.numel() < nbytes:
+                if buf is not None:
+                    buf.record_stream(stream)
+                cls._bufs[key] = None
+                del buf
+                buf = torch.empty(int(nbytes * 1.05) + 4096, dtype=torch.uint8, device=device)
+                cls._bufs[key] = buf
+            return buf
+
+    @classmethod
+    def clear(cls):
+        with cls._lock:
+            cls._bufs.clear()
 
 
 def _stream_ptr(device) -> int:
@@ -44,7 +61,8 @@ class NativeModule(nn.Module):
 
     # ------------------------------------------------------------------ handle management
     def _param_key(self, device):
-        return (str(device),) + tuple((k, v._version, v.data_ptr()) for k, v in self.state_dict(keep_vars=True).items())
+        eps = tuple(m.eps for m in self.modules() if isinstance(m, nn.BatchNorm1d))
+        return (str(device), eps) + tuple((k, v._version, v.data_ptr()) for k, v in self.state_dict(keep_vars=True).items())
 
     def native_handle(self, device: torch.device):
         key = self._param_key(device)
@@ -54,6 +72,9 @@ class NativeModule(nn.Module):
         L = _lib.lib()
         sd = {k: v.detach().to("cpu", torch.float32).contiguous()
               for k, v in self.state_dict().items() if v.dtype.is_floating_point}
+        for name, mod in self.named_modules():       # BatchNorm eps is a module attribute, not a state_dict entry
+            if isinstance(mod, nn.BatchNorm1d) and mod.eps != 1e-5:
+                sd[name + ".eps"] = torch.tensor([mod.eps], dtype=torch.float32)
         arr = (_lib.ArTensor * len(sd))()
         keep = []
         for i, (k, v) in enumerate(sd.items()):
@@ -99,6 +120,24 @@ class NativeModule(nn.Module):
 
     def _out_shape(self, B: int, T: int):
         raise NotImplementedError
+
+    def audit(self, x) -> dict:
+        """Dynamic-range audit (`ar_model_audit_*`): run `forward(x)` layer by layer and return `{layer: max |activation|}`
+        for every fp16 tensor the kernels store.  Activations saturate at +-65504 in fp16 storage; a value of 65504 here
+        means that layer clipped on this input ("dynamic range").  Synchronises the device."""
+        x = self._check_input(x)
+        L = _lib.lib()
+        with torch.cuda.device(x.device):
+            h = self.native_handle(x.device)
+            _lib.check(L.ar_model_audit_enable(h, 1))
+            try:
+                self.forward(x)
+                vals = (C.c_float * _lib.AUDIT_MAX_LAYERS)()
+                n = C.c_int()
+                _lib.check(L.ar_model_audit_read(h, vals, _lib.AUDIT_MAX_LAYERS, C.byref(n)))
+                return {L.ar_model_audit_name(h, i).decode(): float(vals[i]) for i in range(n.value)}
+            finally:
+                L.ar_model_audit_enable(h, 0)
 
     def forward(self, x):
         x = self._check_input(x)

@@ -54,6 +54,12 @@ class StereoSeparator(NativeModule):
 
     def forward_with_state(self, x, state=None):
         """Like forward, but takes / returns the LSTM carry `[B,2,64]` (h, c)."""
+        return self.forward_window(x, state, 0, None)
+
+    def forward_window(self, x, state=None, lstm_start: int = 0, state_pos=None):
+        """Forward on a window of a longer signal (`ar_stereo_forward_window`): convs over all of `x[B,1,T]`, the LSTM
+        scan over steps `[lstm_start, T)` from `state` (None = zeros), returned state taken after step `state_pos - 1`
+        (None = T).  Building block of `RestorationPipeline.restore(mode="exact")`."""
         x = self._check_input(x)
         B, _, T = x.shape
         L = _lib.lib()
@@ -69,7 +75,8 @@ class StereoSeparator(NativeModule):
                 sin = state.to(device=x.device, dtype=torch.float32).contiguous()
                 if sin.shape != new_state.shape:
                     raise RuntimeError(f"state must be {tuple(new_state.shape)}, got {tuple(sin.shape)}")
-            _lib.check(L.ar_stereo_forward_state(h, x.data_ptr(), y.data_ptr(), B, T,
-                                                 sin.data_ptr() if sin is not None else None, new_state.data_ptr(),
-                                                 ws.data_ptr(), ws.numel(), _stream_ptr(x.device)))
+            _lib.check(L.ar_stereo_forward_window(h, x.data_ptr(), y.data_ptr(), B, T, int(lstm_start),
+                                                  T if state_pos is None else int(state_pos),
+                                                  sin.data_ptr() if sin is not None else None, new_state.data_ptr(),
+                                                  ws.data_ptr(), ws.numel(), _stream_ptr(x.device)))
         return y, new_state

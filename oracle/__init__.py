@@ -19,7 +19,11 @@ Parity status
     such function); the oracle restates THIS repo's scheme from the
     oracle model forwards.  With overlap=0 it reduces to the reference's
     `Trainer.generate_test_output` loop (trainer.py:652-681), which is pinned.
+  * whole-file-exact chunking (`restore_exact`: conv halos, chunk starts = 0 mod 8, LSTM state carried): PINNED -- it
+    must reproduce `restore_whole`, i.e. the reference's whole-file forwards (inference.py:59-95), and the golden
+    `chain_whole` vector.
 """
 from .weights import make_state_dict, MODEL_NAMES  # noqa: F401
-from .models import denoiser_forward, super_resolution_forward, stereo_forward  # noqa: F401
-from .pipeline import normalize_audio, chain_forward, restore_chunked, restore_whole, plan_chunks, crossfade_window  # noqa: F401
+from .models import denoiser_forward, super_resolution_forward, stereo_forward, stereo_forward_window  # noqa: F401
+from .pipeline import (normalize_audio, chain_forward, restore_chunked, restore_whole, restore_exact, plan_chunks,  # noqa: F401
+                       crossfade_window)

@@ -27,8 +27,15 @@ def _conv(sd, prefix, x, padding=0, dilation=1):
                     padding=padding, dilation=dilation)
 
 
+_CALIBRATE = None   # while a dict: _bn overwrites the running stats of every BatchNorm it meets with the batch statistics
+
+
 def _bn(sd, prefix, x):
     dt = x.dtype
+    if _CALIBRATE is not None:      # what a training run leaves behind: running stats == statistics of the layer's input
+        sd[prefix + ".running_mean"] = x.mean(dim=(0, 2)).float()
+        sd[prefix + ".running_var"] = x.var(dim=(0, 2), unbiased=False).float()
+        _CALIBRATE[prefix] = float(sd[prefix + ".running_var"].min())
     return F.batch_norm(x, _p(sd, prefix + ".running_mean", dt), _p(sd, prefix + ".running_var", dt),
                         _p(sd, prefix + ".weight", dt), _p(sd, prefix + ".bias", dt),
                         training=False, eps=_EPS)
@@ -168,3 +175,41 @@ def stereo_forward(sd, x, dtype=torch.float32, explicit_lstm=False, state=None, 
     z = z.permute(0, 2, 1).contiguous()                          # [B,64,T] (:113)
     y = torch.cat([stereo_decoder(sd, "left_decoder", z), stereo_decoder(sd, "right_decoder", z)], dim=1)
     return (y, new_state) if return_state else y
+
+
+def stereo_forward_window(sd, x, state=None, lstm_start=0, state_pos=None, dtype=torch.float32):
+    """Restatement of `ar_stereo_forward_window` (THIS repo's whole-file-exact chunking primitive; the reference has no
+    such call): encoder and decoders over all T samples of the segment, the LSTM scan over steps [lstm_start, T) only
+    (earlier hidden states are zero) from `state`, returned state taken after step `state_pos - 1`."""
+    x = x.to(dtype).contiguous()
+    T = x.shape[2]
+    state_pos = T if state_pos is None else state_pos
+    e = stereo_encoder(sd, x).permute(0, 2, 1).contiguous()
+    z = e.new_zeros(e.shape[0], T, sd["lstm.weight_hh_l0"].shape[1])
+    z1, st = _lstm_fast(sd, e[:, lstm_start:state_pos].contiguous(), state)
+    z[:, lstm_start:state_pos] = z1
+    if state_pos < T:
+        z2, _ = _lstm_fast(sd, e[:, state_pos:].contiguous(), st)
+        z[:, state_pos:] = z2
+    z = z.permute(0, 2, 1).contiguous()
+    y = torch.cat([stereo_decoder(sd, "left_decoder", z), stereo_decoder(sd, "right_decoder", z)], dim=1)
+    return y, st
+
+
+def calibrate_batchnorm(name, sd, x):
+    """Trained-like variant of a synthetic checkpoint (test infrastructure): returns a copy of `sd` whose BatchNorm
+    running_mean / running_var are the statistics of each layer's input on the calibration batch `x` -- what training
+    would have accumulated.  Random-init conv outputs have variance << 1, so the BN folds then carry gains >> 1 per
+    layer while the activations stay at unit scale: the realistic case for the fp16 dynamic-range envelope
+    (`make_state_dict` draws var ~ U(0.5, 1.5) instead)."""
+    global _CALIBRATE
+    fwd = {"denoiser": denoiser_forward, "super_resolution": super_resolution_forward, "stereo": stereo_forward}[name]
+    out = {k: v.clone() for k, v in sd.items()}
+    _CALIBRATE = {}
+    try:
+        with torch.no_grad():
+            fwd(out, x)
+        stats = dict(_CALIBRATE)
+    finally:
+        _CALIBRATE = None
+    return out, stats

@@ -26,7 +26,7 @@ import math
 
 import torch
 
-from .models import denoiser_forward, super_resolution_forward, stereo_forward
+from .models import denoiser_forward, super_resolution_forward, stereo_forward, stereo_forward_window
 
 DEFAULT_CHUNK = 44100      # 2.0 s @ 22.05 kHz (trainer.py:652)
 DEFAULT_OVERLAP = 2052     # hop 42048 = 0 mod 8 (denoiser pools)
@@ -120,3 +120,46 @@ def restore_chunked(sds, audio_1n, chunk_size=DEFAULT_CHUNK, overlap=DEFAULT_OVE
     rate = 2 if enable_super_resolution else 1
     y = stitch_chunks(torch.cat(outs, 0), a.shape[-1], chunk_size, overlap, rate)
     return normalize_audio(y) if normalize else y
+
+
+# mode="exact": same constants as ml_audio_restoration_b200/inference.py (receptive fields: SURVEY.md App. E)
+EXACT_HALO, EXACT_STEREO_HALO, EXACT_LSTM_LEAD = 96, 40, 16
+
+
+def restore_exact(sds, audio_1n, chunk_size=DEFAULT_CHUNK, enable_super_resolution=True, dtype=torch.float32, normalize=True):
+    """Whole-file-exact chunked restoration, restated from the oracle forwards: chunks whose starts are
+    multiples of 8 with EXACT_HALO discarded input samples per interior edge for denoise -> super-res, then stereo
+    segments with conv halos and the LSTM (h, c) carried from segment to segment.  Unlike `restore_chunked` this scheme IS
+    pinned by the reference: its result must equal `restore_whole` (inference.py:59-95 on the whole file) to rounding."""
+    a = audio_1n.to(dtype)
+    if normalize:
+        a = normalize_audio(a)
+    N, H = a.shape[-1], EXACT_HALO
+    r = 2 if enable_super_resolution else 1
+    L = chunk_size - chunk_size % 8
+    if L < 4 * H:
+        raise ValueError("chunk_size too small for mode='exact'")
+    hop = L - 2 * H
+    n = 1 if N <= L else -(-(N - 2 * H) // hop)
+    sig = a.new_zeros(1, r * N)
+    for i in range(n):
+        s0, s1 = i * hop, min(N, i * hop + L)
+        z = denoiser_forward(sds["denoiser"], a[:, s0:s1].unsqueeze(0), dtype)
+        if enable_super_resolution:
+            z = super_resolution_forward(sds["super_resolution"], z, dtype)
+        lo = 0 if i == 0 else s0 + H
+        hi = N if i == n - 1 else s0 + hop + H
+        sig[:, r * lo:r * hi] = z[0, :, r * (lo - s0):r * (hi - s0)]
+    M, E, P = r * N, EXACT_STEREO_HALO, EXACT_LSTM_LEAD
+    S2 = (r * L - 2 * E) // 16 * 16
+    out = a.new_zeros(2, M)
+    state = None
+    n_seg = -(-M // S2)
+    for j in range(n_seg):
+        a0, a1 = j * S2, min(M, (j + 1) * S2)
+        e0, e1 = max(0, a0 - E), min(M, a1 + E)
+        y, state = stereo_forward_window(sds["stereo"], sig[:, e0:e1].unsqueeze(0), state,
+                                         lstm_start=0 if j == 0 else a0 - P - e0,
+                                         state_pos=None if j == n_seg - 1 else a1 - P - e0, dtype=dtype)
+        out[:, a0:a1] = y[0, :, a0 - e0:a1 - e0]
+    return normalize_audio(out) if normalize else out

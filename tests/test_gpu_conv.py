@@ -28,7 +28,7 @@ SHAPES = [
     (1, 128, 64, 400, 7, 1),     # decoder layer 1
     (1, 256, 256, 100, 3, 1),    # denoiser bottleneck
     (3, 32, 32, 128, 5, 1),      # SR hf_emphasis, exactly one tile
-    (1, 16, 16, 8, 3, 1),        # tiny
+    (1, 16, 32, 8, 3, 1),        # tiny
 ]
 
 
@@ -71,43 +71,3 @@ def test_k7_heads_tensor_core_vs_cuda_core(state_dicts):
         x = make_input(3, T, seed=T).cuda()
         with torch.no_grad():
             assert_close(ms(x), mt(x), f"stereo heads T={T}: tensor-core vs CUDA-core engine")
-
-
-@pytest.mark.parametrize("T", [8, 100, 124, 125, 126, 127, 128, 129, 250, 251, 254, 255, 381, 1000, 4127])
-@pytest.mark.parametrize("cin,cout", [(128, 64), (64, 32)], ids=["dec1-tg2", "dec2-tg4"])
-def test_tap_grouped_k7_layers(cin, cout, T):
-    """The k7 decoder layers in tap-grouped form (two / four taps side by side along N, shifted sum in the epilogue, tile
-    stride 127 / 125) against torch and against the plain one-tap-per-MMA path of the same engine -- lengths around the
-    tile strides, their multiples and a ragged multi-tile case; batch 3 so dead peer tiles occur."""
-    L = _lib.lib()
-    g = torch.Generator().manual_seed(1000 * cin + T)
-    x = torch.randn(3, cin, T, generator=g)
-    w = torch.randn(cout, cin, 7, generator=g) / (cin * 7) ** 0.5
-    b = torch.randn(cout, generator=g)
-    ref = F.leaky_relu(F.conv1d(operand_round(x).double(), operand_round(w).double(), b.double(), padding=3), 0.2).float()
-    try:
-        _lib.check(L.ar_set_tap_groups(0))
-        plain = debug_conv(x, w, b, lrelu=1)
-        _lib.check(L.ar_set_tap_groups(1))
-        grouped = debug_conv(x, w, b, lrelu=1)
-    finally:
-        L.ar_set_tap_groups(0)
-    assert_close(ref.half().float(), grouped, f"tap-grouped conv {cin}->{cout} T={T}", max_abs=1e-2, min_snr=66.0)
-    # same fp16 operands, fp32 accumulation in a different order: the two paths differ by at most one fp16 rounding
-    assert_close(plain, grouped, f"plain vs tap-grouped {cin}->{cout} T={T}", max_abs=4e-3, min_snr=75.0)
-
-
-def test_tap_groups_leave_the_stereo_forward_unchanged(state_dicts):
-    """StereoSeparator at the BASELINE chunk length with and without tap-grouped decoders."""
-    from gpu_util import make_model
-    from oracle.weights import make_input
-    L = _lib.lib()
-    x = make_input(2, 44100, 77).cuda()
-    try:
-        _lib.check(L.ar_set_tap_groups(0))
-        y0 = make_model("stereo", state_dicts["stereo"])(x)
-        _lib.check(L.ar_set_tap_groups(1))
-        y1 = make_model("stereo", state_dicts["stereo"])(x)
-    finally:
-        L.ar_set_tap_groups(0)
-    assert_close(y0, y1, "stereo forward, plain vs tap-grouped decoders", max_abs=2e-4, min_snr=75.0)

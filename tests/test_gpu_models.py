@@ -81,18 +81,6 @@ def test_noncontiguous_input_is_accepted(models, state_dicts):
     assert_close(ref, y, "stereo non-contiguous")
 
 
-def test_lstm_state_carry_equals_whole_sequence(models, state_dicts):
-    """Two half-length calls with the carried (h,c) == one full-length LSTM scan."""
-    m = models("stereo", "umma")
-    x = make_input(1, 3000).cuda()
-    with torch.no_grad():
-        _, st = m.forward_with_state(x[:, :, :1500])
-        assert st.shape == (1, 2, 64)
-    ref, (hn, cn) = oracle.stereo_forward(state_dicts["stereo"], x[:, :, :1500].cpu(), return_state=True)
-    assert_close(hn[0], st[:, 0], "carried h", max_abs=1e-3, min_snr=50.0)
-    assert_close(cn[0], st[:, 1], "carried c", max_abs=1e-3, min_snr=50.0)
-
-
 def test_stereo_large_batch_tensor_core_lstm(models, state_dicts):
     """More than two sequences per SM switches the recurrence to the tensor-core (mma.sync fp16) kernel;
     ragged length (not a multiple of the 8-step block) and a batch that is not a multiple of 8."""
