@@ -31,7 +31,13 @@ HOP = CHUNK - OVERLAP
 # algorithmic FLOPs (2 x MAC of the reference's conv / convT / LSTM terms) per source audio-second,
 # SURVEY.md 8(d) / BASELINE.md section 2
 CHAIN_GFLOP_PER_AUDIO_S = 51.661
+# of these, the share computed by the tcgen05 conv engine (every Conv1d / ConvTranspose1d with Cin >= 16 + the LSTM input
+# projection): denoiser 147 968, super-res 41 984 MAC per input sample, stereo 473 088 MAC per 44.1 kHz sample
+CONV_GFLOP_PER_AUDIO_S = 2.0 * ((147968 + 41984) * SR + 473088 * 2 * SR) / 1e9          # 50.10
+# per-model algorithmic GFLOP per second of the model's OWN input signal
+MODEL_GFLOP_PER_S = {"denoiser": 6.549, "super_resolution": 1.881, "stereo": 21.615}
 METRIC = "restored audio-sec/sec (full chain)"
+TRAFFIC_FILE = "conv_traffic_r02.json"
 
 
 def conv_algorithmic_bytes_per_audio_s():
@@ -51,16 +57,18 @@ def conv_algorithmic_bytes_per_audio_s():
 
 
 def load_conv_traffic(args):
-    """Measured DRAM bytes per conv launch from the committed ncu capture, if it was taken at this configuration."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "conv_traffic_r01_final.json")) as f:
-            t = json.load(f)
-        c = t["config"]
-        if c["chunks_per_step_per_gpu"] == args.chunks_per_step and c["batch_chunks"] == args.batch_chunks:
-            return t["dram_bytes_per_launch_avg"]
-    except Exception:
-        pass
-    return None
+    """DRAM bytes per conv-engine launch from the COMMITTED ncu capture (a static file, not measured in this run), if it
+    was taken at this configuration and launch count; else None."""
+    for name in (TRAFFIC_FILE, "conv_traffic_r01_final.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f)
+            c = t["config"]
+            if c["chunks_per_step_per_gpu"] == args.chunks_per_step and c["batch_chunks"] == args.batch_chunks:
+                return t["dram_bytes_per_launch_avg"], f"static ncu capture profiles/{name} ({t.get('launches_per_step', '?')} conv launches per step), not measured in this run"
+        except Exception:
+            pass
+    return None, "no committed ncu capture for this configuration"
 
 
 def synth_audio(n, seed, device):
@@ -195,6 +203,143 @@ def step_samples(args):
     return (args.chunks_per_step - 1) * HOP + CHUNK
 
 
+def flush_l2(buf):
+    buf.add_(1.0)     # read + write 512 MB: everything older leaves the 126 MB L2
+
+
+def time_forward(fn, flush_buf, iters=7):
+    """Median device time (ms) of `fn()`; L2 flushed before every timed call (the small configs fit in L2)."""
+    times = []
+    for _ in range(iters):
+        flush_l2(flush_buf)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        times.append(e0.elapsed_time(e1))
+    return sorted(times)[len(times) // 2]
+
+
+def config_lines(pipe, sds, dev, cpu_cores):
+    """BASELINE.json configs 1-4: per-model forwards at their stated batch (eager launch train and CUDA
+    graph replay, next to the oracle port on the host cores) and config 4 as the latency of ONE 3-minute side."""
+    import oracle
+    from oracle.weights import make_input
+    flush_buf = torch.zeros(128 * 1024 * 1024, dtype=torch.float32, device=dev)
+    mods = {"denoiser": pipe.denoiser, "super_resolution": pipe.super_res, "stereo": pipe.stereo}
+    fwd = {"denoiser": oracle.denoiser_forward, "super_resolution": oracle.super_resolution_forward, "stereo": oracle.stereo_forward}
+    out = {}
+    for cfg, name, B in (("cfg1", "denoiser", 2), ("cfg2", "stereo", 4), ("cfg3", "super_resolution", 16)):
+        x = make_input(B, CHUNK)
+        xd = x.to(dev)
+        m = mods[name]
+        with torch.no_grad():
+            for _ in range(3):
+                m(xd)
+            eager_ms = time_forward(lambda: m(xd), flush_buf)
+            g = m.capture(xd)
+            for _ in range(3):
+                g(xd)
+            graph_ms = time_forward(lambda: g(xd), flush_buf)
+            fwd[name](sds[name], x)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                fwd[name](sds[name], x)
+            cpu_ms = (time.perf_counter() - t0) / 3 * 1e3
+        secs = B * CHUNK / SR
+        out[cfg] = {"model": name, "batch": B, "samples": CHUNK, "ms": graph_ms, "ms_eager_launches": eager_ms,
+                    "audio_s_per_s": secs / (graph_ms / 1e3), "tflops": MODEL_GFLOP_PER_S[name] * secs / graph_ms,
+                    "cpu": {"ms": cpu_ms, "audio_s_per_s": secs / (cpu_ms / 1e3), "cores": cpu_cores, "kind": "port"},
+                    "timing": "median of 7, L2 flushed before each call, CUDA-graph replay of the forward"}
+    n = 180 * SR
+    side = synth_audio(n, 4, dev)
+    with torch.no_grad():
+        for _ in range(2):
+            pipe.restore(side, mode="chunked", return_device=True)
+        ms = time_forward(lambda: pipe.restore(side, mode="chunked", return_device=True), flush_buf, iters=5)
+    out["cfg4"] = {"workload": "one synthetic 3-minute 22.05 kHz side, chunked chain (95 chunks, one batch), input+output normalize",
+                   "ms": ms, "audio_s_per_s": 180.0 / (ms / 1e3), "chunks": 95,
+                   "note": "single-file latency: 95 chunks under-fill the GPU (CUDA-core LSTM path, 1 sequence per CTA)"}
+    del flush_buf
+    return out
+
+
+def library_bar(sds, dev, n_chunks=64, batch=16):
+    """SECONDARY baseline (not the reference arm): the oracle-port modules -- the reference's op sequence, stock ATen /
+    cuDNN kernels -- under torch eager on THIS GPU, fp32 and TF32-allowed, same 2 s chunks (batch bounded by the fp32
+    activation memory of eager execution)."""
+    import oracle
+    import oracle.models as om
+    from oracle.weights import make_input
+    dsds = {k: {n: t.to(dev) for n, t in v.items()} for k, v in sds.items()}
+    x = make_input(batch, CHUNK).to(dev)
+    out = {}
+
+    def timed(reps):
+        with torch.no_grad():
+            oracle.chain_forward(dsds, x)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                oracle.chain_forward(dsds, x)
+            e1.record()
+            e1.synchronize()
+        return e0.elapsed_time(e1)
+
+    for label, tf32 in (("fp32", False), ("tf32", True)):
+        old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        try:
+            reps, lstm = n_chunks // batch, "cuDNN RNN"
+            try:
+                ms = timed(reps)
+            except RuntimeError as e:
+                # cuDNN's RNN rejects the 88 200-step sequences of the chain (the reference's README.md:175 warns of
+                # "cuDNN LSTM sequence length limits"): what a user of the reference can do is turn cuDNN off for the LSTM
+                # (convs stay on cuDNN); ATen's native CUDA LSTM then launches a handful of kernels per time step
+                lstm = f"ATen native CUDA LSTM (cuDNN RNN refused seq_len {2 * CHUNK}: {str(e)[:60]})"
+                om.LSTM_WITHOUT_CUDNN = True
+                reps = 1
+                ms = timed(reps)
+            out[label] = {"audio_s_per_s": (reps * batch * CHUNK / SR) / (ms / 1e3), "ms": ms, "chunks": reps * batch, "batch": batch,
+                          "lstm": lstm}
+        except Exception as e:
+            out[label] = {"error": repr(e)[:200]}
+        finally:
+            om.LSTM_WITHOUT_CUDNN = False
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    out["what"] = ("oracle-port modules (reference op sequence: F.conv1d / conv_transpose1d / batch_norm / max_pool1d / "
+                   "torch.lstm ...) under stock torch eager + cuDNN on this GPU; chain on 2 s chunks, no stitching")
+    return out
+
+
+def parity_gate(pipe, sds, x_dev, args):
+    """Outside the timed region: the chain on the step's OWN chunk batch (same batch size => same kernels, tile groups,
+    fused chains, tensor-core LSTM) -- three of its chunks against the oracle.  Both tolerance clauses of north_star."""
+    import ctypes as C
+    import oracle
+    from ml_audio_restoration_b200 import _lib, normalize_audio
+    L = _lib.lib()
+    n = x_dev.shape[1]
+    a = normalize_audio(x_dev)
+    B = min(args.batch_chunks, args.chunks_per_step)
+    chunks = torch.empty((B, 1, CHUNK), dtype=torch.float32, device=x_dev.device)
+    _lib.check(L.ar_split_chunks(a.data_ptr(), n, chunks.data_ptr(), 0, B, CHUNK, OVERLAP, torch.cuda.current_stream().cuda_stream))
+    y = pipe.forward_chunks(chunks)
+    picks = sorted({0, B // 2, B - 1})
+    got = y[picks].cpu()
+    with torch.no_grad():
+        ref = oracle.chain_forward(sds, chunks[picks].cpu())
+    err = float((ref - got).abs().max())
+    snr = float(10 * torch.log10((ref.double() ** 2).sum() / ((ref - got).double() ** 2).sum()))
+    ok = bool(torch.isfinite(got).all()) and err <= 1e-3 and snr >= 60.0
+    return {"chunks": picks, "batch": B, "max_abs_err": err, "snr_db": snr, "tolerance": "max-abs <= 1e-3 AND snr >= 60 dB vs fp32 oracle",
+            "pass": ok}
+
+
 def run_b200(args, rank, world, local_rank):
     import torch.distributed as dist
     from ml_audio_restoration_b200 import RestorationPipeline, _lib
@@ -282,19 +427,41 @@ def run_b200(args, rank, world, local_rank):
     peaks = load_peaks()
     cats = {name: {"ms": p_ms[i], "launches": int(p_ln[i]), "gflop": p_fl[i] / 1e9} for i, name in enumerate(_lib.PROFILE_CATEGORIES)}
     conv = cats["conv"]
-    achieved = (conv["gflop"] / 1e3) / (conv["ms"] / 1e3) if conv["ms"] > 0 else 0.0
+    conv_s = conv["ms"] / 1e3
+    # ALGORITHMIC FLOPs = SURVEY.md 8(d)'s per-SOURCE-second figure x the source seconds of the step: the 2 052-sample
+    # chunk overlap that the chunked scheme recomputes is overhead, not work (it is in `achieved_incl_overlap` only)
+    achieved = (CONV_GFLOP_PER_AUDIO_S * audio_s * args.steps / 1e3) / conv_s if conv_s > 0 else 0.0
+    achieved_incl = (conv["gflop"] / 1e3) / conv_s if conv_s > 0 else 0.0
     conv_bytes = conv_algorithmic_bytes_per_audio_s() * audio_s * args.steps      # algorithmic, this rank
-    hbm_gbs = (conv_bytes / 1e9) / (conv["ms"] / 1e3) if conv["ms"] > 0 else 0.0
+    hbm_gbs = (conv_bytes / 1e9) / conv_s if conv_s > 0 else 0.0
+    traffic, traffic_src = load_conv_traffic(args)
+    lstm = cats["lstm"]
+    lstm_steps = 2 * CHUNK                                                         # serial steps per launch (44.1 kHz, 2 s)
+    lstm_ms_launch = lstm["ms"] / max(1, lstm["launches"])
+    seq_in_flight = min(args.batch_chunks, args.chunks_per_step)
     roofline = {
-        "kernel": "tcgen05 conv engine: conv_umma2_kernel (2-CTA implicit-GEMM Conv1d / ConvT) + conv_chain_kernel "
-                  "(fused dilated blocks + LSTM input projection), all template variants",
+        "kernel": "tcgen05 conv engine: conv_umma2_kernel (2-CTA implicit-GEMM Conv1d / ConvT), conv_chain_kernel "
+                  "(fused dilated blocks + LSTM input projection) and sr_trunk_kernel (fused super-resolution trunk), all template variants",
         "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
         "frac": achieved / peaks["tflops"], "peak_source": f"{peaks['src']} bf16 dense sustained (fp16 operands run at the same rate)",
+        "flops_per_unit": f"{CONV_GFLOP_PER_AUDIO_S:.2f} GFLOP per source audio-second (of the chain's {CHAIN_GFLOP_PER_AUDIO_S}), "
+                          f"x {audio_s:.1f} source seconds per step; chunk-overlap recompute excluded",
+        "achieved_incl_overlap": achieved_incl,
         "avg_launch_ms": conv["ms"] / max(1, conv["launches"]), "launches": conv["launches"],
-        "share_of_step": conv["ms"] / (1e3 * t_s), "traffic": load_conv_traffic(args),
+        "launches_per_step": conv["launches"] // max(1, args.steps),
+        "share_of_step": conv["ms"] / (1e3 * t_s), "traffic": traffic, "traffic_source": traffic_src,
         "algorithmic_bytes_per_launch": conv_bytes / max(1, conv["launches"]),
         "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_gbs / peaks["hbm_gbs"],
-                "note": "same launches against the HBM roofline (algorithmic fp16 activation bytes of the 37 launches)"},
+                "note": "same launches against the HBM roofline (algorithmic fp16 activation bytes per launch)"},
+        "whole_chain": {"achieved": value / world * CHAIN_GFLOP_PER_AUDIO_S / 1e3, "unit": "TFLOP/s",
+                        "frac": value / world * CHAIN_GFLOP_PER_AUDIO_S / 1e3 / peaks["tflops"],
+                        "note": "all kernels of the step (convs, LSTM, stems, tails, normalize, split / overlap-add)"},
+        "lstm": {"kernel": "lstm_mma4w_kernel" if seq_in_flight > 2 * torch.cuda.get_device_properties(dev).multi_processor_count else "lstm_kernel",
+                 "bound": "latency", "ms_per_launch": lstm_ms_launch, "serial_steps_per_launch": lstm_steps,
+                 "ns_per_step": 1e6 * lstm_ms_launch / lstm_steps, "sequences_in_flight": seq_in_flight,
+                 "sequences_per_sm": seq_in_flight / torch.cuda.get_device_properties(dev).multi_processor_count,
+                 "sequence_steps_per_s": seq_in_flight * lstm_steps / (lstm_ms_launch / 1e3) if lstm_ms_launch > 0 else 0.0,
+                 "share_of_step": lstm["ms"] / (1e3 * t_s)},
         "per_category_ms_per_step": {k: v["ms"] / args.steps for k, v in cats.items()},
     }
     line = {
@@ -305,14 +472,25 @@ def run_b200(args, rank, world, local_rank):
         "chain_tflops_per_gpu": value / world * CHAIN_GFLOP_PER_AUDIO_S / 1e3,
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": 16 * n},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "lib": _lib.LIB_PATH,
     }
+    cores = host_threads()
+    line["parity"] = parity_gate(pipe, sds, x_dev, args)
     if world == 1 and not args.no_cpu_baseline:
-        cores = host_threads()
         cpu_chain_rate(1)
         v, dt, secs = cpu_chain_rate(args.cpu_chunks)
         line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
                                 "sample": f"{args.cpu_chunks} chunks ({secs:.1f} s of audio) in {dt:.1f} s, oracle port on torch CPU"}
+    if world == 1 and not args.no_secondary:
+        line["configs"] = config_lines(pipe, sds, dev, cores)
+        line["secondary"] = {"torch_eager_same_gpu": library_bar(sds, dev)}
+        for k in ("fp32", "tf32"):
+            r = line["secondary"]["torch_eager_same_gpu"].get(k, {})
+            if "audio_s_per_s" in r:
+                r["this_repo_over_it"] = (value / world) / r["audio_s_per_s"]
     print(json.dumps(line), flush=True)
+    if not line["parity"]["pass"]:
+        raise SystemExit("bench.py: PARITY GATE FAILED -- the number above is not valid")
     if world > 1:
         dist.destroy_process_group()
 
@@ -328,6 +506,7 @@ def main():
     ap.add_argument("--streams", type=int, default=1, help="chunk batches in flight (LSTM of one overlaps convs of the next)")
     ap.add_argument("--cpu-chunks", type=int, default=32, help="chunks in the bounded CPU sample (32 = 61 s of audio, about 11 s on 16 host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the per-config lines (BASELINE configs 1-4) and the torch-eager same-GPU bar")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -51,6 +51,45 @@ def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+class GraphedForward:
+    """A module forward captured into a CUDA graph for one fixed input shape (`NativeModule.capture`).
+
+    The three models are 15-45 kernel launches each; at the small batches of interactive use (BASELINE configs 1-3:
+    2-16 chunks) the kernels take a few microseconds and the launch train dominates.  Replaying the captured graph issues
+    the whole forward with one driver call.  `__call__(x)` copies `x` into the graph's static input and returns the
+    static output tensor (valid until the next call)."""
+
+    def __init__(self, module, example: torch.Tensor):
+        x = module._check_input(example)
+        self.module = module
+        self.x = x.clone()
+        with torch.no_grad():
+            side = torch.cuda.Stream(x.device)
+            side.wait_stream(torch.cuda.current_stream(x.device))
+            with torch.cuda.stream(side):               # warm up off the capture: packs weights, sets kernel attributes
+                module(self.x)
+            torch.cuda.current_stream(x.device).wait_stream(side)
+            torch.cuda.synchronize(x.device)
+            self.graph = torch.cuda.CUDAGraph()
+            before = set(_Workspace._bufs)
+            with torch.cuda.graph(self.graph):
+                self.y = module(self.x)
+            # the scratch allocated during capture lives in the graph's private pool: it belongs to this graph, not to
+            # whatever later runs on a stream that happens to reuse the capture stream's handle
+            with _Workspace._lock:
+                self._scratch = [_Workspace._bufs.pop(k) for k in set(_Workspace._bufs) - before]
+        self._key = module._param_key(x.device)
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        if x.shape != self.x.shape:
+            raise RuntimeError(f"graph was captured for input {tuple(self.x.shape)}, got {tuple(x.shape)}")
+        if self.module._param_key(self.x.device) != self._key:
+            raise RuntimeError("module parameters changed since the graph was captured; capture again")
+        self.x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.y
+
+
 class NativeModule(nn.Module):
     KIND = -1
 
@@ -120,6 +159,10 @@ class NativeModule(nn.Module):
 
     def _out_shape(self, B: int, T: int):
         raise NotImplementedError
+
+    def capture(self, example: torch.Tensor) -> GraphedForward:
+        """Capture `forward` for inputs shaped like `example` into a CUDA graph (see `GraphedForward`)."""
+        return GraphedForward(self, example)
 
     def audit(self, x) -> dict:
         """Dynamic-range audit (`ar_model_audit_*`): run `forward(x)` layer by layer and return `{layer: max |activation|}`

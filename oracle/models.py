@@ -58,7 +58,7 @@ def detect_impulses(x):
     d1 = F.pad((x[:, :, 1:] - x[:, :, :-1]).abs(), (0, 1))
     d2 = F.pad((d1[:, :, 1:] - d1[:, :, :-1]).abs(), (0, 1))
     score = (d2 * 2.0 + d1 + x.abs() * 0.5) / 3.5
-    box = torch.ones(1, 1, 5, dtype=x.dtype) / 5
+    box = torch.ones(1, 1, 5, dtype=x.dtype, device=x.device) / 5
     return F.conv1d(score, box, padding=2).clamp(0, 1)
 
 
@@ -129,8 +129,18 @@ def lstm_explicit(x_btc, w_ih, w_hh, b_ih, b_hh):
     return torch.stack(out, dim=1)
 
 
+LSTM_WITHOUT_CUDNN = False   # CUDA tensors only (bench.py's same-GPU library bar): cuDNN's RNN rejects 88 200-step sequences
+
+
 def _lstm_fast(sd, x_btc, h0c0=None):
-    """Same recurrence through ATen's fused CPU LSTM (what nn.LSTM dispatches to)."""
+    """Same recurrence through ATen's fused LSTM (what nn.LSTM dispatches to: the CPU kernel here, cuDNN on CUDA tensors)."""
+    if LSTM_WITHOUT_CUDNN and x_btc.is_cuda:
+        with torch.backends.cudnn.flags(enabled=False):
+            return _lstm_call(sd, x_btc, h0c0)
+    return _lstm_call(sd, x_btc, h0c0)
+
+
+def _lstm_call(sd, x_btc, h0c0):
     dt = x_btc.dtype
     B = x_btc.shape[0]
     H = sd["lstm.weight_hh_l0"].shape[1]

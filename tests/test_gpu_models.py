@@ -137,3 +137,19 @@ def test_weight_update_repacks(state_dicts):
         m.reconstruction.bias.add_(0.25)
         y1 = m(x)
     assert_close(y0.cpu() + 0.25, y1, "bias update visible after repack", max_abs=1e-6, min_snr=None)
+
+
+@pytest.mark.parametrize("name,B,T", [("denoiser", 2, 44100), ("super_resolution", 3, 5000), ("stereo", 4, 4100)])
+def test_cuda_graph_capture_replays_the_forward(models, name, B, T):
+    """`module.capture(x)`: the forward's launch train captured into a CUDA graph (BASELINE configs 1-3 are launch-bound at
+    their small batches); replays on new inputs give exactly what the eager forward gives."""
+    m = models(name, "umma")
+    xs = [make_input(B, T, seed=50 + i).cuda() for i in range(3)]
+    with torch.no_grad():
+        g = m.capture(xs[0])
+        for x in xs:
+            want = m(x)
+            got = g(x).clone()
+            assert torch.equal(want, got)
+    with pytest.raises(RuntimeError):
+        g(make_input(B, T + 8).cuda())
