@@ -439,9 +439,10 @@ def run_b200(args, rank, world, local_rank):
     lstm_steps = 2 * CHUNK                                                         # serial steps per launch (44.1 kHz, 2 s)
     lstm_ms_launch = lstm["ms"] / max(1, lstm["launches"])
     seq_in_flight = min(args.batch_chunks, args.chunks_per_step)
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
     roofline = {
         "kernel": "tcgen05 conv engine: conv_umma2_kernel (2-CTA implicit-GEMM Conv1d / ConvT), conv_chain_kernel "
-                  "(fused dilated blocks + LSTM input projection) and sr_trunk_kernel (fused super-resolution trunk), all template variants",
+                  "(fused dilated blocks + LSTM input projection, U-Net 64 -> 128 -> 128 double conv), all template variants",
         "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
         "frac": achieved / peaks["tflops"], "peak_source": f"{peaks['src']} bf16 dense sustained (fp16 operands run at the same rate)",
         "flops_per_unit": f"{CONV_GFLOP_PER_AUDIO_S:.2f} GFLOP per source audio-second (of the chain's {CHAIN_GFLOP_PER_AUDIO_S}), "
@@ -456,10 +457,10 @@ def run_b200(args, rank, world, local_rank):
         "whole_chain": {"achieved": value / world * CHAIN_GFLOP_PER_AUDIO_S / 1e3, "unit": "TFLOP/s",
                         "frac": value / world * CHAIN_GFLOP_PER_AUDIO_S / 1e3 / peaks["tflops"],
                         "note": "all kernels of the step (convs, LSTM, stems, tails, normalize, split / overlap-add)"},
-        "lstm": {"kernel": "lstm_mma4w_kernel" if seq_in_flight > 2 * torch.cuda.get_device_properties(dev).multi_processor_count else "lstm_kernel",
+        "lstm": {"kernel": ("lstm_mmaw_kernel<8>" if seq_in_flight > 8 * sms else "lstm_mmaw_kernel<4>" if seq_in_flight > 2 * sms else "lstm_kernel"),
                  "bound": "latency", "ms_per_launch": lstm_ms_launch, "serial_steps_per_launch": lstm_steps,
                  "ns_per_step": 1e6 * lstm_ms_launch / lstm_steps, "sequences_in_flight": seq_in_flight,
-                 "sequences_per_sm": seq_in_flight / torch.cuda.get_device_properties(dev).multi_processor_count,
+                 "sequences_per_sm": seq_in_flight / sms,
                  "sequence_steps_per_s": seq_in_flight * lstm_steps / (lstm_ms_launch / 1e3) if lstm_ms_launch > 0 else 0.0,
                  "share_of_step": lstm["ms"] / (1e3 * t_s)},
         "per_category_ms_per_step": {k: v["ms"] / args.steps for k, v in cats.items()},
@@ -501,8 +502,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
-    ap.add_argument("--chunks-per-step", type=int, default=1184, help="2 s chunks per GPU per step (1184 = 8 per SM)")
-    ap.add_argument("--batch-chunks", type=int, default=1184, help="chunks per chain launch (1184 = 8 per SM: one full-chip tensor-core LSTM launch)")
+    ap.add_argument("--chunks-per-step", type=int, default=2368, help="2 s chunks per GPU per step (2368 = 16 per SM)")
+    ap.add_argument("--batch-chunks", type=int, default=2368, help="chunks per chain launch (2368 = 16 per SM: one full-chip tensor-core LSTM "
+                    "launch, 8 sequences per CTA x 2 CTAs per SM; the conv phases run on sub-batches around it)")
     ap.add_argument("--streams", type=int, default=1, help="chunk batches in flight (LSTM of one overlaps convs of the next)")
     ap.add_argument("--cpu-chunks", type=int, default=32, help="chunks in the bounded CPU sample (32 = 61 s of audio, about 11 s on 16 host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

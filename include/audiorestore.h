@@ -62,11 +62,12 @@ int ar_version(void);
 /* Select the conv engine used by subsequently created models (default AR_ENGINE_UMMA). */
 int ar_set_conv_engine(int engine);
 
-/* Enable (default) / disable fused multi-layer launches (e.g. the StereoSeparator's dilated block
- * conv k3 -> conv k1 [-> LSTM input projection], stereo_separator.py:49-64,104-106, as one kernel whose
- * intermediates stay in shared memory) for subsequently created models.  Cross-check knob: both settings
- * compute the same fp16-rounded intermediates. */
-int ar_set_fusion(int on);
+/* Fused multi-layer launches (the StereoSeparator's dilated block conv k3 -> conv k1 [-> LSTM input projection],
+ * stereo_separator.py:49-64,104-106, and the U-Net's / residual blocks' conv k3 -> conv k3 pairs, denoiser.py:51-60,
+ * super_resolution.py:104-122, as one kernel whose intermediates stay in shared memory) for subsequently created
+ * models: 0 = layer by layer, 1 (default) = the chains that measured faster than their layers, 2 = every chain that
+ * fits.  Cross-check knob: all settings compute the same fp16-rounded intermediates. */
+int ar_set_fusion(int level);
 
 /* Shared memory one conv CTA may use, in KB (64..227, default 227 = the whole SM).  AR_CORESIDENT_SMEM_KB leaves room
  * for one CTA of the LSTM recurrence on every SM: when chunk batches are pipelined on two streams the latency-bound

@@ -29,6 +29,9 @@ int model_create(int kind, const ar_tensor_t* tensors, int n, int device, Model*
 int model_workspace_bytes(const Model* m, int B, int T, size_t* bytes);
 int model_forward(const Model* m, const float* x, float* y, int B, int T, const float* st_in, float* st_out, void* ws,
                   size_t ws_bytes, cudaStream_t stream, int lstm_start = 0, int state_pos = -1);
+int chain_workspace_bytes(const Model* den, const Model* sr, const Model* st, int B, int T, size_t* bytes);
+int chain_forward(const Model* den, const Model* sr, const Model* st, const float* x, float* y, int B, int T, void* ws,
+                  size_t ws_bytes, cudaStream_t stream);
 void model_destroy(Model* m);
 int model_kind(const Model* m);
 int model_audit_enable(Model* m, int on);
@@ -46,14 +49,13 @@ struct ar_chain_s {
   ar::Model* st;
 };
 
-static inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 extern "C" {
 
 const char* ar_last_error(void) { return ar::last_error(); }
 int ar_version(void) { return 100; }
 int ar_set_conv_engine(int engine) { return ar::set_engine(engine); }
-int ar_set_fusion(int on) { return ar::set_fusion(on); }
+int ar_set_fusion(int level) { return ar::set_fusion(level); }
 int ar_set_conv_smem_kb(int kb) { return ar::set_conv_smem_kb(kb); }
 int ar_resample_length(int64_t n, int orig_sr, int new_sr, int64_t* n_out) {
   if (!n_out || n < 0 || orig_sr < 1 || new_sr < 1) { ar::set_error("resample_length: bad argument"); return AR_ERR_INVALID; }
@@ -140,44 +142,14 @@ int ar_chain_create(ar_model_t denoiser, ar_model_t sr, ar_model_t stereo, ar_ch
 }
 void ar_chain_destroy(ar_chain_t c) { delete c; }
 
-static int chain_layout(ar_chain_t c, int B, int T, size_t* y1, size_t* y2, size_t* ws, size_t* total) {
-  AR_CHECK(c && B >= 1 && T >= 1, AR_ERR_INVALID, "chain: bad argument");
-  const int rate = c->sr ? 2 : 1;
-  size_t w_den = 0, w_sr = 0, w_st = 0;
-  AR_TRY(ar::model_workspace_bytes(c->den, B, T, &w_den));
-  if (c->sr) AR_TRY(ar::model_workspace_bytes(c->sr, B, T, &w_sr));
-  AR_TRY(ar::model_workspace_bytes(c->st, B, rate * T, &w_st));
-  *y1 = align256((size_t)B * T * sizeof(float));
-  *y2 = c->sr ? align256((size_t)B * 2 * T * sizeof(float)) : 0;
-  *ws = std::max(w_den, std::max(w_sr, w_st));
-  *total = *y1 + *y2 + *ws + 256;
-  return AR_OK;
-}
-
 int ar_chain_workspace_bytes(ar_chain_t c, int B, int T, size_t* bytes) {
-  size_t y1, y2, ws;
-  AR_CHECK(bytes != nullptr, AR_ERR_INVALID, "chain: null bytes");
-  return chain_layout(c, B, T, &y1, &y2, &ws, bytes);
+  AR_CHECK(c != nullptr, AR_ERR_INVALID, "chain: null handle");
+  return ar::chain_workspace_bytes(c->den, c->sr, c->st, B, T, bytes);
 }
 
 int ar_chain_forward(ar_chain_t c, const float* x, float* y, int B, int T, void* workspace, size_t workspace_bytes, void* stream) {
-  size_t y1b, y2b, wsb, total;
-  AR_TRY(chain_layout(c, B, T, &y1b, &y2b, &wsb, &total));
-  AR_CHECK(workspace && workspace_bytes >= total, AR_ERR_WORKSPACE, "chain: workspace too small (need " + std::to_string(total) + " bytes)");
-  char* base = reinterpret_cast<char*>(align256(reinterpret_cast<uintptr_t>(workspace)));
-  float* y1 = reinterpret_cast<float*>(base);
-  float* y2 = reinterpret_cast<float*>(base + y1b);
-  void* ws = base + y1b + y2b;
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  AR_TRY(ar::model_forward(c->den, x, y1, B, T, nullptr, nullptr, ws, wsb, s));
-  const float* st_in = y1;
-  int Ts = T;
-  if (c->sr) {
-    AR_TRY(ar::model_forward(c->sr, y1, y2, B, T, nullptr, nullptr, ws, wsb, s));
-    st_in = y2;
-    Ts = 2 * T;
-  }
-  return ar::model_forward(c->st, st_in, y, B, Ts, nullptr, nullptr, ws, wsb, s);
+  AR_CHECK(c != nullptr, AR_ERR_INVALID, "chain: null handle");
+  return ar::chain_forward(c->den, c->sr, c->st, x, y, B, T, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int ar_normalize(float* audio, int64_t n, float target_db, void* scratch, void* stream) {

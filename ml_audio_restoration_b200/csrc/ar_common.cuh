@@ -172,12 +172,14 @@ __device__ __forceinline__ void epilogue_chunk8(const ConvParams& p, int b, int 
   }
 }
 
-// A fused chain (conv_chain.cu): first GEMM = `p` (k-tap conv, input geometry, W1, bias1), then n_gemms-1 pointwise
-// convs whose inputs never leave the SM.  `pl` carries the output geometry of the LAST stage (out*, Tout,
-// out_tblock, N = N[n_gemms-1]); every stage's weights are packed as one 2-CTA pair-slice (two column halves).
+// A fused chain (conv_chain.cu): first GEMM = `p` (k-tap conv, input geometry, W1, bias1), then n_gemms-1 further convs
+// (pointwise, or one k3 conv: taps2 = 3) whose inputs never leave the SM.  `pl` carries the output geometry of the LAST
+// stage (out*, Tout, out_tblock, pool*, res*, N = N[n_gemms-1]); every stage's weights are packed as one 2-CTA pair-slice
+// (two column halves).  p.tiles_per_item counts tiles of chain_tile_stride(taps2) rows.
 struct ChainParams {
   ConvParams p, pl;
   int n_gemms;
+  int taps2;          // taps of the second GEMM: 1 (pointwise) or 3 (k3 -> k3 pairs, tile stride 126)
   const __half* w[3];
   const float* bias[3];
   int N[3];
@@ -186,8 +188,9 @@ struct ChainParams {
 };
 
 // ----------------------------------------------------------------------------- launchers
-bool conv_chain_fits(int Cin, int taps, int dil, const int* N, int n_gemms);   // shared memory / TMEM check for a chain
-int launch_conv_chain(const ChainParams& cp, cudaStream_t stream);  // fused k-tap conv -> pointwise conv(s), 2-CTA engine
+bool conv_chain_fits(int Cin, int taps, int dil, const int* N, int n_gemms, int taps2);   // shape / shared memory / TMEM check
+int chain_tile_stride(int taps2);                                   // output rows per tile: 128, or 126 behind a k3 second stage
+int launch_conv_chain(const ChainParams& cp, cudaStream_t stream);  // fused k-tap conv -> conv(s), 2-CTA engine
 int launch_conv_umma2(const ConvParams& p, cudaStream_t stream);   // the tcgen05 engine (cta_group::2; needs p.cta2)
 int launch_conv_simt(const ConvParams& p, cudaStream_t stream);    // CUDA-core cross-check engine
 

@@ -1,27 +1,39 @@
-// Fused conv chains on the 2-CTA tcgen05 engine: a k-tap (dilated) Conv1d followed by one or two pointwise
-// (k = 1) convs -- the StereoSeparator's `_dilated_block` (stereo_separator.py:49-64: conv k3 dilated + BN +
-// LeakyReLU, conv k1 + BN + LeakyReLU) and, for the last block, the LSTM input projection behind it
-// (stereo_separator.py:104-106) -- computed per 256-row tile pair WITHOUT writing the intermediate
-// activations to HBM:
+// Fused conv chains on the 2-CTA tcgen05 engine: a k-tap (dilated) Conv1d followed by one or two more convs, computed
+// per 256-row tile pair WITHOUT writing the intermediate activations to HBM.  Three shapes of chain are instantiated:
+//
+//   (a) k3 dilated -> k1                 the StereoSeparator's `_dilated_block` (stereo_separator.py:49-64)
+//   (b) k3 dilated -> k1 -> k1 (N = 256) the last block + the LSTM input projection behind it (stereo_separator.py:104-106)
+//   (c) k3 -> k3                         the U-Net's double conv (`_conv_block`, denoiser.py:51-60; max-pool copy fused) and
+//                                        the super-resolution residual block (conv-BN-LReLU-conv-BN + skip,
+//                                        super_resolution.py:104-122; the skip operand is the chain's own input)
 //
 //   G1: D1[256 x N1] (TMEM) = sum_taps A(rows from HBM via bulk copies, tap-shifted descriptors) * W1
 //   E1: D1 -> +bias, LeakyReLU, fp16 -> shared memory, laid out as the K-major no-swizzle A operand of G2
-//   G2: D2[256 x N2] = I1 * W2            (A straight from shared memory, W2 resident like W1)
-//   E2: last stage: the usual fused epilogue to HBM (H8 or time-blocked);  otherwise -> I2 and G3 / E3.
+//   G2: D2[256 x N2] = sum_taps2 I1(tap-shifted) * W2      (A straight from shared memory, W2 resident like W1)
+//   E2: last stage: the usual fused epilogue to HBM (H8 or time-blocked; pool / residual);  otherwise -> I2 and G3 / E3.
 //
-// The unfused layers of these blocks are HBM-bound (k1 128->128: 512 B of activation traffic per row for
-// 32 K MACs), so removing the intermediate write + read halves the traffic of a block; the three-GEMM chain
-// (128 -k3-> 128 -k1-> 128 -k1-> 256) moves 768 B per row instead of 1 792.
+// These layers are HBM-bound when run one by one (k1 128->128: 512 B of activation traffic per row for 32 K MACs; k3
+// 32->32: 128 B per row for 3 K MACs), so removing the intermediate write + read removes 40-60 % of a block's traffic.
 //
-// Warp roles (every stage of the chain has its own issuer and its own epilogue group, so no warp ever
-// waits for a result that depends on work it still has to issue -- a pipeline trace of the first version,
-// where one MMA warp and one epilogue group walked all stages, showed the tensor pipe idle half of the time
-// behind that warp's serial waits):
+// (c): a k3 second stage needs one intermediate row on either side of its outputs, and an MMA produces exactly 128 rows,
+// so a tile yields 126 outputs (tile stride S = 126): G1 computes the intermediate for times [t0 - 1, t0 + 127), G2 reads
+// it with tap shifts 0 / 1 / 2 (two slack rows behind the buffer feed only the two masked output rows).  Intermediate rows
+// whose time lies outside [0, T) are the second conv's ZERO PADDING, not conv-1 outputs: E1 writes zeros there.
+//
+// (b): TMEM holds 512 columns = 128 (G1) + 128 (G2) + 256 (G3), which leaves nothing to double-buffer -- and with single
+// buffers a pipeline trace showed the tensor pipe idle while E1 drains G1's accumulator (period 6 030 cycles for 3 270
+// cycles of MMAs).  G1 and G2 therefore ROTATE through the two 128-column buffers: tile t's G1 fills buffer t mod 2, E1
+// drains it, the SAME buffer then takes tile t's G2 (E1 is done with it by the time I1 is complete), E2 drains it and
+// hands it to G1 of tile t + 2.  G1 of tile t + 1 runs in the other buffer while tile t is in E1 / G2 / E2: G1's
+// accumulator is effectively double-buffered without a column more.  (Running G3 as two N = 128 halves through one
+// accumulator to free columns was measured first: E3 of the first half then sits between the halves, period 7 270.)
+//
+// Warp roles (every stage of the chain has its own issuer and its own epilogue group, so no warp ever waits for a
+// result that depends on work it still has to issue):
 //   warp 0            bulk-copy (TMA) producer: resident weights of all stages, then the activation ring of G1
 //   warp 1 .. NG      issuer of GEMM g = warp-1 (leader CTA issues tcgen05.mma.cta_group::2; the peer's warp zero-pads
 //                     its edge rows / forwards "my operand half is ready" arrivals to the leader)
 //   then NG groups    epilogue group g drains the accumulator of GEMM g: to shared memory (g < NG-1) or to HBM (last)
-// Buffers: two GEMMs -> accumulators and I1 double-buffered; three GEMMs -> single (TMEM 128+128+256 = 512 columns).
 #include "ar_common.cuh"
 #include "umma_ptx.cuh"
 #include "umma_epilogue.cuh"
@@ -31,9 +43,10 @@ namespace ar {
 constexpr int CH_SMEM_BUDGET = 227 * 1024;
 constexpr int CH_BAR_BYTES = 768;
 constexpr int CH_BIAS_BYTES = 2048;      // <= 512 fp32 biases over all stages
-constexpr int CH_RI = TILE_M;            // rows of an intermediate operand (pointwise follow-up convs: no halo)
 constexpr int CH_MAX_STAGES = 16;
 constexpr int CH_PREFETCH = 4;           // tile pairs the L2 prefetch runs ahead of the shared-memory ring
+
+enum ChainEpi { CE_PLAIN = 0, CE_POOL = 1, CE_RES = 2 };
 
 // epilogue warps per stage
 __host__ __device__ constexpr int ch_group_warps(int NG, int g) { return NG == 2 ? 8 : (g == 2 ? 8 : 4); }
@@ -44,7 +57,8 @@ struct ChainCfg {
   int kbs, stages, R, nks, stage_bytes;  // activation ring of the first GEMM
   int w_bytes[3], w_off[3];              // resident weight halves per CTA
   int i_off[2], i_bytes[2], nbI[2];      // intermediate operands (output of GEMM g = input of GEMM g+1)
-  int acc_col[3], nbA[3];                // TMEM columns: GEMM g buffer b at acc_col[g] + b * N[g]
+  int RI;                                // rows of an intermediate operand: 128 + (taps2 - 1)
+  int acc_col[3], nbA[3], acc_n[3];      // TMEM columns: GEMM g buffer b at acc_col[g] + b * acc_n[g]
   int tmem_cols;
   int stage_off, bar_off, bias_off, smem_bytes;
 };
@@ -61,13 +75,19 @@ __device__ __forceinline__ void trace_ev1(long long* tr, int it, int ev) {   // 
   if (tr != nullptr && blockIdx.x == 0 && it < CH_TRACE_TILES) tr[it * 16 + ev] = clock64();
 }
 
-// buffer index / mbarrier phase of the it-th use of a set of nb (1 or 2) buffers
-__device__ __forceinline__ int buf_of(int it, int nb) { return it & (nb - 1); }
-__device__ __forceinline__ uint32_t phase_of(int it, int nb) { return (uint32_t)(it >> (nb - 1)) & 1u; }
+// buffer index / mbarrier phase of the u-th use of a set of nb (1 or 2) buffers
+constexpr int CH_MAX_BUF = 2;
+__device__ __forceinline__ int buf_of(int u, int nb) { return u & (nb - 1); }
+__device__ __forceinline__ uint32_t phase_of(int u, int nb) { return (uint32_t)(u >> (nb >> 1)) & 1u; }   // nb >> 1 == log2(nb) for 1, 2
 
-template <int TAPS, int NG>
+template <int TAPS, int NG, int TAPS2, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ch_threads(NG), 1) __maxnreg__(ch_maxreg(NG))
 conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant__ ChainCfg cfg, int num_pairs) {
+  static_assert(TAPS2 == 1 || NG == 2, "a k-tap second stage is a two-GEMM chain");
+  static_assert(EPI == CE_PLAIN || NG == 2, "pool / residual epilogues belong to the two-GEMM chains");
+  constexpr int S = TILE_M - (TAPS2 - 1);          // tile stride = outputs per tile
+  constexpr int LEAD = (TAPS2 - 1) / 2;            // intermediate row r of a tile is time  tile * S - LEAD + r
+  constexpr bool ROTATE = NG == 3;                 // G1 and G2 share two rotating accumulator buffers (see (b) above)
   extern __shared__ __align__(1024) uint8_t smem[];
   const ConvParams& p = cp.p;
   const uint32_t sbase = smem_u32(smem);
@@ -77,12 +97,13 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (CH_MAX_STAGES + s); };
   constexpr int B0 = 3 * CH_MAX_STAGES;
-  auto tfull_bar = [&](int g, int b) { return bar_base + 8u * (B0 + g * 2 + b); };
-  auto tempty_bar = [&](int g, int b) { return bar_base + 8u * (B0 + 6 + g * 2 + b); };      // leader only
-  auto ifull_bar = [&](int g, int b) { return bar_base + 8u * (B0 + 12 + g * 2 + b); };      // leader only: epilogue group g of BOTH CTAs -> issuer g+1
-  auto iempty_bar = [&](int g, int b) { return bar_base + 8u * (B0 + 20 + g * 2 + b); };
-  const uint32_t w_bar = bar_base + 8u * (B0 + 24);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + cfg.bar_off + 8 * (B0 + 25));
+  auto tfull_bar = [&](int g, int b) { return bar_base + 8u * (B0 + g * CH_MAX_BUF + b); };
+  auto tempty_bar = [&](int g, int b) { return bar_base + 8u * (B0 + 3 * CH_MAX_BUF + g * CH_MAX_BUF + b); };      // leader only
+  auto ifull_bar = [&](int g, int b) { return bar_base + 8u * (B0 + 6 * CH_MAX_BUF + g * CH_MAX_BUF + b); };       // leader only: epilogue group g of BOTH CTAs -> issuer g+1
+  auto iempty_bar = [&](int g, int b) { return bar_base + 8u * (B0 + 8 * CH_MAX_BUF + g * CH_MAX_BUF + b); };
+  const uint32_t w_bar = bar_base + 8u * (B0 + 10 * CH_MAX_BUF);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + cfg.bar_off + 8 * (B0 + 10 * CH_MAX_BUF + 1));
+  static_assert(8 * (B0 + 10 * CH_MAX_BUF + 2) <= CH_BAR_BYTES, "barrier block too small");
   float* const s_bias = reinterpret_cast<float*>(smem + cfg.bias_off);
 
   const int warp = threadIdx.x >> 5;
@@ -97,12 +118,12 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
       mbar_init(empty_bar(s), 1);
     }
     for (int g = 0; g < NG; ++g)
-      for (int b = 0; b < 2; ++b) {
+      for (int b = 0; b < CH_MAX_BUF; ++b) {
         mbar_init(tfull_bar(g, b), 1);
         mbar_init(tempty_bar(g, b), 2 * ch_group_warps(NG, g));
       }
     for (int g = 0; g < NG - 1; ++g)
-      for (int b = 0; b < 2; ++b) {
+      for (int b = 0; b < CH_MAX_BUF; ++b) {
         mbar_init(ifull_bar(g, b), 2 * ch_group_warps(NG, g));
         mbar_init(iempty_bar(g, b), 1);
       }
@@ -124,11 +145,25 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   const int tpi = p.tiles_per_item;
-  const int ppi = (tpi + 1) >> 1;
+  const int ppi = (tpi + 1) >> 1;                  // tile pairs per batch item
   const int R = cfg.R;
+  const int RI = cfg.RI;
   const int pair0 = blockIdx.x >> 1;
   const int pair_step = gridDim.x >> 1;
-  const int n_local = pair0 < num_pairs ? (num_pairs - pair0 + pair_step - 1) / pair_step : 0;
+  const int n_local = pair0 < num_pairs ? (num_pairs - pair0 + pair_step - 1) / pair_step : 0;   // tile pairs of this cluster
+  // this CTA's tile of pair pi of an item, and the first input row (time index) of its run: tile * S - LEAD - pad_left;
+  // an idle half (odd tile count) re-reads the item's last tile, whose rows then get zeroed
+  auto tile0_of = [&](int pi) { return pi * 2 + (int)rank; };
+  auto run_t0 = [&](int pi) {
+    int tl = tile0_of(pi);
+    if (tl > tpi - 1) tl = tpi - 1;
+    return tl * S - LEAD - p.pad_left;
+  };
+  // rows of the run that exist in the padded buffer (the last tile of a stride-126 chain may reach past it)
+  auto run_rows = [&](int t0) {
+    const int avail = p.in_Tp - (HALO + t0);
+    return R < avail ? R : avail;
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer: resident weights, then the activation ring
@@ -145,35 +180,41 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
       }
       int s = 0;
       uint32_t ph = 0;
-      const uint32_t row_bytes = (uint32_t)(R * 16);
+      const uint32_t pitch = (uint32_t)(R * 16);                 // shared-memory distance between 8-channel chunks of a stage
       const long long chunk_stride = (long long)p.in_Tp * 8;
       const int chunks_per_stage = cfg.kbs * 2;
       PairIter pit(pair0, pair_step, ppi), pre(pair0, pair_step, ppi);
-      auto tile_src = [&](const PairIter& pi_) {
-        int tl_in_item = pi_.pi * 2 + (int)rank;
-        if (tl_in_item > tpi - 1) tl_in_item = tpi - 1;   // odd tile count: the idle half re-reads a valid tile (rows get zeroed)
-        return p.in + act_off(p.in_bs, p.in_Tp, pi_.b, p.in_coff8, tl_in_item * TILE_M - p.pad_left);
-      };
       const int n_chunks = p.Cin >> 3;
       // L2 prefetch runs CH_PREFETCH tile pairs ahead of the ring
-      for (int d = 0; d < CH_PREFETCH && d < n_local; ++d, pre.next()) {
-        const __half* ps = tile_src(pre);
-        for (int c = 0; c < n_chunks; ++c, ps += chunk_stride) bulk_prefetch_l2(ps, row_bytes);
+      const int pre_dist = CH_PREFETCH;
+      for (int d = 0; d < pre_dist && d < n_local; ++d, pre.next()) {
+        const int t0 = run_t0(pre.pi);
+        const __half* ps = p.in + act_off(p.in_bs, p.in_Tp, pre.b, p.in_coff8, t0);
+        const uint32_t nb = (uint32_t)(run_rows(t0) * 16);
+        for (int c = 0; c < n_chunks; ++c, ps += chunk_stride) bulk_prefetch_l2(ps, nb);
       }
       for (int it = 0; it < n_local; ++it, pit.next()) {
-        const __half* src = tile_src(pit);
-        const bool do_pre = it + CH_PREFETCH < n_local;
-        const __half* ps = do_pre ? tile_src(pre) : nullptr;
-        if (do_pre) pre.next();
+        const int t0 = run_t0(pit.pi);
+        const __half* src = p.in + act_off(p.in_bs, p.in_Tp, pit.b, p.in_coff8, t0);
+        const uint32_t row_bytes = (uint32_t)(run_rows(t0) * 16);
+        const bool do_pre = it + pre_dist < n_local;
+        const __half* ps = nullptr;
+        uint32_t pre_bytes = 0;
+        if (do_pre) {
+          const int tp = run_t0(pre.pi);
+          ps = p.in + act_off(p.in_bs, p.in_Tp, pre.b, p.in_coff8, tp);
+          pre_bytes = (uint32_t)(run_rows(tp) * 16);
+          pre.next();
+        }
         for (int ks = 0; ks < cfg.nks; ++ks) {
           const uint32_t fb = full_bar(s);
           mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_expect_tx(fb, (uint32_t)cfg.stage_bytes);
+          mbar_expect_tx(fb, (uint32_t)chunks_per_stage * row_bytes);
           uint32_t dst = stage_base + s * cfg.stage_bytes;
           for (int c = 0; c < chunks_per_stage; ++c) {
             bulk_g2s(dst, src, row_bytes, fb);
-            if (do_pre) { bulk_prefetch_l2(ps, row_bytes); ps += chunk_stride; }
-            dst += row_bytes;
+            if (do_pre) { bulk_prefetch_l2(ps, pre_bytes); ps += chunk_stride; }
+            dst += pitch;
             src += chunk_stride;
           }
           if (++s == cfg.stages) { s = 0; ph ^= 1u; }
@@ -199,24 +240,23 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
       const uint32_t full0_leader = mapa_u32(full_bar(0), 0);
       PairIter pit(pair0, pair_step, ppi);
       for (int it = 0; it < n_local; ++it, pit.next()) {
-        const int tl_in_item = pit.pi * 2 + (int)rank;
-        const int t0 = (tl_in_item > tpi - 1 ? tpi - 1 : tl_in_item) * TILE_M;
-        const int tfirst = t0 - p.pad_left;
-        const bool dead = tl_in_item > tpi - 1;
+        const int tfirst = run_t0(pit.pi);
+        const bool dead = tile0_of(pit.pi) > tpi - 1;          // no such tiles: contribute zeros
         const bool edge = dead || (tfirst < 0) || (tfirst + R > p.Tin);
         const int buf = buf_of(it, nbA);
         if (leader) {
-          mbar_wait(tempty_bar(0, buf), phase_of(it, nbA) ^ 1u);
+          // buffer free: drained by E1 of its previous G1 -- or, rotating, by E2 of the G2 that ran in it after that
+          mbar_wait(tempty_bar(ROTATE ? 1 : 0, buf), phase_of(it, nbA) ^ 1u);
           tc_fence_after();
         }
         trace_ev1(cp.trace, it, 0);
-        const uint32_t d_tmem = tmem_base + (uint32_t)(cfg.acc_col[0] + buf * N1);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(cfg.acc_col[0] + buf * cfg.acc_n[0]);
         uint32_t b_addr = w_addr0;
         uint32_t accum = 0u;
         for (int ks = 0; ks < cfg.nks; ++ks) {
           mbar_wait(full_bar(s), ph);                          // leader: own rows landed AND the peer's arrive
           if (ks == 0) trace_ev1(cp.trace, it, 8);
-          if (edge) {  // conv zero padding of this CTA's rows (first / last tiles of an item only)
+          if (edge) {  // conv zero padding of this CTA's rows (first / last tiles of an item only), incl. rows never loaded
             uint8_t* a_ptr = stage_ptr + s * cfg.stage_bytes;
             for (int r = 0; r < R; ++r) {
               const int t = tfirst + r;
@@ -250,33 +290,38 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
     }
     __syncwarp();
   } else if (warp <= NG) {
-    // ------------------------------------------------------------------ issuer of pointwise GEMM g: A = operand written by epilogue group g-1
+    // ------------------------------------------------------------------ issuer of GEMM g >= 1: A = operand written by epilogue group g-1
     const int g = warp - 1;
     mbar_wait(w_bar, 0);
     const int K = cp.N[g - 1], Ng = cp.N[g], Nh = Ng >> 1;
     const int nbI = cfg.nbI[g - 1], nbA = cfg.nbA[g];
     const uint32_t idesc = make_idesc_f16(256, Ng);
-    const uint64_t a_desc_hi = make_desc(0u, (uint32_t)(CH_RI * 16), 128u);
+    const uint64_t a_desc_hi = make_desc(0u, (uint32_t)(RI * 16), 128u);
     const uint64_t b_desc_hi = make_desc(0u, (uint32_t)(Nh * 16), 128u);
+    const uint32_t b_step = (uint32_t)(Nh * 2);
     const uint32_t w_addr0 = (sbase + cfg.w_off[g]) >> 4;
+    const int taps_g = (g == 1) ? TAPS2 : 1;
     // Only the leader issues.  The operand rows each CTA wrote for itself are published by its epilogue warps
     // (fence.proxy.async, then an arrive on the LEADER's barrier -- same relaxed remote arrive as the per-stage
     // "my half is in place" handshake of G1: the data is read by the writer's own SM, only the trigger is remote).
     if (leader && elect_one()) {
       for (int it = 0; it < n_local; ++it) {
         const int bi = buf_of(it, nbI);
-        mbar_wait(ifull_bar(g - 1, bi), phase_of(it, nbI));   // both CTAs' 128 operand rows are in their shared memory
+        mbar_wait(ifull_bar(g - 1, bi), phase_of(it, nbI));   // both CTAs' operand rows are in their shared memory
         const int buf = buf_of(it, nbA);
-        mbar_wait(tempty_bar(g, buf), phase_of(it, nbA) ^ 1u);
+        // accumulator free?  Rotating G2: it is the buffer E1 of this very tile just drained (implied by ifull above)
+        if (!(ROTATE && g == 1)) mbar_wait(tempty_bar(g, buf), phase_of(it, nbA) ^ 1u);
         tc_fence_after();
         trace_ev1(cp.trace, it, g == 1 ? 2 : 10);
-        const uint32_t d_tmem = tmem_base + (uint32_t)(cfg.acc_col[g] + buf * Ng);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(cfg.acc_col[g] + buf * cfg.acc_n[g]);
         uint32_t a_addr = (sbase + cfg.i_off[g - 1] + bi * cfg.i_bytes[g - 1]) >> 4;
         uint32_t b_addr = w_addr0;
         for (int kb = 0; kb < K / 16; ++kb) {
-          umma2_f16(d_tmem, a_desc_hi | (uint64_t)a_addr, b_desc_hi | (uint64_t)b_addr, idesc, kb ? 1u : 0u);
-          a_addr += (uint32_t)(2 * CH_RI);
-          b_addr += (uint32_t)(Nh * 2);
+          for (int j = 0; j < taps_g; ++j)
+            umma2_f16(d_tmem, a_desc_hi | (uint64_t)(a_addr + (uint32_t)j), b_desc_hi | (uint64_t)(b_addr + (uint32_t)j * b_step), idesc,
+                      (kb | j) ? 1u : 0u);
+          a_addr += (uint32_t)(2 * RI);
+          b_addr += (uint32_t)taps_g * b_step;
         }
         umma_commit2(iempty_bar(g - 1, bi));                // both CTAs may overwrite this operand buffer
         umma_commit2(tfull_bar(g, buf));
@@ -293,44 +338,50 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
     const int part = (warp - w0) >> 2, nparts = gw >> 2;     // column part
     const int Ng = cp.N[g];
     const int wcols = Ng / nparts < 16 ? 16 : Ng / nparts;
-    const int col_lo = part * wcols;
+    const int col_lo = part * wcols;                         // first accumulator column (= output channel) of this warp
     const bool active = col_lo < Ng;
     const float slope = cp.lrelu[g] ? LRELU_SLOPE : 1.0f;
     int bias_off = 0;
     for (int i = 0; i < g; ++i) bias_off += cp.N[i];
-    const float* bw = s_bias + bias_off + col_lo;
     const int nbA = cfg.nbA[g];
     const uint32_t tempty0_leader = mapa_u32(tempty_bar(g, 0), 0);
     const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cfg.acc_col[g] + col_lo);
     const bool tracer = (warp == w0);
     if (g < NG - 1) {
       // accumulator -> bias, LeakyReLU, fp16 -> this CTA's operand rows of GEMM g+1
+      const float* bw = s_bias + bias_off + col_lo;
       const float ca = 0.5f * (1.0f + slope), cbk = 0.5f * (1.0f - slope);
       const int nbI = cfg.nbI[g];
       const uint32_t ifull0_leader = mapa_u32(ifull_bar(g, 0), 0);
-      for (int it = 0; it < n_local; ++it) {
+      PairIter pit(pair0, pair_step, ppi);
+      for (int it = 0; it < n_local; ++it, pit.next()) {
         const int buf = buf_of(it, nbA);
         const int bi = buf_of(it, nbI);
+        // a k-tap next stage pads with ZEROS outside [0, T): intermediate rows at those times are not conv outputs
+        bool zero_row = false;
+        if (TAPS2 > 1) {
+          const int tl = tile0_of(pit.pi);
+          const int t = tl * S - LEAD + q * 32 + lane;
+          zero_row = t < 0 || t >= p.Tin || tl > tpi - 1;
+        }
         mbar_wait(tfull_bar(g, buf), phase_of(it, nbA));
         mbar_wait(iempty_bar(g, bi), phase_of(it, nbI) ^ 1u);   // GEMM g+1 of the previous user has read the buffer
         tc_fence_after();
         if (tracer) trace_ev(cp.trace, it, g == 0 ? 4 : 12);
-        const uint32_t taddr = taddr0 + (uint32_t)(buf * Ng);
+        const uint32_t taddr = taddr0 + (uint32_t)(buf * cfg.acc_n[g]);
         uint8_t* const dst = smem + cfg.i_off[g] + bi * cfg.i_bytes[g] + (q * 32 + lane) * 16;
-        for (int cb = 0; active && cb < wcols; cb += 32) {
-          uint32_t a[32];
-          const int ncol = wcols - cb < 32 ? 16 : 32;
-          if (ncol == 32) tmem_ld32_nowait(taddr + cb, a);
-          else tmem_ld16_nowait(taddr + cb, a);
-          tmem_wait_ld();
+        if (active)
+          tmem_stream<16>(taddr, wcols, [&](int cb, const uint32_t (&a)[16], int ncol) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (8 * c < ncol) {
-              const int chunk = ((col_lo + cb) >> 3) + c;
-              *reinterpret_cast<uint4*>(dst + chunk * (CH_RI * 16)) = epi_chunk8<false>(a + 8 * c, bw + cb + 8 * c, ca, cbk, make_uint4(0u, 0u, 0u, 0u));
+            for (int c = 0; c < 2; ++c) {
+              if (8 * c < ncol) {
+                const int chunk = ((col_lo + cb) >> 3) + c;
+                uint4 v = epi_chunk8<false>(a + 8 * c, bw + cb + 8 * c, ca, cbk, make_uint4(0u, 0u, 0u, 0u));
+                if (TAPS2 > 1 && zero_row) v = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(dst + chunk * (RI * 16)) = v;
+              }
             }
-          }
-        }
+          });
         tc_fence_before();
         fence_async_smem();                                    // generic-proxy writes -> visible to the tensor core's async proxy
         __syncwarp();
@@ -342,17 +393,25 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
       }
     } else {
       // accumulator of the last GEMM -> the usual fused epilogue to HBM
+      constexpr bool POOL = EPI == CE_POOL, RES = EPI == CE_RES;
       PairIter pit(pair0, pair_step, ppi);
       for (int it = 0; it < n_local; ++it, pit.next()) {
-        const int tl_in_item = pit.pi * 2 + (int)rank;
-        const int t = tl_in_item * TILE_M + q * 32 + lane;     // >= Tin for a dead tile => every store is masked
-        const EpiRow row = epi_row<MODE_SAME, false, false>(cp.pl, pit.b, t, col_lo);
+        const int tl_in_item = tile0_of(pit.pi);
+        const int u = q * 32 + lane;                           // output row of the tile
+        const int t = tl_in_item * S + u;                      // >= Tin for a dead tile => every store is masked
+        EpiRow row = epi_row<MODE_SAME, POOL, RES>(cp.pl, pit.b, t, col_lo);
+        if (TAPS2 > 1) {                                       // rows S .. 127 of a stride-S tile have no output
+          row.ok0 = row.ok0 && u < S;
+          row.pok = row.pok && u < S;
+        }
         const int buf = buf_of(it, nbA);
         uint4 resv[2];
+        epi_prefetch_res<RES>(row, active, resv);              // residual rows (the chain's own input: L2 hits) before the wait
         mbar_wait(tfull_bar(g, buf), phase_of(it, nbA));
         tc_fence_after();
         if (tracer) trace_ev(cp.trace, it, 6);
-        if (active) epi_store<MODE_SAME, false, false>(row, bw, taddr0 + (uint32_t)(buf * Ng), wcols, slope, resv);
+        if (active)
+          epi_store<MODE_SAME, POOL, RES, 16>(row, s_bias + bias_off + col_lo, taddr0 + (uint32_t)(buf * cfg.acc_n[g]), wcols, slope, resv);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(tempty0_leader + 8u * buf);
@@ -368,19 +427,26 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
 }
 
 // ----------------------------------------------------------------------------- host side
+int chain_tile_stride(int taps2) { return TILE_M - ((taps2 > 1 ? taps2 : 1) - 1); }
+
 static bool pick_chain_cfg(const ChainParams& cp, ChainCfg& c) {
   const ConvParams& p = cp.p;
   const int NG = cp.n_gemms;
+  const int taps2 = cp.taps2 > 1 ? cp.taps2 : 1;
   c.R = TILE_M + (p.taps - 1) * p.dil;
+  c.RI = TILE_M + (taps2 - 1);
   int off = 0, cols = 0;
   for (int g = 0; g < NG; ++g) {
-    const int K = g == 0 ? p.Cin * p.taps : cp.N[g - 1];
+    const int K = g == 0 ? p.Cin * p.taps : cp.N[g - 1] * (g == 1 ? taps2 : 1);
     c.w_bytes[g] = K * (cp.N[g] / 2) * 2;
     c.w_off[g] = off;
     off += (c.w_bytes[g] + 1023) / 1024 * 1024;
-    c.nbA[g] = NG == 2 ? 2 : 1;
+    // two GEMMs: both accumulators double-buffered; three GEMMs: G1 and G2 rotate through the same two buffers, G3 single
+    c.nbA[g] = g == 2 ? 1 : 2;
+    c.acc_n[g] = cp.N[g];
+    if (NG == 3 && g == 1) { c.acc_col[1] = c.acc_col[0]; continue; }
     c.acc_col[g] = cols;
-    cols += c.nbA[g] * cp.N[g];
+    cols += c.nbA[g] * c.acc_n[g];
   }
   if (cols > 512) return false;
   int tc = 32;
@@ -392,11 +458,11 @@ static bool pick_chain_cfg(const ChainParams& cp, ChainCfg& c) {
   // intermediate operand is double-buffered when that still fits.
   for (int kbs = 4; kbs >= 1; kbs >>= 1) {
     if (p.Cin % (16 * kbs)) continue;
-    for (int nbi = (NG == 2 ? 2 : 1); nbi >= 1; --nbi) {
+    for (int nbi = (NG == 2 ? 2 : 1); nbi >= 1; nbi >>= 1) {
       off = w_end;
       for (int g = 0; g < NG - 1; ++g) {
         c.nbI[g] = nbi;
-        c.i_bytes[g] = (cp.N[g] / 8) * CH_RI * 16;
+        c.i_bytes[g] = (cp.N[g] / 8) * c.RI * 16;
         c.i_off[g] = off;
         off += c.nbI[g] * c.i_bytes[g];
       }
@@ -420,35 +486,56 @@ static bool pick_chain_cfg(const ChainParams& cp, ChainCfg& c) {
   return false;
 }
 
-bool conv_chain_fits(int Cin, int taps, int dil, const int* N, int n_gemms) {
+bool conv_chain_fits(int Cin, int taps, int dil, const int* N, int n_gemms, int taps2) {
+  if (n_gemms < 2 || n_gemms > 3 || taps != 3) return false;
+  if (taps2 != 1 && (taps2 != 3 || n_gemms != 2 || dil != 1)) return false;
+  if (n_gemms == 3 && N[0] != N[1]) return false;    // G1 and G2 rotate through the same accumulator buffers
+  for (int g = 0; g + 1 < n_gemms; ++g)
+    if (N[g] > 128) return false;                     // an intermediate operand is at most 128 channels wide
   ChainParams cp{};
   cp.p.Cin = Cin; cp.p.taps = taps; cp.p.dil = dil;
   cp.n_gemms = n_gemms;
+  cp.taps2 = taps2;
   for (int g = 0; g < n_gemms; ++g) cp.N[g] = N[g];
   ChainCfg cfg;
-  return pick_chain_cfg(cp, cfg);
+  if (!pick_chain_cfg(cp, cfg)) return false;
+  // A k3 -> k3 pair whose resident weights leave only a short activation ring runs slower fused than as two launches
+  // (measured: the U-Net's 256 -> 128 -> 128 decoder pair, 147 KB of weights per CTA: 5.5 ms vs 3.5 ms per 1184-chunk step)
+  if (taps2 > 1 && cfg.w_bytes[0] + cfg.w_bytes[1] > 128 * 1024) return false;
+  return true;
 }
 
 int launch_conv_chain(const ChainParams& cp, cudaStream_t stream) {
   const ConvParams& p = cp.p;
   const int NG = cp.n_gemms;
+  const int taps2 = cp.taps2 > 1 ? cp.taps2 : 1;
   AR_CHECK(NG == 2 || NG == 3, AR_ERR_INVALID, "conv_chain: 2 or 3 GEMMs");
   AR_CHECK(p.Cin % 16 == 0 && p.mode == MODE_SAME && p.pool == nullptr && p.res == nullptr, AR_ERR_INVALID, "conv_chain: unsupported first layer");
   AR_CHECK(p.pad_left <= HALO && (p.taps - 1) * p.dil - p.pad_left <= HALO, AR_ERR_INVALID, "conv_chain: conv reach exceeds HALO");
+  AR_CHECK(taps2 == 1 || (taps2 == 3 && NG == 2 && p.taps == 3 && p.dil == 1 && p.pad_left == 1), AR_ERR_INVALID,
+           "conv_chain: a k-tap second stage is implemented for k3 -> k3");
+  AR_CHECK(p.pad_left + (taps2 - 1) / 2 <= HALO, AR_ERR_INVALID, "conv_chain: combined reach exceeds HALO");
   int nb = 0;
   for (int g = 0; g < NG; ++g) {
     AR_CHECK(cp.N[g] % 32 == 0 && cp.N[g] >= 32 && cp.N[g] <= 256, AR_ERR_INVALID, "conv_chain: unsupported channel count");
     AR_CHECK(g == NG - 1 || cp.N[g] <= 128, AR_ERR_INVALID, "conv_chain: intermediate wider than 128 channels");
     nb += cp.N[g];
   }
+  AR_CHECK(NG == 2 || cp.N[0] == cp.N[1], AR_ERR_INVALID, "conv_chain: the first two GEMMs of a three-GEMM chain share their accumulator buffers");
   AR_CHECK(nb * 4 <= CH_BIAS_BYTES, AR_ERR_INVALID, "conv_chain: too many bias entries");
-  AR_CHECK(cp.pl.res == nullptr && cp.pl.pool == nullptr, AR_ERR_INVALID, "conv_chain: no residual / pool epilogue");
+  const int epi = cp.pl.pool != nullptr ? CE_POOL : (cp.pl.res != nullptr ? CE_RES : CE_PLAIN);
+  AR_CHECK(!(cp.pl.pool && cp.pl.res), AR_ERR_INVALID, "conv_chain: pool and residual epilogues are exclusive");
+  AR_CHECK(epi != CE_RES || cp.N[NG - 1] <= 32, AR_ERR_INVALID, "conv_chain: residual epilogue supports at most 32 columns");
+  AR_CHECK(p.tiles_per_item == (p.Tin + chain_tile_stride(taps2) - 1) / chain_tile_stride(taps2), AR_ERR_INVALID,
+           "conv_chain: tiles_per_item does not match the tile stride");
   ChainCfg cfg;
   AR_CHECK(pick_chain_cfg(cp, cfg), AR_ERR_INVALID, "conv_chain: no configuration fits shared memory / TMEM");
   using Kernel = void (*)(ChainParams, ChainCfg, int);
-  struct Entry { int taps, ng; Kernel k; };
+  struct Entry { int taps, ng, taps2, epi; Kernel k; };
   static const Entry table[] = {
-      {3, 2, conv_chain_kernel<3, 2>}, {3, 3, conv_chain_kernel<3, 3>}, {1, 2, conv_chain_kernel<1, 2>},
+      {3, 2, 1, CE_PLAIN, conv_chain_kernel<3, 2, 1, CE_PLAIN>}, {3, 3, 1, CE_PLAIN, conv_chain_kernel<3, 3, 1, CE_PLAIN>},
+      {3, 2, 3, CE_PLAIN, conv_chain_kernel<3, 2, 3, CE_PLAIN>}, {3, 2, 3, CE_POOL, conv_chain_kernel<3, 2, 3, CE_POOL>},
+      {3, 2, 3, CE_RES, conv_chain_kernel<3, 2, 3, CE_RES>},
   };
   static DeviceOnce attrs;
   if (attrs.pending()) {
@@ -457,8 +544,8 @@ int launch_conv_chain(const ChainParams& cp, cudaStream_t stream) {
   }
   Kernel kernel = nullptr;
   for (const Entry& e : table)
-    if (e.taps == p.taps && e.ng == NG) kernel = e.k;
-  AR_CHECK(kernel != nullptr, AR_ERR_INVALID, "conv_chain: no kernel instantiated for this (taps, stages) combination");
+    if (e.taps == p.taps && e.ng == NG && e.taps2 == taps2 && e.epi == epi) kernel = e.k;
+  AR_CHECK(kernel != nullptr, AR_ERR_INVALID, "conv_chain: no kernel instantiated for this (taps, stages, epilogue) combination");
   const int ppi = (p.tiles_per_item + 1) / 2;
   const int num_pairs = p.B * ppi;
   int groups = sm_count() / 2;

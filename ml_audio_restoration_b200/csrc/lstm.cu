@@ -220,28 +220,32 @@ lstm_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, const flo
 }
 
 // ============================================================================ tensor-core recurrence
-// Used when the batch exceeds two sequences per SM (the bench: 8 per SM).  The recurrent mat-vec of a step becomes a
-// [256 x 64] x [64 x 8] product on warp-level tensor-core MMAs (mma.sync m16n8k16, fp16 operands, fp32 accumulate).
-// W_hh is rounded to fp16 like every other weight of the model and h is rounded to fp16 before it is fed back -- it is
-// the same rounded value the decoder convs consume -- while the cell state c, the gate pre-activations and all gate math
-// stay fp32 (tests: direct comparison with the fp32 oracle at 88 200 steps).
+// Used when the batch exceeds two sequences per SM.  The recurrent mat-vec of a step becomes a [256 x 64] x [64 x 8]
+// product on warp-level tensor-core MMAs (mma.sync m16n8k16, fp16 operands, fp32 accumulate).  W_hh is rounded to fp16
+// like every other weight of the model and h is rounded to fp16 before it is fed back -- it is the same rounded value the
+// decoder convs consume -- while the cell state c, the gate pre-activations and all gate math stay fp32 (tests: direct
+// comparison with the fp32 oracle at 88 200 steps).
 //
-// A CTA owns FOUR sequences and an SM holds two such CTAs, i.e. two independent recurrences to interleave: every step is
+// A CTA owns NSEQ sequences and an SM holds two such CTAs, i.e. two independent recurrences to interleave: every step is
 // one serial chain (h exchange -> MMAs -> gate functions -> barrier), and while one CTA sits in its barrier or its
 // gate-function chain the other one issues.  The 8 recurrence warps own 8 hidden units each as two 16-row tiles, (i|f)
-// and (g|o) of those units; the eight MMA columns hold the sequences as (s0 s0 s1 s1 s2 s2 s3 s3), so thread (gid, tig)
-// finds all four gates of cell (unit 8w + gid, sequence tig) in fixed accumulator registers -- no shuffles, no selects --
-// and carries exactly one cell.  h goes through shared memory ([seq][unit] fp16, padded stride: conflict-free 8-byte
-// B-fragment loads).
+// and (g|o) of those units, so thread (gid, tig) finds all four gates of hidden unit 8w + gid for the sequences in MMA
+// columns 2 tig and 2 tig + 1 in fixed accumulator registers -- no shuffles, no selects.
+//   NSEQ = 4  (up to 8 sequences per SM): the eight MMA columns hold the sequences as (s0 s0 s1 s1 s2 s2 s3 s3); a thread
+//             carries ONE cell (unit, sequence tig).  Shortest step: this is the latency-optimal shape.
+//   NSEQ = 8  (more than 8 sequences per SM): eight distinct sequences; a thread carries TWO cells (unit, sequences 2 tig
+//             and 2 tig + 1) whose gate-function chains interleave.  Same 8 MMAs per warp and step for twice the
+//             sequences: at NSEQ = 4 the issue slots are 32 % busy and the step is a latency chain (ncu, round 1), so the
+//             second cell rides in its shadow; the special-function unit (7 ex2 / rcp per cell) becomes the bound.
+// h goes through shared memory ([seq][unit] fp16, padded stride: conflict-free 8-byte B-fragment loads).
 //
 // Warp specialisation: two extra "mover" warps do nothing but data movement -- they stage the next 8-step block of
 // gate pre-activations (cp.async) and flush the previous block's hidden states -- so the eight recurrence warps run the
-// bare step (5 LDS, 8 HMMA, the gate functions, 2 STS) and meet at a named barrier of their own 256 threads.  (With the
-// flush inside the recurrence warps, the warp whose turn it was arrived ~40 instructions late at every step's barrier:
-// 49.8 -> 43.4 ms per 1184-chunk step.)  The two groups meet once per 8-step block (named barrier 1, all 320 threads):
-// by then the movers have long finished (16 cp.async + 4 flush items per thread per block).  The ping-pong index of the
-// h exchange buffer is the step's parity inside the block -- a compile-time constant in the unrolled loop -- and full
-// blocks run without the `step < T` tests.
+// bare step (5 LDS, 8 HMMA, the gate functions, 2 STS per cell) and meet at a named barrier of their own 256 threads.
+// (With the flush inside the recurrence warps, the warp whose turn it was arrived ~40 instructions late at every step's
+// barrier: 49.8 -> 43.4 ms per 1184-chunk step.)  The two groups meet once per 8-step block (named barrier 1, all 320
+// threads): by then the movers have long finished.  The ping-pong index of the h exchange buffer is the step's parity
+// inside the block -- a compile-time constant in the unrolled loop -- and full blocks run without the `step < T` tests.
 constexpr int LM_HS = 80;       // padded row stride of the h exchange buffer (halves): conflict-free 8-byte fragment loads
 constexpr int LM_XS = 264;      // padded per-sequence stride of a staged pre-activation row (halves)
 constexpr int LM_HST = 68;      // padded [seq] row stride of the hidden-state staging buffer (floats): conflict-free stores
@@ -256,54 +260,61 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
-constexpr int L4_SEQ = 4;
-constexpr int L4_THREADS = 256;                    // recurrence warps
-constexpr int L4W_THREADS = L4_THREADS + 64;       // + two mover warps
-constexpr int L4_XSTEP = L4_SEQ * LM_XS + 8;       // halves per staged step (+16 B: the 8 steps that consecutive lanes stage land in 8 bank groups)
-constexpr int L4_XBUF = LSTM_BLK * L4_XSTEP;
-constexpr int L4_HSTEP = L4_SEQ * LM_HST + 4;      // floats per staged step of hidden states
-constexpr int L4_SMEM = 2 * L4_XBUF * 2 + 2 * LSTM_BLK * L4_HSTEP * 4 + 2 * L4_SEQ * LM_HS * 2;
+constexpr int LW_REC = 256;                        // recurrence warps
+constexpr int LW_MOV = 64;                         // two mover warps
+constexpr int LW_THREADS = LW_REC + LW_MOV;
+template <int NSEQ>
+struct LwGeom {
+  static constexpr int XSTEP = NSEQ * LM_XS + 8;       // halves per staged step (+16 B: the 8 steps that consecutive lanes stage land in 8 bank groups)
+  static constexpr int XBUF = LSTM_BLK * XSTEP;
+  static constexpr int HSTEP = NSEQ * LM_HST + 4;      // floats per staged step of hidden states
+  static constexpr int SMEM = 2 * XBUF * 2 + 2 * LSTM_BLK * HSTEP * 4 + 2 * NSEQ * LM_HS * 2;
+};
 
-__global__ void __launch_bounds__(L4W_THREADS, 2)
-lstm_mma4w_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, const float* __restrict__ whh,
-                  __half* __restrict__ hout, long long h_bs, int h_Tp, int B, int T,
-                  const float* __restrict__ state_in, float* __restrict__ state_out) {
+template <int NSEQ>
+__global__ void __launch_bounds__(LW_THREADS, 2)
+lstm_mmaw_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, const float* __restrict__ whh,
+                 __half* __restrict__ hout, long long h_bs, int h_Tp, int B, int T,
+                 const float* __restrict__ state_in, float* __restrict__ state_out) {
+  static_assert(NSEQ == 4 || NSEQ == 8, "four (duplicated columns) or eight sequences per CTA");
+  using G = LwGeom<NSEQ>;
+  constexpr int CELLS = NSEQ / 4;                              // cells per recurrence thread
   extern __shared__ __align__(16) float lm_smem[];
-  __half* const xs = reinterpret_cast<__half*>(lm_smem);       // [2][8 steps][4 seq][264] fp16 staged gate pre-activations
-  float* const hstage = lm_smem + L4_XBUF;                     // [2][8 steps][4 seq][68] fp32
-  __half* const hbuf = reinterpret_cast<__half*>(hstage + 2 * LSTM_BLK * L4_HSTEP);   // [2][4 seq][80] fp16
+  __half* const xs = reinterpret_cast<__half*>(lm_smem);       // [2][8 steps][NSEQ][264] fp16 staged gate pre-activations
+  float* const hstage = lm_smem + G::XBUF;                     // [2][8 steps][NSEQ][68] fp32
+  __half* const hbuf = reinterpret_cast<__half*>(hstage + 2 * LSTM_BLK * G::HSTEP);   // [2][NSEQ][80] fp16
   const int tid = threadIdx.x;
-  const int seq0 = blockIdx.x * L4_SEQ;
+  const int seq0 = blockIdx.x * NSEQ;
   const int nblk = (T + LSTM_BLK - 1) / LSTM_BLK;
   const int nfull = T / LSTM_BLK;
 
-  if (tid >= L4_THREADS) {
+  if (tid >= LW_REC) {
     // ------------------------------------------------------------------ movers (warps 8, 9)
-    const int ht = tid - L4_THREADS;
+    const int ht = tid - LW_REC;
     const uint32_t xs_u32 = (uint32_t)__cvta_generic_to_shared(xs);
-    auto stage_block = [&](int blk) {               // [4 seq][32 chunks][8 steps] 16-byte pieces, 16 per thread
+    auto stage_block = [&](int blk) {               // [NSEQ][32 chunks][8 steps] 16-byte pieces, 4 NSEQ per thread
       const int t0 = blk * LSTM_BLK;
-      const uint32_t dst0 = xs_u32 + (uint32_t)((blk & 1) * L4_XBUF * 2);
+      const uint32_t dst0 = xs_u32 + (uint32_t)((blk & 1) * G::XBUF * 2);
 #pragma unroll 4
-      for (int m = 0; m < 16; ++m) {
-        const int i = ht + 64 * m;
+      for (int m = 0; m < 4 * NSEQ; ++m) {
+        const int i = ht + LW_MOV * m;
         const int sq = i >> 8, piece = i & 255;
         const int ch = piece >> 3, k = piece & 7;
         const int b = min(seq0 + sq, B - 1);
-        cp_async16(dst0 + (uint32_t)((k * L4_XSTEP + sq * LM_XS + ch * 8) * 2), xp + act_off_tb(xp_bs, 32, b, ch, t0 + k));
+        cp_async16(dst0 + (uint32_t)((k * G::XSTEP + sq * LM_XS + ch * 8) * 2), xp + act_off_tb(xp_bs, 32, b, ch, t0 + k));
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto flush_block = [&](int blk) {               // [4 seq][8 chunks][8 steps] 16-byte items, 4 per thread
-      const float* hst = hstage + (blk & 1) * (LSTM_BLK * L4_HSTEP);
+    auto flush_block = [&](int blk) {               // [NSEQ][8 chunks][8 steps] 16-byte items, NSEQ per thread
+      const float* hst = hstage + (blk & 1) * (LSTM_BLK * G::HSTEP);
       const int t0 = blk * LSTM_BLK;
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const int i = ht + 64 * m;
+      for (int m = 0; m < NSEQ; ++m) {
+        const int i = ht + LW_MOV * m;
         const int s = i >> 6, ch = (i >> 3) & 7, kk = i & 7;
         const int b = seq0 + s;
         if (b < B && t0 + kk < T) {
-          const float* src = &hst[kk * L4_HSTEP + s * LM_HST + 8 * ch];
+          const float* src = &hst[kk * G::HSTEP + s * LM_HST + 8 * ch];
           const float4 v0 = *reinterpret_cast<const float4*>(src);
           const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
           const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
@@ -313,12 +324,12 @@ lstm_mma4w_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, con
     };
     stage_block(0);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    asm volatile("bar.sync 1, %0;" ::"n"(L4W_THREADS) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(LW_THREADS) : "memory");
     for (int blk = 0; blk < nblk; ++blk) {
       if (blk + 1 < nblk) stage_block(blk + 1);
       if (blk > 0) flush_block(blk - 1);
       asm volatile("cp.async.wait_group 0;" ::: "memory");
-      asm volatile("bar.sync 1, %0;" ::"n"(L4W_THREADS) : "memory");     // block blk is done, block blk + 1 has landed
+      asm volatile("bar.sync 1, %0;" ::"n"(LW_THREADS) : "memory");     // block blk is done, block blk + 1 has landed
     }
     flush_block(nblk - 1);
     return;
@@ -328,8 +339,6 @@ lstm_mma4w_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, con
   const int warp = tid >> 5, lane = tid & 31;
   const int gid = lane >> 2, tig = lane & 3;
   const int unit = warp * 8 + gid;
-  const int seq = tig;
-  const int bq = min(seq0 + seq, B - 1);
   uint32_t wfrag[2][4][4];
   {
     auto w2 = [&](int row, int k) {
@@ -348,89 +357,117 @@ lstm_mma4w_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, con
       }
     }
   }
-  float c = 0.f, hl = 0.f;
-  if (state_in != nullptr) {
-    hl = state_in[(long long)bq * 2 * LSTM_H + unit];
-    c = state_in[(long long)bq * 2 * LSTM_H + LSTM_H + unit];
-  }
   // position of hidden unit `unit` inside its sequence row: within each 16-unit k-tile the pairs (2j, 2j+1) and
   // (2j+8, 2j+9) that form one thread's B fragment (b0, b1) are made adjacent => one 8-byte load per k-tile
   const int upos = (unit & ~15) + ((((unit & 7) >> 1) * 2 + ((unit >> 3) & 1)) * 2) + (unit & 1);
-  hbuf[seq * LM_HS + upos] = __float2half_rn(hl);
-  const uint2* const hb_rd = reinterpret_cast<const uint2*>(hbuf + (gid >> 1) * LM_HS) + tig;   // B column gid = sequence gid/2
-  __half* const hb_wr = hbuf + seq * LM_HS + upos;
-  const int xoff = seq * LM_XS + unit * 4;          // [unit][i,f,g,o] of this thread's cell inside a staged step
-  const int hoff = seq * LM_HST + unit;
-  asm volatile("bar.sync 1, %0;" ::"n"(L4W_THREADS) : "memory");
+  // this thread's cells: (unit, sequence tig * CELLS + j); the sequence of cell j sits in accumulator column 2 tig + j
+  float c[CELLS], hl[CELLS];
+#pragma unroll
+  for (int j = 0; j < CELLS; ++j) {
+    const int seq = tig * CELLS + j;
+    const int bq = min(seq0 + seq, B - 1);
+    c[j] = 0.f;
+    hl[j] = 0.f;
+    if (state_in != nullptr) {
+      hl[j] = state_in[(long long)bq * 2 * LSTM_H + unit];
+      c[j] = state_in[(long long)bq * 2 * LSTM_H + LSTM_H + unit];
+    }
+    hbuf[seq * LM_HS + upos] = __float2half_rn(hl[j]);
+  }
+  // B column gid = sequence gid (eight distinct) or gid / 2 (four, duplicated)
+  const uint2* const hb_rd = reinterpret_cast<const uint2*>(hbuf + (NSEQ == 8 ? gid : gid >> 1) * LM_HS) + tig;
+  __half* const hb_wr = hbuf + (tig * CELLS) * LM_HS + upos;
+  const int xoff = (tig * CELLS) * LM_XS + unit * 4;          // [unit][i,f,g,o] of this thread's first cell inside a staged step
+  const int hoff = (tig * CELLS) * LM_HST + unit;
+  asm volatile("bar.sync 1, %0;" ::"n"(LW_THREADS) : "memory");
 
   // one step; `cur` (which half of hbuf holds h_{t-1}) is the step's parity inside the block: static when unrolled
   auto step = [&](const __half* xb, float* hst, int k) {
     const int cur = k & 1;
-    const uint2 q = *reinterpret_cast<const uint2*>(xb + k * L4_XSTEP + xoff);
+    uint2 q[CELLS];
+#pragma unroll
+    for (int j = 0; j < CELLS; ++j) q[j] = *reinterpret_cast<const uint2*>(xb + k * G::XSTEP + xoff + j * LM_XS);
     float acc[2][4];
 #pragma unroll
     for (int tl = 0; tl < 2; ++tl)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[tl][i] = 0.f;
-    const uint2* hb = hb_rd + cur * (L4_SEQ * LM_HS / 4);
+    const uint2* hb = hb_rd + cur * (NSEQ * LM_HS / 4);
 #pragma unroll
     for (int kt = 0; kt < 4; ++kt) {
       const uint2 bf = hb[kt * 4];
       mma_f16_16x8x16(acc[0], wfrag[0][kt], bf.x, bf.y);
       mma_f16_16x8x16(acc[1], wfrag[1][kt], bf.x, bf.y);
     }
-    const float2 x_if = __half22float2(*reinterpret_cast<const __half2*>(&q.x));
-    const float2 x_go = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
-    lstm_cell(acc[0][0] + x_if.x, acc[0][2] + x_if.y, acc[1][0] + x_go.x, acc[1][2] + x_go.y, c, hl);
-    hb_wr[(cur ^ 1) * (L4_SEQ * LM_HS)] = __float2half_rn(hl);
-    hst[k * L4_HSTEP + hoff] = hl;
+#pragma unroll
+    for (int j = 0; j < CELLS; ++j) {
+      const float2 x_if = __half22float2(*reinterpret_cast<const __half2*>(&q[j].x));
+      const float2 x_go = __half22float2(*reinterpret_cast<const __half2*>(&q[j].y));
+      lstm_cell(acc[0][j] + x_if.x, acc[0][2 + j] + x_if.y, acc[1][j] + x_go.x, acc[1][2 + j] + x_go.y, c[j], hl[j]);
+      hb_wr[(cur ^ 1) * (NSEQ * LM_HS) + j * LM_HS] = __float2half_rn(hl[j]);
+      hst[k * G::HSTEP + hoff + j * LM_HST] = hl[j];
+    }
   };
   for (int blk = 0; blk < nfull; ++blk) {
-    const __half* xb = xs + (blk & 1) * L4_XBUF;
-    float* hst = hstage + (blk & 1) * (LSTM_BLK * L4_HSTEP);
+    const __half* xb = xs + (blk & 1) * G::XBUF;
+    float* hst = hstage + (blk & 1) * (LSTM_BLK * G::HSTEP);
 #pragma unroll
     for (int k = 0; k < LSTM_BLK; ++k) {
       step(xb, hst, k);
-      if (k < LSTM_BLK - 1) asm volatile("bar.sync 2, %0;" ::"n"(L4_THREADS) : "memory");
-      else asm volatile("bar.sync 1, %0;" ::"n"(L4W_THREADS) : "memory");
+      if (k < LSTM_BLK - 1) asm volatile("bar.sync 2, %0;" ::"n"(LW_REC) : "memory");
+      else asm volatile("bar.sync 1, %0;" ::"n"(LW_THREADS) : "memory");
     }
   }
   if (nfull < nblk) {                                // ragged last block
-    const __half* xb = xs + (nfull & 1) * L4_XBUF;
-    float* hst = hstage + (nfull & 1) * (LSTM_BLK * L4_HSTEP);
+    const __half* xb = xs + (nfull & 1) * G::XBUF;
+    float* hst = hstage + (nfull & 1) * (LSTM_BLK * G::HSTEP);
     const int nst = T - nfull * LSTM_BLK;
 #pragma unroll
     for (int k = 0; k < LSTM_BLK - 1; ++k) {
       if (k < nst) {   // uniform
         step(xb, hst, k);
-        asm volatile("bar.sync 2, %0;" ::"n"(L4_THREADS) : "memory");
+        asm volatile("bar.sync 2, %0;" ::"n"(LW_REC) : "memory");
       }
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(L4W_THREADS) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(LW_THREADS) : "memory");
   }
-  if (state_out != nullptr && seq0 + seq < B) {
-    state_out[(long long)(seq0 + seq) * 2 * LSTM_H + unit] = hl;
-    state_out[(long long)(seq0 + seq) * 2 * LSTM_H + LSTM_H + unit] = c;
+  if (state_out != nullptr) {
+#pragma unroll
+    for (int j = 0; j < CELLS; ++j) {
+      const int b = seq0 + tig * CELLS + j;
+      if (b < B) {
+        state_out[(long long)b * 2 * LSTM_H + unit] = hl[j];
+        state_out[(long long)b * 2 * LSTM_H + LSTM_H + unit] = c[j];
+      }
+    }
   }
 }
 
+template <int NSEQ>
+static int launch_lstm_mmaw(const Act& xp, const float* whh, const Act& h_out, int B, int T, const float* state_in, float* state_out,
+                            cudaStream_t stream) {
+  static DeviceOnce attrs;
+  if (attrs.pending()) {
+    AR_CUDA_OK(cudaFuncSetAttribute(lstm_mmaw_kernel<NSEQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, LwGeom<NSEQ>::SMEM));
+    // two CTAs (53 / 103 KB each) must fit: ask for the largest shared-memory carve-out, the driver's default heuristic sizes
+    // it for ONE CTA and the second recurrence of the SM would run after the first instead of under it
+    AR_CUDA_OK(cudaFuncSetAttribute(lstm_mmaw_kernel<NSEQ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    attrs.done();
+  }
+  lstm_mmaw_kernel<NSEQ><<<(B + NSEQ - 1) / NSEQ, LW_THREADS, LwGeom<NSEQ>::SMEM, stream>>>(xp.h(), xp.bs, xp.Tp, whh, h_out.h(), h_out.bs,
+                                                                                      h_out.Tp, B, T, state_in, state_out);
+  return AR_OK;
+}
 
 int launch_lstm(const Act& xp, const float* whh, const Act& h_out, int B, int T, const float* state_in, float* state_out,
                 cudaStream_t stream) {
   AR_CHECK(T >= 1 && B >= 1, AR_ERR_INVALID, "lstm: empty input");
   // One sequence per CTA on CUDA cores (two CTAs per SM) while that covers the batch; beyond two sequences per SM the
-  // tensor-core kernel: four sequences per CTA x two CTAs per SM.
-  if (B > 2 * sm_count()) {
-    static DeviceOnce attrs;
-    if (attrs.pending()) {
-      AR_CUDA_OK(cudaFuncSetAttribute(lstm_mma4w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L4_SMEM));
-      // two CTAs of 53 KB must fit: ask for the largest shared-memory carve-out, the driver's default heuristic sizes it
-      // for ONE CTA and the second recurrence of the SM would run after the first instead of under it
-      AR_CUDA_OK(cudaFuncSetAttribute(lstm_mma4w_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-      attrs.done();
-    }
-    lstm_mma4w_kernel<<<(B + L4_SEQ - 1) / L4_SEQ, L4W_THREADS, L4_SMEM, stream>>>(xp.h(), xp.bs, xp.Tp, whh, h_out.h(), h_out.bs,
-                                                                            h_out.Tp, B, T, state_in, state_out);
+  // tensor-core kernel, two CTAs per SM: four sequences per CTA up to 8 per SM, eight per CTA beyond that.
+  if (B > 8 * sm_count()) {
+    AR_TRY(launch_lstm_mmaw<8>(xp, whh, h_out, B, T, state_in, state_out, stream));
+  } else if (B > 2 * sm_count()) {
+    AR_TRY(launch_lstm_mmaw<4>(xp, whh, h_out, B, T, state_in, state_out, stream));
   } else {
     lstm_kernel<1, 8><<<B, 256, 0, stream>>>(xp.h(), xp.bs, xp.Tp, whh, h_out.h(), h_out.bs, h_out.Tp, B, T, state_in, state_out);
   }

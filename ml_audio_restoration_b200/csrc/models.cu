@@ -26,9 +26,12 @@ int set_engine(int e) {
   g_engine.store(e);
   return AR_OK;
 }
-static std::atomic<int> g_fuse{1};   // fused multi-layer launches (conv_chain.cu, sr_trunk.cu) for subsequently created models
-int set_fusion(int on) {
-  g_fuse.store(on ? 1 : 0);
+// Fused multi-layer launches (conv_chain.cu) for subsequently created models: 0 = layer by layer, 1 = the chains that
+// measured faster than their layers (product default), 2 = every chain that fits (parity cross-check of the k3 -> k3 kernels)
+static std::atomic<int> g_fuse{1};
+int set_fusion(int level) {
+  if (level < 0 || level > 2) { set_error("fusion level must be 0, 1 or 2"); return AR_ERR_INVALID; }
+  g_fuse.store(level);
   return AR_OK;
 }
 static std::atomic<long long*> g_chain_trace{nullptr};   // debug: device buffer the fused-chain kernels trace their pipeline into
@@ -184,7 +187,7 @@ static bool make_conv(const Table& t, Blob& blob, const std::string& conv, const
 
 struct Model {
   int kind = -1, device = 0, engine = AR_ENGINE_UMMA;
-  int fuse = 1;   // fused conv chains where the engine has them (tcgen05 engine, 2-CTA packing)
+  int fuse = 1;   // fused conv chains (tcgen05 engine, 2-CTA packing): 0 none, 1 measured-faster ones, 2 all that fit
   float* blob = nullptr;
   std::map<std::string, ConvLayer> conv;
   StemP stem{};          // Cin = 1 stem: kernel-parameter weights
@@ -398,7 +401,7 @@ int model_create(int kind, const ar_tensor_t* tensors, int n, int device, Model*
   m->kind = kind;
   m->device = device;
   m->engine = g_engine.load();
-  m->fuse = g_fuse.load() && m->engine == AR_ENGINE_UMMA;
+  m->fuse = m->engine == AR_ENGINE_UMMA ? g_fuse.load() : 0;
   Blob blob;
   bool ok = false;
   if (kind == AR_MODEL_DENOISER) ok = build_denoiser(t, blob, *m);
@@ -427,45 +430,80 @@ int model_create(int kind, const ar_tensor_t* tensors, int n, int device, Model*
 }
 
 // ============================================================================ workspace arena
-// First-fit arena over the caller's workspace.  The same allocation sequence runs in a dry
-// pass (sizes only) to answer *_workspace_bytes and in the real pass.
+// Two-ended first-fit arena over the caller's workspace.  The same allocation sequence runs in a dry pass (sizes only)
+// to answer *_workspace_bytes and in the real pass.  A forward is a chain of producer -> consumer tensors with two or three
+// alive at a time; a one-ended first-fit arena fragments on it (a freed input is never large enough for the next, larger,
+// output: 608 instead of 384 channel-planes at the stereo stage's peak, 103 instead of 68 MB per 2 s chunk).  Here a new
+// tensor goes into a hole if one fits, else to the shorter END (low or high) of the workspace, so consecutive tensors
+// alternate sides and the peak is the largest pair alive together.  High-side offsets count down from `cap`, the dry-run
+// peak, which the real pass therefore needs before it starts.
 struct Arena {
   char* base = nullptr;
   size_t cap = 0, peak = 0;
   bool dry = true;
   struct Blk { size_t off, size; bool used; };
-  std::vector<Blk> blks;
+  struct Side {
+    std::vector<Blk> blks;     // sorted by offset from this side's end of the workspace
+    size_t extent() const {    // bytes from this end up to the last used block
+      for (size_t i = blks.size(); i-- > 0;)
+        if (blks[i].used) return blks[i].off + blks[i].size;
+      return 0;
+    }
+    // extent after a first-fit placement of `bytes` (not committed)
+    size_t extent_with(size_t bytes) const {
+      const size_t e = extent();
+      for (const Blk& b : blks)
+        if (!b.used && b.size >= bytes && b.off + b.size <= e) return e;   // fits into a hole below the extent
+      size_t off = 0;
+      for (size_t i = blks.size(); i-- > 0;)
+        if (blks[i].used) { off = blks[i].off + blks[i].size; break; }
+      return off + bytes;
+    }
+    size_t alloc(size_t bytes) {
+      const size_t e = extent();
+      for (size_t i = 0; i < blks.size(); ++i)
+        if (!blks[i].used && blks[i].size >= bytes && blks[i].off + blks[i].size <= e) {
+          if (blks[i].size > bytes) {
+            Blk rest{blks[i].off + bytes, blks[i].size - bytes, false};
+            blks[i].size = bytes;
+            blks.insert(blks.begin() + i + 1, rest);
+          }
+          blks[i].used = true;
+          return blks[i].off;
+        }
+      while (!blks.empty() && !blks.back().used) blks.pop_back();   // free tail: re-grow from the last used block
+      const size_t off = blks.empty() ? 0 : blks.back().off + blks.back().size;
+      blks.push_back({off, bytes, true});
+      return off;
+    }
+    bool release(size_t off) {
+      for (size_t i = 0; i < blks.size(); ++i)
+        if (blks[i].off == off && blks[i].used) {
+          blks[i].used = false;
+          if (i + 1 < blks.size() && !blks[i + 1].used) { blks[i].size += blks[i + 1].size; blks.erase(blks.begin() + i + 1); }
+          if (i > 0 && !blks[i - 1].used) { blks[i - 1].size += blks[i].size; blks.erase(blks.begin() + i); }
+          return true;
+        }
+      return false;
+    }
+  };
+  Side lo, hi;
+  // returns the byte offset from `base`
   size_t alloc(size_t bytes) {
     bytes = (bytes + 255) / 256 * 256;
-    for (size_t i = 0; i < blks.size(); ++i)
-      if (!blks[i].used && blks[i].size >= bytes) {
-        if (blks[i].size > bytes) {
-          Blk rest{blks[i].off + bytes, blks[i].size - bytes, false};
-          blks[i].size = bytes;
-          blks.insert(blks.begin() + i + 1, rest);
-        }
-        blks[i].used = true;
-        return blks[i].off;
-      }
-    size_t off = blks.empty() ? 0 : blks.back().off + blks.back().size;
-    if (!blks.empty() && !blks.back().used) {  // grow the trailing free block
-      off = blks.back().off;
-      blks.back().size = bytes;
-      blks.back().used = true;
-    } else {
-      blks.push_back({off, bytes, true});
-    }
-    if (off + bytes > peak) peak = off + bytes;
-    return off;
+    // a hole below a side's extent costs nothing; otherwise grow the SHORTER side: the tensor just produced sits on the other
+    // one and the one before it is about to be released, so consecutive tensors alternate ends
+    const bool fits_lo = lo.extent_with(bytes) == lo.extent(), fits_hi = hi.extent_with(bytes) == hi.extent();
+    const bool low = fits_lo ? true : (fits_hi ? false : lo.extent() <= hi.extent());
+    const size_t off = low ? lo.alloc(bytes) : hi.alloc(bytes);
+    const size_t total = lo.extent() + hi.extent();
+    if (total > peak) peak = total;
+    return low ? off : cap - off - bytes;          // dry pass: cap == 0, the value is not used as an address
   }
-  void release(size_t off) {
-    for (size_t i = 0; i < blks.size(); ++i)
-      if (blks[i].off == off && blks[i].used) {
-        blks[i].used = false;
-        if (i + 1 < blks.size() && !blks[i + 1].used) { blks[i].size += blks[i + 1].size; blks.erase(blks.begin() + i + 1); }
-        if (i > 0 && !blks[i - 1].used) { blks[i - 1].size += blks[i].size; blks.erase(blks.begin() + i); }
-        return;
-      }
+  void release_off(size_t off_from_base) {
+    if (lo.release(off_from_base)) return;
+    for (const Blk& b : hi.blks)            // high side: block offsets count down from `cap`
+      if (b.used && cap - b.off - b.size == off_from_base) { hi.release(b.off); return; }
   }
   Act act(int B, int C, int T) {
     Act a;
@@ -475,9 +513,9 @@ struct Arena {
     a.base = base + off;
     return a;
   }
-  void release(const Act& a) { release((size_t)(reinterpret_cast<char*>(a.base) - base)); }
+  void release(const Act& a) { release_off((size_t)(reinterpret_cast<char*>(a.base) - base)); }
   float* plain(size_t floats) { return reinterpret_cast<float*>(base + alloc(floats * sizeof(float))); }
-  void release_plain(float* p) { release((size_t)(reinterpret_cast<char*>(p) - base)); }
+  void release_plain(const float* p) { release_off((size_t)(reinterpret_cast<const char*>(p) - base)); }
 };
 
 struct Ctx {
@@ -541,31 +579,43 @@ static int run_conv(Ctx& c, const std::string& name, const Act& in, const Act& o
   return AR_OK;
 }
 
-// A k-tap conv followed by one or two pointwise convs as ONE fused launch (conv_chain.cu).  `o` describes the
-// LAST stage's output (lrelu, time-blocked layout); intermediate stages apply LeakyReLU (they are
-// `_dilated_block` halves, stereo_separator.py:49-64).
+// A k-tap conv followed by one or two more convs as ONE fused launch (conv_chain.cu): pointwise follow-ups (the stereo
+// `_dilated_block`, stereo_separator.py:49-64, and the LSTM input projection behind the last one) or one k3 follow-up (the
+// U-Net double conv, denoiser.py:51-60, and the super-resolution residual block, super_resolution.py:104-122).  `o`
+// describes the LAST stage's output (lrelu, layout, pool copy, residual operand); intermediate stages apply LeakyReLU.
 static bool can_chain(const Ctx& c, std::initializer_list<const char*> names) {
   if (!c.m->fuse || c.m->audit || c.m->engine != AR_ENGINE_UMMA) return false;   // the audit looks at every intermediate
   bool first = true;
-  int prevN = 0, Cin = 0, taps = 0, dil = 0, N[3] = {0, 0, 0}, ng = 0;
+  int prevN = 0, Cin = 0, taps = 0, dil = 0, taps2 = 1, N[3] = {0, 0, 0}, ng = 0;
   for (const char* n : names) {
     auto it = c.m->conv.find(n);
     if (it == c.m->conv.end() || ng == 3) return false;
     const ConvLayer& L = it->second;
     if (!L.cta2 || L.n_slices != 2) return false;
-    if (!first && (L.taps != 1 || L.Cin != prevN)) return false;
     if (first) { Cin = L.Cin; taps = L.taps; dil = L.dil; }
+    else {
+      if (L.Cin != prevN || L.dil != 1) return false;
+      if (ng == 1) taps2 = L.taps;
+      else if (L.taps != 1) return false;
+    }
     prevN = L.N;
     N[ng++] = L.N;
     first = false;
   }
-  return conv_chain_fits(Cin, taps, dil, N, ng);
+  if (!conv_chain_fits(Cin, taps, dil, N, ng, taps2)) return false;
+  // k3 -> k3 pairs (tile stride 126) pay off only for wide layers.  Per 1184-chunk step, fused vs two launches (ncu,
+  // profiles/README_r02.md): 64 -> 128 -> 128 1.97 vs 2.30 ms; 32 -> 64 -> 64 2.40 vs 2.33; 128 -> 64 -> 64 3.28 vs 2.90;
+  // 64 -> 32 -> 32 3.55 vs 2.77; super-resolution block 32 -> 32 -> 32 (+ skip) 3.80 vs 2.72 -- with 32 / 64 columns a tile
+  // pair is ~100 cycles of MMAs behind a ~2 000-cycle G1 -> E1 -> G2 -> E2 handshake chain, two tiles in flight.
+  if (taps2 > 1 && c.m->fuse < 2 && (N[0] < 128 || N[1] < 128)) return false;
+  return true;
 }
 
 static int run_chain(Ctx& c, std::initializer_list<const char*> names, const Act& in, const Act& out, const ConvOpt& o = ConvOpt()) {
   if (c.ar.dry) return AR_OK;
   ChainParams cp;
   std::memset(&cp, 0, sizeof(cp));
+  cp.taps2 = 1;
   double macs = 0.0;
   int g = 0;
   for (const char* n : names) {
@@ -575,8 +625,9 @@ static int run_chain(Ctx& c, std::initializer_list<const char*> names, const Act
       p.in = in.h(); p.in_bs = in.bs; p.in_Tp = in.Tp; p.in_coff8 = o.in_coff8;
       p.Tin = in.T; p.Cin = L.Cin; p.taps = L.taps; p.dil = L.dil; p.pad_left = L.pad_left;
       p.N = L.N; p.n_slices = L.n_slices; p.cta2 = 1; p.mode = MODE_SAME; p.lrelu = 1;
-      p.B = c.B; p.tiles_per_item = (in.T + TILE_M - 1) / TILE_M;
+      p.B = c.B;
     }
+    if (g == 1) cp.taps2 = L.taps;
     cp.w[g] = reinterpret_cast<const __half*>(c.m->blob + L.w_off);
     cp.bias[g] = c.m->blob + L.b_off;
     cp.N[g] = L.N;
@@ -586,16 +637,37 @@ static int run_chain(Ctx& c, std::initializer_list<const char*> names, const Act
   }
   cp.n_gemms = g;
   cp.lrelu[g - 1] = o.lrelu;
+  const int stride = chain_tile_stride(cp.taps2);
+  cp.p.tiles_per_item = (in.T + stride - 1) / stride;
   cp.p.w = cp.w[0]; cp.p.bias = cp.bias[0];
   cp.pl = cp.p;
   cp.pl.N = cp.N[g - 1]; cp.pl.bias = cp.bias[g - 1]; cp.pl.lrelu = o.lrelu;
   cp.pl.out = out.h(); cp.pl.out_bs = out.bs; cp.pl.out_Tp = out.Tp; cp.pl.out_coff8 = o.out_coff8;
   cp.pl.Tout = o.Tout >= 0 ? o.Tout : out.T;
   cp.pl.out_tblock = o.out_tblock;
+  if (o.pool) { cp.pl.pool = o.pool->h(); cp.pl.pool_bs = o.pool->bs; cp.pl.pool_Tp = o.pool->Tp; cp.pl.pool_coff8 = 0; }
+  if (o.res) { cp.pl.res = o.res->h(); cp.pl.res_bs = o.res->bs; cp.pl.res_Tp = o.res->Tp; cp.pl.res_coff8 = 0; }
   long long* const trace = g_chain_trace.load();
   cp.trace = trace ? trace + (size_t)(g_chain_trace_slot.fetch_add(1) % 4) * 1024 : nullptr;
   ProfScope ps(CAT_CONV, c.stream, 2.0 * macs * (double)c.B * (double)in.T);
   return launch_conv_chain(cp, c.stream);
+}
+
+// A double conv (first -> second) through the fused k3 -> k3 chain when it fits, else as two launches through `mid`.
+static int run_pair(Ctx& c, const char* first, const char* second, const Act& in, int mid_channels, const Act& out, const ConvOpt& o = ConvOpt()) {
+  if (can_chain(c, {first, second})) {
+    ConvOpt oc = o;
+    return run_chain(c, {first, second}, in, out, oc);
+  }
+  Act mid = c.ar.act(c.B, mid_channels, in.T);
+  ConvOpt o1;
+  o1.in_coff8 = o.in_coff8;
+  AR_TRY(run_conv(c, first, in, mid, o1));
+  ConvOpt o2 = o;
+  o2.in_coff8 = 0;
+  AR_TRY(run_conv(c, second, mid, out, o2));
+  c.ar.release(mid);
+  return AR_OK;
 }
 
 // the stereo k7 output heads run on the tensor core (final_umma.cu) with the tcgen05 engine, on CUDA cores with the cross-check engine
@@ -616,54 +688,38 @@ static int denoiser_forward(Ctx& c, const float* x, float* y, int T) {
   ConvOpt o; o.pool = &p0;
   AR_TRY(run_conv(c, "enc0b", e0a, cat0, o));                 // skip s0 -> cat0[0:32], pooled -> p0
   A.release(e0a);
-  Act e1a = A.act(B, 64, T1);
-  AR_TRY(run_conv(c, "enc1a", p0, e1a));
-  A.release(p0);
+  // levels 1, 2 and the three decoder levels: each double conv (denoiser.py:51-60) is ONE fused k3 -> k3 launch whose
+  // intermediate stays in shared memory (the bottleneck's 256-channel intermediate does not fit: two launches)
   Act cat1 = A.act(B, 128, T1), p1 = A.act(B, 64, T2);
   o = ConvOpt(); o.pool = &p1;
-  AR_TRY(run_conv(c, "enc1b", e1a, cat1, o));
-  A.release(e1a);
-  Act e2a = A.act(B, 128, T2);
-  AR_TRY(run_conv(c, "enc2a", p1, e2a));
-  A.release(p1);
+  AR_TRY(run_pair(c, "enc1a", "enc1b", p0, 64, cat1, o));
+  A.release(p0);
   Act cat2 = A.act(B, 256, T2), p2 = A.act(B, 128, T3);
   o = ConvOpt(); o.pool = &p2;
-  AR_TRY(run_conv(c, "enc2b", e2a, cat2, o));
-  A.release(e2a);
-  Act b0 = A.act(B, 256, T3);
-  AR_TRY(run_conv(c, "bot_a", p2, b0));
-  A.release(p2);
+  AR_TRY(run_pair(c, "enc2a", "enc2b", p1, 128, cat2, o));
+  A.release(p1);
   Act b1 = A.act(B, 256, T3);
-  AR_TRY(run_conv(c, "bot_b", b0, b1));
-  A.release(b0);
+  AR_TRY(run_pair(c, "bot_a", "bot_b", p2, 256, b1));
+  A.release(p2);
   // decoder level 0: up-conv writes the upper channel half of the concat buffer (skip first, :124)
   o = ConvOpt(); o.mode = MODE_INTERLEAVE2; o.lrelu = 0; o.out_coff8 = 128 / 8; o.Tout = T2;
   AR_TRY(run_conv(c, "up0", b1, cat2, o));
   A.release(b1);
-  Act d0a = A.act(B, 128, T2);
-  AR_TRY(run_conv(c, "dec0a", cat2, d0a));
-  A.release(cat2);
   Act d0b = A.act(B, 128, T2);
-  AR_TRY(run_conv(c, "dec0b", d0a, d0b));
-  A.release(d0a);
+  AR_TRY(run_pair(c, "dec0a", "dec0b", cat2, 128, d0b));
+  A.release(cat2);
   o = ConvOpt(); o.mode = MODE_INTERLEAVE2; o.lrelu = 0; o.out_coff8 = 64 / 8; o.Tout = T1;
   AR_TRY(run_conv(c, "up1", d0b, cat1, o));
   A.release(d0b);
-  Act d1a = A.act(B, 64, T1);
-  AR_TRY(run_conv(c, "dec1a", cat1, d1a));
-  A.release(cat1);
   Act d1b = A.act(B, 64, T1);
-  AR_TRY(run_conv(c, "dec1b", d1a, d1b));
-  A.release(d1a);
+  AR_TRY(run_pair(c, "dec1a", "dec1b", cat1, 64, d1b));
+  A.release(cat1);
   o = ConvOpt(); o.mode = MODE_INTERLEAVE2; o.lrelu = 0; o.out_coff8 = 32 / 8; o.Tout = T;
   AR_TRY(run_conv(c, "up2", d1b, cat0, o));
   A.release(d1b);
-  Act d2a = A.act(B, 32, T);
-  AR_TRY(run_conv(c, "dec2a", cat0, d2a));
-  A.release(cat0);
   Act f = A.act(B, 32, T);
-  AR_TRY(run_conv(c, "dec2b", d2a, f));
-  A.release(d2a);
+  AR_TRY(run_pair(c, "dec2a", "dec2b", cat0, 32, f));
+  A.release(cat0);
   // the cross-check engine keeps the whole transient detector on CUDA cores
   if (c.m->engine == AR_ENGINE_UMMA) {
     Act h1 = A.act(B, 32, T);
@@ -694,13 +750,14 @@ static int sr_forward(Ctx& c, const float* x, float* y, int T) {
   }
   AR_TRY(audit_act(c, "stem", f0, 0, 4, T));
   Act r = f0;
+  static const char* const RA[4] = {"rb0a", "rb1a", "rb2a", "rb3a"};
+  static const char* const RB[4] = {"rb0b", "rb1b", "rb2b", "rb3b"};
   for (int i = 0; i < 4; ++i) {
-    Act o1 = A.act(B, 32, T);
-    AR_TRY(run_conv(c, "rb" + std::to_string(i) + "a", r, o1));
+    // one residual block (conv-BN-LReLU-conv-BN + skip, super_resolution.py:104-122) = ONE fused k3 -> k3 launch; the
+    // skip operand is the block's own input
     Act r2 = A.act(B, 32, T);
     ConvOpt o; o.lrelu = 0; o.res = &r;
-    AR_TRY(run_conv(c, "rb" + std::to_string(i) + "b", o1, r2, o));
-    A.release(o1);
+    AR_TRY(run_pair(c, RA[i], RB[i], r, 32, r2, o));
     if (i > 0) A.release(r);
     r = r2;
   }
@@ -733,16 +790,16 @@ static int sr_forward(Ctx& c, const float* x, float* y, int T) {
 // (ar_stereo_forward_window), where a segment carries conv halos on both sides of the range whose state it hands on.
 struct LstmWindow { int lstm_start = 0, state_pos = -1; };
 
-static int stereo_forward(Ctx& c, const float* x, float* y, int T, const float* state_in, float* state_out,
-                          LstmWindow w = LstmWindow()) {
-  AR_CHECK(T >= 1, AR_ERR_INVALID, "stereo: empty input");
-  if (w.state_pos < 0) w.state_pos = T;
-  AR_CHECK(w.lstm_start >= 0 && w.lstm_start < w.state_pos && w.state_pos <= T && w.lstm_start % 8 == 0 &&
-               (w.state_pos % 8 == 0 || w.state_pos == T),
-           AR_ERR_INVALID, "stereo: LSTM window must satisfy 0 <= lstm_start < state_pos <= T, both multiples of 8 (state_pos may be T)");
+// The forward in three phases, so that the chain (chain_forward below) can run them on different batch splits:
+//   encode  stem + dilated encoder + LSTM input projection  x[B,1,T] -> xp (gate pre-activations, time-blocked fp16)
+//   scan    the LSTM recurrence                             xp -> h
+//   decode  both decoders + output heads                    h -> y[B,2,T]
+// `xp` of stereo_encode: a tensor the caller allocated (base != nullptr), else it is allocated here, as late as possible.
+static int stereo_encode(Ctx& c, const float* x, int T, Act& xp) {
   const Model& m = *c.m;
   const int B = c.B;
   Arena& A = c.ar;
+  const bool own_xp = xp.base == nullptr && xp.C == 0;
   Act cur = A.act(B, 32, T);
   if (!A.dry) {
     ProfScope ps(CAT_STEM, c.stream, 2.0 * 224 * (double)B * T);
@@ -753,12 +810,11 @@ static int stereo_forward(Ctx& c, const float* x, float* y, int T, const float* 
   static const char* const NA[4] = {"enc1a", "enc2a", "enc3a", "enc4a"};
   static const char* const NB[4] = {"enc1b", "enc2b", "enc3b", "enc4b"};
   ConvOpt oxp; oxp.lrelu = 0; oxp.out_tblock = 1;   // gate pre-activations, time-blocked: the recurrence streams 4 KB runs
-  Act xp{};
   bool xp_done = false;
   for (int i = 0; i < 4; ++i) {
     if (i == 3 && can_chain(c, {NA[i], NB[i], "xproj"})) {
       // last dilated block + LSTM input projection: 128 -k3 d8-> 128 -k1-> 128 -k1-> 256 in one launch
-      xp = A.act(B, 256, T);
+      if (own_xp) xp = A.act(B, 256, T);
       AR_TRY(run_chain(c, {NA[i], NB[i], "xproj"}, cur, xp, oxp));
       A.release(cur);
       xp_done = true;
@@ -778,36 +834,47 @@ static int stereo_forward(Ctx& c, const float* x, float* y, int T, const float* 
     }
   }
   if (!xp_done) {
-    xp = A.act(B, 256, T);   // fp16 storage costs < 0.1 dB, halves the LSTM's HBM stream
+    if (own_xp) xp = A.act(B, 256, T);   // fp16 storage costs < 0.1 dB, halves the LSTM's HBM stream
     AR_TRY(run_conv(c, "xproj", cur, xp, oxp));
     A.release(cur);
   }
-  Act h = A.act(B, 64, T);
-  if (!A.dry) {
-    ProfScope ps(CAT_LSTM, c.stream, 2.0 * 16384 * (double)B * (T - w.lstm_start), w.state_pos < T ? 2 : 1);
-    // a scan over steps [t0, t1) is the same kernel on base pointers advanced by t0 rows (t0 % 8 == 0 keeps the 8-step
-    // blocks of the time-blocked pre-activations aligned)
-    auto scan = [&](int t0, int t1, const float* st_in, float* st_out) {
-      Act xs = xp, hs = h;
-      xs.base = xp.h() + (long long)(t0 / 8) * 32 * 64;
-      hs.base = h.h() + (long long)t0 * 8;
-      xs.T = hs.T = t1 - t0;
-      return launch_lstm(xs, m.blob + m.whh_off, hs, B, t1 - t0, st_in, st_out, c.stream);
-    };
-    if (w.lstm_start > 0)   // rows [0, lstm_start) of all 8 chunks of every item: zero hidden states
-      AR_CUDA_OK(cudaMemset2DAsync(h.h() + (long long)HALO * 8, (size_t)h.Tp * 16, 0, (size_t)w.lstm_start * 16, (size_t)B * 8, c.stream));
-    if (w.state_pos < T) {
-      AR_CHECK(state_out != nullptr, AR_ERR_INVALID, "stereo: an interior state_pos needs state_out");
-      AR_TRY(scan(w.lstm_start, w.state_pos, state_in, state_out));
-      AR_TRY(scan(w.state_pos, T, state_out, nullptr));
-    } else {
-      AR_TRY(scan(w.lstm_start, T, state_in, state_out));
-    }
+  return AR_OK;
+}
+
+static int stereo_scan(Ctx& c, const Act& xp, const Act& h, int T, const float* state_in, float* state_out, const LstmWindow& w) {
+  if (c.ar.dry) return AR_OK;
+  const Model& m = *c.m;
+  const int B = c.B;
+  ProfScope ps(CAT_LSTM, c.stream, 2.0 * 16384 * (double)B * (T - w.lstm_start), w.state_pos < T ? 2 : 1);
+  // a scan over steps [t0, t1) is the same kernel on base pointers advanced by t0 rows (t0 % 8 == 0 keeps the 8-step
+  // blocks of the time-blocked pre-activations aligned)
+  auto scan = [&](int t0, int t1, const float* st_in, float* st_out) {
+    Act xs = xp, hs = h;
+    xs.base = xp.h() + (long long)(t0 / 8) * 32 * 64;
+    hs.base = h.h() + (long long)t0 * 8;
+    xs.T = hs.T = t1 - t0;
+    return launch_lstm(xs, m.blob + m.whh_off, hs, B, t1 - t0, st_in, st_out, c.stream);
+  };
+  if (w.lstm_start > 0)   // rows [0, lstm_start) of all 8 chunks of every item: zero hidden states
+    AR_CUDA_OK(cudaMemset2DAsync(h.h() + (long long)HALO * 8, (size_t)h.Tp * 16, 0, (size_t)w.lstm_start * 16, (size_t)B * 8, c.stream));
+  if (w.state_pos < T) {
+    AR_CHECK(state_out != nullptr, AR_ERR_INVALID, "stereo: an interior state_pos needs state_out");
+    AR_TRY(scan(w.lstm_start, w.state_pos, state_in, state_out));
+    AR_TRY(scan(w.state_pos, T, state_out, nullptr));
+  } else {
+    AR_TRY(scan(w.lstm_start, T, state_in, state_out));
   }
-  A.release(xp);
+  return AR_OK;
+}
+
+// `h_owned`: h is an arena tensor of this batch and is released as soon as the first layer has consumed it
+static int stereo_decode(Ctx& c, const Act& h, float* y, int T, bool h_owned) {
+  const Model& m = *c.m;
+  const int B = c.B;
+  Arena& A = c.ar;
   Act d0 = A.act(B, 256, T);
   AR_TRY(run_conv(c, "dec0", h, d0));
-  A.release(h);
+  if (h_owned) A.release(h);
   Act d1 = A.act(B, 128, T);
   ConvOpt o;
   AR_TRY(run_conv(c, "dec1L", d0, d1, o));
@@ -830,6 +897,114 @@ static int stereo_forward(Ctx& c, const float* x, float* y, int T, const float* 
   }
   A.release(d2);
   return AR_OK;
+}
+
+static int check_window(LstmWindow& w, int T) {
+  AR_CHECK(T >= 1, AR_ERR_INVALID, "stereo: empty input");
+  if (w.state_pos < 0) w.state_pos = T;
+  AR_CHECK(w.lstm_start >= 0 && w.lstm_start < w.state_pos && w.state_pos <= T && w.lstm_start % 8 == 0 &&
+               (w.state_pos % 8 == 0 || w.state_pos == T),
+           AR_ERR_INVALID, "stereo: LSTM window must satisfy 0 <= lstm_start < state_pos <= T, both multiples of 8 (state_pos may be T)");
+  return AR_OK;
+}
+
+static int stereo_forward(Ctx& c, const float* x, float* y, int T, const float* state_in, float* state_out,
+                          LstmWindow w = LstmWindow()) {
+  AR_TRY(check_window(w, T));
+  Arena& A = c.ar;
+  Act xp{};
+  AR_TRY(stereo_encode(c, x, T, xp));
+  Act h = A.act(c.B, 64, T);
+  AR_TRY(stereo_scan(c, xp, h, T, state_in, state_out, w));
+  A.release(xp);
+  return stereo_decode(c, h, y, T, true);
+}
+
+// ---------------------------------------------------------------------------- inference.py:59-95, chunk batches
+// denoise -> super-resolve -> stereo on B independent chunks.  Up to 8 chunks per SM the three forwards run one after the
+// other on the whole batch.  Beyond that the batch exists for the LSTM's sake -- its recurrence is a latency chain per
+// sequence, and 16 sequences per SM (lstm_mmaw_kernel<8>) cost barely more per step than 8 -- while the convs gain nothing
+// from it and their activations (45 - 68 MB per chunk) would not fit: so the conv phases run on sub-batches around ONE scan,
+//   for each sub-batch:  denoiser, super-resolution, stereo encoder  ->  its slice of the gate pre-activations xp
+//   LSTM scan over all B sequences                                    ->  h
+//   for each sub-batch:  decoders                                     ->  its slice of y
+// and the workspace holds xp (45 MB per chunk) / h (11 MB per chunk) for the batch plus the conv scratch of one sub-batch.
+static int chain_run(Ctx& c, const Model* den, const Model* sr, const Model* st, const float* x, float* y, int B, int T) {
+  Arena& A = c.ar;
+  const int rate = sr ? 2 : 1, Ts = rate * T;
+  const int full = 8 * sm_count();
+  const int sub_front = B <= full ? B : full / 2, sub_back = B <= full ? B : full;
+  auto front = [&](int b0, int nb, Act& xp) {      // chunks [b0, b0 + nb) -> xp (allocated inside when xp is empty)
+    c.B = nb;
+    float* y1 = A.plain((size_t)nb * T);
+    c.m = den;
+    AR_TRY(denoiser_forward(c, x + (size_t)b0 * T, y1, T));
+    const float* st_in = y1;
+    float* y2 = nullptr;
+    if (sr) {
+      y2 = A.plain((size_t)nb * Ts);
+      c.m = sr;
+      AR_TRY(sr_forward(c, y1, y2, T));
+      A.release_plain(y1);
+      st_in = y2;
+    }
+    c.m = st;
+    AR_TRY(stereo_encode(c, st_in, Ts, xp));
+    A.release_plain(sr ? y2 : y1);
+    return (int)AR_OK;
+  };
+  LstmWindow w;
+  AR_TRY(check_window(w, Ts));
+  if (B <= full) {
+    Act xp{};
+    AR_TRY(front(0, B, xp));
+    Act h = A.act(B, 64, Ts);
+    AR_TRY(stereo_scan(c, xp, h, Ts, nullptr, nullptr, w));
+    A.release(xp);
+    return stereo_decode(c, h, y, Ts, true);
+  }
+  Act xp = A.act(B, 256, Ts);
+  for (int b0 = 0; b0 < B; b0 += sub_front) {
+    Act v = xp;
+    v.base = xp.h() + (long long)b0 * xp.bs;
+    AR_TRY(front(b0, std::min(sub_front, B - b0), v));
+  }
+  Act h = A.act(B, 64, Ts);
+  c.m = st;
+  c.B = B;
+  AR_TRY(stereo_scan(c, xp, h, Ts, nullptr, nullptr, w));
+  A.release(xp);
+  for (int b0 = 0; b0 < B; b0 += sub_back) {
+    Act v = h;
+    v.base = h.h() + (long long)b0 * h.bs;
+    c.B = std::min(sub_back, B - b0);
+    AR_TRY(stereo_decode(c, v, y + (size_t)b0 * 2 * Ts, Ts, false));
+  }
+  A.release(h);
+  return AR_OK;
+}
+
+int chain_workspace_bytes(const Model* den, const Model* sr, const Model* st, int B, int T, size_t* bytes) {
+  AR_CHECK(den && st && bytes && B >= 1 && T >= 1, AR_ERR_INVALID, "chain: bad argument");
+  Ctx c;
+  c.ar.dry = true;
+  AR_TRY(chain_run(c, den, sr, st, nullptr, nullptr, B, T));
+  *bytes = c.ar.peak + 256;
+  return AR_OK;
+}
+
+int chain_forward(const Model* den, const Model* sr, const Model* st, const float* x, float* y, int B, int T, void* ws,
+                  size_t ws_bytes, cudaStream_t stream) {
+  AR_CHECK(x && y, AR_ERR_INVALID, "chain: null tensor");
+  size_t need = 0;
+  AR_TRY(chain_workspace_bytes(den, sr, st, B, T, &need));
+  AR_CHECK(ws != nullptr && ws_bytes >= need, AR_ERR_WORKSPACE, "chain: workspace too small (need " + std::to_string(need) + " bytes)");
+  Ctx c;
+  c.stream = stream;
+  c.ar.dry = false;
+  c.ar.base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) / 256 * 256);
+  c.ar.cap = need - 256;        // == the dry-run peak: high-side tensors are placed down from it
+  return chain_run(c, den, sr, st, x, y, B, T);
 }
 
 static int dispatch(Ctx& c, const float* x, float* y, int T, const float* st_in, float* st_out, LstmWindow w = LstmWindow()) {
@@ -862,7 +1037,7 @@ int model_forward(const Model* m, const float* x, float* y, int B, int T, const 
   c.ar.dry = false;
   uintptr_t a = (reinterpret_cast<uintptr_t>(ws) + 255) / 256 * 256;
   c.ar.base = reinterpret_cast<char*>(a);
-  c.ar.cap = ws_bytes;
+  c.ar.cap = need - 256;        // == the dry-run peak: high-side tensors are placed down from it
   LstmWindow w;
   w.lstm_start = lstm_start;
   w.state_pos = state_pos;
@@ -921,16 +1096,20 @@ int debug_conv(const float* x, const float* w_host, const float* bias_host, floa
   }
   Blob blob;
   ConvLayer L = blob.push_gemm(g);
-  Arena A;
-  A.dry = true;
-  Act in = A.act(B, Cin, T), out = A.act(B, Cout, T);
+  Arena D;
+  D.dry = true;
+  D.act(B, Cin, T);
+  D.act(B, Cout, T);
   float* dblob = nullptr;
   char* dws = nullptr;
   AR_CUDA_OK(cudaMalloc(&dblob, blob.host.size() * sizeof(float)));
-  AR_CUDA_OK(cudaMalloc(&dws, A.peak));
+  AR_CUDA_OK(cudaMalloc(&dws, D.peak));
   AR_CUDA_OK(cudaMemcpyAsync(dblob, blob.host.data(), blob.host.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
-  in.base = dws + (reinterpret_cast<char*>(in.base) - (char*)nullptr);
-  out.base = dws + (reinterpret_cast<char*>(out.base) - (char*)nullptr);
+  Arena A;
+  A.dry = false;
+  A.base = dws;
+  A.cap = D.peak;
+  Act in = A.act(B, Cin, T), out = A.act(B, Cout, T);
   int rc = launch_plain_to_c4(x, B, Cin, T, in, stream);
   if (rc == AR_OK) {
     ConvParams p;

@@ -139,21 +139,50 @@ __device__ __forceinline__ uint4 epi_chunk8(const uint32_t* a, const float* bias
   return make_uint4(cvt_half2_sat(v[0], v[1]), cvt_half2_sat(v[2], v[3]), cvt_half2_sat(v[4], v[5]), cvt_half2_sat(v[6], v[7]));
 }
 
-template <int MODE, bool POOL, bool RES>
+// Walks `wcols` accumulator columns (16, or a multiple of 32) of this warp's TMEM lanes in blocks of 32 and hands each
+// block to f(first column of the block, registers, columns in the block).  The TMEM load of block k + 1 is issued BEFORE
+// the math of block k (two register sets), so its latency hides behind that math instead of stalling the warp once per
+// block -- ncu showed the epilogue warps of the fused chains waiting on exactly these loads (long_scoreboard, 45 % of the
+// stall samples).
+// W = columns per block: 32 where registers are plentiful (single-layer engine: one CTA of 320 threads per SM), 16 in the
+// fused-chain kernels (600+ threads: two 32-column register sets would spill).
+template <int W>
+__device__ __forceinline__ void tmem_ld_block(uint32_t taddr, uint32_t (&a)[W]) {
+  if (W == 32) tmem_ld32_nowait(taddr, reinterpret_cast<uint32_t(&)[32]>(a));
+  else tmem_ld16_nowait(taddr, a);
+}
+template <int W, class F>
+__device__ __forceinline__ void tmem_stream(uint32_t taddr, int wcols, F&& f) {
+  uint32_t a0[W], a1[W];
+  if (wcols < W) {                       // 16 columns through the 32-wide walker
+    tmem_ld16_nowait(taddr, a0);
+    tmem_wait_ld();
+    f(0, a0, 16);
+    return;
+  }
+  tmem_ld_block<W>(taddr, a0);
+  for (int cb = 0; cb < wcols; cb += 2 * W) {
+    tmem_wait_ld();
+    if (cb + W < wcols) tmem_ld_block<W>(taddr + cb + W, a1);
+    f(cb, a0, W);
+    if (cb + W < wcols) {
+      tmem_wait_ld();
+      if (cb + 2 * W < wcols) tmem_ld_block<W>(taddr + cb + 2 * W, a0);
+      f(cb + W, a1, W);
+    }
+  }
+}
+
+template <int MODE, bool POOL, bool RES, int W = 32>
 __device__ __forceinline__ void epi_store(const EpiRow& r, const float* s_bias_w /* bias of this warp's first column */, uint32_t taddr,
                                           int wcols, float slope, const uint4 (&resv)[2]) {
   const float ca = 0.5f * (1.0f + slope), cb = 0.5f * (1.0f - slope);
-  for (int cb0 = 0; cb0 < wcols; cb0 += 32) {
-    uint32_t a[32];
-    const int ncol = wcols - cb0 < 32 ? 16 : 32;     // wcols is 16 or a multiple of 32
-    if (ncol == 32) tmem_ld32_nowait(taddr + cb0, a);
-    else tmem_ld16_nowait(taddr + cb0, a);
-    tmem_wait_ld();
+  tmem_stream<W>(taddr, wcols, [&](int cb0, const uint32_t (&a)[W], int ncol) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < W / 8; ++c) {
       if (8 * c < ncol) {
-        const uint4 packed = epi_chunk8<RES>(a + 8 * c, s_bias_w + cb0 + 8 * c, ca, cb, resv[c & 1]);
         const int ch = (cb0 >> 3) + c;               // 8-column chunk index within this warp's range
+        const uint4 packed = epi_chunk8<RES>(a + 8 * c, s_bias_w + cb0 + 8 * c, ca, cb, resv[ch & 1]);
         if (r.ok0) *reinterpret_cast<uint4*>(r.o0 + (long long)ch * r.ostride) = packed;
         if (MODE == MODE_INTERLEAVE2) {
           if (r.ok1) *reinterpret_cast<uint4*>(r.o1 + (long long)ch * r.ostride) = make_uint4(0u, 0u, 0u, 0u);
@@ -167,7 +196,7 @@ __device__ __forceinline__ void epi_store(const EpiRow& r, const float* s_bias_w
         }
       }
     }
-  }
+  });
 }
 
 // (variant, taps) -> kernel instantiation table shared by both engines' launchers

@@ -159,14 +159,29 @@ class RestorationPipeline:
                                           self._stream()))
         return out
 
-    def max_batch(self, chunk_size: int, budget_bytes: int) -> int:
-        """Largest chunk batch whose chain workspace fits in `budget_bytes`."""
-        L = _lib.lib()
+    def workspace_bytes(self, batch: int, chunk_size: int) -> int:
+        """Chain workspace of one `forward_chunks` call on `batch` chunks (`ar_chain_workspace_bytes`)."""
         need = C.c_size_t()
         with torch.cuda.device(self.device):
-            c = self.chain()
-            _lib.check(L.ar_chain_workspace_bytes(c, 1, chunk_size, C.byref(need)))
-        return max(1, int(budget_bytes // max(1, need.value)))
+            _lib.check(_lib.lib().ar_chain_workspace_bytes(self.chain(), batch, chunk_size, C.byref(need)))
+        return need.value
+
+    def max_batch(self, chunk_size: int, budget_bytes: int) -> int:
+        """Largest chunk batch (up to 8 per SM) whose chain workspace fits in `budget_bytes`."""
+        return max(1, int(budget_bytes // max(1, self.workspace_bytes(1, chunk_size))))
+
+    def auto_batch(self, n_chunks: int, chunk_size: int, streams: int = 1) -> int:
+        """Chunks per chain launch.  16 per SM when the workspace allows it (one tensor-core LSTM scan, 8 sequences per CTA,
+        two CTAs per SM, fills the chip; the chain runs its conv phases on sub-batches around it), else 8 per SM (4 per
+        CTA), else whatever fits."""
+        free, _ = torch.cuda.mem_get_info(self.device)
+        held = sum(b.numel() for b in (self._ws or {}).values() if b is not None)     # cached workspaces get reused
+        budget = int((free + held) * 0.85) // max(1, streams)
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        for per_sm in (16, 8):
+            if n_chunks > (per_sm // 2) * sms and self.workspace_bytes(min(n_chunks, per_sm * sms), chunk_size) <= budget:
+                return min(n_chunks, per_sm * sms)
+        return min(n_chunks, 8 * sms, self.max_batch(chunk_size, budget))
 
     # ------------------------------------------------------------------ public entry points
     @torch.no_grad()
@@ -405,11 +420,7 @@ class RestorationPipeline:
         c0 = max(lo - 1, 0)
         cnt_all = hi - c0
         if batch_chunks <= 0:
-            # eight chunks per SM: one launch of the tensor-core LSTM scan (8 sequences per CTA) then fills the
-            # chip; bounded by what the workspace of `streams` concurrent batches may take
-            free, _ = torch.cuda.mem_get_info(self.device)
-            sms = torch.cuda.get_device_properties(self.device).multi_processor_count
-            batch_chunks = min(cnt_all, 8 * sms, self.max_batch(chunk_size, int(free * 0.6) // max(1, streams)))
+            batch_chunks = self.auto_batch(cnt_all, chunk_size, streams)
         y_all = torch.empty((cnt_all, 2, r * chunk_size), dtype=torch.float32, device=self.device)
         firsts = list(range(c0, hi, batch_chunks))
         n_streams = max(1, min(streams, len(firsts)))

@@ -132,16 +132,21 @@ class NativeModule(nn.Module):
         return h
 
     def _release(self):
-        if getattr(self, "_handle", None) is not None:
+        h = self.__dict__.get("_handle")
+        if h is not None:
             try:
-                _lib.lib().ar_model_destroy(self._handle)
+                _lib.lib().ar_model_destroy(h)
             except Exception:
                 pass
-            self._handle = None
-            self._handle_key = None
+        # plain attribute writes: nn.Module.__setattr__ is not usable while the interpreter shuts down
+        self.__dict__["_handle"] = None
+        self.__dict__["_handle_key"] = None
 
     def __del__(self):
-        self._release()
+        try:
+            self._release()
+        except Exception:
+            pass
 
     # ------------------------------------------------------------------ forward plumbing
     def _check_input(self, x: torch.Tensor) -> torch.Tensor:

@@ -11,13 +11,14 @@ MAX_ABS = 1e-3      # north_star tolerance: max abs error <= 1e-3 ...
 MIN_SNR_DB = 60.0   # ... or >= 60 dB SNR; the tests demand both unless stated
 
 
-def make_model(name, sd, engine=_lib.ENGINE_UMMA, device="cuda", fusion=True):
+def make_model(name, sd, engine=_lib.ENGINE_UMMA, device="cuda", fusion=1):
+    """fusion: 0 layer by layer, 1 / True the product default, 2 every fused chain that fits (ar_set_fusion)."""
     m = CLS[name]()
     m.load_state_dict(sd, strict=True)
     m = m.to(device).eval()
     L = _lib.lib()
     _lib.check(L.ar_set_conv_engine(engine))
-    _lib.check(L.ar_set_fusion(1 if fusion else 0))
+    _lib.check(L.ar_set_fusion(int(fusion)))
     try:
         m.native_handle(torch.device("cuda", torch.cuda.current_device()))
     finally:

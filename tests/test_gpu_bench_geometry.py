@@ -1,6 +1,7 @@
 """GPU: direct oracle parity ON THE GEOMETRY THE BENCH TIMES -- batches beyond two sequences per SM (tensor-core LSTM
-`lstm_mma4w_kernel`, tile groups, fused chains all active), full-length 2 s chunks, BASELINE config 4 in full -- plus the
-LSTM carry (`state_in`), the whole-file-exact chunked mode and the dynamic-range envelope of the fp16 storage."""
+`lstm_mmaw_kernel<4>`, tile groups, fused chains all active) and beyond eight per SM (`lstm_mmaw_kernel<8>`, the chain's
+sub-batched conv phases around one scan), full-length 2 s chunks, BASELINE config 4 in full -- plus the LSTM carry
+(`state_in`), the whole-file-exact chunked mode and the dynamic-range envelope of the fp16 storage."""
 import numpy as np
 import pytest
 import torch
@@ -20,6 +21,12 @@ def big_batch():
     return 2 * torch.cuda.get_device_properties(0).multi_processor_count + 8      # 304 on a B200
 
 
+def huge_batch():
+    """Smallest convenient batch beyond eight sequences per SM: the eight-sequences-per-CTA LSTM kernel and the chain's
+    sub-batched conv phases; not a multiple of 8 (a ragged last CTA)."""
+    return 8 * torch.cuda.get_device_properties(0).multi_processor_count + 13     # 1197 on a B200
+
+
 @pytest.fixture(scope="module")
 def pipe(state_dicts):
     return RestorationPipeline.from_state_dicts(state_dicts["denoiser"], state_dicts["super_resolution"],
@@ -37,11 +44,47 @@ def test_chain_at_bench_batch_vs_oracle(pipe, state_dicts):
     assert_close(ref, y[picks], f"chain B={B} T={T}: chunks {picks} vs oracle")
 
 
-def test_stereo_tensor_core_lstm_full_length_vs_oracle(state_dicts):
-    """StereoSeparator alone at B >= 304, T = 88 200 (the stage's length in the chain): `lstm_mma4w_kernel` over 88 200
-    steps against the fp32 oracle DIRECTLY (not via the CUDA-core kernel) -- fp16 W_hh and fp16 h feedback over the full
-    scan is where drift would show.  Both tolerance clauses."""
-    B, T = big_batch(), 88200
+def test_chain_sixteen_chunks_per_sm_vs_oracle(pipe, state_dicts):
+    """The bench's own launch: 16 chunks of 44 100 samples per SM (2368 on a B200) in ONE `ar_chain_forward` -- conv phases
+    on sub-batches, one `lstm_mmaw_kernel<8>` scan over all sequences; chunks from every sub-batch meet the oracle."""
+    B, T = 16 * torch.cuda.get_device_properties(0).multi_processor_count, 44100
+    free, _ = torch.cuda.mem_get_info()
+    if pipe.workspace_bytes(B, T) > 0.9 * free:
+        pytest.skip("not enough device memory for the 16-per-SM batch")
+    x = make_input(B, T, seed=35)
+    y = pipe.forward_chunks(x.cuda()).cpu()
+    pipe._ws = None                                             # hand the 130 GB workspace back
+    torch.cuda.empty_cache()
+    picks = sorted({0, B // 4 - 1, B // 4, B // 2 + 3, 3 * B // 4, B - 1})
+    ref = opipe.chain_forward(state_dicts, x[picks])
+    assert_close(ref, y[picks], f"chain B={B} T={T}: chunks {picks} vs oracle")
+
+
+def test_chain_sub_batched_equals_single_batches(pipe, state_dicts):
+    """Beyond 8 chunks per SM the chain runs denoiser / super-resolution / encoder and the decoders on sub-batches around one
+    scan: same kernels on the same operands per chunk, so the result equals the chain run on slices of at most 8 per SM
+    (only the LSTM kernel differs: 8 instead of 4 sequences per CTA, same MMAs in the same order), and the oracle."""
+    B, T = huge_batch(), 1037
+    x = make_input(B, T, seed=36)
+    xd = x.cuda()
+    y = pipe.forward_chunks(xd)
+    cut = 8 * torch.cuda.get_device_properties(0).multi_processor_count
+    y_head = pipe.forward_chunks(xd[:cut].contiguous())         # tensor-core LSTM, 4 sequences per CTA: the same arithmetic
+    diff = float((y[:cut] - y_head).abs().max())
+    print(f"sub-batched chain vs single batch: max|diff|={diff:.3e}  bitwise equal: {torch.equal(y[:cut], y_head)}")
+    assert diff <= 1e-6
+    y_tail = pipe.forward_chunks(xd[cut:].contiguous())         # 13 chunks: the CUDA-core fp32 recurrence
+    assert_close(y_tail, y[cut:], "last sub-batch vs its own small-batch run")
+    picks = [0, cut // 2 - 1, cut // 2, cut - 1, cut, B - 1]
+    assert_close(opipe.chain_forward(state_dicts, x[picks]), y[picks].cpu(), f"chain B={B} T={T}: chunks {picks} vs oracle")
+
+
+@pytest.mark.parametrize("size", ["4-per-cta", "8-per-cta"])
+def test_stereo_tensor_core_lstm_full_length_vs_oracle(state_dicts, size):
+    """StereoSeparator alone at B >= 304 (`lstm_mmaw_kernel<4>`) and B >= 1197 (`lstm_mmaw_kernel<8>`), T = 88 200 (the
+    stage's length in the chain): 88 200 steps against the fp32 oracle DIRECTLY (not via the CUDA-core kernel) -- fp16
+    W_hh and fp16 h feedback over the full scan is where drift would show.  Both tolerance clauses."""
+    B, T = (big_batch() if size == "4-per-cta" else huge_batch()), 88200
     m = make_model("stereo", state_dicts["stereo"])
     x = make_input(B, T, seed=32)
     with torch.no_grad():
@@ -74,14 +117,28 @@ def test_config4_full_side_vs_oracle(pipe, state_dicts):
     assert_close(ref, y, "config 4: 180 s side, 95 chunks, normalize on, vs oracle")
 
 
-@pytest.mark.parametrize("big", [False, True], ids=["cuda-core-lstm", "tensor-core-lstm"])
+def test_stereo_eight_sequences_per_cta_every_sequence_vs_oracle(state_dicts):
+    """`lstm_mmaw_kernel<8>` (more than 8 sequences per SM): EVERY sequence of a ragged batch (1197 = 149 full CTAs + 5
+    sequences) and ragged length (203 = 25 blocks + 3 steps) against the oracle, outputs and final (h, c)."""
+    m = make_model("stereo", state_dicts["stereo"])
+    B, T = huge_batch(), 203
+    x = make_input(B, T, seed=37)
+    ref, (hn, cn) = oracle.stereo_forward(state_dicts["stereo"], x, return_state=True)
+    with torch.no_grad():
+        y, st = m.forward_with_state(x.cuda())
+    assert_close(ref, y, f"stereo B={B} T={T} (8 sequences per CTA)")
+    assert_close(hn[0], st[:, 0], "carried h (8 sequences per CTA)", max_abs=1e-3, min_snr=50.0)
+    assert_close(cn[0], st[:, 1], "carried c (8 sequences per CTA)", max_abs=1e-3, min_snr=50.0)
+
+
+@pytest.mark.parametrize("big", [0, 1, 2], ids=["cuda-core-lstm", "tensor-core-lstm-4", "tensor-core-lstm-8"])
 def test_lstm_state_in_two_halves_equal_one_scan(state_dicts, big):
     """Feed the carried (h, c) back: forward(first half) -> state -> forward(second half, state) must reproduce the LSTM
     part of ONE scan over the whole sequence (stereo_separator.py:106-107).  The conv halves differ near the cut (each
     half zero-pads there), so outputs are compared where the cut is out of conv reach (30 samples), the states everywhere;
     both recurrence kernels; and against the oracle fed the same way."""
     m = make_model("stereo", state_dicts["stereo"])
-    B, T = (big_batch(), 2048) if big else (3, 3000)
+    B, T = [(3, 3000), (big_batch(), 2048), (huge_batch(), 2048)][big]
     cut = T // 2 - (T // 2) % 8
     x = make_input(B, T, seed=33)
     xd = x.cuda()

@@ -110,6 +110,24 @@ def test_fused_chains_match_layer_by_layer(state_dicts, B, T):
         assert_close(oracle.stereo_forward(state_dicts["stereo"], x), yf, f"stereo fused vs oracle B={B} T={T}")
 
 
+@pytest.mark.parametrize("name", ["denoiser", "super_resolution"])
+@pytest.mark.parametrize("B,T", [(1, 8), (2, 125), (1, 126), (3, 127), (1, 252), (2, 253), (1, 1009), (5, 4099), (150, 1100)])
+def test_fused_double_convs_match_layer_by_layer(state_dicts, name, B, T):
+    """The fused k3 -> k3 launches (U-Net double convs with the max-pool copy, super-resolution residual blocks with the
+    skip add; conv_chain.cu, tile stride 126) compute the same fp16-rounded intermediates as the layer-by-layer launches:
+    outputs agree far inside the tolerance, and both agree with the oracle.  Lengths around the 126-row tile stride and its
+    multiples (at every U-Net level: T, T/2, T/4), odd tile counts (idle peer CTA), and B=150 for the steady-state pipeline."""
+    fused = make_model(name, state_dicts[name], fusion=2)      # every pair that fits, not only the measured-faster ones
+    plain = make_model(name, state_dicts[name], fusion=0)
+    x = make_input(B, T, seed=B * 11 + T)
+    with torch.no_grad():
+        yf = fused(x.cuda())
+        yp = plain(x.cuda())
+    assert_close(yp, yf, f"{name} fused vs layer-by-layer B={B} T={T}", max_abs=2e-5, min_snr=90.0)
+    if B <= 5:
+        assert_close(FWD[name](state_dicts[name], x), yf, f"{name} fused vs oracle B={B} T={T}")
+
+
 def test_error_behaviour(models, state_dicts):
     den = models("denoiser", "umma")
     with pytest.raises(RuntimeError):          # reference: RuntimeError from max_pool1d for T < 8

@@ -10,14 +10,15 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ml_audio_restoration_b200 import _lib  # noqa: E402
-from ml_audio_restoration_b200.models import StereoSeparator  # noqa: E402
+from ml_audio_restoration_b200.models import StereoSeparator, AudioSuperResolution, AudioDenoiser  # noqa: E402
 
 
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 148
     T = int(sys.argv[2]) if len(sys.argv) > 2 else 44100
+    which = sys.argv[3] if len(sys.argv) > 3 else "stereo"
     torch.manual_seed(0)
-    m = StereoSeparator().cuda().eval()
+    m = {"stereo": StereoSeparator, "sr": lambda: AudioSuperResolution(upscale_factor=2), "denoiser": AudioDenoiser}[which]().cuda().eval()
     x = 0.1 * torch.randn(B, 1, T, device="cuda")
     with torch.no_grad():
         m(x)
@@ -29,7 +30,7 @@ def main():
     torch.cuda.synchronize()
     L.ar_debug_chain_trace(None)
     tr = buf.cpu().view(4, 64, 1, 16)
-    names = ["G1i0", "G1i1", "G2rdy", "G2i", "E1b", "E1e", "ELb", "ELe", "full0", "peer0", "G3rdy", "G3i", "E2b", "E2e", "fullL", "peerL"]
+    names = ["G1i0", "G1i1", "G2rdy", "G2i", "E1b", "E1e", "ELb", "ELe", "full0", "fullN", "G3rdy", "G3i", "E2b", "E2e", "Pend", "Pbeg"]
     for k in range(4):
         t = tr[k]
         if int(t.max()) == 0:
