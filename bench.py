@@ -34,13 +34,16 @@ CHAIN_GFLOP_PER_AUDIO_S = 51.661
 # of these, the share computed by the tcgen05 conv engine (every Conv1d / ConvTranspose1d with Cin >= 16 + the LSTM input
 # projection): denoiser 147 968, super-res 41 984 MAC per input sample, stereo 473 088 MAC per 44.1 kHz sample
 CONV_GFLOP_PER_AUDIO_S = 2.0 * ((147968 + 41984) * SR + 473088 * 2 * SR) / 1e9          # 50.10
+# beyond 8 sequences per SM the scan kernel computes the LSTM input projection itself (lstm_proj.cu): 32 768 MAC per 44.1 kHz
+# sample leave the conv engine's account
+CONV_GFLOP_PER_AUDIO_S_FUSED_SCAN = 2.0 * ((147968 + 41984) * SR + (473088 - 32768) * 2 * SR) / 1e9     # 47.21
 # per-model algorithmic GFLOP per second of the model's OWN input signal
 MODEL_GFLOP_PER_S = {"denoiser": 6.549, "super_resolution": 1.881, "stereo": 21.615}
 METRIC = "restored audio-sec/sec (full chain)"
 TRAFFIC_FILE = "conv_traffic_r02.json"
 
 
-def conv_algorithmic_bytes_per_audio_s():
+def conv_algorithmic_bytes_per_audio_s(fused_scan=False):
     """fp16 activation bytes (inputs read + outputs written, incl. pooled copies and residual operands) that the
     conv engine's 37 launches per chunk batch must move per source audio-second: entries are
     (bytes per row, rows per audio-second) per tensor stream of a launch; the stereo encoder entries are the FUSED
@@ -51,7 +54,7 @@ def conv_algorithmic_bytes_per_audio_s():
            (256, r // 2), (128, r // 2), (64, r), (192, r), (128, r),
            (128, r)]                         # first transient-detector layer (32 -> 16 padded to 32 columns)
     sr = [(128, r)] * 4 + [(192, r)] * 5 + [(64, r), (64, 2 * r), (128, 2 * r)]
-    st = [(192, 2 * r), (384, 2 * r), (512, 2 * r), (768, 2 * r),                     # fused enc1, enc2, enc3, enc4 + xproj
+    st = [(192, 2 * r), (384, 2 * r), (512, 2 * r), (512 if fused_scan else 768, 2 * r),   # fused enc1, enc2, enc3, enc4 (+ xproj)
           (640, 2 * r), (384, 2 * r), (384, 2 * r), (192, 2 * r), (192, 2 * r)]       # dec0 (L+R), dec1 L/R, dec2 L/R
     return float(sum(b * n for b, n in den + sr + st))
 
@@ -430,22 +433,25 @@ def run_b200(args, rank, world, local_rank):
     conv_s = conv["ms"] / 1e3
     # ALGORITHMIC FLOPs = SURVEY.md 8(d)'s per-SOURCE-second figure x the source seconds of the step: the 2 052-sample
     # chunk overlap that the chunked scheme recomputes is overhead, not work (it is in `achieved_incl_overlap` only)
-    achieved = (CONV_GFLOP_PER_AUDIO_S * audio_s * args.steps / 1e3) / conv_s if conv_s > 0 else 0.0
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    seq_in_flight = min(args.batch_chunks, args.chunks_per_step)
+    fused_scan = seq_in_flight > 8 * sms
+    conv_gflop = CONV_GFLOP_PER_AUDIO_S_FUSED_SCAN if fused_scan else CONV_GFLOP_PER_AUDIO_S
+    achieved = (conv_gflop * audio_s * args.steps / 1e3) / conv_s if conv_s > 0 else 0.0
     achieved_incl = (conv["gflop"] / 1e3) / conv_s if conv_s > 0 else 0.0
-    conv_bytes = conv_algorithmic_bytes_per_audio_s() * audio_s * args.steps      # algorithmic, this rank
+    conv_bytes = conv_algorithmic_bytes_per_audio_s(fused_scan) * audio_s * args.steps      # algorithmic, this rank
     hbm_gbs = (conv_bytes / 1e9) / conv_s if conv_s > 0 else 0.0
     traffic, traffic_src = load_conv_traffic(args)
     lstm = cats["lstm"]
     lstm_steps = 2 * CHUNK                                                         # serial steps per launch (44.1 kHz, 2 s)
     lstm_ms_launch = lstm["ms"] / max(1, lstm["launches"])
-    seq_in_flight = min(args.batch_chunks, args.chunks_per_step)
-    sms = torch.cuda.get_device_properties(dev).multi_processor_count
     roofline = {
         "kernel": "tcgen05 conv engine: conv_umma2_kernel (2-CTA implicit-GEMM Conv1d / ConvT), conv_chain_kernel "
                   "(fused dilated blocks + LSTM input projection, U-Net 64 -> 128 -> 128 double conv), all template variants",
         "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
         "frac": achieved / peaks["tflops"], "peak_source": f"{peaks['src']} bf16 dense sustained (fp16 operands run at the same rate)",
-        "flops_per_unit": f"{CONV_GFLOP_PER_AUDIO_S:.2f} GFLOP per source audio-second (of the chain's {CHAIN_GFLOP_PER_AUDIO_S}), "
+        "flops_per_unit": f"{conv_gflop:.2f} GFLOP per source audio-second (of the chain's {CHAIN_GFLOP_PER_AUDIO_S}"
+                          + ("; the LSTM input projection, 2.89, runs inside the scan kernel" if fused_scan else "") + "), "
                           f"x {audio_s:.1f} source seconds per step; chunk-overlap recompute excluded",
         "achieved_incl_overlap": achieved_incl,
         "avg_launch_ms": conv["ms"] / max(1, conv["launches"]), "launches": conv["launches"],
@@ -457,7 +463,7 @@ def run_b200(args, rank, world, local_rank):
         "whole_chain": {"achieved": value / world * CHAIN_GFLOP_PER_AUDIO_S / 1e3, "unit": "TFLOP/s",
                         "frac": value / world * CHAIN_GFLOP_PER_AUDIO_S / 1e3 / peaks["tflops"],
                         "note": "all kernels of the step (convs, LSTM, stems, tails, normalize, split / overlap-add)"},
-        "lstm": {"kernel": ("lstm_mmaw_kernel<8>" if seq_in_flight > 8 * sms else "lstm_mmaw_kernel<4>" if seq_in_flight > 2 * sms else "lstm_kernel"),
+        "lstm": {"kernel": ("lstm_proj_kernel (tcgen05 input projection + mma.sync recurrence)" if fused_scan else "lstm_mmaw_kernel<4>" if seq_in_flight > 2 * sms else "lstm_kernel"),
                  "bound": "latency", "ms_per_launch": lstm_ms_launch, "serial_steps_per_launch": lstm_steps,
                  "ns_per_step": 1e6 * lstm_ms_launch / lstm_steps, "sequences_in_flight": seq_in_flight,
                  "sequences_per_sm": seq_in_flight / sms,

@@ -11,52 +11,9 @@
 // h that feeds the decoder convs is rounded to TF32.
 #include "ar_common.cuh"
 #include "pointwise.cuh"
+#include "lstm_cell.cuh"
 
 namespace ar {
-
-constexpr int LSTM_H = 64;
-constexpr int LSTM_BLK = 8;  // steps per output flush / input prefetch block
-
-// ex2.approx-based gates: |rel err| ~ 2^-21, far below the TF32 noise of the surrounding convs,
-// and ~5x fewer issue slots than expf + IEEE division on the per-step critical path.
-__device__ __forceinline__ float ex2_f(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float rcp_f(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// Gate pre-activations arrive PRE-SCALED (models.cu scales the rows of W_ih, W_hh and the biases at pack time):
-//   p_i, p_f, p_o = log2(e) * (gate pre-activation),   p_g = 2 log2(e) * (cell-candidate pre-activation),
-// so every gate function is an ex2 of the negated input with no multiply in front of it.
-// One LSTM cell update with 5 ex2 + 2 rcp (the special-function unit, 16 lanes/clk/SM, and the issue slots are the
-// throughput limits of the tensor-core recurrence kernels): the three gate functions of the cell state share ONE
-// reciprocal,
-//   s(f) c + s(i) tanh(g) = [ c (1+b)(1+d) + (1-d)(1+a) ] / [ (1+a)(1+b)(1+d) ],  a=e^-f, b=e^-i, d=e^-2g,
-// and so do s(o) tanh(c').  Only the lower side needs a clamp (e^-x overflows for very negative x; for large x it
-// underflows to 0, which is exact enough): -20 natural units changes a gate by < 3e-9 and keeps the product of three
-// exponentials finite.
-constexpr float LSTM_L2E = 1.4426950408889634f;
-__device__ __forceinline__ void lstm_cell(float pi, float pf, float pg, float po, float& c, float& h) {
-  pi = fmaxf(pi, -20.f * LSTM_L2E);
-  pf = fmaxf(pf, -20.f * LSTM_L2E);
-  pg = fmaxf(pg, -40.f * LSTM_L2E);
-  po = fmaxf(po, -20.f * LSTM_L2E);
-  const float a = ex2_f(-pf), b = ex2_f(-pi), d = ex2_f(-pg);
-  const float bd = (1.f + b) * (1.f + d);
-  const float num = fmaf(c, bd, (1.f - d) * (1.f + a));
-  c = num * rcp_f((1.f + a) * bd);
-  const float cc = fmaxf(c, -20.f);
-  const float q = ex2_f(-po), e = ex2_f(-2.f * LSTM_L2E * cc);
-  h = (1.f - e) * rcp_f((1.f + q) * (1.f + e));
-}
-// pre-scaled variants for the CUDA-core kernel (x already multiplied by log2(e), resp. 2 log2(e))
-__device__ __forceinline__ float sigmoid_s(float x) { return rcp_f(1.0f + ex2_f(-x)); }
-__device__ __forceinline__ float tanh_s(float x) { return 1.0f - 2.0f * rcp_f(ex2_f(x) + 1.0f); }
-__device__ __forceinline__ float tanh_f(float x) { return 1.0f - 2.0f * rcp_f(ex2_f(2.8853900817779268f * x) + 1.0f); }
 
 // Packed 2-wide fp32 FMA (Blackwell FFMA2): halves the FMA issue slots of the 64-term dot product.
 __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
@@ -246,19 +203,7 @@ lstm_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, const flo
 // barrier: 49.8 -> 43.4 ms per 1184-chunk step.)  The two groups meet once per 8-step block (named barrier 1, all 320
 // threads): by then the movers have long finished.  The ping-pong index of the h exchange buffer is the step's parity
 // inside the block -- a compile-time constant in the unrolled loop -- and full blocks run without the `step < T` tests.
-constexpr int LM_HS = 80;       // padded row stride of the h exchange buffer (halves): conflict-free 8-byte fragment loads
-constexpr int LM_XS = 264;      // padded per-sequence stride of a staged pre-activation row (halves)
 constexpr int LM_HST = 68;      // padded [seq] row stride of the hidden-state staging buffer (floats): conflict-free stores
-
-__device__ __forceinline__ void mma_f16_16x8x16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
 
 constexpr int LW_REC = 256;                        // recurrence warps
 constexpr int LW_MOV = 64;                         // two mover warps
@@ -340,26 +285,8 @@ lstm_mmaw_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, cons
   const int gid = lane >> 2, tig = lane & 3;
   const int unit = warp * 8 + gid;
   uint32_t wfrag[2][4][4];
-  {
-    auto w2 = [&](int row, int k) {
-      const __half2 h = __floats2half2_rn(whh[row * LSTM_H + k], whh[row * LSTM_H + k + 1]);
-      return *reinterpret_cast<const uint32_t*>(&h);
-    };
-#pragma unroll
-    for (int tl = 0; tl < 2; ++tl) {
-      const int row_lo = (2 * tl) * LSTM_H + unit, row_hi = (2 * tl + 1) * LSTM_H + unit;
-#pragma unroll
-      for (int kt = 0; kt < 4; ++kt) {
-        wfrag[tl][kt][0] = w2(row_lo, kt * 16 + 2 * tig);
-        wfrag[tl][kt][1] = w2(row_hi, kt * 16 + 2 * tig);
-        wfrag[tl][kt][2] = w2(row_lo, kt * 16 + 2 * tig + 8);
-        wfrag[tl][kt][3] = w2(row_hi, kt * 16 + 2 * tig + 8);
-      }
-    }
-  }
-  // position of hidden unit `unit` inside its sequence row: within each 16-unit k-tile the pairs (2j, 2j+1) and
-  // (2j+8, 2j+9) that form one thread's B fragment (b0, b1) are made adjacent => one 8-byte load per k-tile
-  const int upos = (unit & ~15) + ((((unit & 7) >> 1) * 2 + ((unit >> 3) & 1)) * 2) + (unit & 1);
+  load_whh_frags(whh, unit, tig, wfrag);
+  const int upos = h_exchange_pos(unit);
   // this thread's cells: (unit, sequence tig * CELLS + j); the sequence of cell j sits in accumulator column 2 tig + j
   float c[CELLS], hl[CELLS];
 #pragma unroll

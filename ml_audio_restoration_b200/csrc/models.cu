@@ -197,6 +197,7 @@ struct Model {
   size_t fin_umma_off = 0;   // the same heads packed as a tap-along-N tensor-core operand (final_umma.cu)
   int fin_heads = 0;
   size_t whh_off = 0;
+  size_t wih_umma_off = 0;   // W_ih^T packed for the scan kernel that computes its own input projection (lstm_proj.cu)
   // dynamic-range audit (ar_model_audit_*): while on, forwards run layer by layer and fold max |activation| of every
   // fp16 tensor they write into audit_dev[slot]; names are recorded in launch order.  Not re-entrant.
   bool audit = false;
@@ -352,6 +353,13 @@ static bool build_stereo(const Table& t, Blob& blob, Model& m) {
     g.bias[op] = (bih[o] + bhh[o]) * sc;
   }
   m.conv["xproj"] = blob.push_gemm(g);
+  {
+    std::vector<uint16_t> pk;
+    pack_lstm_proj(g.G.data(), pk);
+    std::vector<float> raw((pk.size() + 1) / 2);
+    std::memcpy(raw.data(), pk.data(), pk.size() * 2);
+    m.wih_umma_off = blob.push(raw);
+  }
   {
     std::vector<float> whh_s(256 * 64);
     for (int o = 0; o < 256; ++o)
@@ -795,7 +803,11 @@ struct LstmWindow { int lstm_start = 0, state_pos = -1; };
 //   scan    the LSTM recurrence                             xp -> h
 //   decode  both decoders + output heads                    h -> y[B,2,T]
 // `xp` of stereo_encode: a tensor the caller allocated (base != nullptr), else it is allocated here, as late as possible.
-static int stereo_encode(Ctx& c, const float* x, int T, Act& xp) {
+// With `proj_in_scan` the scan kernel computes the input projection itself (lstm_proj.cu: batches beyond 8 sequences per SM)
+// and `xp` is the encoder output e4b (128 channels, plain H8) instead of the 256 gate pre-activations.
+static bool proj_in_scan(const Model& m, int B_scan) { return m.engine == AR_ENGINE_UMMA && m.fuse && !m.audit && B_scan > 8 * sm_count(); }
+
+static int stereo_encode(Ctx& c, const float* x, int T, Act& xp, bool fused_proj) {
   const Model& m = *c.m;
   const int B = c.B;
   Arena& A = c.ar;
@@ -812,7 +824,19 @@ static int stereo_encode(Ctx& c, const float* x, int T, Act& xp) {
   ConvOpt oxp; oxp.lrelu = 0; oxp.out_tblock = 1;   // gate pre-activations, time-blocked: the recurrence streams 4 KB runs
   bool xp_done = false;
   for (int i = 0; i < 4; ++i) {
-    if (i == 3 && can_chain(c, {NA[i], NB[i], "xproj"})) {
+    if (i == 3 && fused_proj) {
+      if (own_xp) xp = A.act(B, 128, T);
+      if (can_chain(c, {NA[i], NB[i]})) {
+        AR_TRY(run_chain(c, {NA[i], NB[i]}, cur, xp));
+      } else {
+        Act t = A.act(B, 128, T);
+        AR_TRY(run_conv(c, NA[i], cur, t));
+        AR_TRY(run_conv(c, NB[i], t, xp));
+        A.release(t);
+      }
+      A.release(cur);
+      return AR_OK;
+    } else if (i == 3 && can_chain(c, {NA[i], NB[i], "xproj"})) {
       // last dilated block + LSTM input projection: 128 -k3 d8-> 128 -k1-> 128 -k1-> 256 in one launch
       if (own_xp) xp = A.act(B, 256, T);
       AR_TRY(run_chain(c, {NA[i], NB[i], "xproj"}, cur, xp, oxp));
@@ -841,18 +865,24 @@ static int stereo_encode(Ctx& c, const float* x, int T, Act& xp) {
   return AR_OK;
 }
 
-static int stereo_scan(Ctx& c, const Act& xp, const Act& h, int T, const float* state_in, float* state_out, const LstmWindow& w) {
+static int stereo_scan(Ctx& c, const Act& xp, const Act& h, int T, const float* state_in, float* state_out, const LstmWindow& w,
+                       bool fused_proj) {
   if (c.ar.dry) return AR_OK;
   const Model& m = *c.m;
   const int B = c.B;
-  ProfScope ps(CAT_LSTM, c.stream, 2.0 * 16384 * (double)B * (T - w.lstm_start), w.state_pos < T ? 2 : 1);
+  ProfScope ps(CAT_LSTM, c.stream, 2.0 * (fused_proj ? 16384 + 32768 : 16384) * (double)B * (T - w.lstm_start), w.state_pos < T ? 2 : 1);
   // a scan over steps [t0, t1) is the same kernel on base pointers advanced by t0 rows (t0 % 8 == 0 keeps the 8-step
   // blocks of the time-blocked pre-activations aligned)
   auto scan = [&](int t0, int t1, const float* st_in, float* st_out) {
     Act xs = xp, hs = h;
-    xs.base = xp.h() + (long long)(t0 / 8) * 32 * 64;
     hs.base = h.h() + (long long)t0 * 8;
     xs.T = hs.T = t1 - t0;
+    if (fused_proj) {
+      xs.base = xp.h() + (long long)t0 * 8;
+      return launch_lstm_proj(xs, reinterpret_cast<const __half*>(m.blob + m.wih_umma_off), m.blob + m.conv.at("xproj").b_off,
+                              m.blob + m.whh_off, hs, B, t1 - t0, st_in, st_out, c.stream);
+    }
+    xs.base = xp.h() + (long long)(t0 / 8) * 32 * 64;
     return launch_lstm(xs, m.blob + m.whh_off, hs, B, t1 - t0, st_in, st_out, c.stream);
   };
   if (w.lstm_start > 0)   // rows [0, lstm_start) of all 8 chunks of every item: zero hidden states
@@ -912,10 +942,11 @@ static int stereo_forward(Ctx& c, const float* x, float* y, int T, const float* 
                           LstmWindow w = LstmWindow()) {
   AR_TRY(check_window(w, T));
   Arena& A = c.ar;
+  const bool fp = proj_in_scan(*c.m, c.B);
   Act xp{};
-  AR_TRY(stereo_encode(c, x, T, xp));
+  AR_TRY(stereo_encode(c, x, T, xp, fp));
   Act h = A.act(c.B, 64, T);
-  AR_TRY(stereo_scan(c, xp, h, T, state_in, state_out, w));
+  AR_TRY(stereo_scan(c, xp, h, T, state_in, state_out, w, fp));
   A.release(xp);
   return stereo_decode(c, h, y, T, true);
 }
@@ -928,12 +959,16 @@ static int stereo_forward(Ctx& c, const float* x, float* y, int T, const float* 
 //   for each sub-batch:  denoiser, super-resolution, stereo encoder  ->  its slice of the gate pre-activations xp
 //   LSTM scan over all B sequences                                    ->  h
 //   for each sub-batch:  decoders                                     ->  its slice of y
-// and the workspace holds xp (45 MB per chunk) / h (11 MB per chunk) for the batch plus the conv scratch of one sub-batch.
+// and the workspace holds the scan's input (the encoder output, 23 MB per chunk: the scan kernel of such batches computes
+// the LSTM input projection itself, lstm_proj.cu) / h (11 MB per chunk) for the batch plus the conv scratch of one sub-batch.
 static int chain_run(Ctx& c, const Model* den, const Model* sr, const Model* st, const float* x, float* y, int B, int T) {
   Arena& A = c.ar;
   const int rate = sr ? 2 : 1, Ts = rate * T;
   const int full = 8 * sm_count();
-  const int sub_front = B <= full ? B : full / 2, sub_back = B <= full ? B : full;
+  const bool fp = proj_in_scan(*st, B);
+  // sub-batches: 8 per SM; 4 per SM in front of a scan that reads stored pre-activations (256 channels for the whole batch
+  // leave less room for the encoder's scratch)
+  const int sub_front = B <= full ? B : (fp ? full : full / 2), sub_back = B <= full ? B : full;
   auto front = [&](int b0, int nb, Act& xp) {      // chunks [b0, b0 + nb) -> xp (allocated inside when xp is empty)
     c.B = nb;
     float* y1 = A.plain((size_t)nb * T);
@@ -949,7 +984,7 @@ static int chain_run(Ctx& c, const Model* den, const Model* sr, const Model* st,
       st_in = y2;
     }
     c.m = st;
-    AR_TRY(stereo_encode(c, st_in, Ts, xp));
+    AR_TRY(stereo_encode(c, st_in, Ts, xp, fp));
     A.release_plain(sr ? y2 : y1);
     return (int)AR_OK;
   };
@@ -959,11 +994,11 @@ static int chain_run(Ctx& c, const Model* den, const Model* sr, const Model* st,
     Act xp{};
     AR_TRY(front(0, B, xp));
     Act h = A.act(B, 64, Ts);
-    AR_TRY(stereo_scan(c, xp, h, Ts, nullptr, nullptr, w));
+    AR_TRY(stereo_scan(c, xp, h, Ts, nullptr, nullptr, w, fp));
     A.release(xp);
     return stereo_decode(c, h, y, Ts, true);
   }
-  Act xp = A.act(B, 256, Ts);
+  Act xp = A.act(B, fp ? 128 : 256, Ts);
   for (int b0 = 0; b0 < B; b0 += sub_front) {
     Act v = xp;
     v.base = xp.h() + (long long)b0 * xp.bs;
@@ -972,7 +1007,7 @@ static int chain_run(Ctx& c, const Model* den, const Model* sr, const Model* st,
   Act h = A.act(B, 64, Ts);
   c.m = st;
   c.B = B;
-  AR_TRY(stereo_scan(c, xp, h, Ts, nullptr, nullptr, w));
+  AR_TRY(stereo_scan(c, xp, h, Ts, nullptr, nullptr, w, fp));
   A.release(xp);
   for (int b0 = 0; b0 < B; b0 += sub_back) {
     Act v = h;

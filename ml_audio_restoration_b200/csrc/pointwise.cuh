@@ -51,5 +51,9 @@ int launch_c4_to_plain(const Act& in, int B, int C, int T, float* y, cudaStream_
 // h_out: H8 fp16 [B][64 ch]; state_in/out: [B][2][64] (h, c) or nullptr.
 int launch_lstm(const Act& xp, const float* whh, const Act& h_out, int B, int T, const float* state_in, float* state_out,
                 cudaStream_t stream);
+// scan that computes its own input projection on the tensor pipe (lstm_proj.cu): x = encoder output, 128 channels
+void pack_lstm_proj(const float* G, std::vector<uint16_t>& out);
+int launch_lstm_proj(const Act& x, const __half* wih_packed, const float* bias, const float* whh, const Act& h_out, int B, int T,
+                     const float* state_in, float* state_out, cudaStream_t stream);
 
 }  // namespace ar

@@ -1,6 +1,6 @@
 """GPU: direct oracle parity ON THE GEOMETRY THE BENCH TIMES -- batches beyond two sequences per SM (tensor-core LSTM
-`lstm_mmaw_kernel<4>`, tile groups, fused chains all active) and beyond eight per SM (`lstm_mmaw_kernel<8>`, the chain's
-sub-batched conv phases around one scan), full-length 2 s chunks, BASELINE config 4 in full -- plus the LSTM carry
+`lstm_mmaw_kernel<4>`, tile groups, fused chains all active) and beyond eight per SM (`lstm_proj_kernel`: input projection
+inside the scan; the chain's sub-batched conv phases around one scan), full-length 2 s chunks, BASELINE config 4 in full -- plus the LSTM carry
 (`state_in`), the whole-file-exact chunked mode and the dynamic-range envelope of the fp16 storage."""
 import numpy as np
 import pytest
@@ -46,7 +46,7 @@ def test_chain_at_bench_batch_vs_oracle(pipe, state_dicts):
 
 def test_chain_sixteen_chunks_per_sm_vs_oracle(pipe, state_dicts):
     """The bench's own launch: 16 chunks of 44 100 samples per SM (2368 on a B200) in ONE `ar_chain_forward` -- conv phases
-    on sub-batches, one `lstm_mmaw_kernel<8>` scan over all sequences; chunks from every sub-batch meet the oracle."""
+    on sub-batches, one `lstm_proj_kernel` scan over all sequences; chunks from every sub-batch meet the oracle."""
     B, T = 16 * torch.cuda.get_device_properties(0).multi_processor_count, 44100
     free, _ = torch.cuda.mem_get_info()
     if pipe.workspace_bytes(B, T) > 0.9 * free:
@@ -63,7 +63,7 @@ def test_chain_sixteen_chunks_per_sm_vs_oracle(pipe, state_dicts):
 def test_chain_sub_batched_equals_single_batches(pipe, state_dicts):
     """Beyond 8 chunks per SM the chain runs denoiser / super-resolution / encoder and the decoders on sub-batches around one
     scan: same kernels on the same operands per chunk, so the result equals the chain run on slices of at most 8 per SM
-    (only the LSTM kernel differs: 8 instead of 4 sequences per CTA, same MMAs in the same order), and the oracle."""
+    (only the scan differs: it computes the same fp16 pre-activations itself and runs 16 sequences per CTA), and the oracle."""
     B, T = huge_batch(), 1037
     x = make_input(B, T, seed=36)
     xd = x.cuda()
@@ -81,7 +81,7 @@ def test_chain_sub_batched_equals_single_batches(pipe, state_dicts):
 
 @pytest.mark.parametrize("size", ["4-per-cta", "8-per-cta"])
 def test_stereo_tensor_core_lstm_full_length_vs_oracle(state_dicts, size):
-    """StereoSeparator alone at B >= 304 (`lstm_mmaw_kernel<4>`) and B >= 1197 (`lstm_mmaw_kernel<8>`), T = 88 200 (the
+    """StereoSeparator alone at B >= 304 (`lstm_mmaw_kernel<4>`) and B >= 1197 (`lstm_proj_kernel`), T = 88 200 (the
     stage's length in the chain): 88 200 steps against the fp32 oracle DIRECTLY (not via the CUDA-core kernel) -- fp16
     W_hh and fp16 h feedback over the full scan is where drift would show.  Both tolerance clauses."""
     B, T = (big_batch() if size == "4-per-cta" else huge_batch()), 88200
@@ -117,18 +117,28 @@ def test_config4_full_side_vs_oracle(pipe, state_dicts):
     assert_close(ref, y, "config 4: 180 s side, 95 chunks, normalize on, vs oracle")
 
 
-def test_stereo_eight_sequences_per_cta_every_sequence_vs_oracle(state_dicts):
-    """`lstm_mmaw_kernel<8>` (more than 8 sequences per SM): EVERY sequence of a ragged batch (1197 = 149 full CTAs + 5
-    sequences) and ragged length (203 = 25 blocks + 3 steps) against the oracle, outputs and final (h, c)."""
-    m = make_model("stereo", state_dicts["stereo"])
+@pytest.mark.parametrize("fusion", [1, 0], ids=["projection-in-scan", "stored-pre-activations"])
+def test_stereo_beyond_eight_per_sm_every_sequence_vs_oracle(state_dicts, fusion):
+    """More than 8 sequences per SM: the scan kernel that computes the LSTM input projection itself (`lstm_proj_kernel`:
+    tcgen05 GEMM per 8-step block + two 8-sequence recurrence groups per CTA; product path) and, layer by layer,
+    `lstm_mmaw_kernel<8>` on stored pre-activations (cross-check path).  EVERY sequence of a ragged batch (1197 = 74 full
+    CTAs of 16 + 13 sequences) and ragged length (203 = 25 blocks + 3 steps) against the oracle, outputs and final (h, c);
+    the two paths against each other (same fp16 pre-activations => the same recurrence)."""
+    m = make_model("stereo", state_dicts["stereo"], fusion=fusion)
     B, T = huge_batch(), 203
     x = make_input(B, T, seed=37)
     ref, (hn, cn) = oracle.stereo_forward(state_dicts["stereo"], x, return_state=True)
     with torch.no_grad():
         y, st = m.forward_with_state(x.cuda())
-    assert_close(ref, y, f"stereo B={B} T={T} (8 sequences per CTA)")
-    assert_close(hn[0], st[:, 0], "carried h (8 sequences per CTA)", max_abs=1e-3, min_snr=50.0)
-    assert_close(cn[0], st[:, 1], "carried c (8 sequences per CTA)", max_abs=1e-3, min_snr=50.0)
+    assert_close(ref, y, f"stereo B={B} T={T} (beyond 8 sequences per SM, fusion={fusion})")
+    assert_close(hn[0], st[:, 0], "carried h", max_abs=1e-3, min_snr=50.0)
+    assert_close(cn[0], st[:, 1], "carried c", max_abs=1e-3, min_snr=50.0)
+    if fusion == 1:
+        other = make_model("stereo", state_dicts["stereo"], fusion=0)
+        with torch.no_grad():
+            y0, st0 = other.forward_with_state(x.cuda())
+        assert_close(y0, y, "projection inside the scan vs stored pre-activations", max_abs=2e-5, min_snr=90.0)
+        assert_close(st0, st, "final states, projection inside the scan vs stored pre-activations", max_abs=2e-5, min_snr=90.0)
 
 
 @pytest.mark.parametrize("big", [0, 1, 2], ids=["cuda-core-lstm", "tensor-core-lstm-4", "tensor-core-lstm-8"])
