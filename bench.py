@@ -55,7 +55,7 @@ def conv_algorithmic_bytes_per_audio_s(fused_scan=False):
            (128, r)]                         # first transient-detector layer (32 -> 16 padded to 32 columns)
     sr = [(128, r)] * 4 + [(192, r)] * 5 + [(64, r), (64, 2 * r), (128, 2 * r)]
     st = [(192, 2 * r), (384, 2 * r), (512, 2 * r), (512 if fused_scan else 768, 2 * r),   # fused enc1, enc2, enc3, enc4 (+ xproj)
-          (640, 2 * r), (384, 2 * r), (384, 2 * r), (192, 2 * r), (192, 2 * r)]       # dec0 (L+R), dec1 L/R, dec2 L/R
+          (640, 2 * r), (320, 2 * r), (320, 2 * r)]                                    # dec0 (L+R), fused dec1 -> dec2 per side
     return float(sum(b * n for b, n in den + sr + st))
 
 

@@ -3,6 +3,8 @@
 //
 //   (a) k3 dilated -> k1                 the StereoSeparator's `_dilated_block` (stereo_separator.py:49-64)
 //   (b) k3 dilated -> k1 -> k1 (N = 256) the last block + the LSTM input projection behind it (stereo_separator.py:104-106)
+//   (d) k7 -> k7                         two consecutive decoder layers of the StereoSeparator (stereo_separator.py:66-83:
+//                                        128 -> 64 -> 32 per side), tile stride 122
 //   (c) k3 -> k3                         the U-Net's double conv (`_conv_block`, denoiser.py:51-60; max-pool copy fused) and
 //                                        the super-resolution residual block (conv-BN-LReLU-conv-BN + skip,
 //                                        super_resolution.py:104-122; the skip operand is the chain's own input)
@@ -487,8 +489,9 @@ static bool pick_chain_cfg(const ChainParams& cp, ChainCfg& c) {
 }
 
 bool conv_chain_fits(int Cin, int taps, int dil, const int* N, int n_gemms, int taps2) {
-  if (n_gemms < 2 || n_gemms > 3 || taps != 3) return false;
-  if (taps2 != 1 && (taps2 != 3 || n_gemms != 2 || dil != 1)) return false;
+  if (n_gemms < 2 || n_gemms > 3 || (taps != 3 && taps != 7)) return false;
+  if (taps == 7 && taps2 != 7) return false;                                      // k7 only as the k7 -> k7 decoder pair
+  if (taps2 != 1 && (taps2 != taps || n_gemms != 2 || dil != 1)) return false;
   if (n_gemms == 3 && N[0] != N[1]) return false;    // G1 and G2 rotate through the same accumulator buffers
   for (int g = 0; g + 1 < n_gemms; ++g)
     if (N[g] > 128) return false;                     // an intermediate operand is at most 128 channels wide
@@ -512,8 +515,8 @@ int launch_conv_chain(const ChainParams& cp, cudaStream_t stream) {
   AR_CHECK(NG == 2 || NG == 3, AR_ERR_INVALID, "conv_chain: 2 or 3 GEMMs");
   AR_CHECK(p.Cin % 16 == 0 && p.mode == MODE_SAME && p.pool == nullptr && p.res == nullptr, AR_ERR_INVALID, "conv_chain: unsupported first layer");
   AR_CHECK(p.pad_left <= HALO && (p.taps - 1) * p.dil - p.pad_left <= HALO, AR_ERR_INVALID, "conv_chain: conv reach exceeds HALO");
-  AR_CHECK(taps2 == 1 || (taps2 == 3 && NG == 2 && p.taps == 3 && p.dil == 1 && p.pad_left == 1), AR_ERR_INVALID,
-           "conv_chain: a k-tap second stage is implemented for k3 -> k3");
+  AR_CHECK(taps2 == 1 || (taps2 == p.taps && NG == 2 && p.dil == 1 && p.pad_left == (p.taps - 1) / 2), AR_ERR_INVALID,
+           "conv_chain: a k-tap second stage is implemented for k3 -> k3 and k7 -> k7");
   AR_CHECK(p.pad_left + (taps2 - 1) / 2 <= HALO, AR_ERR_INVALID, "conv_chain: combined reach exceeds HALO");
   int nb = 0;
   for (int g = 0; g < NG; ++g) {
@@ -535,7 +538,7 @@ int launch_conv_chain(const ChainParams& cp, cudaStream_t stream) {
   static const Entry table[] = {
       {3, 2, 1, CE_PLAIN, conv_chain_kernel<3, 2, 1, CE_PLAIN>}, {3, 3, 1, CE_PLAIN, conv_chain_kernel<3, 3, 1, CE_PLAIN>},
       {3, 2, 3, CE_PLAIN, conv_chain_kernel<3, 2, 3, CE_PLAIN>}, {3, 2, 3, CE_POOL, conv_chain_kernel<3, 2, 3, CE_POOL>},
-      {3, 2, 3, CE_RES, conv_chain_kernel<3, 2, 3, CE_RES>},
+      {3, 2, 3, CE_RES, conv_chain_kernel<3, 2, 3, CE_RES>},     {7, 2, 7, CE_PLAIN, conv_chain_kernel<7, 2, 7, CE_PLAIN>},
   };
   static DeviceOnce attrs;
   if (attrs.pending()) {

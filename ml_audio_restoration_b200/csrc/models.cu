@@ -615,7 +615,7 @@ static bool can_chain(const Ctx& c, std::initializer_list<const char*> names) {
   // profiles/README_r02.md): 64 -> 128 -> 128 1.97 vs 2.30 ms; 32 -> 64 -> 64 2.40 vs 2.33; 128 -> 64 -> 64 3.28 vs 2.90;
   // 64 -> 32 -> 32 3.55 vs 2.77; super-resolution block 32 -> 32 -> 32 (+ skip) 3.80 vs 2.72 -- with 32 / 64 columns a tile
   // pair is ~100 cycles of MMAs behind a ~2 000-cycle G1 -> E1 -> G2 -> E2 handshake chain, two tiles in flight.
-  if (taps2 > 1 && c.m->fuse < 2 && (N[0] < 128 || N[1] < 128)) return false;
+  if (taps2 == 3 && c.m->fuse < 2 && (N[0] < 128 || N[1] < 128)) return false;
   return true;
 }
 
@@ -905,18 +905,14 @@ static int stereo_decode(Ctx& c, const Act& h, float* y, int T, bool h_owned) {
   Act d0 = A.act(B, 256, T);
   AR_TRY(run_conv(c, "dec0", h, d0));
   if (h_owned) A.release(h);
-  Act d1 = A.act(B, 128, T);
-  ConvOpt o;
-  AR_TRY(run_conv(c, "dec1L", d0, d1, o));
-  o.in_coff8 = 128 / 8; o.out_coff8 = 64 / 8;
-  AR_TRY(run_conv(c, "dec1R", d0, d1, o));
-  A.release(d0);
+  // per side: decoder layers 3 and 6 (128 -> 64 -> 32, both k7) as ONE fused k7 -> k7 launch when the chain kernel has them
+  // (the 64-channel intermediate stays in shared memory), else two launches through a 64-channel tensor
   Act d2 = A.act(B, 64, T);
-  o = ConvOpt();
-  AR_TRY(run_conv(c, "dec2L", d1, d2, o));
-  o.in_coff8 = 64 / 8; o.out_coff8 = 32 / 8;
-  AR_TRY(run_conv(c, "dec2R", d1, d2, o));
-  A.release(d1);
+  ConvOpt o;
+  AR_TRY(run_pair(c, "dec1L", "dec2L", d0, 64, d2, o));
+  o.in_coff8 = 128 / 8; o.out_coff8 = 32 / 8;
+  AR_TRY(run_pair(c, "dec1R", "dec2R", d0, 64, d2, o));
+  A.release(d0);
   if (!A.dry) {
     const int coff[2] = {0, 32 / 8};
     ProfScope ps(CAT_TAIL, c.stream, 2.0 * 448 * (double)B * T);
