@@ -130,7 +130,7 @@ int ar_stereo_forward_window(ar_model_t m, const float* x, float* y, int B, int 
  * Any B is one call.  Up to 8 chunks per SM the three forwards run on the whole batch; beyond that (16 per SM fills
  * the chip with ONE launch of the LSTM scan kernel) the convs run on sub-batches of 8 per SM around a single scan over
  * all B sequences, which then computes the LSTM input projection itself -- ar_chain_workspace_bytes accounts for it
- * (about 68 MB per chunk up to 8 per SM, 45 MB per chunk at 16 per SM). */
+ * (about 68 MB per chunk up to 8 per SM, 54 MB per chunk at 16 per SM: 128 GB for 2368 two-second chunks). */
 int ar_chain_create(ar_model_t denoiser, ar_model_t sr, ar_model_t stereo, ar_chain_t* out);
 void ar_chain_destroy(ar_chain_t c);
 int ar_chain_workspace_bytes(ar_chain_t c, int B, int T, size_t* bytes);
