@@ -30,6 +30,12 @@
 // accumulator is effectively double-buffered without a column more.  (Running G3 as two N = 128 halves through one
 // accumulator to free columns was measured first: E3 of the first half then sits between the halves, period 7 270.)
 //
+// Tile groups: with 32 / 64 output columns a tile is ~100 cycles of MMAs and ~150 cycles of epilogue work behind four mbarrier
+// hand-overs of 400-900 cycles each (G1 -> E1 -> G2 -> E2; pipeline trace: 1 560 cycles per tile pair for the super-resolution
+// block, 2.2 x what its HBM traffic needs).  Narrow k3 chains therefore move G = 2 or 4 CONSECUTIVE tiles per pipeline step:
+// one contiguous run of (G - 1) S + R input rows per channel chunk, G accumulators per buffer in TMEM, G intermediate tiles
+// per shared-memory buffer, one hand-over per group.
+//
 // Warp roles (every stage of the chain has its own issuer and its own epilogue group, so no warp ever waits for a
 // result that depends on work it still has to issue):
 //   warp 0            bulk-copy (TMA) producer: resident weights of all stages, then the activation ring of G1
@@ -59,8 +65,10 @@ struct ChainCfg {
   int kbs, stages, R, nks, stage_bytes;  // activation ring of the first GEMM
   int w_bytes[3], w_off[3];              // resident weight halves per CTA
   int i_off[2], i_bytes[2], nbI[2];      // intermediate operands (output of GEMM g = input of GEMM g+1)
-  int RI;                                // rows of an intermediate operand: 128 + (taps2 - 1)
-  int acc_col[3], nbA[3], acc_n[3];      // TMEM columns: GEMM g buffer b at acc_col[g] + b * acc_n[g]
+  int RI;                                // rows of ONE TILE of an intermediate operand: 128 + (taps2 - 1)
+  int G;                                 // tiles per group: a CTA works on G consecutive tiles per pipeline step (narrow k3 chains)
+  int i_tile[2];                         // bytes of one tile of intermediate operand g (a buffer holds G of them)
+  int acc_col[3], nbA[3], acc_n[3];      // TMEM columns: GEMM g buffer b, tile i at acc_col[g] + b * acc_n[g] + i * N[g]
   int tmem_cols;
   int stage_off, bar_off, bias_off, smem_bytes;
 };
@@ -82,9 +90,12 @@ constexpr int CH_MAX_BUF = 2;
 __device__ __forceinline__ int buf_of(int u, int nb) { return u & (nb - 1); }
 __device__ __forceinline__ uint32_t phase_of(int u, int nb) { return (uint32_t)(u >> (nb >> 1)) & 1u; }   // nb >> 1 == log2(nb) for 1, 2
 
-template <int TAPS, int NG, int TAPS2, int EPI>
+// GRP: compiled with tile groups (cfg.G tiles per pipeline step, narrow k3 chains); false pins G = 1 at compile time so the
+// wide chains keep their register allocation
+template <int TAPS, int NG, int TAPS2, int EPI, bool GRP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ch_threads(NG), 1) __maxnreg__(ch_maxreg(NG))
 conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant__ ChainCfg cfg, int num_pairs) {
+  static_assert(!GRP || (NG == 2 && TAPS == 3), "tile groups are for the narrow two-GEMM k3 chains");
   static_assert(TAPS2 == 1 || NG == 2, "a k-tap second stage is a two-GEMM chain");
   static_assert(EPI == CE_PLAIN || NG == 2, "pool / residual epilogues belong to the two-GEMM chains");
   constexpr int S = TILE_M - (TAPS2 - 1);          // tile stride = outputs per tile
@@ -146,22 +157,24 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tpi = p.tiles_per_item;
-  const int ppi = (tpi + 1) >> 1;                  // tile pairs per batch item
-  const int R = cfg.R;
+  const int tpi = p.tiles_per_item;                // tiles (of S output rows) per batch item
+  const int G = GRP ? cfg.G : 1;                   // tiles per group
+  const int gpi = (tpi + G - 1) / G;               // groups per batch item
+  const int ppi = (gpi + 1) >> 1;                  // group pairs per batch item
+  const int R = cfg.R;                             // input rows of a group's run: (G - 1) S + 128 + (taps - 1) dil
   const int RI = cfg.RI;
   const int pair0 = blockIdx.x >> 1;
   const int pair_step = gridDim.x >> 1;
-  const int n_local = pair0 < num_pairs ? (num_pairs - pair0 + pair_step - 1) / pair_step : 0;   // tile pairs of this cluster
-  // this CTA's tile of pair pi of an item, and the first input row (time index) of its run: tile * S - LEAD - pad_left;
-  // an idle half (odd tile count) re-reads the item's last tile, whose rows then get zeroed
-  auto tile0_of = [&](int pi) { return pi * 2 + (int)rank; };
+  const int n_local = pair0 < num_pairs ? (num_pairs - pair0 + pair_step - 1) / pair_step : 0;   // group pairs of this cluster
+  // this CTA's group of pair pi of an item, and the first input row (time index) of its run: group * G * S - LEAD - pad_left;
+  // an idle half (odd group count) re-reads the item's last group, whose rows then get zeroed
+  auto group_of = [&](int pi) { return pi * 2 + (int)rank; };
   auto run_t0 = [&](int pi) {
-    int tl = tile0_of(pi);
-    if (tl > tpi - 1) tl = tpi - 1;
-    return tl * S - LEAD - p.pad_left;
+    int gl = group_of(pi);
+    if (gl > gpi - 1) gl = gpi - 1;
+    return gl * G * S - LEAD - p.pad_left;
   };
-  // rows of the run that exist in the padded buffer (the last tile of a stride-126 chain may reach past it)
+  // rows of the run that exist in the padded buffer (the last group may reach past it)
   auto run_rows = [&](int t0) {
     const int avail = p.in_Tp - (HALO + t0);
     return R < avail ? R : avail;
@@ -243,7 +256,7 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
       PairIter pit(pair0, pair_step, ppi);
       for (int it = 0; it < n_local; ++it, pit.next()) {
         const int tfirst = run_t0(pit.pi);
-        const bool dead = tile0_of(pit.pi) > tpi - 1;          // no such tiles: contribute zeros
+        const bool dead = group_of(pit.pi) > gpi - 1;          // no such group: contribute zeros
         const bool edge = dead || (tfirst < 0) || (tfirst + R > p.Tin);
         const int buf = buf_of(it, nbA);
         if (leader) {
@@ -252,19 +265,18 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
           tc_fence_after();
         }
         trace_ev1(cp.trace, it, 0);
-        const uint32_t d_tmem = tmem_base + (uint32_t)(cfg.acc_col[0] + buf * cfg.acc_n[0]);
+        const uint32_t d_tmem0 = tmem_base + (uint32_t)(cfg.acc_col[0] + buf * cfg.acc_n[0]);
         uint32_t b_addr = w_addr0;
-        uint32_t accum = 0u;
         for (int ks = 0; ks < cfg.nks; ++ks) {
           mbar_wait(full_bar(s), ph);                          // leader: own rows landed AND the peer's arrive
           if (ks == 0) trace_ev1(cp.trace, it, 8);
-          if (edge) {  // conv zero padding of this CTA's rows (first / last tiles of an item only), incl. rows never loaded
+          if (edge) {  // conv zero padding of this CTA's rows (first / last groups of an item only), incl. rows never loaded
             uint8_t* a_ptr = stage_ptr + s * cfg.stage_bytes;
-            for (int r = 0; r < R; ++r) {
-              const int t = tfirst + r;
-              if (dead || t < 0 || t >= p.Tin)
-                for (int c = 0; c < cfg.kbs * 2; ++c)
-                  *reinterpret_cast<float4*>(a_ptr + (c * R + r) * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int r_lo = dead ? R : (tfirst < 0 ? -tfirst : 0);                 // rows [0, r_lo) lie before the signal
+            const int r_hi = dead ? R : (p.Tin - tfirst < R ? p.Tin - tfirst : R);  // rows [r_hi, R) behind it
+            for (int c = 0; c < cfg.kbs * 2; ++c) {
+              for (int r = 0; r < r_lo; ++r) *reinterpret_cast<float4*>(a_ptr + (c * R + r) * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int r = r_hi < 0 ? 0 : r_hi; r < R; ++r) *reinterpret_cast<float4*>(a_ptr + (c * R + r) * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             fence_async_smem();
           }
@@ -272,16 +284,21 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
             if (edge) mbar_arrive_remote_release(full0_leader + 8u * s);   // zero-padding writes must be visible
             else mbar_arrive_remote(full0_leader + 8u * s);
           } else {
-            uint32_t a_addr = (stage_base + s * cfg.stage_bytes) >> 4;
-            for (int kb = 0; kb < cfg.kbs; ++kb) {
+            const uint32_t a_stage = (stage_base + s * cfg.stage_bytes) >> 4;
+            for (int i = 0; i < G; ++i) {                      // the tiles of the group: same stage, rows shifted by i * S
+              uint32_t a_addr = a_stage + (uint32_t)(i * S);
+              uint32_t bw = b_addr;
+              const uint32_t d_tmem = d_tmem0 + (uint32_t)(i * N1);
+              for (int kb = 0; kb < cfg.kbs; ++kb) {
 #pragma unroll
-              for (int j = 0; j < TAPS; ++j)
-                umma2_f16(d_tmem, a_desc_hi | (uint64_t)(a_addr + (uint32_t)j * dil_u),
-                          b_desc_hi | (uint64_t)(b_addr + (uint32_t)j * b_step), idesc, (j == 0) ? accum : 1u);
-              accum = 1u;
-              b_addr += (uint32_t)TAPS * b_step;
-              a_addr += a_step;
+                for (int j = 0; j < TAPS; ++j)
+                  umma2_f16(d_tmem, a_desc_hi | (uint64_t)(a_addr + (uint32_t)j * dil_u),
+                            b_desc_hi | (uint64_t)(bw + (uint32_t)j * b_step), idesc, (ks | kb | j) ? 1u : 0u);
+                bw += (uint32_t)TAPS * b_step;
+                a_addr += a_step;
+              }
             }
+            b_addr += (uint32_t)(cfg.kbs * TAPS) * b_step;
             umma_commit2(empty_bar(s));
             if (ks == cfg.nks - 1) umma_commit2(tfull_bar(0, buf));
           }
@@ -315,15 +332,17 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
         if (!(ROTATE && g == 1)) mbar_wait(tempty_bar(g, buf), phase_of(it, nbA) ^ 1u);
         tc_fence_after();
         trace_ev1(cp.trace, it, g == 1 ? 2 : 10);
-        const uint32_t d_tmem = tmem_base + (uint32_t)(cfg.acc_col[g] + buf * cfg.acc_n[g]);
-        uint32_t a_addr = (sbase + cfg.i_off[g - 1] + bi * cfg.i_bytes[g - 1]) >> 4;
-        uint32_t b_addr = w_addr0;
-        for (int kb = 0; kb < K / 16; ++kb) {
-          for (int j = 0; j < taps_g; ++j)
-            umma2_f16(d_tmem, a_desc_hi | (uint64_t)(a_addr + (uint32_t)j), b_desc_hi | (uint64_t)(b_addr + (uint32_t)j * b_step), idesc,
-                      (kb | j) ? 1u : 0u);
-          a_addr += (uint32_t)(2 * RI);
-          b_addr += (uint32_t)taps_g * b_step;
+        for (int i = 0; i < G; ++i) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(cfg.acc_col[g] + buf * cfg.acc_n[g] + i * Ng);
+          uint32_t a_addr = (sbase + cfg.i_off[g - 1] + bi * cfg.i_bytes[g - 1] + i * cfg.i_tile[g - 1]) >> 4;
+          uint32_t b_addr = w_addr0;
+          for (int kb = 0; kb < K / 16; ++kb) {
+            for (int j = 0; j < taps_g; ++j)
+              umma2_f16(d_tmem, a_desc_hi | (uint64_t)(a_addr + (uint32_t)j), b_desc_hi | (uint64_t)(b_addr + (uint32_t)j * b_step), idesc,
+                        (kb | j) ? 1u : 0u);
+            a_addr += (uint32_t)(2 * RI);
+            b_addr += (uint32_t)taps_g * b_step;
+          }
         }
         umma_commit2(iempty_bar(g - 1, bi));                // both CTAs may overwrite this operand buffer
         umma_commit2(tfull_bar(g, buf));
@@ -359,31 +378,36 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
       for (int it = 0; it < n_local; ++it, pit.next()) {
         const int buf = buf_of(it, nbA);
         const int bi = buf_of(it, nbI);
-        // a k-tap next stage pads with ZEROS outside [0, T): intermediate rows at those times are not conv outputs
-        bool zero_row = false;
-        if (TAPS2 > 1) {
-          const int tl = tile0_of(pit.pi);
-          const int t = tl * S - LEAD + q * 32 + lane;
-          zero_row = t < 0 || t >= p.Tin || tl > tpi - 1;
-        }
         mbar_wait(tfull_bar(g, buf), phase_of(it, nbA));
         mbar_wait(iempty_bar(g, bi), phase_of(it, nbI) ^ 1u);   // GEMM g+1 of the previous user has read the buffer
         tc_fence_after();
         if (tracer) trace_ev(cp.trace, it, g == 0 ? 4 : 12);
-        const uint32_t taddr = taddr0 + (uint32_t)(buf * cfg.acc_n[g]);
-        uint8_t* const dst = smem + cfg.i_off[g] + bi * cfg.i_bytes[g] + (q * 32 + lane) * 16;
-        if (active)
-          tmem_stream<16>(taddr, wcols, [&](int cb, const uint32_t (&a)[16], int ncol) {
+        const int gl = group_of(pit.pi);
+        // a k-tap next stage pads with ZEROS outside [0, T): intermediate rows at those times are not conv outputs
+        auto zero_row_of = [&](int i) {
+          if (TAPS2 == 1) return false;
+          const int t = (gl * G + i) * S - LEAD + q * 32 + lane;
+          return t < 0 || t >= p.Tin || gl > gpi - 1;
+        };
+        auto taddr_of = [&](int i) { return taddr0 + (uint32_t)(buf * cfg.acc_n[g] + i * Ng); };
+        auto dst_of = [&](int i) { return smem + cfg.i_off[g] + bi * cfg.i_bytes[g] + i * cfg.i_tile[g] + (q * 32 + lane) * 16; };
+        auto put = [&](int i, int cb, const uint32_t* a, int ncol) {     // <= 16 columns of tile i -> operand rows
+          const bool zr = zero_row_of(i);
+          uint8_t* const dst = dst_of(i);
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              if (8 * c < ncol) {
-                const int chunk = ((col_lo + cb) >> 3) + c;
-                uint4 v = epi_chunk8<false>(a + 8 * c, bw + cb + 8 * c, ca, cbk, make_uint4(0u, 0u, 0u, 0u));
-                if (TAPS2 > 1 && zero_row) v = make_uint4(0u, 0u, 0u, 0u);
-                *reinterpret_cast<uint4*>(dst + chunk * (RI * 16)) = v;
-              }
+          for (int c = 0; c < 2; ++c) {
+            if (8 * c < ncol) {
+              const int chunk = ((col_lo + cb) >> 3) + c;
+              uint4 v = epi_chunk8<false>(a + 8 * c, bw + cb + 8 * c, ca, cbk, make_uint4(0u, 0u, 0u, 0u));
+              if (zr) v = make_uint4(0u, 0u, 0u, 0u);
+              *reinterpret_cast<uint4*>(dst + chunk * (RI * 16)) = v;
             }
-          });
+          }
+        };
+        if (active) {
+          for (int i = 0; i < G; ++i)
+            tmem_stream<16>(taddr_of(i), wcols, [&](int cb, const uint32_t (&a)[16], int ncol) { put(i, cb, a, ncol); });
+        }
         tc_fence_before();
         fence_async_smem();                                    // generic-proxy writes -> visible to the tensor core's async proxy
         __syncwarp();
@@ -398,22 +422,31 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
       constexpr bool POOL = EPI == CE_POOL, RES = EPI == CE_RES;
       PairIter pit(pair0, pair_step, ppi);
       for (int it = 0; it < n_local; ++it, pit.next()) {
-        const int tl_in_item = tile0_of(pit.pi);
+        const int gl = group_of(pit.pi);
         const int u = q * 32 + lane;                           // output row of the tile
-        const int t = tl_in_item * S + u;                      // >= Tin for a dead tile => every store is masked
-        EpiRow row = epi_row<MODE_SAME, POOL, RES>(cp.pl, pit.b, t, col_lo);
-        if (TAPS2 > 1) {                                       // rows S .. 127 of a stride-S tile have no output
-          row.ok0 = row.ok0 && u < S;
-          row.pok = row.pok && u < S;
-        }
         const int buf = buf_of(it, nbA);
-        uint4 resv[2];
-        epi_prefetch_res<RES>(row, active, resv);              // residual rows (the chain's own input: L2 hits) before the wait
-        mbar_wait(tfull_bar(g, buf), phase_of(it, nbA));
-        tc_fence_after();
-        if (tracer) trace_ev(cp.trace, it, 6);
-        if (active)
-          epi_store<MODE_SAME, POOL, RES, 16>(row, s_bias + bias_off + col_lo, taddr0 + (uint32_t)(buf * cfg.acc_n[g]), wcols, slope, resv);
+        auto row_of = [&](int i) {
+          const int t = (gl * G + i) * S + u;                  // >= Tin for a dead tile => every store is masked
+          EpiRow row = epi_row<MODE_SAME, POOL, RES>(cp.pl, pit.b, t, col_lo);
+          if (TAPS2 > 1) {                                     // rows S .. 127 of a stride-S tile have no output
+            row.ok0 = row.ok0 && u < S;
+            row.pok = row.pok && u < S;
+          }
+          return row;
+        };
+        auto taddr_of = [&](int i) { return taddr0 + (uint32_t)(buf * cfg.acc_n[g] + i * Ng); };
+        const float* const bias_w = s_bias + bias_off + col_lo;
+        for (int i = 0; i < G; ++i) {
+          const EpiRow row = row_of(i);
+          uint4 resv[2];
+          epi_prefetch_res<RES>(row, active, resv);            // residual rows (the chain's own input: L2 hits) before the wait
+          if (i == 0) {
+            mbar_wait(tfull_bar(g, buf), phase_of(it, nbA));
+            tc_fence_after();
+            if (tracer) trace_ev(cp.trace, it, 6);
+          }
+          if (active) epi_store<MODE_SAME, POOL, RES, 16>(row, bias_w, taddr_of(i), wcols, slope, resv);
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(tempty0_leader + 8u * buf);
@@ -431,57 +464,70 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
 // ----------------------------------------------------------------------------- host side
 int chain_tile_stride(int taps2) { return TILE_M - ((taps2 > 1 ? taps2 : 1) - 1); }
 
+// tiles per group for a chain: narrow k3 chains (every GEMM at most 64 columns wide) take as many as TMEM allows, up to 4
+static int chain_group_tiles(const ChainParams& cp) {
+  if (cp.n_gemms != 2 || cp.p.taps != 3 || cp.N[0] > 64 || cp.N[1] > 64) return 1;
+  int G = 4;
+  while (G > 1 && 2 * G * (cp.N[0] + cp.N[1]) > 512) G >>= 1;
+  return G;
+}
+
 static bool pick_chain_cfg(const ChainParams& cp, ChainCfg& c) {
   const ConvParams& p = cp.p;
   const int NG = cp.n_gemms;
   const int taps2 = cp.taps2 > 1 ? cp.taps2 : 1;
-  c.R = TILE_M + (p.taps - 1) * p.dil;
-  c.RI = TILE_M + (taps2 - 1);
-  int off = 0, cols = 0;
-  for (int g = 0; g < NG; ++g) {
-    const int K = g == 0 ? p.Cin * p.taps : cp.N[g - 1] * (g == 1 ? taps2 : 1);
-    c.w_bytes[g] = K * (cp.N[g] / 2) * 2;
-    c.w_off[g] = off;
-    off += (c.w_bytes[g] + 1023) / 1024 * 1024;
-    // two GEMMs: both accumulators double-buffered; three GEMMs: G1 and G2 rotate through the same two buffers, G3 single
-    c.nbA[g] = g == 2 ? 1 : 2;
-    c.acc_n[g] = cp.N[g];
-    if (NG == 3 && g == 1) { c.acc_col[1] = c.acc_col[0]; continue; }
-    c.acc_col[g] = cols;
-    cols += c.nbA[g] * c.acc_n[g];
-  }
-  if (cols > 512) return false;
-  int tc = 32;
-  while (tc < cols) tc <<= 1;
-  c.tmem_cols = tc;
-  const int w_end = off;
-  // Every stage costs the issuer a barrier round trip (~200 cycles) and the tensor pipe's queue is only ~6 MMAs deep, so
-  // stages are as large as still leaves >= 4 of them (the L2 prefetch, not the ring, covers HBM latency); the
-  // intermediate operand is double-buffered when that still fits.
-  for (int kbs = 4; kbs >= 1; kbs >>= 1) {
-    if (p.Cin % (16 * kbs)) continue;
-    for (int nbi = (NG == 2 ? 2 : 1); nbi >= 1; nbi >>= 1) {
-      off = w_end;
-      for (int g = 0; g < NG - 1; ++g) {
-        c.nbI[g] = nbi;
-        c.i_bytes[g] = (cp.N[g] / 8) * c.RI * 16;
-        c.i_off[g] = off;
-        off += c.nbI[g] * c.i_bytes[g];
-      }
-      c.stage_off = off;
-      const int room = conv_smem_budget() - CH_BAR_BYTES - CH_BIAS_BYTES - off;
-      c.kbs = kbs;
-      c.stage_bytes = kbs * 2 * c.R * 16;
-      int stages = room / c.stage_bytes;
-      if (stages > CH_MAX_STAGES) stages = CH_MAX_STAGES;
-      if (stages >= 4 || (kbs == 1 && stages >= 2)) {
-        c.stages = stages;
-        c.nks = p.Cin / (16 * kbs);
-        c.bar_off = c.stage_off + stages * c.stage_bytes;
-        c.bar_off = (c.bar_off + 15) / 16 * 16;
-        c.bias_off = c.bar_off + CH_BAR_BYTES;
-        c.smem_bytes = c.bias_off + CH_BIAS_BYTES;
-        return true;
+  const int S = chain_tile_stride(taps2);
+  for (int G = chain_group_tiles(cp); G >= 1; G >>= 1) {
+    c.G = G;
+    c.R = (G - 1) * S + TILE_M + (p.taps - 1) * p.dil;
+    c.RI = TILE_M + (taps2 - 1);
+    int off = 0, cols = 0;
+    for (int g = 0; g < NG; ++g) {
+      const int K = g == 0 ? p.Cin * p.taps : cp.N[g - 1] * (g == 1 ? taps2 : 1);
+      c.w_bytes[g] = K * (cp.N[g] / 2) * 2;
+      c.w_off[g] = off;
+      off += (c.w_bytes[g] + 1023) / 1024 * 1024;
+      // two GEMMs: both accumulators double-buffered; three GEMMs: G1 and G2 rotate through the same two buffers, G3 single
+      c.nbA[g] = g == 2 ? 1 : 2;
+      c.acc_n[g] = G * cp.N[g];
+      if (NG == 3 && g == 1) { c.acc_col[1] = c.acc_col[0]; continue; }
+      c.acc_col[g] = cols;
+      cols += c.nbA[g] * c.acc_n[g];
+    }
+    if (cols > 512) continue;
+    int tc = 32;
+    while (tc < cols) tc <<= 1;
+    c.tmem_cols = tc;
+    const int w_end = off;
+    // Every stage costs the issuer a barrier round trip (~200 cycles) and the tensor pipe's queue is only ~6 MMAs deep, so
+    // stages are as large as still leaves >= 4 of them (the L2 prefetch, not the ring, covers HBM latency); the
+    // intermediate operand is double-buffered when that still fits.
+    for (int kbs = 4; kbs >= 1; kbs >>= 1) {
+      if (p.Cin % (16 * kbs)) continue;
+      for (int nbi = (NG == 2 ? 2 : 1); nbi >= 1; nbi >>= 1) {
+        off = w_end;
+        for (int g = 0; g < NG - 1; ++g) {
+          c.nbI[g] = nbi;
+          c.i_tile[g] = (cp.N[g] / 8) * c.RI * 16;
+          c.i_bytes[g] = G * c.i_tile[g];
+          c.i_off[g] = off;
+          off += c.nbI[g] * c.i_bytes[g];
+        }
+        c.stage_off = off;
+        const int room = conv_smem_budget() - CH_BAR_BYTES - CH_BIAS_BYTES - off;
+        c.kbs = kbs;
+        c.stage_bytes = kbs * 2 * c.R * 16;
+        int stages = room / c.stage_bytes;
+        if (stages > CH_MAX_STAGES) stages = CH_MAX_STAGES;
+        if (stages >= 4 || (kbs == 1 && stages >= 2)) {
+          c.stages = stages;
+          c.nks = p.Cin / (16 * kbs);
+          c.bar_off = c.stage_off + stages * c.stage_bytes;
+          c.bar_off = (c.bar_off + 15) / 16 * 16;
+          c.bias_off = c.bar_off + CH_BAR_BYTES;
+          c.smem_bytes = c.bias_off + CH_BIAS_BYTES;
+          return true;
+        }
       }
     }
   }
@@ -533,12 +579,15 @@ int launch_conv_chain(const ChainParams& cp, cudaStream_t stream) {
            "conv_chain: tiles_per_item does not match the tile stride");
   ChainCfg cfg;
   AR_CHECK(pick_chain_cfg(cp, cfg), AR_ERR_INVALID, "conv_chain: no configuration fits shared memory / TMEM");
+  AR_CHECK(!cp.pl.out_tblock || (cfg.G == 1 && cp.N[NG - 1] > 32), AR_ERR_INVALID, "conv_chain: time-blocked output only for wide ungrouped chains");
   using Kernel = void (*)(ChainParams, ChainCfg, int);
-  struct Entry { int taps, ng, taps2, epi; Kernel k; };
+  struct Entry { int taps, ng, taps2, epi, grp; Kernel k; };
   static const Entry table[] = {
-      {3, 2, 1, CE_PLAIN, conv_chain_kernel<3, 2, 1, CE_PLAIN>}, {3, 3, 1, CE_PLAIN, conv_chain_kernel<3, 3, 1, CE_PLAIN>},
-      {3, 2, 3, CE_PLAIN, conv_chain_kernel<3, 2, 3, CE_PLAIN>}, {3, 2, 3, CE_POOL, conv_chain_kernel<3, 2, 3, CE_POOL>},
-      {3, 2, 3, CE_RES, conv_chain_kernel<3, 2, 3, CE_RES>},     {7, 2, 7, CE_PLAIN, conv_chain_kernel<7, 2, 7, CE_PLAIN>},
+      {3, 2, 1, CE_PLAIN, 0, conv_chain_kernel<3, 2, 1, CE_PLAIN, false>}, {3, 3, 1, CE_PLAIN, 0, conv_chain_kernel<3, 3, 1, CE_PLAIN, false>},
+      {3, 2, 3, CE_PLAIN, 0, conv_chain_kernel<3, 2, 3, CE_PLAIN, false>}, {3, 2, 3, CE_POOL, 0, conv_chain_kernel<3, 2, 3, CE_POOL, false>},
+      {3, 2, 3, CE_RES, 0, conv_chain_kernel<3, 2, 3, CE_RES, false>},     {7, 2, 7, CE_PLAIN, 0, conv_chain_kernel<7, 2, 7, CE_PLAIN, false>},
+      {3, 2, 1, CE_PLAIN, 1, conv_chain_kernel<3, 2, 1, CE_PLAIN, true>},  {3, 2, 3, CE_PLAIN, 1, conv_chain_kernel<3, 2, 3, CE_PLAIN, true>},
+      {3, 2, 3, CE_POOL, 1, conv_chain_kernel<3, 2, 3, CE_POOL, true>},    {3, 2, 3, CE_RES, 1, conv_chain_kernel<3, 2, 3, CE_RES, true>},
   };
   static DeviceOnce attrs;
   if (attrs.pending()) {
@@ -547,9 +596,10 @@ int launch_conv_chain(const ChainParams& cp, cudaStream_t stream) {
   }
   Kernel kernel = nullptr;
   for (const Entry& e : table)
-    if (e.taps == p.taps && e.ng == NG && e.taps2 == taps2 && e.epi == epi) kernel = e.k;
+    if (e.taps == p.taps && e.ng == NG && e.taps2 == taps2 && e.epi == epi && e.grp == (cfg.G > 1 ? 1 : 0)) kernel = e.k;
   AR_CHECK(kernel != nullptr, AR_ERR_INVALID, "conv_chain: no kernel instantiated for this (taps, stages, epilogue) combination");
-  const int ppi = (p.tiles_per_item + 1) / 2;
+  const int gpi = (p.tiles_per_item + cfg.G - 1) / cfg.G;      // tile groups per item; a cluster takes two of them per step
+  const int ppi = (gpi + 1) / 2;
   const int num_pairs = p.B * ppi;
   int groups = sm_count() / 2;
   if (groups > num_pairs) groups = num_pairs;

@@ -591,7 +591,7 @@ static int run_conv(Ctx& c, const std::string& name, const Act& in, const Act& o
 // `_dilated_block`, stereo_separator.py:49-64, and the LSTM input projection behind the last one) or one k3 follow-up (the
 // U-Net double conv, denoiser.py:51-60, and the super-resolution residual block, super_resolution.py:104-122).  `o`
 // describes the LAST stage's output (lrelu, layout, pool copy, residual operand); intermediate stages apply LeakyReLU.
-static bool can_chain(const Ctx& c, std::initializer_list<const char*> names) {
+static bool can_chain(const Ctx& c, std::initializer_list<const char*> names, bool residual = false) {
   if (!c.m->fuse || c.m->audit || c.m->engine != AR_ENGINE_UMMA) return false;   // the audit looks at every intermediate
   bool first = true;
   int prevN = 0, Cin = 0, taps = 0, dil = 0, taps2 = 1, N[3] = {0, 0, 0}, ng = 0;
@@ -611,11 +611,11 @@ static bool can_chain(const Ctx& c, std::initializer_list<const char*> names) {
     first = false;
   }
   if (!conv_chain_fits(Cin, taps, dil, N, ng, taps2)) return false;
-  // k3 -> k3 pairs (tile stride 126) pay off only for wide layers.  Per 1184-chunk step, fused vs two launches (ncu,
-  // profiles/README_r02.md): 64 -> 128 -> 128 1.97 vs 2.30 ms; 32 -> 64 -> 64 2.40 vs 2.33; 128 -> 64 -> 64 3.28 vs 2.90;
-  // 64 -> 32 -> 32 3.55 vs 2.77; super-resolution block 32 -> 32 -> 32 (+ skip) 3.80 vs 2.72 -- with 32 / 64 columns a tile
-  // pair is ~100 cycles of MMAs behind a ~2 000-cycle G1 -> E1 -> G2 -> E2 handshake chain, two tiles in flight.
-  if (taps2 == 3 && c.m->fuse < 2 && (N[0] < 128 || N[1] < 128)) return false;
+  // k3 -> k3 pairs (tile stride 126; tile groups of 2 / 4 for the narrow ones): every U-Net double conv is faster fused than
+  // as two launches (per 1184-chunk step, ncu: 32 -> 64 -> 64 + pool 1.77 vs 2.37 ms, 64 -> 128 -> 128 + pool 1.90 vs 2.40,
+  // 128 -> 64 -> 64 2.62 vs 2.86, 64 -> 32 -> 32 2.14 vs 2.77).  The super-resolution block (32 -> 32 -> 32 + skip) is not: its
+  // residual epilogue reads the skip rows per tile behind the accumulator wait (3.8 vs 2.7 ms; profiles/README_r02.md).
+  if (taps2 == 3 && c.m->fuse < 2 && residual) return false;
   return true;
 }
 
@@ -663,7 +663,7 @@ static int run_chain(Ctx& c, std::initializer_list<const char*> names, const Act
 
 // A double conv (first -> second) through the fused k3 -> k3 chain when it fits, else as two launches through `mid`.
 static int run_pair(Ctx& c, const char* first, const char* second, const Act& in, int mid_channels, const Act& out, const ConvOpt& o = ConvOpt()) {
-  if (can_chain(c, {first, second})) {
+  if (can_chain(c, {first, second}, o.res != nullptr)) {
     ConvOpt oc = o;
     return run_chain(c, {first, second}, in, out, oc);
   }

@@ -173,29 +173,35 @@ __device__ __forceinline__ void tmem_stream(uint32_t taddr, int wcols, F&& f) {
   }
 }
 
+// one block of W accumulator columns (already in registers) -> bias / activation / residual -> stores of this thread's row
+template <int MODE, bool POOL, bool RES, int W>
+__device__ __forceinline__ void epi_store_block(const EpiRow& r, const float* s_bias_w, int cb0, const uint32_t (&a)[W], int ncol,
+                                                float ca, float cb, const uint4 (&resv)[2]) {
+#pragma unroll
+  for (int c = 0; c < W / 8; ++c) {
+    if (8 * c < ncol) {
+      const int ch = (cb0 >> 3) + c;               // 8-column chunk index within this warp's range
+      const uint4 packed = epi_chunk8<RES>(a + 8 * c, s_bias_w + cb0 + 8 * c, ca, cb, resv[ch & 1]);
+      if (r.ok0) *reinterpret_cast<uint4*>(r.o0 + (long long)ch * r.ostride) = packed;
+      if (MODE == MODE_INTERLEAVE2) {
+        if (r.ok1) *reinterpret_cast<uint4*>(r.o1 + (long long)ch * r.ostride) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      if (POOL) {  // MaxPool1d(2,2), floor: rows (t, t+1) live in neighbouring lanes; max of rounded == rounded max
+        float q[8], m[8];
+        unpack_half8(packed, q);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = fmaxf(q[i], __shfl_down_sync(0xffffffffu, q[i], 1));
+        if (r.pok) *reinterpret_cast<uint4*>(r.prow + (long long)ch * r.pstride) = pack_half8(m);
+      }
+    }
+  }
+}
 template <int MODE, bool POOL, bool RES, int W = 32>
 __device__ __forceinline__ void epi_store(const EpiRow& r, const float* s_bias_w /* bias of this warp's first column */, uint32_t taddr,
                                           int wcols, float slope, const uint4 (&resv)[2]) {
   const float ca = 0.5f * (1.0f + slope), cb = 0.5f * (1.0f - slope);
   tmem_stream<W>(taddr, wcols, [&](int cb0, const uint32_t (&a)[W], int ncol) {
-#pragma unroll
-    for (int c = 0; c < W / 8; ++c) {
-      if (8 * c < ncol) {
-        const int ch = (cb0 >> 3) + c;               // 8-column chunk index within this warp's range
-        const uint4 packed = epi_chunk8<RES>(a + 8 * c, s_bias_w + cb0 + 8 * c, ca, cb, resv[ch & 1]);
-        if (r.ok0) *reinterpret_cast<uint4*>(r.o0 + (long long)ch * r.ostride) = packed;
-        if (MODE == MODE_INTERLEAVE2) {
-          if (r.ok1) *reinterpret_cast<uint4*>(r.o1 + (long long)ch * r.ostride) = make_uint4(0u, 0u, 0u, 0u);
-        }
-        if (POOL) {  // MaxPool1d(2,2), floor: rows (t, t+1) live in neighbouring lanes; max of rounded == rounded max
-          float q[8], m[8];
-          unpack_half8(packed, q);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) m[i] = fmaxf(q[i], __shfl_down_sync(0xffffffffu, q[i], 1));
-          if (r.pok) *reinterpret_cast<uint4*>(r.prow + (long long)ch * r.pstride) = pack_half8(m);
-        }
-      }
-    }
+    epi_store_block<MODE, POOL, RES, W>(r, s_bias_w, cb0, a, ncol, ca, cb, resv);
   });
 }
 
