@@ -337,9 +337,16 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
           uint32_t a_addr = (sbase + cfg.i_off[g - 1] + bi * cfg.i_bytes[g - 1] + i * cfg.i_tile[g - 1]) >> 4;
           uint32_t b_addr = w_addr0;
           for (int kb = 0; kb < K / 16; ++kb) {
-            for (int j = 0; j < taps_g; ++j)
-              umma2_f16(d_tmem, a_desc_hi | (uint64_t)(a_addr + (uint32_t)j), b_desc_hi | (uint64_t)(b_addr + (uint32_t)j * b_step), idesc,
-                        (kb | j) ? 1u : 0u);
+            if (NG == 2) {                                     // the second GEMM of a two-GEMM chain: taps known at compile time
+#pragma unroll
+              for (int j = 0; j < TAPS2; ++j)
+                umma2_f16(d_tmem, a_desc_hi | (uint64_t)(a_addr + (uint32_t)j), b_desc_hi | (uint64_t)(b_addr + (uint32_t)j * b_step), idesc,
+                          (kb | j) ? 1u : 0u);
+            } else {
+              for (int j = 0; j < taps_g; ++j)
+                umma2_f16(d_tmem, a_desc_hi | (uint64_t)(a_addr + (uint32_t)j), b_desc_hi | (uint64_t)(b_addr + (uint32_t)j * b_step), idesc,
+                          (kb | j) ? 1u : 0u);
+            }
             a_addr += (uint32_t)(2 * RI);
             b_addr += (uint32_t)taps_g * b_step;
           }
@@ -404,7 +411,18 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
             }
           }
         };
-        if (active) {
+        if (GRP && active && wcols == 16) {
+          // 16 columns per warp = ONE TMEM load per tile: two tiles of the group are loaded before the wait, or every tile pays
+          // a full load latency for ~40 instructions of work
+          for (int i = 0; i < G; i += 2) {
+            uint32_t a0[16], a1[16];
+            tmem_ld16_nowait(taddr_of(i), a0);
+            if (i + 1 < G) tmem_ld16_nowait(taddr_of(i + 1), a1);
+            tmem_wait_ld();
+            put(i, 0, a0, 16);
+            if (i + 1 < G) put(i + 1, 0, a1, 16);
+          }
+        } else if (active) {
           for (int i = 0; i < G; ++i)
             tmem_stream<16>(taddr_of(i), wcols, [&](int cb, const uint32_t (&a)[16], int ncol) { put(i, cb, a, ncol); });
         }
@@ -436,16 +454,50 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
         };
         auto taddr_of = [&](int i) { return taddr0 + (uint32_t)(buf * cfg.acc_n[g] + i * Ng); };
         const float* const bias_w = s_bias + bias_off + col_lo;
-        for (int i = 0; i < G; ++i) {
-          const EpiRow row = row_of(i);
-          uint4 resv[2];
-          epi_prefetch_res<RES>(row, active, resv);            // residual rows (the chain's own input: L2 hits) before the wait
-          if (i == 0) {
-            mbar_wait(tfull_bar(g, buf), phase_of(it, nbA));
-            tc_fence_after();
-            if (tracer) trace_ev(cp.trace, it, 6);
+        if (GRP && RES) {
+          // Residual rows of ALL tiles of the group (the chain's own input: L2 hits, ~700 cycles) are requested before the
+          // accumulator is awaited; fetched tile by tile behind the wait they cost a load latency per tile (pipeline trace:
+          // 3 900 cycles of epilogue per 4-tile group, the slowest stage of the chain).  Tile i of the group is tile 0 shifted
+          // by i * S rows of the same item: one address computation, per tile only the masks.
+          const EpiRow base = row_of(0);
+          const int t0 = gl * G * S + u;
+          uint4 res[4][2];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+              res[i][c] = (i < G && active && t0 + i * S < cp.pl.Tin) ? *reinterpret_cast<const uint4*>(base.rrow + (long long)i * S * 8 + c * base.rstride)
+                                                                     : make_uint4(0u, 0u, 0u, 0u);
           }
-          if (active) epi_store<MODE_SAME, POOL, RES, 16>(row, bias_w, taddr_of(i), wcols, slope, resv);
+          mbar_wait(tfull_bar(g, buf), phase_of(it, nbA));
+          tc_fence_after();
+          if (tracer) trace_ev(cp.trace, it, 6);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (i < G && active) {
+              EpiRow r = base;
+              const int t = t0 + i * S;
+              r.in_ok = t < cp.pl.Tin;
+              r.ok0 = r.in_ok && t < cp.pl.Tout && u < S;
+              r.o0 += (long long)i * S * 16;
+              uint32_t a[16];                                  // the residual epilogue has <= 32 columns: 16 per warp, one load
+              tmem_ld16_nowait(taddr_of(i), a);
+              tmem_wait_ld();
+              epi_store_block<MODE_SAME, POOL, RES, 16>(r, bias_w, 0, a, 16, 0.5f * (1.0f + slope), 0.5f * (1.0f - slope), res[i]);
+            }
+          }
+        } else {
+          for (int i = 0; i < G; ++i) {
+            const EpiRow row = row_of(i);
+            uint4 resv[2];
+            epi_prefetch_res<RES>(row, active, resv);          // residual rows (the chain's own input: L2 hits) before the wait
+            if (i == 0) {
+              mbar_wait(tfull_bar(g, buf), phase_of(it, nbA));
+              tc_fence_after();
+              if (tracer) trace_ev(cp.trace, it, 6);
+            }
+            if (active) epi_store<MODE_SAME, POOL, RES, 16>(row, bias_w, taddr_of(i), wcols, slope, resv);
+          }
         }
         tc_fence_before();
         __syncwarp();

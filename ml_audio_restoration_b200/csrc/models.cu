@@ -611,11 +611,12 @@ static bool can_chain(const Ctx& c, std::initializer_list<const char*> names, bo
     first = false;
   }
   if (!conv_chain_fits(Cin, taps, dil, N, ng, taps2)) return false;
-  // k3 -> k3 pairs (tile stride 126; tile groups of 2 / 4 for the narrow ones): every U-Net double conv is faster fused than
-  // as two launches (per 1184-chunk step, ncu: 32 -> 64 -> 64 + pool 1.77 vs 2.37 ms, 64 -> 128 -> 128 + pool 1.90 vs 2.40,
-  // 128 -> 64 -> 64 2.62 vs 2.86, 64 -> 32 -> 32 2.14 vs 2.77).  The super-resolution block (32 -> 32 -> 32 + skip) is not: its
-  // residual epilogue reads the skip rows per tile behind the accumulator wait (3.8 vs 2.7 ms; profiles/README_r02.md).
-  if (taps2 == 3 && c.m->fuse < 2 && residual) return false;
+  // k3 -> k3 pairs (tile stride 126; tile groups of 2 / 4 for the narrow ones) are all faster fused than as two launches
+  // (per 1184-chunk step, ncu: 32 -> 64 -> 64 + pool 1.77 vs 2.37 ms, 64 -> 128 -> 128 + pool 1.90 vs 2.40, 128 -> 64 -> 64 2.62 vs
+  // 2.86, 64 -> 32 -> 32 2.14 vs 2.77; the super-resolution block 32 -> 32 -> 32 + skip ~1.9 vs 2.7 once its residual rows are
+  // requested for a whole tile group ahead of the accumulator wait: model 17.5 vs 20.5 ms).  Without tile groups the narrow ones
+  // lost (2.4 - 3.8 ms): profiles/README_r02.md.
+  (void)residual;
   return true;
 }
 
