@@ -45,15 +45,19 @@ TRAFFIC_FILE = "conv_traffic_r02.json"
 
 def conv_algorithmic_bytes_per_audio_s(fused_scan=False):
     """fp16 activation bytes (inputs read + outputs written, incl. pooled copies and residual operands) that the
-    conv engine's 37 launches per chunk batch must move per source audio-second: entries are
-    (bytes per row, rows per audio-second) per tensor stream of a launch; the stereo encoder entries are the FUSED
-    chains (dilated block, and the last block + LSTM input projection), whose intermediates never reach HBM."""
+    conv engine's launches of one chunk batch must move per source audio-second: entries are
+    (bytes per row, rows per audio-second) per tensor stream of a launch.  Fused chains count their input and output only
+    (U-Net double convs, super-resolution residual blocks -- whose skip operand is the block's own input --, the stereo
+    dilated blocks, decoder layers 3 + 6 per side): their intermediates never reach HBM."""
     r = SR                                   # denoiser / SR input rate; stereo runs at 2r
-    den = [(160, r), (192, r // 2), (320, r // 2), (384, r // 4), (640, r // 4), (768, r // 8), (1024, r // 8),
-           (512, r // 8), (256, r // 4), (768, r // 4), (512, r // 4), (256, r // 4), (128, r // 2), (384, r // 2),
-           (256, r // 2), (128, r // 2), (64, r), (192, r), (128, r),
-           (128, r)]                         # first transient-detector layer (32 -> 16 padded to 32 columns)
-    sr = [(128, r)] * 4 + [(192, r)] * 5 + [(64, r), (64, 2 * r), (128, 2 * r)]
+    den = [(160, r),                                             # enc0b + pooled copy
+           (256, r // 2), (512, r // 4),                         # fused enc1 / enc2 double convs + pooled copies
+           (768, r // 8), (1024, r // 8),                        # bottleneck
+           (512, r // 8), (256, r // 4), (768, r // 4), (512, r // 4),        # up0 (in, out), dec0a, dec0b
+           (256, r // 4), (128, r // 2), (384, r // 2),          # up1 (in, out), fused dec1 double conv
+           (128, r // 2), (64, r), (192, r),                     # up2 (in, out), fused dec2 double conv
+           (128, r)]                                             # first transient-detector layer (32 -> 16 padded to 32 columns)
+    sr = [(128, r)] * 4 + [(192, r)] + [(64, r), (64, 2 * r), (128, 2 * r)]  # 4 fused residual blocks, middle (+ skip), up (in, out), hf
     st = [(192, 2 * r), (384, 2 * r), (512, 2 * r), (512 if fused_scan else 768, 2 * r),   # fused enc1, enc2, enc3, enc4 (+ xproj)
           (640, 2 * r), (320, 2 * r), (320, 2 * r)]                                    # dec0 (L+R), fused dec1 -> dec2 per side
     return float(sum(b * n for b, n in den + sr + st))
