@@ -198,8 +198,12 @@ def test_bench_algorithmic_constants():
     # 51.661 GFLOP per source audio-second; unfused fp16 conv traffic ~354 MB per audio-second
     assert bench.CHAIN_GFLOP_PER_AUDIO_S == pytest.approx(2e-9 * (148504 * 22050 + 42656 * 22050 + 490144 * 44100), rel=1e-4)
     # 357.0 MB per audio-second layer by layer (incl. 2.8 MB for the first transient-detector layer, which runs in the conv
-    # engine); the fused stereo chains (enc k3 -> k1 [-> xproj]) remove 101.6 MB of it
-    assert bench.conv_algorithmic_bytes_per_audio_s() == pytest.approx(255.4e6, rel=1e-3)
+    # engine); the fused launches remove their intermediates: stereo dilated blocks [+ xproj] 101.6 MB, decoder layers 3 + 6
+    # per side 22.6 MB, U-Net double convs 11.3 MB, super-resolution residual blocks 16.9 MB -> 204.6 MB; with the LSTM input
+    # projection inside the scan kernel (batches beyond 8 per SM) its 256-channel output is gone too -> 193.3 MB
+    assert bench.conv_algorithmic_bytes_per_audio_s() == pytest.approx(204.6e6, rel=1e-3)
+    assert bench.conv_algorithmic_bytes_per_audio_s(True) == pytest.approx(193.3e6, rel=1e-3)
+    assert bench.CONV_GFLOP_PER_AUDIO_S - bench.CONV_GFLOP_PER_AUDIO_S_FUSED_SCAN == pytest.approx(2e-9 * 32768 * 44100, rel=1e-6)
 
 
 def test_butter_design_matches_scipy():
