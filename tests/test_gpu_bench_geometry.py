@@ -141,6 +141,21 @@ def test_stereo_beyond_eight_per_sm_every_sequence_vs_oracle(state_dicts, fusion
         assert_close(st0, st, "final states, projection inside the scan vs stored pre-activations", max_abs=2e-5, min_snr=90.0)
 
 
+@pytest.mark.parametrize("T", [1, 5, 8, 9, 16, 17, 24])
+def test_scan_with_projection_short_sequences(state_dicts, T):
+    """`lstm_proj_kernel` pipeline edges: one, two and three 8-step blocks, full and ragged (prologue-only GEMMs, first use of the
+    second accumulator, first recycled staging slot), at a batch beyond 8 sequences per SM; every sequence vs the oracle."""
+    m = make_model("stereo", state_dicts["stereo"])
+    B = huge_batch()
+    x = make_input(B, T, seed=40 + T)
+    ref, (hn, cn) = oracle.stereo_forward(state_dicts["stereo"], x, return_state=True)
+    with torch.no_grad():
+        y, st = m.forward_with_state(x.cuda())
+    assert_close(ref, y, f"stereo B={B} T={T}", min_snr=55.0 if T < 8 else 60.0)
+    assert_close(hn[0], st[:, 0], "carried h", max_abs=1e-3, min_snr=50.0)
+    assert_close(cn[0], st[:, 1], "carried c", max_abs=1e-3, min_snr=50.0)
+
+
 @pytest.mark.parametrize("big", [0, 1, 2], ids=["cuda-core-lstm", "tensor-core-lstm-4", "tensor-core-lstm-8"])
 def test_lstm_state_in_two_halves_equal_one_scan(state_dicts, big):
     """Feed the carried (h, c) back: forward(first half) -> state -> forward(second half, state) must reproduce the LSTM
