@@ -8,7 +8,7 @@
 
 One "step" = one synthetic mono file of `--chunks-per-step` 2-second chunks per GPU pushed through
 `RestorationPipeline.restore(mode="chunked")` (input normalise, chunk, chain, overlap-add, output
-normalise).  It is a slice of BASELINE.json's 10-hour sweep: 1184 chunks = 2257.7 s, so 16 steps
+normalise).  It is a slice of BASELINE.json's 10-hour sweep: 2368 chunks = 4515.7 s, so 8 steps
 are 10 h.  Files are independent => ranks share nothing (weak scaling, no collective on the data
 path; NCCL is used only for the timing barrier / max-over-ranks).
 Prints ONE JSON line (rank 0).
