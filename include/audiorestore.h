@@ -217,7 +217,7 @@ int ar_debug_conv1d(const float* x, const float* w_host, const float* bias_host,
                     int engine, void* stream);
 
 /* Debug / tuning hook: while dev_buf != NULL, every fused-chain launch records clock64() timestamps of the
- * pipeline events of its first 64 tile pairs (cluster 0) into slot (k mod 4) of dev_buf[4][64*16] (device int64),
+ * pipeline events of its first 64 tile pairs (cluster 0) into slot (k mod 8) of dev_buf[8][64*16] (device int64),
  * k = launches since this call. */
 int ar_debug_chain_trace(long long* dev_buf);
 

@@ -35,7 +35,7 @@ int set_fusion(int level) {
   return AR_OK;
 }
 static std::atomic<long long*> g_chain_trace{nullptr};   // debug: device buffer the fused-chain kernels trace their pipeline into
-static std::atomic<int> g_chain_trace_slot{0};           // launch k after ar_debug_chain_trace() writes slot k % 4 of [4][64*16]
+static std::atomic<int> g_chain_trace_slot{0};           // launch k after ar_debug_chain_trace() writes slot k % 8 of [8][64*16]
 int set_chain_trace(long long* dev_buf) { g_chain_trace.store(dev_buf); g_chain_trace_slot.store(0); return AR_OK; }
 
 // ============================================================================ weight folding / packing
@@ -657,7 +657,7 @@ static int run_chain(Ctx& c, std::initializer_list<const char*> names, const Act
   if (o.pool) { cp.pl.pool = o.pool->h(); cp.pl.pool_bs = o.pool->bs; cp.pl.pool_Tp = o.pool->Tp; cp.pl.pool_coff8 = 0; }
   if (o.res) { cp.pl.res = o.res->h(); cp.pl.res_bs = o.res->bs; cp.pl.res_Tp = o.res->Tp; cp.pl.res_coff8 = 0; }
   long long* const trace = g_chain_trace.load();
-  cp.trace = trace ? trace + (size_t)(g_chain_trace_slot.fetch_add(1) % 4) * 1024 : nullptr;
+  cp.trace = trace ? trace + (size_t)(g_chain_trace_slot.fetch_add(1) % 8) * 1024 : nullptr;
   ProfScope ps(CAT_CONV, c.stream, 2.0 * macs * (double)c.B * (double)in.T);
   return launch_conv_chain(cp, c.stream);
 }

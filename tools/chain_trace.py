@@ -24,16 +24,16 @@ def main():
     x = 0.1 * torch.randn(B, 1, T, device="cuda")
     with torch.no_grad():
         m(x)
-    buf = torch.zeros(4 * 1024, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(8 * 1024, dtype=torch.int64, device="cuda")
     L = _lib.lib()
     L.ar_debug_chain_trace(buf.data_ptr())
     with torch.no_grad():
         m(x)
     torch.cuda.synchronize()
     L.ar_debug_chain_trace(None)
-    tr = buf.cpu().view(4, 64, 1, 16)
+    tr = buf.cpu().view(8, 64, 1, 16)
     names = ["G1i0", "G1i1", "G2rdy", "G2i", "E1b", "E1e", "ELb", "ELe", "full0", "fullN", "G3rdy", "G3i", "E2b", "E2e", "Pend", "Pbeg"]
-    for k in range(4):
+    for k in range(8):
         t = tr[k]
         if int(t.max()) == 0:
             continue
