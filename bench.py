@@ -57,7 +57,7 @@ def conv_algorithmic_bytes_per_audio_s(fused_scan=False):
            (256, r // 4), (128, r // 2), (384, r // 2),          # up1 (in, out), fused dec1 double conv
            (128, r // 2), (64, r), (192, r),                     # up2 (in, out), fused dec2 double conv
            (128, r)]                                             # first transient-detector layer (32 -> 16 padded to 32 columns)
-    sr = [(128, r)] * 4 + [(192, r)] + [(64, r), (64, 2 * r), (128, 2 * r)]  # 4 fused residual blocks, middle (+ skip), up (in, out), hf
+    sr = [(128, r)] * 4 + [(192, r)] + [(64, r), (64, 2 * r), (68, 2 * r)]   # 4 fused residual blocks, middle (+ skip), up (in, out), fused hf + head (fp32 out)
     st = [(192, 2 * r), (384, 2 * r), (512, 2 * r), (512 if fused_scan else 768, 2 * r),   # fused enc1, enc2, enc3, enc4 (+ xproj)
           (640, 2 * r), (320, 2 * r), (320, 2 * r)]                                    # dec0 (L+R), fused dec1 -> dec2 per side
     return float(sum(b * n for b, n in den + sr + st))

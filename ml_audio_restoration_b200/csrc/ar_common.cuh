@@ -179,7 +179,9 @@ __device__ __forceinline__ void epilogue_chunk8(const ConvParams& p, int b, int 
 struct ChainParams {
   ConvParams p, pl;
   int n_gemms;
-  int taps2;          // taps of the second GEMM: 1 (pointwise) or 3 (k3 -> k3 pairs, tile stride 126)
+  int taps2;          // taps of the second GEMM: 1 (pointwise), or k (tile stride 128 - (k - 1): k3 -> k3 126, k7 behind it 122)
+  float* head_y;      // CE_HEAD chains (k5 -> k7 output head): plain fp32 output [B][Tout], column 0 of the last GEMM ...
+  const float* head_xlr;   // ... plus the linear x2 interpolation of this low-rate signal [B][Tout / 2] (super_resolution.py:96-99)
   const __half* w[3];
   const float* bias[3];
   int N[3];

@@ -5,6 +5,9 @@
 //   (b) k3 dilated -> k1 -> k1 (N = 256) the last block + the LSTM input projection behind it (stereo_separator.py:104-106)
 //   (d) k7 -> k7                         two consecutive decoder layers of the StereoSeparator (stereo_separator.py:66-83:
 //                                        128 -> 64 -> 32 per side), tile stride 122
+//   (e) k5 -> k7 (one output column)     the super-resolution tail: hf_emphasis (k5 32 -> 32 + LeakyReLU) and the
+//                                        reconstruction head (k7 32 -> 1) + linear x2 interpolation residual
+//                                        (super_resolution.py:56-62, 92-99), tile stride 122, plain fp32 output
 //   (c) k3 -> k3                         the U-Net's double conv (`_conv_block`, denoiser.py:51-60; max-pool copy fused) and
 //                                        the super-resolution residual block (conv-BN-LReLU-conv-BN + skip,
 //                                        super_resolution.py:104-122; the skip operand is the chain's own input)
@@ -54,7 +57,7 @@ constexpr int CH_BIAS_BYTES = 2048;      // <= 512 fp32 biases over all stages
 constexpr int CH_MAX_STAGES = 16;
 constexpr int CH_PREFETCH = 4;           // tile pairs the L2 prefetch runs ahead of the shared-memory ring
 
-enum ChainEpi { CE_PLAIN = 0, CE_POOL = 1, CE_RES = 2 };
+enum ChainEpi { CE_PLAIN = 0, CE_POOL = 1, CE_RES = 2, CE_HEAD = 3 };
 
 // epilogue warps per stage
 __host__ __device__ constexpr int ch_group_warps(int NG, int g) { return NG == 2 ? 8 : (g == 2 ? 8 : 4); }
@@ -95,9 +98,9 @@ __device__ __forceinline__ uint32_t phase_of(int u, int nb) { return (uint32_t)(
 template <int TAPS, int NG, int TAPS2, int EPI, bool GRP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ch_threads(NG), 1) __maxnreg__(ch_maxreg(NG))
 conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant__ ChainCfg cfg, int num_pairs) {
-  static_assert(!GRP || (NG == 2 && TAPS == 3), "tile groups are for the narrow two-GEMM k3 chains");
+  static_assert(!GRP || (NG == 2 && (TAPS == 3 || TAPS == 5)), "tile groups are for the narrow two-GEMM k3 / k5 chains");
   static_assert(TAPS2 == 1 || NG == 2, "a k-tap second stage is a two-GEMM chain");
-  static_assert(EPI == CE_PLAIN || NG == 2, "pool / residual epilogues belong to the two-GEMM chains");
+  static_assert(EPI == CE_PLAIN || NG == 2, "pool / residual / head epilogues belong to the two-GEMM chains");
   constexpr int S = TILE_M - (TAPS2 - 1);          // tile stride = outputs per tile
   constexpr int LEAD = (TAPS2 - 1) / 2;            // intermediate row r of a tile is time  tile * S - LEAD + r
   constexpr bool ROTATE = NG == 3;                 // G1 and G2 share two rotating accumulator buffers (see (b) above)
@@ -443,6 +446,46 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
         const int gl = group_of(pit.pi);
         const int u = q * 32 + lane;                           // output row of the tile
         const int buf = buf_of(it, nbA);
+        if (EPI == CE_HEAD) {
+          // Output head: column 0 of the accumulator is the k7 32 -> 1 conv; + bias + the linear x2 interpolation of the
+          // low-rate input (App. B.3: x[s] weight 0.75, the neighbour 0.25, edge-clamped), written as plain fp32 [B][Tout].
+          // The low-rate samples of all tiles of the group are requested before the accumulator is awaited.
+          const int Tout = cp.pl.Tout, Tl = Tout >> 1;
+          const bool mine = active && col_lo == 0;
+          const int t0 = gl * G * S + u;
+          float x0[4], x1[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            x0[i] = x1[i] = 0.f;
+            const int t = t0 + i * S;
+            if (i < G && mine && u < S && t < Tout) {
+              const float* xl = cp.head_xlr + (long long)pit.b * Tl;
+              const int s2 = t >> 1;
+              const int nb = (t & 1) ? (s2 + 1 < Tl ? s2 + 1 : Tl - 1) : (s2 > 0 ? s2 - 1 : 0);
+              x0[i] = __ldg(xl + s2);
+              x1[i] = __ldg(xl + nb);
+            }
+          }
+          mbar_wait(tfull_bar(g, buf), phase_of(it, nbA));
+          tc_fence_after();
+          if (tracer) trace_ev(cp.trace, it, 6);
+          const float b0 = s_bias[bias_off];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int t = t0 + i * S;
+            if (i < G && mine) {
+              uint32_t a[16];
+              tmem_ld16_nowait(taddr0 + (uint32_t)(buf * cfg.acc_n[g] + i * Ng), a);
+              tmem_wait_ld();
+              if (u < S && t < Tout) cp.head_y[(long long)pit.b * Tout + t] = __uint_as_float(a[0]) + b0 + 0.75f * x0[i] + 0.25f * x1[i];
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(tempty0_leader + 8u * buf);
+          if (tracer) trace_ev(cp.trace, it, 7);
+          continue;
+        }
         auto row_of = [&](int i) {
           const int t = (gl * G + i) * S + u;                  // >= Tin for a dead tile => every store is masked
           EpiRow row = epi_row<MODE_SAME, POOL, RES>(cp.pl, pit.b, t, col_lo);
@@ -518,7 +561,7 @@ int chain_tile_stride(int taps2) { return TILE_M - ((taps2 > 1 ? taps2 : 1) - 1)
 
 // tiles per group for a chain: narrow k3 chains (every GEMM at most 64 columns wide) take as many as TMEM allows, up to 4
 static int chain_group_tiles(const ChainParams& cp) {
-  if (cp.n_gemms != 2 || cp.p.taps != 3 || cp.N[0] > 64 || cp.N[1] > 64) return 1;
+  if (cp.n_gemms != 2 || (cp.p.taps != 3 && cp.p.taps != 5) || cp.N[0] > 64 || cp.N[1] > 64) return 1;
   int G = 4;
   while (G > 1 && 2 * G * (cp.N[0] + cp.N[1]) > 512) G >>= 1;
   return G;
@@ -587,9 +630,10 @@ static bool pick_chain_cfg(const ChainParams& cp, ChainCfg& c) {
 }
 
 bool conv_chain_fits(int Cin, int taps, int dil, const int* N, int n_gemms, int taps2) {
-  if (n_gemms < 2 || n_gemms > 3 || (taps != 3 && taps != 7)) return false;
+  if (n_gemms < 2 || n_gemms > 3 || (taps != 3 && taps != 5 && taps != 7)) return false;
   if (taps == 7 && taps2 != 7) return false;                                      // k7 only as the k7 -> k7 decoder pair
-  if (taps2 != 1 && (taps2 != taps || n_gemms != 2 || dil != 1)) return false;
+  if (taps == 5 && taps2 != 7) return false;                                      // k5 only in front of the k7 output head
+  if (taps2 != 1 && ((taps2 != taps && taps != 5) || n_gemms != 2 || dil != 1)) return false;
   if (n_gemms == 3 && N[0] != N[1]) return false;    // G1 and G2 rotate through the same accumulator buffers
   for (int g = 0; g + 1 < n_gemms; ++g)
     if (N[g] > 128) return false;                     // an intermediate operand is at most 128 channels wide
@@ -613,8 +657,8 @@ int launch_conv_chain(const ChainParams& cp, cudaStream_t stream) {
   AR_CHECK(NG == 2 || NG == 3, AR_ERR_INVALID, "conv_chain: 2 or 3 GEMMs");
   AR_CHECK(p.Cin % 16 == 0 && p.mode == MODE_SAME && p.pool == nullptr && p.res == nullptr, AR_ERR_INVALID, "conv_chain: unsupported first layer");
   AR_CHECK(p.pad_left <= HALO && (p.taps - 1) * p.dil - p.pad_left <= HALO, AR_ERR_INVALID, "conv_chain: conv reach exceeds HALO");
-  AR_CHECK(taps2 == 1 || (taps2 == p.taps && NG == 2 && p.dil == 1 && p.pad_left == (p.taps - 1) / 2), AR_ERR_INVALID,
-           "conv_chain: a k-tap second stage is implemented for k3 -> k3 and k7 -> k7");
+  AR_CHECK(taps2 == 1 || ((taps2 == p.taps || (p.taps == 5 && taps2 == 7)) && NG == 2 && p.dil == 1 && p.pad_left == (p.taps - 1) / 2),
+           AR_ERR_INVALID, "conv_chain: a k-tap second stage is implemented for k3 -> k3, k7 -> k7 and k5 -> k7");
   AR_CHECK(p.pad_left + (taps2 - 1) / 2 <= HALO, AR_ERR_INVALID, "conv_chain: combined reach exceeds HALO");
   int nb = 0;
   for (int g = 0; g < NG; ++g) {
@@ -624,7 +668,9 @@ int launch_conv_chain(const ChainParams& cp, cudaStream_t stream) {
   }
   AR_CHECK(NG == 2 || cp.N[0] == cp.N[1], AR_ERR_INVALID, "conv_chain: the first two GEMMs of a three-GEMM chain share their accumulator buffers");
   AR_CHECK(nb * 4 <= CH_BIAS_BYTES, AR_ERR_INVALID, "conv_chain: too many bias entries");
-  const int epi = cp.pl.pool != nullptr ? CE_POOL : (cp.pl.res != nullptr ? CE_RES : CE_PLAIN);
+  const int epi = cp.head_y != nullptr ? CE_HEAD : cp.pl.pool != nullptr ? CE_POOL : (cp.pl.res != nullptr ? CE_RES : CE_PLAIN);
+  AR_CHECK(epi != CE_HEAD || (cp.head_xlr != nullptr && cp.pl.pool == nullptr && cp.pl.res == nullptr && p.taps == 5 && taps2 == 7),
+           AR_ERR_INVALID, "conv_chain: the output-head epilogue belongs to the k5 -> k7 chain");
   AR_CHECK(!(cp.pl.pool && cp.pl.res), AR_ERR_INVALID, "conv_chain: pool and residual epilogues are exclusive");
   AR_CHECK(epi != CE_RES || cp.N[NG - 1] <= 32, AR_ERR_INVALID, "conv_chain: residual epilogue supports at most 32 columns");
   AR_CHECK(p.tiles_per_item == (p.Tin + chain_tile_stride(taps2) - 1) / chain_tile_stride(taps2), AR_ERR_INVALID,
@@ -640,6 +686,7 @@ int launch_conv_chain(const ChainParams& cp, cudaStream_t stream) {
       {3, 2, 3, CE_RES, 0, conv_chain_kernel<3, 2, 3, CE_RES, false>},     {7, 2, 7, CE_PLAIN, 0, conv_chain_kernel<7, 2, 7, CE_PLAIN, false>},
       {3, 2, 1, CE_PLAIN, 1, conv_chain_kernel<3, 2, 1, CE_PLAIN, true>},  {3, 2, 3, CE_PLAIN, 1, conv_chain_kernel<3, 2, 3, CE_PLAIN, true>},
       {3, 2, 3, CE_POOL, 1, conv_chain_kernel<3, 2, 3, CE_POOL, true>},    {3, 2, 3, CE_RES, 1, conv_chain_kernel<3, 2, 3, CE_RES, true>},
+      {5, 2, 7, CE_HEAD, 1, conv_chain_kernel<5, 2, 7, CE_HEAD, true>},    {5, 2, 7, CE_HEAD, 0, conv_chain_kernel<5, 2, 7, CE_HEAD, false>},
   };
   static DeviceOnce attrs;
   if (attrs.pending()) {

@@ -310,8 +310,18 @@ static bool build_sr(const Table& t, Blob& blob, Model& m) {
   const float* WR = t.get("reconstruction.weight", {1, 32, 7});
   const float* BR = t.get("reconstruction.bias", {1});
   if (!WR || !BR) return false;
+  // The head's weights are rounded to fp16 for BOTH ways it runs (fused behind hf_emphasis on the tensor core; CUDA-core
+  // kernel layer by layer), so the two paths compute from the same operands
+  auto r16 = [](float v) { const uint16_t b = half_bits_host(v); __half h; std::memcpy(&h, &b, 2); return __half2float(h); };
+  Gemm gh;
+  gh.init(32, 32, 7, 1, 3);
   for (int c = 0; c < 32; ++c)
-    for (int j = 0; j < 7; ++j) m.fin.w[0][j][c] = WR[c * 7 + j];
+    for (int j = 0; j < 7; ++j) {
+      m.fin.w[0][j][c] = r16(WR[c * 7 + j]);
+      gh.at(j, c, 0) = WR[c * 7 + j];
+    }
+  gh.bias[0] = BR[0];
+  m.conv["head"] = blob.push_gemm(gh);
   m.fin.bias[0] = BR[0];
   m.fin_heads = 1;
   {
@@ -541,6 +551,8 @@ struct ConvOpt {
   const Act* pool = nullptr;
   const Act* res = nullptr;
   int Tout = -1;
+  float* head_y = nullptr;          // fused output head (run_chain only): plain fp32 output and the low-rate interpolation source
+  const float* head_xlr = nullptr;
 };
 
 // Dynamic-range audit hook: fold max |value| of the channel window a layer just wrote into the model's audit slot `name`.
@@ -656,6 +668,8 @@ static int run_chain(Ctx& c, std::initializer_list<const char*> names, const Act
   cp.pl.out_tblock = o.out_tblock;
   if (o.pool) { cp.pl.pool = o.pool->h(); cp.pl.pool_bs = o.pool->bs; cp.pl.pool_Tp = o.pool->Tp; cp.pl.pool_coff8 = 0; }
   if (o.res) { cp.pl.res = o.res->h(); cp.pl.res_bs = o.res->bs; cp.pl.res_Tp = o.res->Tp; cp.pl.res_coff8 = 0; }
+  cp.head_y = o.head_y;
+  cp.head_xlr = o.head_xlr;
   long long* const trace = g_chain_trace.load();
   cp.trace = trace ? trace + (size_t)(g_chain_trace_slot.fetch_add(1) % 8) * 1024 : nullptr;
   ProfScope ps(CAT_CONV, c.stream, 2.0 * macs * (double)c.B * (double)in.T);
@@ -779,6 +793,14 @@ static int sr_forward(Ctx& c, const float* x, float* y, int T) {
   o = ConvOpt(); o.mode = MODE_INTERLEAVE2; o.Tout = 2 * T;
   AR_TRY(run_conv(c, "up", mid, u, o));
   A.release(mid);
+  if (can_chain(c, {"hf", "head"})) {
+    // hf_emphasis (k5 + LeakyReLU) and the reconstruction head (k7 32 -> 1) + interpolation residual as ONE fused launch:
+    // the 32-channel tensor at the output rate (128 B per output sample written + read back) never reaches HBM
+    ConvOpt oh; oh.lrelu = 0; oh.head_y = y; oh.head_xlr = x; oh.Tout = 2 * T;
+    AR_TRY(run_chain(c, {"hf", "head"}, u, u, oh));
+    A.release(u);
+    return AR_OK;
+  }
   Act h = A.act(B, 32, 2 * T);
   AR_TRY(run_conv(c, "hf", u, h));
   A.release(u);
