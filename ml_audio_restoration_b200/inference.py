@@ -465,6 +465,49 @@ class RestorationPipeline:
         return out[:, begin:end].contiguous()
 
 
+@torch.no_grad()
+def restore_sharded(pipes, audio: torch.Tensor, chunk_size: int = DEFAULT_CHUNK, overlap: int = DEFAULT_OVERLAP,
+                    batch_chunks: int = 0, normalize: bool = True) -> torch.Tensor:
+    """ONE file on several GPUs of this process (the by-chunk partition): `pipes[r]` -- a
+    `RestorationPipeline` per device, same weights -- restores the contiguous chunk range `shard_range(n_chunks, r, world)`.
+    No exchange between the GPUs on the data path: every shard recomputes the one chunk left of its span, so its seam
+    cross-fade is exact.  `normalize_audio` is global over the file: the input is normalised once on `pipes[0]`'s device
+    and copied to the others, the shards come back to it and the concatenated output is normalised there.  The chain
+    launches are asynchronous, so the shards run concurrently; the result (on `pipes[0]`'s device for device input, else
+    on the host) equals `pipes[0].restore(audio, mode="chunked", ...)`."""
+    if not pipes:
+        raise ValueError("restore_sharded: no pipelines")
+    if audio.dim() == 1:
+        audio = audio.unsqueeze(0)
+    if audio.dim() != 2 or audio.shape[0] != 1:
+        raise RuntimeError(f"expected mono audio [1, N], got {tuple(audio.shape)}")
+    N = audio.shape[1]
+    n_chunks = len(plan_chunks(N, chunk_size, overlap))
+    world = min(len(pipes), n_chunks)
+    head = pipes[0]
+    was_host = not audio.is_cuda
+    with torch.cuda.device(head.device):
+        a = audio.to(head.device, torch.float32).contiguous()
+        if a.data_ptr() == audio.data_ptr():
+            a = a.clone()
+        if normalize:
+            head._normalize_(a)
+        torch.cuda.current_stream(head.device).synchronize()     # the peers read `a` on their own streams
+    parts = []
+    for r in range(world):
+        p = pipes[r]
+        a_r = a if p.device == head.device else a.to(p.device)
+        parts.append(p.restore(a_r, mode="chunked", chunk_size=chunk_size, overlap=overlap, batch_chunks=batch_chunks,
+                               normalize=False, chunk_range=shard_range(n_chunks, r, world), return_device=True))
+    for r in range(world):
+        torch.cuda.current_stream(pipes[r].device).synchronize()
+    with torch.cuda.device(head.device):
+        y = torch.cat([t.to(head.device) for t in parts], dim=1)
+        if normalize:
+            head._normalize_(y)
+        return y.cpu() if was_host else y
+
+
 def chunked_model_eval(model, waveform: torch.Tensor, chunk_size: int = 2 * 22050) -> torch.Tensor:
     """The tensor part of `Trainer.generate_test_output` (src/training/trainer.py:652-681) for ONE model: cut `[1,N]`
     into `chunk_size` pieces, zero-pad the last one, run the model per chunk (LSTM state reset per chunk), strip the

@@ -372,6 +372,44 @@ def test_two_devices_in_one_process(state_dicts):
     assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[3])
 
 
+def test_restore_sharded_on_one_device(pipe):
+    """The sharded single-file entry point on ONE GPU (three "ranks" share cuda:0): equals the plain chunked restore."""
+    from ml_audio_restoration_b200 import restore_sharded
+    audio = make_input(1, 6 * 1792 + 999, 76, scale=0.2)[0]
+    for normalize in (False, True):
+        one = pipe.restore(audio, mode="chunked", chunk_size=2048, overlap=256, normalize=normalize)
+        got = restore_sharded([pipe, pipe, pipe], audio, chunk_size=2048, overlap=256, normalize=normalize)
+        assert torch.equal(one, got)
+    with pytest.raises(ValueError):
+        restore_sharded([], audio)
+
+
+def test_one_file_sharded_over_two_gpus(state_dicts):
+    """SURVEY.md 8e, by-chunk partition on REAL devices: one file split by chunk range over cuda:0 and cuda:1 (each shard
+    recomputes the chunk left of its span, no exchange on the data path) equals the single-GPU chunked restore -- bit for bit
+    without normalisation, and with the global input / output `normalize_audio` around it."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from ml_audio_restoration_b200 import restore_sharded
+    pipes = [RestorationPipeline.from_state_dicts(state_dicts["denoiser"], state_dicts["super_resolution"],
+                                                  state_dicts["stereo"], dev) for dev in ("cuda:0", "cuda:1")]
+    audio = make_input(1, 7 * 1792 + 500, 77, scale=0.2)[0]            # 8 chunks of 2048 / overlap 256, ragged tail
+    for normalize in (False, True):
+        one = pipes[0].restore(audio, mode="chunked", chunk_size=2048, overlap=256, normalize=normalize)
+        two = restore_sharded(pipes, audio, chunk_size=2048, overlap=256, normalize=normalize)
+        assert two.shape == one.shape and not two.is_cuda
+        if normalize:
+            assert torch.allclose(one, two, rtol=0, atol=1e-6)
+        else:
+            assert torch.equal(one, two)
+    dev_in = audio.to("cuda:0")
+    assert restore_sharded(pipes, dev_in, chunk_size=2048, overlap=256).device == torch.device("cuda:0")
+    # more pipelines than chunks: the surplus ones stay idle
+    short = make_input(1, 1500, 78, scale=0.2)[0]
+    assert torch.equal(restore_sharded(pipes, short, chunk_size=2048, overlap=256),
+                       pipes[0].restore(short, mode="chunked", chunk_size=2048, overlap=256))
+
+
 def test_forwards_on_two_streams_do_not_share_scratch(state_dicts):
     """Module forwards are stream-safe like the reference nn.Modules: concurrent forwards on two streams use separate
     workspaces and give the results of serial execution."""
