@@ -477,7 +477,7 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
               uint32_t a[16];
               tmem_ld16_nowait(taddr0 + (uint32_t)(buf * cfg.acc_n[g] + i * Ng), a);
               tmem_wait_ld();
-              if (u < S && t < Tout) cp.head_y[(long long)pit.b * Tout + t] = __uint_as_float(a[0]) + b0 + 0.75f * x0[i] + 0.25f * x1[i];
+              if (u < S && t < Tout) __stcs(cp.head_y + (long long)pit.b * Tout + t, __uint_as_float(a[0]) + b0 + 0.75f * x0[i] + 0.25f * x1[i]);
             }
           }
           tc_fence_before();
@@ -509,7 +509,7 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp, const __grid_constant_
           for (int i = 0; i < 4; ++i) {
 #pragma unroll
             for (int c = 0; c < 2; ++c)
-              res[i][c] = (i < G && active && t0 + i * S < cp.pl.Tin) ? *reinterpret_cast<const uint4*>(base.rrow + (long long)i * S * 8 + c * base.rstride)
+              res[i][c] = (i < G && active && t0 + i * S < cp.pl.Tin) ? __ldcs(reinterpret_cast<const uint4*>(base.rrow + (long long)i * S * 8 + c * base.rstride))
                                                                      : make_uint4(0u, 0u, 0u, 0u);
           }
           mbar_wait(tfull_bar(g, buf), phase_of(it, nbA));

@@ -86,7 +86,7 @@ __device__ __forceinline__ void epi_prefetch_res(const EpiRow& r, bool active, u
   if (RES) {
 #pragma unroll
     for (int c = 0; c < 2; ++c)
-      resv[c] = (r.in_ok && active) ? *reinterpret_cast<const uint4*>(r.rrow + c * r.rstride) : make_uint4(0u, 0u, 0u, 0u);
+      resv[c] = (r.in_ok && active) ? __ldcs(reinterpret_cast<const uint4*>(r.rrow + c * r.rstride)) : make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
@@ -182,7 +182,9 @@ __device__ __forceinline__ void epi_store_block(const EpiRow& r, const float* s_
     if (8 * c < ncol) {
       const int ch = (cb0 >> 3) + c;               // 8-column chunk index within this warp's range
       const uint4 packed = epi_chunk8<RES>(a + 8 * c, s_bias_w + cb0 + 8 * c, ca, cb, resv[ch & 1]);
-      if (r.ok0) *reinterpret_cast<uint4*>(r.o0 + (long long)ch * r.ostride) = packed;
+      // activations are written once and read by the NEXT launch, gigabytes later: streaming (evict-first) stores keep the
+      // L2 for the rows still to be read (operand prefetch window, residual re-read)
+      if (r.ok0) __stcs(reinterpret_cast<uint4*>(r.o0 + (long long)ch * r.ostride), packed);
       if (MODE == MODE_INTERLEAVE2) {
         if (r.ok1) *reinterpret_cast<uint4*>(r.o1 + (long long)ch * r.ostride) = make_uint4(0u, 0u, 0u, 0u);
       }
@@ -191,7 +193,7 @@ __device__ __forceinline__ void epi_store_block(const EpiRow& r, const float* s_
         unpack_half8(packed, q);
 #pragma unroll
         for (int i = 0; i < 8; ++i) m[i] = fmaxf(q[i], __shfl_down_sync(0xffffffffu, q[i], 1));
-        if (r.pok) *reinterpret_cast<uint4*>(r.prow + (long long)ch * r.pstride) = pack_half8(m);
+        if (r.pok) __stcs(reinterpret_cast<uint4*>(r.prow + (long long)ch * r.pstride), pack_half8(m));
       }
     }
   }
