@@ -55,7 +55,7 @@ constexpr int CH_SMEM_BUDGET = 227 * 1024;
 constexpr int CH_BAR_BYTES = 768;
 constexpr int CH_BIAS_BYTES = 2048;      // <= 512 fp32 biases over all stages
 constexpr int CH_MAX_STAGES = 16;
-constexpr int CH_PREFETCH = 4;           // tile pairs the L2 prefetch runs ahead of the shared-memory ring
+constexpr int CH_PREFETCH = 2;           // tile pairs the L2 prefetch runs ahead of the shared-memory ring
 
 enum ChainEpi { CE_PLAIN = 0, CE_POOL = 1, CE_RES = 2, CE_HEAD = 3 };
 

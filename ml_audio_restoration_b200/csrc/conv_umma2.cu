@@ -25,7 +25,7 @@ constexpr int UMMA2_THREADS = 64 + 32 * EPI2_WARPS;
 constexpr int SMEM2_BUDGET = 227 * 1024;
 constexpr int BAR2_BYTES = 512;
 constexpr int BIAS2_BYTES = 1024;
-constexpr int UMMA2_PREFETCH = 4;   // tile pairs the L2 prefetch runs ahead of the shared-memory ring
+constexpr int UMMA2_PREFETCH = 2;   // tile pairs the L2 prefetch runs ahead of the shared-memory ring
 
 struct Umma2Cfg {
   int kbs, stages, R;
