@@ -153,6 +153,18 @@ int ar_normalize(float* audio, int64_t n, float target_db, void* scratch, void* 
 int ar_resample_length(int64_t n, int orig_sr, int new_sr, int64_t* n_out);
 int ar_resample_mono(const float* x, int channels, int64_t n, int orig_sr, int new_sr, float* y, int64_t n_out, void* stream);
 int ar_pcm16_to_float(const int16_t* pcm, int channels, int64_t n, float* y, void* stream);
+/*   ar_pcm_to_float   : the same for every sample encoding a RIFF/WAVE `data` chunk carries -- interleaved little-endian
+ *                       frames [n][channels] of `format` -> planar fp32 [channels][n], scaled as soundfile's float32
+ *                       read (:24) scales them: unsigned 8-bit (x - 128) / 128, signed 16 / 24 (packed) / 32-bit
+ *                       x / 2^(bits-1), IEEE float32 as is, float64 rounded to nearest.  `raw` must be aligned to the
+ *                       sample size (the packed 24-bit format to 1). */
+#define AR_PCM_U8 1
+#define AR_PCM_S16 2
+#define AR_PCM_S24 3
+#define AR_PCM_S32 4
+#define AR_PCM_F32 5
+#define AR_PCM_F64 6
+int ar_pcm_to_float(const void* raw, int format, int channels, int64_t n, float* y, void* stream);
 
 /* Synthetic 78 rpm degradation generator (simulate_vinyl_artifacts, audio_processing.py:122-226).
  * The random draws (np.random levels / pop plan, torch.randn noise tensors) stay with the caller; these entry points

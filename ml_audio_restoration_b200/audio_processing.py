@@ -204,53 +204,36 @@ def simulate_vinyl_artifacts(audio: torch.Tensor, sample_rate: int, impulse_rate
 
 # ----------------------------------------------------------------------------- minimal WAV I/O
 def _read_wav(path: str):
+    """Host read of an audio file as `[C, N]` float32 (the reference's `sf.read(..., dtype='float32')`,
+    audio_processing.py:24): soundfile when it is installed, else the RIFF/WAVE reader of this module (8 / 16 / 24 / 32-bit
+    integer PCM, 32 / 64-bit IEEE float, plain or WAVE_FORMAT_EXTENSIBLE)."""
     try:
         import soundfile as sf  # optional
         data, sr = sf.read(path, always_2d=True, dtype="float32")
         return torch.from_numpy(np.ascontiguousarray(data.T)), sr
     except ImportError:
         pass
-    try:
-        with wave.open(path, "rb") as w:
-            sr, nch, width, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
-            raw = w.readframes(n)
-    except wave.Error:
-        return _read_float_wav(path)
-    if width == 2:
+    fmt, nch, sr, frames, offset = wav_info(path)
+    width = _PCM_WIDTH[fmt]
+    with open(path, "rb") as f:
+        f.seek(offset)
+        raw = f.read(frames * nch * width)
+    if fmt == _PCM_S16:
         a = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
-    elif width == 4:
+    elif fmt == _PCM_S32:
         a = np.frombuffer(raw, dtype="<i4").astype(np.float32) / 2147483648.0
-    elif width == 3:
+    elif fmt == _PCM_S24:
         b = np.frombuffer(raw, dtype=np.uint8).reshape(-1, 3).astype(np.int32)
         v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
         v = np.where(v & 0x800000, v - (1 << 24), v)
         a = v.astype(np.float32) / 8388608.0
-    elif width == 1:
+    elif fmt == _PCM_U8:
         a = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
+    elif fmt == _PCM_F32:
+        a = np.frombuffer(raw, dtype="<f4").astype(np.float32)
     else:
-        raise RuntimeError(f"unsupported WAV sample width {width}")
-    return torch.from_numpy(np.ascontiguousarray(a.reshape(-1, nch).T)), sr
-
-
-def _read_float_wav(path: str):
-    """32-bit IEEE-float WAV (format tag 3), which the stdlib `wave` module rejects."""
-    import struct
-    with open(path, "rb") as f:
-        blob = f.read()
-    if blob[:4] != b"RIFF" or blob[8:12] != b"WAVE":
-        raise RuntimeError(f"{path}: not a RIFF/WAVE file")
-    pos, fmt, data = 12, None, None
-    while pos + 8 <= len(blob):
-        cid, size = struct.unpack_from("<4sI", blob, pos)
-        if cid == b"fmt ":
-            fmt = struct.unpack_from("<HHIIHH", blob, pos + 8)
-        elif cid == b"data":
-            data = blob[pos + 8:pos + 8 + size]
-        pos += 8 + size + (size & 1)
-    if fmt is None or data is None or fmt[0] != 3 or fmt[5] != 32:
-        raise RuntimeError(f"{path}: unsupported WAV encoding")
-    a = np.frombuffer(data, dtype="<f4").reshape(-1, fmt[1])
-    return torch.from_numpy(np.array(a.T, dtype=np.float32, order="C")), fmt[2]
+        a = np.frombuffer(raw, dtype="<f8").astype(np.float32)
+    return torch.from_numpy(np.ascontiguousarray(a.astype(np.float32).reshape(-1, nch).T)), sr
 
 
 def load_audio(file_path: str, sample_rate: int = 22050, mono: bool = True):
@@ -280,28 +263,81 @@ def resample_mono_cuda(audio: torch.Tensor, sr: int, sample_rate: int = 22050) -
     return y
 
 
+# sample encodings of `ar_pcm_to_float` (include/audiorestore.h AR_PCM_*)
+_PCM_U8, _PCM_S16, _PCM_S24, _PCM_S32, _PCM_F32, _PCM_F64 = 1, 2, 3, 4, 5, 6
+_PCM_WIDTH = {_PCM_U8: 1, _PCM_S16: 2, _PCM_S24: 3, _PCM_S32: 4, _PCM_F32: 4, _PCM_F64: 8}
+
+
+def wav_info(path: str):
+    """Header of a RIFF/WAVE file: (AR_PCM_* format, channels, sample rate, frames, byte offset of the samples).
+    Handles format tags 1 (integer PCM), 3 (IEEE float) and 0xFFFE (WAVE_FORMAT_EXTENSIBLE wrapping either);
+    raises RuntimeError for anything else (compressed WAVs, non-WAV containers)."""
+    import struct
+    with open(path, "rb") as f:
+        head = f.read(12)
+        if len(head) < 12 or head[:4] != b"RIFF" or head[8:12] != b"WAVE":
+            raise RuntimeError(f"{path}: not a RIFF/WAVE file")
+        fmt = None
+        while True:
+            hdr = f.read(8)
+            if len(hdr) < 8:
+                raise RuntimeError(f"{path}: no data chunk")
+            cid, size = struct.unpack("<4sI", hdr)
+            if cid == b"fmt ":
+                body = f.read(size + (size & 1))
+                tag, nch, sr, _, align, bits = struct.unpack_from("<HHIIHH", body, 0)
+                if tag == 0xFFFE and size >= 26:
+                    tag = struct.unpack_from("<H", body, 24)[0]          # first two bytes of the sub-format GUID
+                fmt = (tag, nch, sr, align, bits)
+            elif cid == b"data":
+                if fmt is None:
+                    raise RuntimeError(f"{path}: data chunk before fmt chunk")
+                offset = f.tell()
+                f.seek(0, 2)
+                size = min(size, f.tell() - offset)                      # tolerate a truncated / streaming-length header
+                break
+            else:
+                f.seek(size + (size & 1), 1)
+    tag, nch, sr, align, bits = fmt
+    code = {(1, 8): _PCM_U8, (1, 16): _PCM_S16, (1, 24): _PCM_S24, (1, 32): _PCM_S32, (3, 32): _PCM_F32, (3, 64): _PCM_F64}.get((tag, bits))
+    if code is None or nch < 1 or align != nch * bits // 8:
+        raise RuntimeError(f"{path}: unsupported WAV encoding (format tag {tag}, {bits} bits)")
+    return code, nch, sr, size // align, offset
+
+
+def decode_pcm_cuda(raw: torch.Tensor, fmt: int, channels: int, frames: int) -> torch.Tensor:
+    """Raw interleaved sample bytes (uint8 CUDA tensor) -> planar `[channels, frames]` float32 (`ar_pcm_to_float`)."""
+    if not raw.is_cuda or raw.dtype != torch.uint8:
+        raise RuntimeError("decode_pcm_cuda: expected a uint8 CUDA tensor -- this build has no CPU fallback")
+    planar = torch.empty((channels, frames), dtype=torch.float32, device=raw.device)
+    with torch.cuda.device(raw.device):
+        _lib.check(_lib.lib().ar_pcm_to_float(raw.data_ptr(), fmt, channels, frames, planar.data_ptr(),
+                                              torch.cuda.current_stream(raw.device).cuda_stream))
+    return planar
+
+
 def load_audio_cuda(file_path: str, sample_rate: int = 22050, device="cuda"):
-    """`load_audio(..., mono=True)` with the arithmetic on the GPU: 16-bit PCM files are uploaded as raw
-    int16 frames (half the H2D bytes of float32) from pinned memory, decoded, mixed to mono and resampled on the device.
-    Returns (audio [1,N] float32 CUDA, sample_rate)."""
+    """`load_audio(..., mono=True)` with the arithmetic on the GPU: the `data` chunk of a WAV file --
+    8 / 16 / 24 / 32-bit integer PCM, 32 / 64-bit IEEE float, plain or WAVE_FORMAT_EXTENSIBLE -- is uploaded as the raw
+    bytes it is (a 16-bit file costs half the H2D bytes of float32) from pinned memory, then decoded, mixed to mono and
+    resampled on the device.  Other containers go through `_read_wav` (soundfile, when installed) and only the mix and
+    the resampling run on the GPU.  Returns (audio [1,N] float32 CUDA, sample_rate)."""
     dev = torch.device(device)
-    raw = None
     try:
-        with wave.open(file_path, "rb") as w:
-            sr, nch, width, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
-            raw = w.readframes(n) if width == 2 else None
-    except wave.Error:
-        # IEEE-float WAV (format tag 3) -- what `save_audio` / the reference's `torchaudio.save` write by default and the
-        # stdlib `wave` module rejects ("unknown format: 3"): `_read_wav` decodes it on the host
-        raw = None
-    if raw is None:                                    # other encodings: host decode, device mix + resample
+        fmt, nch, sr, frames, offset = wav_info(file_path)
+    except RuntimeError:
         audio, sr = _read_wav(file_path)
         return resample_mono_cuda(audio.to(dev), sr, sample_rate), sample_rate
-    pcm = torch.frombuffer(bytearray(raw), dtype=torch.int16).pin_memory().to(dev, non_blocking=True)
-    planar = torch.empty((nch, n), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
-        _lib.check(_lib.lib().ar_pcm16_to_float(pcm.data_ptr(), nch, n, planar.data_ptr(),
-                                                torch.cuda.current_stream(dev).cuda_stream))
+    if frames < 1:
+        raise RuntimeError(f"{file_path}: no audio frames")
+    width = _PCM_WIDTH[fmt]
+    host = torch.empty(frames * nch * width, dtype=torch.uint8).pin_memory()
+    with open(file_path, "rb") as f:
+        f.seek(offset)
+        got = f.readinto(host.numpy())
+    if got != host.numel():
+        raise RuntimeError(f"{file_path}: truncated data chunk")
+    planar = decode_pcm_cuda(host.to(dev, non_blocking=True), fmt, nch, frames)
     return resample_mono_cuda(planar, sr, sample_rate), sample_rate
 
 

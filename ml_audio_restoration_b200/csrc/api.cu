@@ -18,6 +18,7 @@ long long resample_length(long long n, int orig_sr, int new_sr);
 int launch_resample_mono(const float* x, int channels, long long n, int orig_sr, int new_sr, float* y, long long n_out,
                          cudaStream_t stream);
 int launch_pcm16(const short* pcm, int channels, long long n, float* y, cudaStream_t stream);
+int launch_pcm_decode(const void* raw, int format, int channels, long long n, float* y, cudaStream_t stream);
 int butter(int order, double wn, int highpass, double* b, double* a);
 int launch_vinyl_mix(const float* audio, const float* noise, float level, const void* pops, int n_pops, int sample_rate,
                      float* y, int rows, long long n, cudaStream_t stream);
@@ -67,6 +68,9 @@ int ar_resample_mono(const float* x, int channels, int64_t n, int orig_sr, int n
 }
 int ar_pcm16_to_float(const int16_t* pcm, int channels, int64_t n, float* y, void* stream) {
   return ar::launch_pcm16(pcm, channels, n, y, reinterpret_cast<cudaStream_t>(stream));
+}
+int ar_pcm_to_float(const void* raw, int format, int channels, int64_t n, float* y, void* stream) {
+  return ar::launch_pcm_decode(raw, format, channels, n, y, reinterpret_cast<cudaStream_t>(stream));
 }
 int ar_butter(int order, double wn, int highpass, double* b, double* a) { return ar::butter(order, wn, highpass, b, a); }
 int ar_vinyl_mix(const float* audio, const float* surface_noise, float surface_level, const ar_pop_t* pops, int n_pops,

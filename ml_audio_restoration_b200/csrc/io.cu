@@ -109,6 +109,34 @@ __global__ void pcm16_kernel(const short* __restrict__ pcm, int channels, long l
   for (int c = 0; c < channels; ++c) y[(long long)c * n + i] = (float)pcm[i * channels + c] * (1.0f / 32768.0f);
 }
 
+// any WAV sample encoding -> planar fp32 [channels][n], scaled as soundfile's float32 read scales it (integers by
+// 2^(bits-1), 8-bit is unsigned with a bias of 128, floats as they are): FMT = AR_PCM_* of include/audiorestore.h
+template <int FMT>
+__global__ void pcm_decode_kernel(const unsigned char* __restrict__ raw, int channels, long long n, float* __restrict__ y) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int c = 0; c < channels; ++c) {
+    const long long s = i * channels + c;
+    float v;
+    if (FMT == AR_PCM_U8) {
+      v = ((float)raw[s] - 128.0f) * (1.0f / 128.0f);
+    } else if (FMT == AR_PCM_S16) {
+      v = (float)reinterpret_cast<const short*>(raw)[s] * (1.0f / 32768.0f);
+    } else if (FMT == AR_PCM_S24) {
+      const unsigned char* p = raw + 3 * s;                      // packed little-endian, sign in the top byte
+      const int w = (int)p[0] | ((int)p[1] << 8) | ((int)(signed char)p[2] << 16);
+      v = (float)w * (1.0f / 8388608.0f);
+    } else if (FMT == AR_PCM_S32) {
+      v = __int2float_rn(reinterpret_cast<const int*>(raw)[s]) * (1.0f / 2147483648.0f);
+    } else if (FMT == AR_PCM_F32) {
+      v = reinterpret_cast<const float*>(raw)[s];
+    } else {
+      v = __double2float_rn(reinterpret_cast<const double*>(raw)[s]);
+    }
+    y[(long long)c * n + i] = v;
+  }
+}
+
 int launch_resample_mono(const float* x, int channels, long long n, int orig_sr, int new_sr, float* y, long long n_out,
                          cudaStream_t stream) {
   AR_CHECK(x && y && channels >= 1 && n >= 1 && orig_sr >= 1 && new_sr >= 1, AR_ERR_INVALID, "resample: bad argument");
@@ -129,6 +157,23 @@ int launch_resample_mono(const float* x, int channels, long long n, int orig_sr,
 int launch_pcm16(const short* pcm, int channels, long long n, float* y, cudaStream_t stream) {
   AR_CHECK(pcm && y && channels >= 1 && n >= 1, AR_ERR_INVALID, "pcm16: bad argument");
   pcm16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pcm, channels, n, y);
+  AR_CUDA_OK(cudaGetLastError());
+  return AR_OK;
+}
+
+int launch_pcm_decode(const void* raw, int format, int channels, long long n, float* y, cudaStream_t stream) {
+  AR_CHECK(raw && y && channels >= 1 && n >= 1, AR_ERR_INVALID, "pcm decode: bad argument");
+  const unsigned char* r = reinterpret_cast<const unsigned char*>(raw);
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  switch (format) {
+    case AR_PCM_U8:  pcm_decode_kernel<AR_PCM_U8><<<grid, 256, 0, stream>>>(r, channels, n, y); break;
+    case AR_PCM_S16: pcm_decode_kernel<AR_PCM_S16><<<grid, 256, 0, stream>>>(r, channels, n, y); break;
+    case AR_PCM_S24: pcm_decode_kernel<AR_PCM_S24><<<grid, 256, 0, stream>>>(r, channels, n, y); break;
+    case AR_PCM_S32: pcm_decode_kernel<AR_PCM_S32><<<grid, 256, 0, stream>>>(r, channels, n, y); break;
+    case AR_PCM_F32: pcm_decode_kernel<AR_PCM_F32><<<grid, 256, 0, stream>>>(r, channels, n, y); break;
+    case AR_PCM_F64: pcm_decode_kernel<AR_PCM_F64><<<grid, 256, 0, stream>>>(r, channels, n, y); break;
+    default: AR_CHECK(false, AR_ERR_INVALID, "pcm decode: unknown sample format");
+  }
   AR_CUDA_OK(cudaGetLastError());
   return AR_OK;
 }

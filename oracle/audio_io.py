@@ -63,6 +63,62 @@ def pcm16_to_float(pcm: np.ndarray) -> np.ndarray:
     return np.ascontiguousarray((np.asarray(pcm, dtype=np.int16).astype(np.float32) / np.float32(32768.0)).T)
 
 
+PCM_U8, PCM_S16, PCM_S24, PCM_S32, PCM_F32, PCM_F64 = 1, 2, 3, 4, 5, 6     # AR_PCM_* of include/audiorestore.h
+
+
+def pcm_to_float(raw: bytes, fmt: int, channels: int) -> np.ndarray:
+    """The sample bytes of a WAV `data` chunk (interleaved little-endian frames) -> planar fp32 [C, N], scaled as
+    soundfile's dtype='float32' read scales them (audio_processing.py:24): integers by 2^(bits-1), unsigned 8-bit with a
+    bias of 128, floats unchanged (float64 rounded to nearest)."""
+    if fmt == PCM_U8:
+        a = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - np.float32(128.0)) / np.float32(128.0)
+    elif fmt == PCM_S16:
+        a = np.frombuffer(raw, dtype="<i2").astype(np.float32) / np.float32(32768.0)
+    elif fmt == PCM_S24:
+        b = np.frombuffer(raw, dtype=np.uint8).reshape(-1, 3).astype(np.int32)
+        v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+        v = np.where(v & 0x800000, v - (1 << 24), v)
+        a = v.astype(np.float32) / np.float32(8388608.0)
+    elif fmt == PCM_S32:
+        a = np.frombuffer(raw, dtype="<i4").astype(np.float32) / np.float32(2147483648.0)
+    elif fmt == PCM_F32:
+        a = np.frombuffer(raw, dtype="<f4").astype(np.float32)
+    elif fmt == PCM_F64:
+        a = np.frombuffer(raw, dtype="<f8").astype(np.float32)
+    else:
+        raise ValueError(f"unknown sample format {fmt}")
+    return np.ascontiguousarray(a.reshape(-1, channels).T)
+
+
+def write_wav(path: str, samples: np.ndarray, fmt: int, sample_rate: int, extensible: bool = False, junk: bool = False) -> bytes:
+    """Test helper: `samples` [N, C] (already of the encoding's numpy type; for PCM_S24 int32 values in [-2^23, 2^23)) as a
+    RIFF/WAVE file with format tag 1 / 3 or WAVE_FORMAT_EXTENSIBLE, optionally with an odd-sized LIST chunk in front of
+    `data`.  Returns the bytes of the data chunk."""
+    import struct
+    n, ch = samples.shape
+    bits = {PCM_U8: 8, PCM_S16: 16, PCM_S24: 24, PCM_S32: 32, PCM_F32: 32, PCM_F64: 64}[fmt]
+    tag = 3 if fmt in (PCM_F32, PCM_F64) else 1
+    if fmt == PCM_S24:
+        v = samples.astype(np.int32) & 0xFFFFFF
+        data = np.stack([v & 0xFF, (v >> 8) & 0xFF, (v >> 16) & 0xFF], axis=-1).astype(np.uint8).tobytes()
+    else:
+        dt = {PCM_U8: np.uint8, PCM_S16: "<i2", PCM_S32: "<i4", PCM_F32: "<f4", PCM_F64: "<f8"}[fmt]
+        data = np.ascontiguousarray(samples).astype(dt).tobytes()
+    align = ch * bits // 8
+    if extensible:
+        guid = struct.pack("<H", tag) + bytes.fromhex("000000001000800000aa00389b71")
+        fmt_body = struct.pack("<HHIIHHHHI", 0xFFFE, ch, sample_rate, sample_rate * align, align, bits, 22, bits, 0) + guid
+    else:
+        fmt_body = struct.pack("<HHIIHH", tag, ch, sample_rate, sample_rate * align, align, bits)
+    chunks = struct.pack("<4sI", b"fmt ", len(fmt_body)) + fmt_body
+    if junk:
+        chunks += struct.pack("<4sI", b"LIST", 5) + b"abcde" + b"\0"          # odd size: padded to even
+    chunks += struct.pack("<4sI", b"data", len(data)) + data + (b"\0" if len(data) & 1 else b"")
+    with open(path, "wb") as f:
+        f.write(struct.pack("<4sI", b"RIFF", 4 + len(chunks)) + b"WAVE" + chunks)
+    return data
+
+
 def load_front_end(x: np.ndarray, sr: int, sample_rate: int = 22050, mono: bool = True) -> np.ndarray:
     """mono mix then resample, in the reference's order (audio_processing.py:32-39)."""
     if mono and x.shape[0] > 1:

@@ -64,3 +64,69 @@ def test_wav_helpers_round_trip(tmp_path):
     mono, sr = load_audio(p32, sample_rate=22050)   # host path: mean + torchaudio resample == oracle front end
     ref = audio_io.load_front_end(a.numpy(), 44100, 22050)
     assert sr == 22050 and mono.shape == ref.shape and float(np.abs(mono.numpy() - ref).max()) <= 2e-6
+
+
+# ----------------------------------------------------------------------------- WAV sample encodings (host logic + oracle)
+FORMATS = [audio_io.PCM_U8, audio_io.PCM_S16, audio_io.PCM_S24, audio_io.PCM_S32, audio_io.PCM_F32, audio_io.PCM_F64]
+
+
+def encoding_samples(fmt, n, ch, seed):
+    """[n, ch] samples of the encoding's numpy type, full range incl. the extreme codes."""
+    rng = np.random.default_rng(seed)
+    if fmt == audio_io.PCM_U8:
+        a = rng.integers(0, 256, size=(n, ch)).astype(np.uint8)
+        a[0, 0], a[1, 0] = 0, 255
+    elif fmt == audio_io.PCM_S16:
+        a = rng.integers(-32768, 32768, size=(n, ch)).astype(np.int16)
+        a[0, 0], a[1, 0] = -32768, 32767
+    elif fmt == audio_io.PCM_S24:
+        a = rng.integers(-(1 << 23), 1 << 23, size=(n, ch)).astype(np.int32)
+        a[0, 0], a[1, 0] = -(1 << 23), (1 << 23) - 1
+    elif fmt == audio_io.PCM_S32:
+        a = rng.integers(-(1 << 31), 1 << 31, size=(n, ch)).astype(np.int32)
+        a[0, 0], a[1, 0] = -(1 << 31), (1 << 31) - 1
+    elif fmt == audio_io.PCM_F32:
+        a = (rng.standard_normal((n, ch)) * 0.3).astype(np.float32)
+    else:
+        a = rng.standard_normal((n, ch)) * 0.3
+    return a
+
+
+@pytest.mark.parametrize("fmt", FORMATS)
+@pytest.mark.parametrize("extensible", [False, True])
+def test_wav_header_parser_and_oracle_decode(tmp_path, fmt, extensible):
+    """`wav_info` finds the data chunk of plain and WAVE_FORMAT_EXTENSIBLE files (odd-sized chunk in front); the oracle's
+    decode equals scipy's reader for the sample extraction and libsndfile's 2^(bits-1) convention for the scale."""
+    from scipy.io import wavfile
+    from ml_audio_restoration_b200.audio_processing import wav_info, _read_wav
+    n, ch, sr = 1001, 2 if fmt != audio_io.PCM_F64 else 3, 44100
+    a = encoding_samples(fmt, n, ch, 7 + fmt)
+    path = str(tmp_path / "x.wav")
+    data = audio_io.write_wav(path, a, fmt, sr, extensible=extensible, junk=True)
+    code, nch, rate, frames, offset = wav_info(path)
+    assert (code, nch, rate, frames) == (fmt, ch, sr, n)
+    with open(path, "rb") as f:
+        f.seek(offset)
+        assert f.read(len(data)) == data
+    y = audio_io.pcm_to_float(data, fmt, ch)
+    assert y.shape == (ch, n) and y.dtype == np.float32
+    rate2, raw = wavfile.read(path)                       # scipy: unscaled samples (24-bit left-justified in int32)
+    assert rate2 == sr
+    scale = {audio_io.PCM_U8: None, audio_io.PCM_S16: 32768.0, audio_io.PCM_S24: 2147483648.0, audio_io.PCM_S32: 2147483648.0}.get(fmt, 1.0)
+    ref = (raw.astype(np.float64) - 128.0) / 128.0 if scale is None else raw.astype(np.float64) / scale
+    assert np.abs(y.astype(np.float64) - ref.T).max() <= 2.0 ** -24        # one fp32 rounding (32-bit ints, float64 input)
+    host, rate3 = _read_wav(path)                          # the package's host reader (stdlib `wave` / float parser)
+    assert rate3 == sr and np.array_equal(host.numpy(), y)
+
+
+def test_wav_header_parser_rejects_other_files(tmp_path):
+    from ml_audio_restoration_b200.audio_processing import wav_info
+    p = tmp_path / "not.wav"
+    p.write_bytes(b"OggS" + b"\0" * 64)
+    with pytest.raises(RuntimeError):
+        wav_info(str(p))
+    import struct
+    body = b"WAVE" + struct.pack("<4sIHHIIHH", b"fmt ", 16, 2, 1, 8000, 4000, 256, 4) + struct.pack("<4sI", b"data", 0)   # ADPCM
+    p.write_bytes(struct.pack("<4sI", b"RIFF", len(body)) + body)
+    with pytest.raises(RuntimeError):
+        wav_info(str(p))
