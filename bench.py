@@ -63,6 +63,24 @@ def conv_algorithmic_bytes_per_audio_s(fused_scan=False):
     return float(sum(b * n for b, n in den + sr + st))
 
 
+def elementwise_algorithmic_bytes(n_chunks, n):
+    """Algorithmic HBM bytes per step of the CUDA-core (elementwise / Cin = 1 / Cout = 1) passes, per profile category
+    (DESIGN.md 3): what each kernel must read and write once, counted over the samples it processes (chunk samples for
+    the model stems / tails, file samples for normalize and overlap-add)."""
+    c = n_chunks * CHUNK                    # 22.05 kHz chunk samples of the step (the stereo net runs on 2c)
+    return {
+        # fp32 sample in (4 B) + 32 fp16 channels out (64 B): denoiser k3 stem, super-resolution k7 stem, stereo k7 stem @ 2c
+        "stem": 68.0 * (c + c + 2 * c),
+        # denoiser tail: 32-channel features (64 B) + 16 transient-detector channels (32 B) + x (4 B) in, 4 B out;
+        # stereo heads: 2 sides x 32 fp16 channels (128 B) in, L + R fp32 (8 B) out per 44.1 kHz sample
+        "tail": 104.0 * c + 136.0 * 2 * c,
+        # normalize_audio on the mono input (n) and the stereo output (2 x 2n): one reduction read + scale read + write
+        "normalize": 12.0 * (n + 4 * n),
+        # split: read + write every chunk sample; overlap-add: read both channels of every output-rate chunk, write 2 x 2n
+        "chunk": 8.0 * c + 4.0 * (2 * 2 * c) + 4.0 * (2 * 2 * n),
+    }
+
+
 def load_conv_traffic(args):
     """DRAM bytes per conv-engine launch from the COMMITTED ncu capture (a static file, not measured in this run), if it
     was taken at this configuration and launch count; else None."""
@@ -481,6 +499,12 @@ def run_b200(args, rank, world, local_rank):
                  "share_of_step": lstm["ms"] / (1e3 * t_s)},
         "per_category_ms_per_step": {k: v["ms"] / args.steps for k, v in cats.items()},
     }
+    # the elementwise / single-channel passes against the HBM roofline (north_star: "reported in achieved HBM GB/s")
+    roofline["elementwise_hbm"] = {"unit": "GB/s", "peak": peaks["hbm_gbs"], "categories": {
+        k: {"algorithmic_gb_per_step": b / 1e9, "ms_per_step": cats[k]["ms"] / args.steps,
+            "achieved": (b / 1e9) / (cats[k]["ms"] / args.steps / 1e3) if cats[k]["ms"] > 0 else 0.0,
+            "frac": (b / 1e9) / (cats[k]["ms"] / args.steps / 1e3) / peaks["hbm_gbs"] if cats[k]["ms"] > 0 else 0.0}
+        for k, b in elementwise_algorithmic_bytes(args.chunks_per_step, n).items()}}
     line = {
         "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

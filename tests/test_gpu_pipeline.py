@@ -109,6 +109,33 @@ def test_split_and_overlap_add_identities(pipe):
         _lib.check(L.ar_num_chunks(100, 10, 6, C.byref(C.c_int())))
 
 
+@pytest.mark.parametrize("N,chunk,ov,rate,C_", [(5 * 42048 + 44100, 44100, 2052, 2, 2), (3 * 1000 + 1024, 1024, 24, 2, 2),
+                                                 (7 * 96 + 128, 128, 32, 1, 1), (44100, 44100, 2052, 2, 2)])
+def test_overlap_add_vector_path_equals_scalar_path_and_oracle(N, chunk, ov, rate, C_):
+    """The four-samples-per-thread overlap-add (taken when chunk, hop, overlap at the output rate are multiples of 4 and the
+    buffers are 16-byte aligned) against the one-sample-per-thread kernel (forced here by a 4-byte-offset output buffer):
+    bit-identical; both against the oracle's stitch (oracle/pipeline.py:99)."""
+    import ctypes as C
+    from ml_audio_restoration_b200 import _lib
+    L = _lib.lib()
+    n = C.c_int()
+    _lib.check(L.ar_num_chunks(N, chunk, ov, C.byref(n)))
+    n = n.value
+    g = torch.Generator().manual_seed(N % 977)
+    y = torch.randn(n, C_, rate * chunk, generator=g)
+    yd = y.cuda()
+    s = torch.cuda.current_stream().cuda_stream
+    out_v = torch.empty(C_, rate * N, device="cuda")
+    _lib.check(L.ar_overlap_add(yd.data_ptr(), out_v.data_ptr(), N, n, C_, chunk, ov, rate, s))
+    raw = torch.empty(C_ * rate * N + 1, device="cuda")
+    out_s = raw[1:].view(C_, rate * N)                        # 4-byte offset: not 16-byte aligned -> scalar kernel
+    assert out_s.data_ptr() % 16 != 0
+    _lib.check(L.ar_overlap_add(yd.data_ptr(), out_s.data_ptr(), N, n, C_, chunk, ov, rate, s))
+    assert torch.equal(out_v, out_s)
+    ref = opipe.stitch_chunks(y, N, chunk, ov, rate)
+    assert float((ref - out_v.cpu()).abs().max()) <= 2e-6
+
+
 @pytest.mark.parametrize("name,N", [("denoiser", 5 * 44100 + 1234), ("stereo", 2 * 44100), ("super_resolution", 44100 + 17)])
 def test_chunked_model_eval_matches_trainer_loop(state_dicts, name, N):
     """Drop-in of the reference's only chunked inference, Trainer.generate_test_output (trainer.py:652-681): 2 s chunks,

@@ -29,7 +29,7 @@ for k in order[starts[-1]:]:
     a[0] += 1; a[1] += ms; a[2] += gb
     extra = f"  {gb:7.2f} GB {gb / ms:6.2f} TB/s" if gb and ms else ""
     print(f"{ms:8.3f} ms {x['grid']:>15} {x['block']:>13} {n}{extra}")
-    if "ola_kernel" in n:
+    if "ola_kernel" in n or "ola4_kernel" in n:
         break
 print(f"total {tot_ms:.2f} ms, {tot_gb:.1f} GB DRAM")
 print("--- by kernel")

@@ -28,7 +28,7 @@ last = order.index(ids[-1])
 sel = []
 for k in order[last:]:
     n = per[k]["name"]
-    if "ola_kernel" in n:
+    if "ola_kernel" in n or "ola4_kernel" in n:
         break
     if "conv_umma2_kernel" in n or "conv_chain_kernel" in n or "conv_umma_kernel" in n:
         sel.append(per[k])
