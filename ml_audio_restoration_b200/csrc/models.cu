@@ -214,7 +214,7 @@ static bool stem_pack(const Table& t, Blob& blob, const std::string& conv, const
   if (!W || !fold_bn(t, conv, bn, 32, f)) return false;
   std::memset(&s, 0, sizeof(s));
   for (int o = 0; o < 32; ++o) {
-    for (int j = 0; j < k; ++j) s.w[o][j] = W[o * k + j] * f.s[o];
+    for (int j = 0; j < k; ++j) s.w[j][o] = W[o * k + j] * f.s[o];
     s.b[o] = f.b[o];
   }
   s.taps = k;

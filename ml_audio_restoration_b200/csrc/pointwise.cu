@@ -10,6 +10,10 @@ namespace ar {
 // ============================================================================ stem: Cin = 1
 // x[B][T] plain fp32 -> H8 fp16 out (32 channels): conv(k taps, pad k/2) + folded BN bias + LeakyReLU.
 // denoiser.py:54 (encoder.0.0), super_resolution.py:25 (initial.0), stereo_separator.py:25.
+// Two output channels per instruction: `fma.rn.f32x2` (SASS FFMA2) takes the weight pair (2i, 2i+1) of a tap as ONE 8-byte
+// constant-bank / uniform-register operand and broadcasts the input sample, so a k7 stem is 112 FFMA2 instead of 224 FFMA per
+// sample (the kernel was FFMA-issue-bound: 470 instructions per sample behind 68 bytes).  Same accumulation order per channel
+// as the scalar form (bias, then taps 0..k-1): bit-identical results.
 template <int TAPS>
 __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ x, int T, const __grid_constant__ StemP w,
                                                    __half* __restrict__ out, long long out_bs, int out_Tp, int lrelu) {
@@ -17,22 +21,32 @@ __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ x, 
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   const float* xb = x + (long long)b * T;
-  float xin[TAPS];
+  unsigned long long xin[TAPS];
 #pragma unroll
   for (int j = 0; j < TAPS; ++j) {
     const int ti = t + j - TAPS / 2;
-    xin[j] = (ti >= 0 && ti < T) ? __ldg(xb + ti) : 0.f;
+    const float v = (ti >= 0 && ti < T) ? __ldg(xb + ti) : 0.f;
+    xin[j] = f2_pack(v, v);
   }
   const float slope = lrelu ? LRELU_SLOPE : 1.0f;
+  const unsigned long long slope2 = f2_pack(slope, slope);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     float v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float a = w.b[8 * c + i];
+    for (int i = 0; i < 4; ++i) {
+      unsigned long long a = f2_pack(w.b[8 * c + 2 * i], w.b[8 * c + 2 * i + 1]), s;
 #pragma unroll
-      for (int j = 0; j < TAPS; ++j) a = fmaf(w.w[8 * c + i][j], xin[j], a);   // weights: constant-bank operands
-      v[i] = fmaxf(a, slope * a);
+      for (int j = 0; j < TAPS; ++j) {
+        const unsigned long long wj = f2_pack(w.w[j][8 * c + 2 * i], w.w[j][8 * c + 2 * i + 1]);
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(wj), "l"(xin[j]));
+      }
+      asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(s) : "l"(a), "l"(slope2));
+      float a0, a1, s0, s1;
+      f2_unpack(a, a0, a1);
+      f2_unpack(s, s0, s1);
+      v[2 * i] = fmaxf(a0, s0);
+      v[2 * i + 1] = fmaxf(a1, s1);
     }
     *reinterpret_cast<uint4*>(out + act_off(out_bs, out_Tp, b, c, t)) = pack_half8(v);
   }
@@ -223,18 +237,30 @@ __global__ void __launch_bounds__(DT) den_tail_kernel(const __half* __restrict__
   if (tid < DT - 2) {
     const int r = tid;
     const int t = t0 - 1 + r;
-    float acc[8];
+    // two output channels per FFMA2 (weight pair = one 8-byte constant-bank operand, input broadcast); per channel the same
+    // accumulation order as the scalar form in the PRE = false branch above (bias, then per tap and 4-channel group w, z, y, x)
+    unsigned long long acc2[4];
 #pragma unroll
-    for (int o = 0; o < 8; ++o) acc[o] = w.b1[o];
+    for (int o = 0; o < 4; ++o) acc2[o] = f2_pack(w.b1[2 * o], w.b1[2 * o + 1]);
 #pragma unroll
     for (int j = 0; j < 3; ++j)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const float4 v = s0[c][r + j];
+        const float vin[4] = {v.w, v.z, v.y, v.x};
 #pragma unroll
-        for (int o = 0; o < 8; ++o)
-          acc[o] = fmaf(v.x, w.w1[j][4 * c][o], fmaf(v.y, w.w1[j][4 * c + 1][o], fmaf(v.z, w.w1[j][4 * c + 2][o], fmaf(v.w, w.w1[j][4 * c + 3][o], acc[o]))));
+        for (int k = 0; k < 4; ++k) {
+          const unsigned long long vv = f2_pack(vin[k], vin[k]);
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            const unsigned long long ww = f2_pack(w.w1[j][4 * c + 3 - k][2 * o], w.w1[j][4 * c + 3 - k][2 * o + 1]);
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[o]) : "l"(vv), "l"(ww));
+          }
+        }
       }
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) f2_unpack(acc2[o], acc[2 * o], acc[2 * o + 1]);
     const bool ok = (t >= 0 && t < T);
 #pragma unroll
     for (int o = 0; o < 8; ++o) acc[o] = ok ? (acc[o] > 0.f ? acc[o] : LRELU_SLOPE * acc[o]) : 0.f;

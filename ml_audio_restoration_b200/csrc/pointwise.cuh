@@ -8,7 +8,7 @@ namespace ar {
 
 // Weights of the CUDA-core tail kernels travel as __grid_constant__ kernel parameters (the parameter space is constant
 // bank 0): every FFMA then takes its weight as a c[0][imm] operand -- no weight loads at all in the inner loops.
-struct DenTailP {        // transient detector 32->16->8->1 (k3) + final 1x1 conv, denoiser.py:39-48
+struct alignas(16) DenTailP {   // transient detector 32->16->8->1 (k3) + final 1x1 conv, denoiser.py:39-48
   float w0[3][32][16];   // [tap][cin][cout]
   float b0[16];
   float w1[3][16][8];
@@ -17,8 +17,8 @@ struct DenTailP {        // transient detector 32->16->8->1 (k3) + final 1x1 con
   float wf[32];
   float b2, bf;
 };
-struct StemP {           // Cin = 1 first conv (+ folded BN): 32 x taps weights, 32 biases
-  float w[32][7];
+struct alignas(16) StemP {   // Cin = 1 first conv (+ folded BN): taps x 32 weights, 32 biases
+  float w[7][32];        // [tap][channel]: the channel pair (2i, 2i+1) of a tap is one 8-byte constant-bank operand of a packed FFMA2
   float b[32];
   int taps;
 };

@@ -95,14 +95,6 @@ __device__ __forceinline__ void epi_prefetch_res(const EpiRow& r, bool active, u
 //   ca*v + cb*|v| with ca = (1+slope)/2, cb = (1-slope)/2 (two FMA-pipe ops instead of FMUL + FMNMX on the half-rate ALU
 //   pipe; slope = 1 gives exactly v), and ONE saturating convert for the round-to-fp16 + clamp-to-+-65504
 //   (F2FP.SATFINITE.F16.F32.PACK_AB).  2.5 instructions per column instead of 5.75.
-__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void f2_unpack(unsigned long long v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
 __device__ __forceinline__ uint32_t cvt_half2_sat(float lo, float hi) {   // round to nearest, saturate to the finite fp16 range
   uint32_t r;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));

@@ -136,6 +136,9 @@ def test_error_behaviour(models, state_dicts):
         den(make_input(1, 64))
     with pytest.raises(RuntimeError):
         den(make_input(1, 64).cuda().squeeze(1))
+    for name, shape in (("denoiser", (0, 1, 64)), ("super_resolution", (0, 1, 128)), ("stereo", (0, 2, 64))):
+        y = models(name, "umma")(torch.zeros(0, 1, 64, device="cuda"))      # reference: an empty batch gives an empty output
+        assert tuple(y.shape) == shape and y.is_cuda and y.dtype == torch.float32
     den.train()
     with pytest.raises(NotImplementedError):
         den(make_input(1, 64).cuda())
