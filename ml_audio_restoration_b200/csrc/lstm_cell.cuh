@@ -44,6 +44,50 @@ __device__ __forceinline__ void lstm_cell(float pi, float pf, float pg, float po
   const float q = ex2_f(-po), e = ex2_f(-2.f * LSTM_L2E * cc);
   h = (1.f - e) * rcp_f((1.f + q) * (1.f + e));
 }
+// Two cells per call with the fp32 adds / multiplies as packed 2-wide instructions (FADD2 / FMUL2 / FFMA2: one issue slot for both
+// cells; the special-function calls and the clamps stay scalar).  Operation for operation the same IEEE arithmetic as `lstm_cell`,
+// so the results are bit-identical; it only shortens the recurrence warps' instruction stream (the scan kernels are bound by issue
+// slots and the special-function unit together).
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ void lstm_cell2(float pi0, float pi1, float pf0, float pf1, float pg0, float pg1, float po0, float po1,
+                                           float (&c)[2], float (&h)[2]) {
+  const unsigned long long one = f2_pack(1.f, 1.f);
+  const unsigned long long a = f2_pack(ex2_f(-fmaxf(pf0, -20.f * LSTM_L2E)), ex2_f(-fmaxf(pf1, -20.f * LSTM_L2E)));
+  const unsigned long long b = f2_pack(ex2_f(-fmaxf(pi0, -20.f * LSTM_L2E)), ex2_f(-fmaxf(pi1, -20.f * LSTM_L2E)));
+  const unsigned long long d = f2_pack(ex2_f(-fmaxf(pg0, -40.f * LSTM_L2E)), ex2_f(-fmaxf(pg1, -40.f * LSTM_L2E)));
+  const unsigned long long a1 = f2_add(one, a);
+  const unsigned long long bd = f2_mul(f2_add(one, b), f2_add(one, d));
+  const unsigned long long num = f2_fma(f2_pack(c[0], c[1]), bd, f2_mul(f2_sub(one, d), a1));
+  float den0, den1;
+  f2_unpack(f2_mul(a1, bd), den0, den1);
+  f2_unpack(f2_mul(num, f2_pack(rcp_f(den0), rcp_f(den1))), c[0], c[1]);
+  const unsigned long long q = f2_pack(ex2_f(-fmaxf(po0, -20.f * LSTM_L2E)), ex2_f(-fmaxf(po1, -20.f * LSTM_L2E)));
+  float ea0, ea1;                                     // -2 log2(e) max(c, -20): the argument of the tanh exponential
+  f2_unpack(f2_mul(f2_pack(fmaxf(c[0], -20.f), fmaxf(c[1], -20.f)), f2_pack(-2.f * LSTM_L2E, -2.f * LSTM_L2E)), ea0, ea1);
+  const unsigned long long e = f2_pack(ex2_f(ea0), ex2_f(ea1));
+  float hd0, hd1;
+  f2_unpack(f2_mul(f2_add(one, q), f2_add(one, e)), hd0, hd1);
+  f2_unpack(f2_mul(f2_sub(one, e), f2_pack(rcp_f(hd0), rcp_f(hd1))), h[0], h[1]);
+}
 // pre-scaled variants for the CUDA-core kernel (x already multiplied by log2(e), resp. 2 log2(e))
 __device__ __forceinline__ float sigmoid_s(float x) { return rcp_f(1.0f + ex2_f(-x)); }
 __device__ __forceinline__ float tanh_s(float x) { return 1.0f - 2.0f * rcp_f(ex2_f(x) + 1.0f); }
