@@ -327,17 +327,17 @@ lstm_mmaw_kernel(const __half* __restrict__ xp, long long xp_bs, int xp_Tp, cons
       mma_f16_16x8x16(acc[1], wfrag[1][kt], bf.x, bf.y);
     }
     if constexpr (CELLS == 2) {   // both cells of the thread through the packed 2-wide update (bit-identical to lstm_cell)
-      const float2 x_if0 = __half22float2(*reinterpret_cast<const __half2*>(&q[0].x)), x_go0 = __half22float2(*reinterpret_cast<const __half2*>(&q[0].y));
-      const float2 x_if1 = __half22float2(*reinterpret_cast<const __half2*>(&q[CELLS - 1].x)), x_go1 = __half22float2(*reinterpret_cast<const __half2*>(&q[CELLS - 1].y));
-      lstm_cell2(acc[0][0] + x_if0.x, acc[0][1] + x_if1.x, acc[0][2] + x_if0.y, acc[0][3] + x_if1.y,
-                 acc[1][0] + x_go0.x, acc[1][1] + x_go1.x, acc[1][2] + x_go0.y, acc[1][3] + x_go1.y, c, hl);
+      float pi[2], pf[2], pg[2], po[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) lstm_preact(acc[0][j], acc[0][2 + j], acc[1][j], acc[1][2 + j], q[j * (CELLS - 1)], pi[j], pf[j], pg[j], po[j]);
+      lstm_cell2(pi[0], pi[1], pf[0], pf[1], pg[0], pg[1], po[0], po[1], c, hl);
     }
 #pragma unroll
     for (int j = 0; j < CELLS; ++j) {
       if constexpr (CELLS != 2) {
-        const float2 x_if = __half22float2(*reinterpret_cast<const __half2*>(&q[j].x));
-        const float2 x_go = __half22float2(*reinterpret_cast<const __half2*>(&q[j].y));
-        lstm_cell(acc[0][j] + x_if.x, acc[0][2 + j] + x_if.y, acc[1][j] + x_go.x, acc[1][2 + j] + x_go.y, c[j], hl[j]);
+        float pi, pf, pg, po;
+        lstm_preact(acc[0][j], acc[0][2 + j], acc[1][j], acc[1][2 + j], q[j], pi, pf, pg, po);
+        lstm_cell(pi, pf, pg, po, c[j], hl[j]);
       }
       hb_wr[(cur ^ 1) * (NSEQ * LM_HS) + j * LM_HS] = __float2half_rn(hl[j]);
       hst[k * G::HSTEP + hoff + j * LM_HST] = hl[j];

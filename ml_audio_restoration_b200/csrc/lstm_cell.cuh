@@ -68,6 +68,26 @@ __device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsig
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
   return r;
 }
+// acc + (fp16 pre-activation) in ONE instruction: the mixed-precision add of sm_100 (`add.rn.f32.f16`, SASS FHADD) converts the half
+// operand exactly and rounds once -- the same value as __half2float followed by an fp32 add, without the separate conversion.
+__device__ __forceinline__ float add_f32_f16(float a, unsigned short h) {
+  float r;
+  asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(r) : "h"(h), "f"(a));
+  return r;
+}
+__device__ __forceinline__ void half2_split(uint32_t v, unsigned short& lo, unsigned short& hi) {
+  asm("mov.b32 {%0, %1}, %2;" : "=h"(lo), "=h"(hi) : "r"(v));
+}
+// gate pre-activations of one cell: accumulator (i, f, g, o) + staged fp16 (i, f | g, o)
+__device__ __forceinline__ void lstm_preact(float ai, float af, float ag, float ao, uint2 x, float& pi, float& pf, float& pg, float& po) {
+  unsigned short xi, xf, xg, xo;
+  half2_split(x.x, xi, xf);
+  half2_split(x.y, xg, xo);
+  pi = add_f32_f16(ai, xi);
+  pf = add_f32_f16(af, xf);
+  pg = add_f32_f16(ag, xg);
+  po = add_f32_f16(ao, xo);
+}
 __device__ __forceinline__ void lstm_cell2(float pi0, float pi1, float pf0, float pf1, float pg0, float pg1, float po0, float po1,
                                            float (&c)[2], float (&h)[2]) {
   const unsigned long long one = f2_pack(1.f, 1.f);
