@@ -30,6 +30,23 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib().ar_version() >= 100
 
 
+def test_library_is_sm100a_native_code():
+    """The shipped library is sm_100a machine code with the Blackwell instructions the design rests on: tcgen05.mma
+    (UTCHMMA, 1- and 2-CTA), TMEM loads (LDTM), bulk-async TMA copies and L2 prefetches (UBLKCP / UBLKPF), the LSTM's warp MMA
+    (HMMA.16816), packed 2-wide fp32 (FFMA2) and the mixed-precision add (FHADD) -- no PTX-only / JIT path."""
+    import shutil
+    import subprocess
+    from ml_audio_restoration_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not installed")
+    elf = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf and "sm_90" not in elf, elf
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for op in ("UTCHMMA.2CTA", "UTCHMMA", "LDTM", "UBLKCP", "UBLKPF", "HMMA.16816.F32", "FFMA2", "FHADD", "STG.E.EF"):
+        assert op in sass, f"{op} missing from the SASS of {_lib.LIB_PATH}"
+
+
 def test_num_chunks_matches_oracle_plan():
     from ml_audio_restoration_b200 import _lib, plan_chunks
     L = _lib.lib()
